@@ -1,0 +1,195 @@
+/*
+ * similari_b200.h -- C ABI of the B200-native association engine (libsimilari_b200.so).
+ *
+ * Drop-in boundary for Similari's per-frame cost-matrix + assignment hot path.  The reference has no C ABI
+ * (it is a Rust crate with PyO3 classes); these entry points are what a Rust `extern "C"` block inside
+ * Sort / BatchSort / VisualSort / BatchVisualSort (or the ctypes/PyO3 layer) binds in place of
+ *     TrackStore::foreign_track_distances  (src/track/store.rs:429-460)
+ *   + Voting::winners                       (src/trackers/sort/voting.rs:30-100, src/trackers/visual_sort/voting.rs:45-100)
+ *   + TrackStore::merge_external / add_track (src/track/store.rs:625-691)
+ * INTEGRATION.md shows the Rust-side and Python-side bindings.  All paths cited below are relative to the
+ * reference tree (insight-platform/Similari, crate similari-trackers-rs v0.26.12).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller allocates every output; the library never frees caller memory;
+ *   - a box is 6 floats (xc, yc, angle, aspect, height, confidence) = Universal2DBox (src/utils/bbox.rs:79-87);
+ *     angle == NaN encodes Option::None;
+ *   - custom_object_id == INT64_MIN encodes Option::None; feature quality NULL means 1.0 (unwrap_or(1.0),
+ *     src/trackers/visual_sort/simple_api.rs:141-151);
+ *   - every function returns 0 on success, a negative sb200_status otherwise (the reference panics instead);
+ *     sb200_last_error() returns the message of the calling thread's last failure;
+ *   - a tracker handle is single-threaded (`&mut self` in the reference); handles are independent;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with SB200_ERR_CUDA.
+ */
+#ifndef SIMILARI_B200_H
+#define SIMILARI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_VERSION 1
+
+typedef enum {
+  SB200_OK = 0,
+  SB200_ERR_INVALID = -1,   /* bad argument (the reference's assert!/panic paths) */
+  SB200_ERR_CUDA = -2,      /* CUDA runtime error or no device */
+  SB200_ERR_CAPACITY = -3,  /* problem exceeds a documented device limit */
+  SB200_ERR_INTERNAL = -4
+} sb200_status;
+
+/* TrackerKind: which reference tracker's semantics the handle follows (id numbering, voting cascade).
+ *   SORT             src/trackers/sort/simple_api.rs:21-29
+ *   BATCH_SORT       src/trackers/sort/batch_api.rs:46-53
+ *   VISUAL_SORT      src/trackers/visual_sort/simple_api.rs
+ *   BATCH_VISUAL_SORT src/trackers/visual_sort/batch_api.rs */
+#define SB200_KIND_SORT 0
+#define SB200_KIND_BATCH_SORT 1
+#define SB200_KIND_VISUAL_SORT 2
+#define SB200_KIND_BATCH_VISUAL_SORT 3
+/* PositionalMetricType, src/trackers/sort.rs:364-369 */
+#define SB200_POS_MAHA 0
+#define SB200_POS_IOU 1
+/* VisualSortMetricType, src/trackers/visual_sort/metric.rs:20-24 */
+#define SB200_VIS_EUCLIDEAN 0
+#define SB200_VIS_COSINE 1
+/* VotingType, src/trackers/sort.rs:357-362 */
+#define SB200_VOTING_VISUAL 0
+#define SB200_VOTING_POSITIONAL 1
+#define SB200_MAX_CONSTRAINTS 8
+#define SB200_NONE_ID INT64_MIN
+
+/* Constructor arguments of the four trackers folded into one struct:
+ *   Sort::new / BatchSort::new              src/trackers/sort/simple_api.rs:41-50, batch_api.rs:157-167
+ *   VisualSortOptions + VisualMetricBuilder src/trackers/visual_sort/options.rs:10-205, metric/builder.rs:9-42 */
+typedef struct {
+  int32_t kind;
+  int32_t positional_kind;        /* method / positional_metric */
+  float iou_threshold;            /* PositionalMetricType::IoU(t) */
+  float min_confidence;           /* min_confidence / positional_min_confidence */
+  int32_t max_idle_epochs;
+  int32_t history_length;         /* bbox_history / kept_history_length (only the last boxes are kept on device) */
+  float kalman_position_weight;
+  float kalman_velocity_weight;
+  int32_t n_constraints;          /* SpatioTemporalConstraints: (epoch_delta, max_distance) pairs */
+  int32_t constraint_epochs[SB200_MAX_CONSTRAINTS];
+  float constraint_max_dist[SB200_MAX_CONSTRAINTS];
+  int32_t visual_kind;
+  float visual_threshold;
+  int32_t feature_dim;            /* D; 0 for Sort / BatchSort */
+  int32_t visual_max_observations;
+  int32_t visual_min_votes;
+  int32_t visual_minimal_track_length;
+  float visual_minimal_area;
+  float visual_minimal_quality_use;
+  float visual_minimal_quality_collect;
+  float visual_minimal_own_area_percentage_use;
+  float visual_minimal_own_area_percentage_collect;
+  int32_t max_scenes_hint;            /* capacity hints (0 = grow on demand) */
+  int32_t max_tracks_per_scene_hint;
+  int32_t max_dets_per_scene_hint;
+  int32_t device;                     /* CUDA device ordinal */
+} sb200_options;
+
+/* Fills `o` with the reference's defaults (PySort::new defaults, src/trackers/sort/simple_api.rs:461-470;
+ * VisualMetricBuilder::default, src/trackers/visual_sort/metric/builder.rs:26-42). */
+void sb200_options_default(sb200_options* o);
+
+typedef struct sb200_tracker sb200_tracker;
+
+/* Per-detection result columns = SortTrack (src/trackers/sort.rs:286-311) as struct-of-arrays.  Any pointer
+ * may be NULL (that column is then neither computed into host memory nor copied back). */
+typedef struct {
+  uint64_t* ids;            /* SortTrack.id */
+  uint32_t* epochs;         /* SortTrack.epoch */
+  uint32_t* lengths;        /* SortTrack.length */
+  uint8_t* voting_types;    /* SortTrack.voting_type (SB200_VOTING_*) */
+  float* predicted_boxes;   /* [total][6] SortTrack.predicted_bbox */
+  float* observed_boxes;    /* [total][6] SortTrack.observed_bbox */
+} sb200_predict_out;
+
+const char* sb200_last_error(void);
+int sb200_device_count(void);
+
+/* ---- tracker lifecycle (Sort::new ... ) ---- */
+int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out);
+void sb200_tracker_destroy(sb200_tracker* t);
+/* Makes the tracker launch on `cuda_stream` (a cudaStream_t) instead of its own stream, so that a caller can
+ * bracket the work with its own CUDA events. */
+int sb200_tracker_set_stream(sb200_tracker* t, void* cuda_stream);
+
+/* ---- the hot path ----
+ * One call == Sort::predict_with_scene (n_scenes = 1, src/trackers/sort/simple_api.rs:110-196) or
+ * BatchSort::predict / BatchVisualSort::predict over a PredictionBatchRequest (src/trackers/sort/batch_api.rs:222-290,
+ * src/trackers/visual_sort/batch_api.rs:213-317, src/trackers/batch.rs:12-38) flattened as:
+ *   scene_ids[n_scenes], det_offsets[n_scenes+1] (CSR over detections),
+ *   boxes[total][6], features[total][D] or NULL, has_feature[total] or NULL (all present),
+ *   quality[total] or NULL, custom_ids[total] or NULL, own_area[total] or NULL
+ *   (own-area shares of exclusively_owned_areas, computed by the caller; src/utils/clipping/bbox_own_areas.rs).
+ * All pointers are HOST pointers; inputs are copied to the device and the requested result columns copied back
+ * before the call returns (results in input order, like the reference's Vec<SortTrack>). */
+int sb200_predict_batch(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids, const int32_t* det_offsets,
+                        const float* boxes, const float* features, const uint8_t* has_feature, const float* quality,
+                        const int64_t* custom_ids, const float* own_area, const sb200_predict_out* out);
+/* Same call with boxes / features / has_feature / quality / custom_ids / own_area and every non-NULL `out` column
+ * being DEVICE pointers (inputs already resident in HBM).  scene_ids and det_offsets stay host pointers.
+ * The call is asynchronous on the tracker's stream except for one 4-byte-per-scene status read-back. */
+int sb200_predict_batch_device(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids,
+                               const int32_t* det_offsets, const float* boxes, const float* features,
+                               const uint8_t* has_feature, const float* quality, const int64_t* custom_ids,
+                               const float* own_area, const sb200_predict_out* out);
+
+/* ---- TrackerAPI (src/trackers/tracker_api.rs:27-117) ---- */
+int sb200_skip_epochs(sb200_tracker* t, uint64_t scene_id, int32_t n);
+int64_t sb200_current_epoch(sb200_tracker* t, uint64_t scene_id);
+int64_t sb200_active_tracks(sb200_tracker* t);                 /* sum(active_shard_stats()) */
+int sb200_set_auto_waste(sb200_tracker* t, int32_t periodicity);
+int sb200_clear_wasted(sb200_tracker* t);
+/* wasted(): drains up to `cap` wasted tracks; returns the count (>= 0) or a negative status. */
+int64_t sb200_wasted(sb200_tracker* t, int64_t cap, uint64_t* ids, uint64_t* scene_ids, uint32_t* epochs,
+                     uint32_t* lengths, float* predicted_boxes, float* observed_boxes);
+/* idle_tracks_with_scene() (src/trackers/sort/simple_api.rs:198-215) */
+int64_t sb200_idle_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uint64_t* ids, uint32_t* epochs,
+                          uint32_t* lengths, float* predicted_boxes, float* observed_boxes);
+/* Debug / parity: dense dump of one scene's store in store order.  states: [n][30] = mean[10] + 5 x (Pxx,Pxv,Pvx,Pvv). */
+int64_t sb200_scene_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uint64_t* ids, float* boxes,
+                           float* states30, int32_t* feature_counts);
+/* Debug / parity: last frame's positional cost matrix of a scene ([m][n] f32, NaN == None). */
+int64_t sb200_last_costs(sb200_tracker* t, uint64_t scene_id, int64_t cap, float* out, int32_t* m, int32_t* n);
+/* Per-stage device times (ms) of the last predict call: prep, positional cost, visual cost, voting, apply. */
+int sb200_last_stage_ms(sb200_tracker* t, float* out5);
+
+/* ---- stateless operators (host pointers) used by parity tests and by callers that keep their own state ----
+ * Positional cost matrix = SortMetric::metric over all pairs (src/trackers/sort/metric.rs:38-77):
+ * out[m][n] = IoU*conf (>= thr) or (100 - d^2)/conf, NaN == None.  track_states30 only for Mahalanobis. */
+int sb200_sort_cost_matrix(int32_t positional_kind, float iou_threshold, float min_confidence, float pos_weight,
+                           float vel_weight, const float* cand_boxes, int32_t m, const float* track_boxes,
+                           const float* track_states30, int32_t n, float* out_mn, int32_t device);
+/* Visual cost matrix = euclidean / cosine (src/distance.rs:9-47) + is_ok/distance_to_weight
+ * (src/trackers/visual_sort/metric.rs:52-64); out[m][n], NaN == None. */
+int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* cand_features, int32_t m,
+                             const float* track_features, int32_t n, int32_t d, float* out_mn, int32_t device);
+/* SortVoting::winners on a dense cost matrix (NaN == None): winner[m] = track index or -1 (new track). */
+int sb200_sort_voting(float threshold, const float* cost_mn, int32_t m, int32_t n, int32_t* winner, int32_t device);
+/* VisualVoting::winners on dense matrices: pos[m][n], vis[m][n][k] (NaN == None). */
+int sb200_visual_voting(float positional_threshold, int32_t min_votes, const float* pos_mn, const float* vis_mnk,
+                        int32_t m, int32_t n, int32_t k, int32_t* winner, uint8_t* voting_type, int32_t device);
+/* Kalman filter steps on packed states (src/utils/kalman/kalman_2d_box.rs:58-148), n states at once. */
+int sb200_kalman_initiate(float pos_weight, float vel_weight, const float* boxes, int32_t n, float* states30, int32_t device);
+int sb200_kalman_predict(float pos_weight, float vel_weight, const float* in30, int32_t n, float* out30, int32_t device);
+int sb200_kalman_update(float pos_weight, float vel_weight, const float* in30, const float* boxes, int32_t n,
+                        float* out30, int32_t device);
+/* nms (src/utils/nms.rs:32-72): scores NULL or NaN entries == None; out_idx = kept input indices in rank order;
+ * returns kept count or negative status. */
+int64_t sb200_nms(const float* boxes, const float* scores, int32_t n, float nms_threshold, float score_threshold,
+                  int32_t has_score_threshold, int32_t* out_idx, int32_t device);
+
+/* Pinned host memory for callers that want the predict H2D/D2H copies to run at full PCIe speed. */
+void* sb200_host_alloc(size_t bytes);
+void sb200_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

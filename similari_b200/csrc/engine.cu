@@ -1,0 +1,761 @@
+// engine.cu -- host side of libsimilari_b200.so: the C ABI of include/similari_b200.h, device memory management
+// and the per-frame launch sequence (prep -> positional cost -> visual cost -> voting -> apply).
+// There is no CPU execution path in this library: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/similari_b200.h"
+#include "sb_engine.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(x)                                                                                  \
+  do {                                                                                         \
+    cudaError_t e_ = (x);                                                                      \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(SB200_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// grow-only device buffer
+struct DBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    size_t nb = std::max(need, bytes + bytes / 2);
+    void* np = nullptr;
+    cudaError_t e = cudaMalloc(&np, nb);
+    if (e != cudaSuccess) return fail(SB200_ERR_CUDA, "cudaMalloc(%zu) failed: %s", nb, cudaGetErrorString(e));
+    if (p) cudaFree(p);
+    p = np;
+    bytes = nb;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HBuf {  // grow-only pinned host buffer
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    size_t nb = std::max(need, bytes + bytes / 2);
+    void* np = nullptr;
+    cudaError_t e = cudaMallocHost(&np, nb);
+    if (e != cudaSuccess) return fail(SB200_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", nb, cudaGetErrorString(e));
+    if (p) cudaFreeHost(p);
+    p = np;
+    bytes = nb;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+int make_params(const sb200_options& o, sb::Params* out) {
+  sb::Params p;
+  memset(&p, 0, sizeof(p));
+  if (o.kind < 0 || o.kind > 3) return fail(SB200_ERR_INVALID, "unknown tracker kind %d", o.kind);
+  if (o.positional_kind != SB200_POS_MAHA && o.positional_kind != SB200_POS_IOU)
+    return fail(SB200_ERR_INVALID, "unknown positional metric %d", o.positional_kind);
+  p.kind = o.kind;
+  p.positional_kind = o.positional_kind;
+  p.visual_kind = o.visual_kind;
+  p.iou_threshold = o.iou_threshold;
+  p.min_confidence = o.min_confidence;
+  p.pos_weight = o.kalman_position_weight;
+  p.vel_weight = o.kalman_velocity_weight;
+  p.max_idle_epochs = o.max_idle_epochs;
+  if (o.max_idle_epochs < 0) return fail(SB200_ERR_INVALID, "max_idle_epochs must be >= 0");
+  if (o.n_constraints < 0 || o.n_constraints > SB200_MAX_CONSTRAINTS)
+    return fail(SB200_ERR_INVALID, "at most %d spatio-temporal constraints", SB200_MAX_CONSTRAINTS);
+  // SpatioTemporalConstraints::add_constraints: stable sort by epoch, dedup keeping the first
+  std::vector<std::pair<int, float>> c;
+  for (int i = 0; i < o.n_constraints; ++i) {
+    if (!(o.constraint_max_dist[i] > 0.0f))
+      return fail(SB200_ERR_INVALID, "The distance is expected to be a positive float");
+    c.emplace_back(o.constraint_epochs[i], o.constraint_max_dist[i]);
+  }
+  std::stable_sort(c.begin(), c.end(), [](const std::pair<int, float>& a, const std::pair<int, float>& b) { return a.first < b.first; });
+  c.erase(std::unique(c.begin(), c.end(), [](const std::pair<int, float>& a, const std::pair<int, float>& b) { return a.first == b.first; }), c.end());
+  p.n_constraints = (int)c.size();
+  for (size_t i = 0; i < c.size(); ++i) { p.constraint_epochs[i] = c[i].first; p.constraint_max_dist[i] = c[i].second; }
+  p.is_visual = o.kind == SB200_KIND_VISUAL_SORT || o.kind == SB200_KIND_BATCH_VISUAL_SORT;
+  p.is_batch = o.kind == SB200_KIND_BATCH_SORT || o.kind == SB200_KIND_BATCH_VISUAL_SORT;
+  if (p.is_visual) {
+    if (o.visual_kind != SB200_VIS_EUCLIDEAN && o.visual_kind != SB200_VIS_COSINE)
+      return fail(SB200_ERR_INVALID, "unknown visual metric %d", o.visual_kind);
+    if (o.feature_dim <= 0) return fail(SB200_ERR_INVALID, "feature_dim must be > 0 for visual trackers");
+    if (o.visual_max_observations < 1 || o.visual_max_observations > sb::kMaxObs)
+      return fail(SB200_ERR_CAPACITY, "visual_max_observations must be in [1, %d]", sb::kMaxObs);
+    p.visual_threshold = o.visual_threshold;
+    p.feature_dim = o.feature_dim;
+    p.d8 = (o.feature_dim + 7) / 8 * 8;
+    p.max_obs = o.visual_max_observations;
+    p.min_votes = o.visual_min_votes;
+    p.min_track_length = o.visual_minimal_track_length;
+    p.min_area = o.visual_minimal_area;
+    p.min_quality_use = o.visual_minimal_quality_use;
+    p.min_quality_collect = o.visual_minimal_quality_collect;
+    p.min_own_use = o.visual_minimal_own_area_percentage_use;
+    p.min_own_collect = o.visual_minimal_own_area_percentage_collect;
+    p.use_own_area = (o.visual_minimal_own_area_percentage_collect + o.visual_minimal_own_area_percentage_use) > 0.0f;
+  } else {
+    p.max_obs = 1;
+    p.d8 = 8;
+  }
+  *out = p;
+  return 0;
+}
+
+}  // namespace
+
+struct sb200_tracker {
+  sb200_options opts{};
+  sb::Params P{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev[6]{};
+  float stage_ms[5]{};
+  // scene table
+  std::unordered_map<uint64_t, int> slot_of;
+  std::vector<uint64_t> scene_of_slot;
+  std::vector<uint32_t> epoch;      // host epoch db
+  std::vector<int> n_tracks;        // host mirror
+  int scene_cap = 0, track_cap = 0;
+  uint64_t id_counter = 0;
+  int auto_waste_counter = 100, auto_waste_periodicity = 100;
+  int64_t wasted_count = 0;
+  // device track store
+  sb::TrackStore ts{};
+  DBuf b_id, b_epoch, b_length, b_custom, b_vt, b_pred, b_obs, b_radius, b_kst, b_vert, b_feat, b_fnorm2, b_obs_phys,
+      b_obs_hasf, b_obs_q, b_obs_n, b_feat_cnt;
+  DBuf b_ntracks, b_cur_epoch, b_scene_ids;
+  // wasted
+  sb::WastedBuf wb{};
+  DBuf w_count, w_id, w_scene, w_epoch, w_length, w_pred, w_obs;
+  // frame buffers
+  DBuf f_in_boxes, f_in_feat, f_in_hasf, f_in_quality, f_in_custom, f_in_own;
+  DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
+      f_status, f_featdst;
+  DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
+  HBuf h_scenes, h_small;
+  // last frame bookkeeping (for sb200_last_costs)
+  std::vector<sb::SceneDesc> last_scenes;
+
+  ~sb200_tracker() {
+    cudaSetDevice(device);
+    DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
+                   &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
+                   &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_in_boxes,
+                   &f_in_feat, &f_in_hasf, &f_in_quality, &f_in_custom, &f_in_own, &f_cbox, &f_cradius, &f_cconf,
+                   &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
+                   &f_featdst, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
+    for (DBuf* b : all) b->release();
+    h_scenes.release();
+    h_small.release();
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+
+  // (re)allocates the track store for scene_cap x track_cap rows, preserving the live rows
+  template <typename T>
+  int regrow(DBuf& b, T** field, int width, int new_scenes, int new_tracks) {
+    size_t row = (size_t)width * sizeof(T);
+    DBuf nb;
+    int rc = nb.ensure(std::max<size_t>(1, (size_t)new_scenes * new_tracks * row));
+    if (rc) return rc;
+    if (b.p && scene_cap > 0 && track_cap > 0) {
+      cudaError_t e = cudaMemcpy2DAsync(nb.p, (size_t)new_tracks * row, b.p, (size_t)track_cap * row,
+                                        (size_t)std::min(track_cap, new_tracks) * row, (size_t)scene_cap,
+                                        cudaMemcpyDeviceToDevice, stream);
+      if (e != cudaSuccess) return fail(SB200_ERR_CUDA, "store regrow copy failed: %s", cudaGetErrorString(e));
+      e = cudaStreamSynchronize(stream);
+      if (e != cudaSuccess) return fail(SB200_ERR_CUDA, "store regrow sync failed: %s", cudaGetErrorString(e));
+    }
+    b.release();
+    b = nb;
+    *field = b.as<T>();
+    return 0;
+  }
+
+  int ensure_store(int need_scenes, int need_tracks) {
+    if (need_scenes <= scene_cap && need_tracks <= track_cap) return 0;
+    int ns = scene_cap, nt = track_cap;
+    if (need_scenes > ns) ns = std::max(need_scenes, std::max(4, ns * 2));
+    if (need_tracks > nt) nt = std::max(need_tracks, std::max(64, nt * 2));
+    const int K = P.max_obs;
+    int rc = 0;
+    if ((rc = regrow(b_id, &ts.id, 1, ns, nt))) return rc;
+    if ((rc = regrow(b_epoch, &ts.epoch, 1, ns, nt))) return rc;
+    if ((rc = regrow(b_length, &ts.length, 1, ns, nt))) return rc;
+    if ((rc = regrow(b_custom, &ts.custom, 1, ns, nt))) return rc;
+    if ((rc = regrow(b_vt, &ts.vt, 1, ns, nt))) return rc;
+    if ((rc = regrow(b_pred, &ts.pred, 6, ns, nt))) return rc;
+    if ((rc = regrow(b_obs, &ts.obs, 6, ns, nt))) return rc;
+    if ((rc = regrow(b_radius, &ts.radius, 1, ns, nt))) return rc;
+    if ((rc = regrow(b_kst, &ts.kst, sb::kStateFloats, ns, nt))) return rc;
+    if (P.positional_kind == SB200_POS_IOU)
+      if ((rc = regrow(b_vert, &ts.vert, 8, ns, nt))) return rc;
+    if (P.is_visual) {
+      if ((rc = regrow(b_feat, &ts.feat, K * P.d8, ns, nt))) return rc;
+      if ((rc = regrow(b_fnorm2, &ts.fnorm2, K, ns, nt))) return rc;
+      if ((rc = regrow(b_obs_phys, &ts.obs_phys, K, ns, nt))) return rc;
+      if ((rc = regrow(b_obs_hasf, &ts.obs_hasf, K, ns, nt))) return rc;
+      if ((rc = regrow(b_obs_q, &ts.obs_q, K, ns, nt))) return rc;
+      if ((rc = regrow(b_obs_n, &ts.obs_n, 1, ns, nt))) return rc;
+      if ((rc = regrow(b_feat_cnt, &ts.feat_cnt, 1, ns, nt))) return rc;
+    }
+    if (ns != scene_cap) {
+      // per-slot small arrays
+      DBuf n1, n2, n3;
+      if ((rc = n1.ensure(sizeof(int) * ns))) return rc;
+      if ((rc = n2.ensure(sizeof(unsigned int) * ns))) return rc;
+      if ((rc = n3.ensure(sizeof(unsigned long long) * ns))) return rc;
+      CU(cudaMemsetAsync(n1.p, 0, sizeof(int) * ns, stream));
+      if (b_ntracks.p && scene_cap > 0)
+        CU(cudaMemcpyAsync(n1.p, b_ntracks.p, sizeof(int) * scene_cap, cudaMemcpyDeviceToDevice, stream));
+      CU(cudaStreamSynchronize(stream));
+      b_ntracks.release(); b_cur_epoch.release(); b_scene_ids.release();
+      b_ntracks = n1; b_cur_epoch = n2; b_scene_ids = n3;
+    }
+    scene_cap = ns;
+    track_cap = nt;
+    ts.track_cap = nt;
+    return 0;
+  }
+
+  int slot_for(uint64_t scene_id, bool create) {
+    auto it = slot_of.find(scene_id);
+    if (it != slot_of.end()) return it->second;
+    if (!create) return -1;
+    int s = (int)scene_of_slot.size();
+    slot_of[scene_id] = s;
+    scene_of_slot.push_back(scene_id);
+    epoch.push_back(0);
+    n_tracks.push_back(0);
+    return s;
+  }
+
+  int ensure_wasted(int64_t need) {
+    if (need <= wb.cap) return 0;
+    int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(1024, (int64_t)wb.cap * 2));
+    // wasted records are drained by sb200_wasted; growing preserves the pending ones
+    DBuf nid, nsc, nep, nle, npr, nob;
+    int rc;
+    if ((rc = nid.ensure(8 * ncap)) || (rc = nsc.ensure(8 * ncap)) || (rc = nep.ensure(4 * ncap)) ||
+        (rc = nle.ensure(4 * ncap)) || (rc = npr.ensure(24 * ncap)) || (rc = nob.ensure(24 * ncap)))
+      return rc;
+    if (wasted_count > 0) {
+      CU(cudaMemcpyAsync(nid.p, w_id.p, 8 * wasted_count, cudaMemcpyDeviceToDevice, stream));
+      CU(cudaMemcpyAsync(nsc.p, w_scene.p, 8 * wasted_count, cudaMemcpyDeviceToDevice, stream));
+      CU(cudaMemcpyAsync(nep.p, w_epoch.p, 4 * wasted_count, cudaMemcpyDeviceToDevice, stream));
+      CU(cudaMemcpyAsync(nle.p, w_length.p, 4 * wasted_count, cudaMemcpyDeviceToDevice, stream));
+      CU(cudaMemcpyAsync(npr.p, w_pred.p, 24 * wasted_count, cudaMemcpyDeviceToDevice, stream));
+      CU(cudaMemcpyAsync(nob.p, w_obs.p, 24 * wasted_count, cudaMemcpyDeviceToDevice, stream));
+      CU(cudaStreamSynchronize(stream));
+    }
+    w_id.release(); w_scene.release(); w_epoch.release(); w_length.release(); w_pred.release(); w_obs.release();
+    w_id = nid; w_scene = nsc; w_epoch = nep; w_length = nle; w_pred = npr; w_obs = nob;
+    if (!w_count.p) {
+      if ((rc = w_count.ensure(sizeof(int)))) return rc;
+      CU(cudaMemsetAsync(w_count.p, 0, sizeof(int), stream));
+    }
+    wb.cap = (int)ncap;
+    wb.count = w_count.as<int>();
+    wb.id = w_id.as<unsigned long long>();
+    wb.scene = w_scene.as<unsigned long long>();
+    wb.epoch = w_epoch.as<unsigned int>();
+    wb.length = w_length.as<unsigned int>();
+    wb.pred = w_pred.as<float>();
+    wb.obs = w_obs.as<float>();
+    return 0;
+  }
+
+  // TrackerAPI::auto_waste (src/trackers/tracker_api.rs:81-88)
+  int run_waste() {
+    int n_slots = (int)scene_of_slot.size();
+    if (n_slots == 0) return 0;
+    int64_t active = 0;
+    int max_n = 0;
+    for (int v : n_tracks) { active += v; max_n = std::max(max_n, v); }
+    if (active == 0) return 0;
+    int rc = ensure_wasted(wasted_count + active);
+    if (rc) return rc;
+    if ((rc = h_small.ensure((size_t)n_slots * 16))) return rc;
+    unsigned int* he = h_small.as<unsigned int>();
+    for (int s = 0; s < n_slots; ++s) he[s] = epoch[s];
+    CU(cudaMemcpyAsync(b_cur_epoch.p, he, sizeof(unsigned int) * n_slots, cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream));
+    unsigned long long* hs = h_small.as<unsigned long long>();
+    for (int s = 0; s < n_slots; ++s) hs[s] = scene_of_slot[s];
+    CU(cudaMemcpyAsync(b_scene_ids.p, hs, sizeof(unsigned long long) * n_slots, cudaMemcpyHostToDevice, stream));
+    sb::launch_waste(P, ts, n_slots, b_cur_epoch.as<unsigned int>(), b_scene_ids.as<unsigned long long>(),
+                     b_ntracks.as<int>(), wb, max_n, stream);
+    CU(cudaGetLastError());
+    int* hn = h_small.as<int>();
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaMemcpyAsync(hn, b_ntracks.p, sizeof(int) * n_slots, cudaMemcpyDeviceToHost, stream));
+    int hc = 0;
+    CU(cudaMemcpyAsync(&hc, w_count.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    for (int s = 0; s < n_slots; ++s) n_tracks[s] = hn[s];
+    wasted_count = hc;
+    return 0;
+  }
+
+  int predict(int32_t n_scenes, const uint64_t* scene_ids, const int32_t* det_offsets, const float* boxes,
+              const float* features, const uint8_t* has_feature, const float* quality, const int64_t* custom_ids,
+              const float* own_area, const sb200_predict_out* out, bool device_io);
+};
+
+int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const int32_t* det_offsets, const float* boxes,
+                           const float* features, const uint8_t* has_feature, const float* quality,
+                           const int64_t* custom_ids, const float* own_area, const sb200_predict_out* out,
+                           bool device_io) {
+  CU(cudaSetDevice(device));
+  if (n_scenes < 0) return fail(SB200_ERR_INVALID, "n_scenes must be >= 0");
+  if (n_scenes > 0 && (!scene_ids || !det_offsets)) return fail(SB200_ERR_INVALID, "scene_ids / det_offsets are NULL");
+  const int total = n_scenes > 0 ? det_offsets[n_scenes] : 0;
+  if (n_scenes > 0 && det_offsets[0] != 0) return fail(SB200_ERR_INVALID, "det_offsets[0] must be 0");
+  for (int s = 0; s < n_scenes; ++s)
+    if (det_offsets[s + 1] < det_offsets[s]) return fail(SB200_ERR_INVALID, "det_offsets must be non-decreasing");
+  if (total > 0 && !boxes) return fail(SB200_ERR_INVALID, "boxes is NULL");
+  if (!P.is_visual) { features = nullptr; has_feature = nullptr; quality = nullptr; own_area = nullptr; }
+  // auto-waste tick (src/trackers/sort/simple_api.rs:115-120)
+  if (auto_waste_counter == 0) {
+    int rc = run_waste();
+    if (rc) return rc;
+    auto_waste_counter = auto_waste_periodicity;
+  } else auto_waste_counter -= 1;
+  if (n_scenes == 0) return 0;
+
+  // scene slots, epochs (EpochDb::next_epoch, src/trackers/epoch_db.rs:35-49)
+  std::vector<sb::SceneDesc> sd(n_scenes);
+  {
+    std::unordered_map<uint64_t, int> seen;
+    for (int s = 0; s < n_scenes; ++s)
+      if (!seen.emplace(scene_ids[s], s).second) return fail(SB200_ERR_INVALID, "scene %llu appears twice in one request", (unsigned long long)scene_ids[s]);
+  }
+  int max_m = 0, max_n = 0, need_tracks = 0;
+  long long pos_total = 0, vis_total = 0;
+  for (int s = 0; s < n_scenes; ++s) {
+    int slot = slot_for(scene_ids[s], true);
+    sb::SceneDesc& d = sd[s];
+    d.slot = slot;
+    d.m = det_offsets[s + 1] - det_offsets[s];
+    d.n = n_tracks[slot];
+    d.det_base = det_offsets[s];
+    d.pos_off = pos_total;
+    d.vis_off = vis_total;
+    d.scene_id = scene_ids[s];
+    d.pad = 0;
+    pos_total += (long long)d.m * d.n;
+    if (P.is_visual) vis_total += (long long)d.m * d.n * P.max_obs;
+    max_m = std::max(max_m, d.m);
+    max_n = std::max(max_n, d.n);
+    need_tracks = std::max(need_tracks, d.n + d.m);
+  }
+  {
+    int hint_t = std::max(need_tracks, opts.max_tracks_per_scene_hint);
+    int hint_s = std::max((int)scene_of_slot.size(), opts.max_scenes_hint);
+    int rc = ensure_store(hint_s, hint_t);
+    if (rc) return rc;
+  }
+  for (int s = 0; s < n_scenes; ++s) {
+    epoch[sd[s].slot] += 1;
+    sd[s].epoch = epoch[sd[s].slot];
+  }
+  // frame buffers
+  int rc = 0;
+  const size_t T = (size_t)std::max(total, 1);
+  if ((rc = f_cbox.ensure(T * 24)) || (rc = f_cradius.ensure(T * 4)) || (rc = f_cconf.ensure(T * 4)) ||
+      (rc = f_winner.ensure(T * 4)) || (rc = f_cvt.ensure(T)) || (rc = f_scenes.ensure(sizeof(sb::SceneDesc) * n_scenes)) ||
+      (rc = f_newcount.ensure(4 * (size_t)n_scenes)) || (rc = f_status.ensure(4 * (size_t)n_scenes)) ||
+      (rc = f_pos.ensure(std::max<size_t>(4, (size_t)pos_total * 4))))
+    return rc;
+  if (P.positional_kind == SB200_POS_IOU && (rc = f_cvert.ensure(T * 64))) return rc;
+  if (P.is_visual) {
+    if ((rc = f_cflags.ensure(T)) || (rc = f_cnorm2.ensure(T * 4)) || (rc = f_featdst.ensure(T * 4)) ||
+        (rc = f_vis.ensure(std::max<size_t>(4, (size_t)vis_total * 4))))
+      return rc;
+  }
+  sb::Frame f;
+  memset(&f, 0, sizeof(f));
+  f.total = total;
+  // inputs
+  if (device_io) {
+    f.in_boxes = boxes; f.in_feat = features; f.in_hasf = has_feature; f.in_quality = quality;
+    f.in_custom = reinterpret_cast<const long long*>(custom_ids); f.in_own = own_area;
+  } else {
+    if ((rc = f_in_boxes.ensure(T * 24))) return rc;
+    if (total > 0) CU(cudaMemcpyAsync(f_in_boxes.p, boxes, (size_t)total * 24, cudaMemcpyHostToDevice, stream));
+    f.in_boxes = f_in_boxes.as<float>();
+    if (features && total > 0) {
+      size_t fb = (size_t)total * P.feature_dim * 4;
+      if ((rc = f_in_feat.ensure(fb))) return rc;
+      CU(cudaMemcpyAsync(f_in_feat.p, features, fb, cudaMemcpyHostToDevice, stream));
+      f.in_feat = f_in_feat.as<float>();
+      if (has_feature) {
+        if ((rc = f_in_hasf.ensure(T))) return rc;
+        CU(cudaMemcpyAsync(f_in_hasf.p, has_feature, (size_t)total, cudaMemcpyHostToDevice, stream));
+        f.in_hasf = f_in_hasf.as<unsigned char>();
+      }
+    }
+    if (quality && total > 0) {
+      if ((rc = f_in_quality.ensure(T * 4))) return rc;
+      CU(cudaMemcpyAsync(f_in_quality.p, quality, (size_t)total * 4, cudaMemcpyHostToDevice, stream));
+      f.in_quality = f_in_quality.as<float>();
+    }
+    if (custom_ids && total > 0) {
+      if ((rc = f_in_custom.ensure(T * 8))) return rc;
+      CU(cudaMemcpyAsync(f_in_custom.p, custom_ids, (size_t)total * 8, cudaMemcpyHostToDevice, stream));
+      f.in_custom = f_in_custom.as<long long>();
+    }
+    if (own_area && total > 0) {
+      if ((rc = f_in_own.ensure(T * 4))) return rc;
+      CU(cudaMemcpyAsync(f_in_own.p, own_area, (size_t)total * 4, cudaMemcpyHostToDevice, stream));
+      f.in_own = f_in_own.as<float>();
+    }
+  }
+  f.c_box = f_cbox.as<float>(); f.c_radius = f_cradius.as<float>(); f.c_conf = f_cconf.as<float>();
+  f.c_vert = f_cvert.as<double>(); f.c_flags = f_cflags.as<unsigned char>(); f.c_norm2 = f_cnorm2.as<float>();
+  f.winner = f_winner.as<int>(); f.c_vt = f_cvt.as<unsigned char>(); f.pos = f_pos.as<float>(); f.vis = f_vis.as<float>();
+  f.scenes = f_scenes.as<sb::SceneDesc>(); f.new_count = f_newcount.as<int>(); f.status = f_status.as<int>();
+  f.feat_dst = P.is_visual ? f_featdst.as<int>() : nullptr;
+  // outputs
+  sb200_predict_out o{};
+  if (out) o = *out;
+  if (device_io) {
+    f.o_ids = reinterpret_cast<unsigned long long*>(o.ids); f.o_epochs = o.epochs; f.o_lengths = o.lengths;
+    f.o_vt = o.voting_types; f.o_pred = o.predicted_boxes; f.o_obs = o.observed_boxes;
+  } else {
+    if (o.ids) { if ((rc = o_ids.ensure(T * 8))) return rc; f.o_ids = o_ids.as<unsigned long long>(); }
+    if (o.epochs) { if ((rc = o_epochs.ensure(T * 4))) return rc; f.o_epochs = o_epochs.as<unsigned int>(); }
+    if (o.lengths) { if ((rc = o_lengths.ensure(T * 4))) return rc; f.o_lengths = o_lengths.as<unsigned int>(); }
+    if (o.voting_types) { if ((rc = o_vt.ensure(T))) return rc; f.o_vt = o_vt.as<unsigned char>(); }
+    if (o.predicted_boxes) { if ((rc = o_pred.ensure(T * 24))) return rc; f.o_pred = o_pred.as<float>(); }
+    if (o.observed_boxes) { if ((rc = o_obs.ensure(T * 24))) return rc; f.o_obs = o_obs.as<float>(); }
+  }
+  // scene descriptors
+  if ((rc = h_scenes.ensure(sizeof(sb::SceneDesc) * n_scenes))) return rc;
+  memcpy(h_scenes.p, sd.data(), sizeof(sb::SceneDesc) * n_scenes);
+  CU(cudaMemcpyAsync(f_scenes.p, h_scenes.p, sizeof(sb::SceneDesc) * n_scenes, cudaMemcpyHostToDevice, stream));
+  CU(cudaMemsetAsync(f_status.p, 0, 4 * (size_t)n_scenes, stream));
+
+  CU(cudaEventRecord(ev[0], stream));
+  sb::launch_prep(P, f, n_scenes, max_m, stream);
+  CU(cudaEventRecord(ev[1], stream));
+  sb::launch_pos_cost(P, ts, f, n_scenes, max_m, max_n, stream);
+  CU(cudaEventRecord(ev[2], stream));
+  sb::launch_vis_cost(P, ts, f, n_scenes, max_m, max_n, stream);
+  CU(cudaEventRecord(ev[3], stream));
+  int vr = sb::launch_voting(P, ts, f, n_scenes, max_m, max_n, stream);
+  if (vr == -3) return fail(SB200_ERR_CAPACITY, "scene too large for the on-chip assignment solver (m=%d, n=%d)", max_m, max_n);
+  if (vr != 0) return fail(SB200_ERR_CUDA, "voting launch failed: %s", cudaGetErrorString((cudaError_t)vr));
+  CU(cudaEventRecord(ev[4], stream));
+  sb::launch_apply(P, ts, f, n_scenes, max_m, id_counter, b_ntracks.as<int>(), stream);
+  CU(cudaEventRecord(ev[5], stream));
+  CU(cudaGetLastError());
+
+  // results back
+  if (!device_io && total > 0) {
+    if (o.ids) CU(cudaMemcpyAsync(o.ids, f.o_ids, (size_t)total * 8, cudaMemcpyDeviceToHost, stream));
+    if (o.epochs) CU(cudaMemcpyAsync(o.epochs, f.o_epochs, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    if (o.lengths) CU(cudaMemcpyAsync(o.lengths, f.o_lengths, (size_t)total * 4, cudaMemcpyDeviceToHost, stream));
+    if (o.voting_types) CU(cudaMemcpyAsync(o.voting_types, f.o_vt, (size_t)total, cudaMemcpyDeviceToHost, stream));
+    if (o.predicted_boxes) CU(cudaMemcpyAsync(o.predicted_boxes, f.o_pred, (size_t)total * 24, cudaMemcpyDeviceToHost, stream));
+    if (o.observed_boxes) CU(cudaMemcpyAsync(o.observed_boxes, f.o_obs, (size_t)total * 24, cudaMemcpyDeviceToHost, stream));
+  }
+  if ((rc = h_small.ensure((size_t)n_scenes * 8 + 64))) return rc;
+  int* h_new = h_small.as<int>();
+  int* h_status = h_new + n_scenes;
+  CU(cudaMemcpyAsync(h_new, f.new_count, 4 * (size_t)n_scenes, cudaMemcpyDeviceToHost, stream));
+  CU(cudaMemcpyAsync(h_status, f.status, 4 * (size_t)n_scenes, cudaMemcpyDeviceToHost, stream));
+  CU(cudaStreamSynchronize(stream));
+  long long new_total = 0;
+  for (int s = 0; s < n_scenes; ++s) {
+    if (h_status[s]) return fail(SB200_ERR_INTERNAL, "track store overflow in scene %llu", (unsigned long long)sd[s].scene_id);
+    n_tracks[sd[s].slot] = sd[s].n + h_new[s];
+    new_total += h_new[s];
+  }
+  id_counter += P.is_batch ? (uint64_t)total : (uint64_t)new_total;
+  for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
+  last_scenes = sd;
+  return 0;
+}
+
+// =============================================================================================== C ABI
+extern "C" {
+
+const char* sb200_last_error(void) { return g_err.c_str(); }
+void sb200__set_error(const char* msg) { g_err = msg ? msg : ""; }  // used by ops.cu / nms
+
+int sb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void sb200_options_default(sb200_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->kind = SB200_KIND_SORT;
+  o->positional_kind = SB200_POS_MAHA;
+  o->iou_threshold = 0.3f;
+  o->min_confidence = 0.05f;
+  o->max_idle_epochs = 5;
+  o->history_length = 1;
+  o->kalman_position_weight = 1.0f / 20.0f;
+  o->kalman_velocity_weight = 1.0f / 160.0f;
+  o->visual_kind = SB200_VIS_EUCLIDEAN;
+  o->visual_threshold = 3.402823466e+38f;
+  o->visual_max_observations = 5;
+  o->visual_min_votes = 1;
+  o->visual_minimal_track_length = 3;
+}
+
+int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out) {
+  if (!opts || !out) return fail(SB200_ERR_INVALID, "opts / out is NULL");
+  *out = nullptr;
+  int ndev = sb200_device_count();
+  if (ndev <= 0) return fail(SB200_ERR_CUDA, "no CUDA device available (this library has no CPU execution path)");
+  if (opts->device < 0 || opts->device >= ndev) return fail(SB200_ERR_INVALID, "device %d out of range (%d devices)", opts->device, ndev);
+  sb::Params P;
+  int rc = make_params(*opts, &P);
+  if (rc) return rc;
+  CU(cudaSetDevice(opts->device));
+  sb200_tracker* t = new sb200_tracker();
+  t->opts = *opts;
+  t->P = P;
+  t->device = opts->device;
+  cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+  for (auto& ev : t->ev) {
+    e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
+  }
+  if (opts->max_scenes_hint > 0 || opts->max_tracks_per_scene_hint > 0) {
+    rc = t->ensure_store(std::max(1, opts->max_scenes_hint), std::max(64, opts->max_tracks_per_scene_hint));
+    if (rc) { delete t; return rc; }
+  }
+  *out = t;
+  return 0;
+}
+
+void sb200_tracker_destroy(sb200_tracker* t) { delete t; }
+
+int sb200_tracker_set_stream(sb200_tracker* t, void* cuda_stream) {
+  if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
+  CU(cudaSetDevice(t->device));
+  CU(cudaStreamSynchronize(t->stream));
+  if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
+  t->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  t->own_stream = false;
+  return 0;
+}
+
+int sb200_predict_batch(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids, const int32_t* det_offsets,
+                        const float* boxes, const float* features, const uint8_t* has_feature, const float* quality,
+                        const int64_t* custom_ids, const float* own_area, const sb200_predict_out* out) {
+  if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
+  return t->predict(n_scenes, scene_ids, det_offsets, boxes, features, has_feature, quality, custom_ids, own_area, out, false);
+}
+
+int sb200_predict_batch_device(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids,
+                               const int32_t* det_offsets, const float* boxes, const float* features,
+                               const uint8_t* has_feature, const float* quality, const int64_t* custom_ids,
+                               const float* own_area, const sb200_predict_out* out) {
+  if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
+  return t->predict(n_scenes, scene_ids, det_offsets, boxes, features, has_feature, quality, custom_ids, own_area, out, true);
+}
+
+int sb200_skip_epochs(sb200_tracker* t, uint64_t scene_id, int32_t n) {
+  if (!t || n < 0) return fail(SB200_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(t->device));
+  int slot = t->slot_for(scene_id, true);
+  int rc = t->ensure_store((int)t->scene_of_slot.size(), std::max(t->track_cap, 64));
+  if (rc) return rc;
+  t->epoch[slot] += (uint32_t)n;
+  return t->run_waste();  // skip_epochs_for_scene ends with auto_waste (tracker_api.rs:48-51)
+}
+
+int64_t sb200_current_epoch(sb200_tracker* t, uint64_t scene_id) {
+  if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
+  int slot = t->slot_for(scene_id, false);
+  return slot < 0 ? 0 : (int64_t)t->epoch[slot];
+}
+
+int64_t sb200_active_tracks(sb200_tracker* t) {
+  if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
+  int64_t n = 0;
+  for (int v : t->n_tracks) n += v;
+  return n;
+}
+
+int sb200_set_auto_waste(sb200_tracker* t, int32_t periodicity) {
+  if (!t || periodicity < 0) return fail(SB200_ERR_INVALID, "bad arguments");
+  t->auto_waste_periodicity = periodicity;
+  t->auto_waste_counter = 0;  // set_auto_waste resets the counter (tracker_api.rs:29-33)
+  return 0;
+}
+
+int sb200_clear_wasted(sb200_tracker* t) {
+  if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
+  CU(cudaSetDevice(t->device));
+  if (t->w_count.p) CU(cudaMemsetAsync(t->w_count.p, 0, sizeof(int), t->stream));
+  CU(cudaStreamSynchronize(t->stream));
+  t->wasted_count = 0;
+  return 0;
+}
+
+int64_t sb200_wasted(sb200_tracker* t, int64_t cap, uint64_t* ids, uint64_t* scene_ids, uint32_t* epochs,
+                     uint32_t* lengths, float* predicted_boxes, float* observed_boxes) {
+  if (!t || cap < 0) return fail(SB200_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(t->device));
+  int rc = t->run_waste();  // wasted() starts with auto_waste (tracker_api.rs:90-91)
+  if (rc) return rc;
+  int64_t n = std::min<int64_t>(cap, t->wasted_count);
+  if (n == 0) return 0;
+  cudaStream_t st = t->stream;
+  if (ids) CU(cudaMemcpyAsync(ids, t->wb.id, 8 * n, cudaMemcpyDeviceToHost, st));
+  if (scene_ids) CU(cudaMemcpyAsync(scene_ids, t->wb.scene, 8 * n, cudaMemcpyDeviceToHost, st));
+  if (epochs) CU(cudaMemcpyAsync(epochs, t->wb.epoch, 4 * n, cudaMemcpyDeviceToHost, st));
+  if (lengths) CU(cudaMemcpyAsync(lengths, t->wb.length, 4 * n, cudaMemcpyDeviceToHost, st));
+  if (predicted_boxes) CU(cudaMemcpyAsync(predicted_boxes, t->wb.pred, 24 * n, cudaMemcpyDeviceToHost, st));
+  if (observed_boxes) CU(cudaMemcpyAsync(observed_boxes, t->wb.obs, 24 * n, cudaMemcpyDeviceToHost, st));
+  // drain: shift the remaining records to the front
+  int64_t rest = t->wasted_count - n;
+  if (rest > 0) {
+    // overlapping device-to-device moves are done through a temporary
+    DBuf tmp;
+    if ((rc = tmp.ensure((size_t)rest * 24))) return rc;
+    auto shift = [&](void* base, size_t el) -> int {
+      CU(cudaMemcpyAsync(tmp.p, (char*)base + n * el, rest * el, cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(base, tmp.p, rest * el, cudaMemcpyDeviceToDevice, st));
+      return 0;
+    };
+    if ((rc = shift(t->wb.id, 8)) || (rc = shift(t->wb.scene, 8)) || (rc = shift(t->wb.epoch, 4)) ||
+        (rc = shift(t->wb.length, 4)) || (rc = shift(t->wb.pred, 24)) || (rc = shift(t->wb.obs, 24)))
+      return rc;
+    CU(cudaStreamSynchronize(st));
+    tmp.release();
+  }
+  int newc = (int)rest;
+  CU(cudaMemcpyAsync(t->w_count.p, &newc, sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  t->wasted_count = rest;
+  return n;
+}
+
+static int64_t dump_scene(sb200_tracker* t, uint64_t scene_id, int64_t cap, bool idle_only, uint64_t* ids,
+                          uint32_t* epochs, uint32_t* lengths, float* pred, float* obs, float* states30,
+                          int32_t* feat_counts) {
+  if (!t || cap < 0) return fail(SB200_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(t->device));
+  int slot = t->slot_for(scene_id, false);
+  if (slot < 0) return 0;
+  int n = t->n_tracks[slot];
+  if (n == 0) return 0;
+  size_t base = (size_t)slot * t->track_cap;
+  std::vector<uint64_t> hid(n);
+  std::vector<uint32_t> hep(n), hle(n);
+  std::vector<float> hpr((size_t)n * 6), hob((size_t)n * 6), hst((size_t)n * 30);
+  std::vector<unsigned char> hfc(n, 0);
+  cudaStream_t st = t->stream;
+  CU(cudaMemcpyAsync(hid.data(), t->ts.id + base, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hep.data(), t->ts.epoch + base, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hle.data(), t->ts.length + base, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hpr.data(), t->ts.pred + base * 6, 24 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hob.data(), t->ts.obs + base * 6, 24 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hst.data(), t->ts.kst + base * 30, 120 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (t->P.is_visual) CU(cudaMemcpyAsync(hfc.data(), t->ts.feat_cnt + base, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  int64_t k = 0;
+  for (int j = 0; j < n && k < cap; ++j) {
+    // SortLookup::IdleLookup (src/trackers/sort.rs:190-208): last_updated_epoch != current epoch of the scene
+    if (idle_only && hep[j] == t->epoch[slot]) continue;
+    if (ids) ids[k] = hid[j];
+    if (epochs) epochs[k] = hep[j];
+    if (lengths) lengths[k] = hle[j];
+    if (pred) memcpy(pred + k * 6, &hpr[(size_t)j * 6], 24);
+    if (obs) memcpy(obs + k * 6, &hob[(size_t)j * 6], 24);
+    if (states30) memcpy(states30 + k * 30, &hst[(size_t)j * 30], 120);
+    if (feat_counts) feat_counts[k] = hfc[j];
+    ++k;
+  }
+  return k;
+}
+
+int64_t sb200_idle_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uint64_t* ids, uint32_t* epochs,
+                          uint32_t* lengths, float* predicted_boxes, float* observed_boxes) {
+  return dump_scene(t, scene_id, cap, true, ids, epochs, lengths, predicted_boxes, observed_boxes, nullptr, nullptr);
+}
+
+int64_t sb200_scene_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uint64_t* ids, float* boxes,
+                           float* states30, int32_t* feature_counts) {
+  return dump_scene(t, scene_id, cap, false, ids, nullptr, nullptr, boxes, nullptr, states30, feature_counts);
+}
+
+int64_t sb200_last_costs(sb200_tracker* t, uint64_t scene_id, int64_t cap, float* out, int32_t* m, int32_t* n) {
+  if (!t || !out || !m || !n) return fail(SB200_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(t->device));
+  for (const sb::SceneDesc& d : t->last_scenes) {
+    if (d.scene_id != scene_id) continue;
+    *m = d.m; *n = d.n;
+    int64_t cnt = std::min<int64_t>(cap, (int64_t)d.m * d.n);
+    if (cnt > 0) {
+      CU(cudaMemcpyAsync(out, t->f_pos.as<float>() + d.pos_off, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, t->stream));
+      CU(cudaStreamSynchronize(t->stream));
+    }
+    return cnt;
+  }
+  *m = 0; *n = 0;
+  return 0;
+}
+
+int sb200_last_stage_ms(sb200_tracker* t, float* out5) {
+  if (!t || !out5) return fail(SB200_ERR_INVALID, "bad arguments");
+  memcpy(out5, t->stage_ms, sizeof(float) * 5);
+  return 0;
+}
+
+void* sb200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); g_err = "cudaMallocHost failed"; return nullptr; }
+  return p;
+}
+void sb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,451 @@
+// kernels_assign.cu -- the voting stage: one CTA per scene.
+//
+// Replaces Voting::winners of the reference on the dense per-scene cost matrices (NaN == None):
+//   SortVoting::winners      src/trackers/sort/voting.rs:30-100   (i64 weights, diagonal "new track" columns,
+//                            pathfinding::kuhn_munkres maximum-weight assignment)
+//   BestFitVoting::winners   src/track/voting/best.rs:52-128      (greedy on sum_k (max_dist - d_k) weights)
+//   VisualVoting::winners    src/trackers/visual_sort/voting.rs:45-100 (BestFit cascade, then SortVoting on the rest)
+//
+// Kuhn-Munkres keeps the exact label/slack formulation of pathfinding (rows in order, lowest-index column of
+// minimal slack) so that the assignment -- including ties -- is the one the oracle computes.  The column state
+// (slack, ly, alternating, slackx, yx) lives in shared memory; every thread owns a strided set of columns, and a
+// root iteration is one pass over the owned columns plus one block-wide lexicographic (slack, column) argmin.
+// The weight matrix is never materialised: w(row, col) is derived on the fly from the f32 cost matrix
+// (L2-resident: m*n*4 B per scene) and the diagonal / zero columns are implicit.
+//
+// BestFit needs no sort on a GPU: in the reference's greedy pass over the weight-sorted list an element wins its
+// track iff it is the FIRST element naming that track, i.e. the column-wise argmax of the weight matrix, and a
+// query's decision is its first element, i.e. its row-wise argmax.  Both are plain reductions.
+#include "sb_engine.cuh"
+
+namespace sb {
+
+constexpr int VT_THREADS = 512;
+constexpr int NWARPS = VT_THREADS / 32;
+constexpr int kNone = -1, kSelf = -2;
+
+struct MinPair { long long v; int y; };
+
+__device__ __forceinline__ MinPair min_pair(MinPair a, MinPair b) {
+  return (b.v < a.v || (b.v == a.v && b.y < a.y)) ? b : a;
+}
+__device__ __forceinline__ MinPair warp_min(MinPair a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MinPair b;
+    b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    b.y = __shfl_xor_sync(0xffffffffu, a.y, o);
+    a = min_pair(a, b);
+  }
+  return a;
+}
+
+struct BestPair { double w; int i; };  // maximise w, tie -> smaller index
+__device__ __forceinline__ BestPair best_pair(BestPair a, BestPair b) {
+  if (b.i < 0) return a;
+  if (a.i < 0) return b;
+  return (b.w > a.w || (b.w == a.w && b.i < a.i)) ? b : a;
+}
+
+__device__ __forceinline__ unsigned int enc_f32(float v) {  // order-preserving f32 -> u32
+  unsigned int u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_f32(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// per-scene maximum over all valid visual entries ("max_dist" of best.rs:58,72-74), init -1.0
+__global__ void vis_max_kernel(Params p, Frame f, unsigned int* scene_max) {
+  const SceneDesc sc = f.scenes[blockIdx.y];
+  const long long cnt = (long long)sc.m * sc.n * p.max_obs;
+  const float* v = f.vis + sc.vis_off;
+  float mx = -1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x) {
+    float e = v[i];
+    if (!is_nan(e) && mx < e) mx = e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float t = __shfl_xor_sync(0xffffffffu, mx, o);
+    if (mx < t) mx = t;
+  }
+  if ((threadIdx.x & 31) == 0) atomicMax(scene_max + blockIdx.y, enc_f32(mx));
+}
+__global__ void vis_max_init_kernel(unsigned int* scene_max, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scene_max[i] = enc_f32(-1.0f);
+}
+
+struct VoteSmem {
+  long long* slack; long long* ly; long long* lx; long long* rmax;
+  int* slackx; int* alt; int* yx; int* xy; int* row_cand; int* col_trk; int* first_m; int* row_of_m;
+  int* fw; int* cnt_m;
+  unsigned char* inS; unsigned char* excl; unsigned char* seen_m;
+};
+
+__host__ __device__ inline size_t vote_smem_bytes(int M, int N) {
+  size_t ny = (size_t)M + N;
+  size_t b = 0;
+  b += ny * 8 * 2;            // slack, ly
+  b += (size_t)M * 8 * 2;     // lx, rmax
+  b += ny * 4 * 3;            // slackx, alt, yx
+  b += (size_t)M * 4 * 5;     // xy, row_cand, row_of_m, fw, cnt_m
+  b += (size_t)N * 4 * 2;     // col_trk, first_m
+  b += (size_t)M * 2 + N;     // inS, seen_m, excl
+  return b + 64;
+}
+
+__device__ inline VoteSmem carve(unsigned char* base, int M, int N) {
+  VoteSmem s;
+  size_t ny = (size_t)M + N;
+  long long* p8 = reinterpret_cast<long long*>(base);
+  s.slack = p8; p8 += ny;
+  s.ly = p8; p8 += ny;
+  s.lx = p8; p8 += M;
+  s.rmax = p8; p8 += M;
+  int* p4 = reinterpret_cast<int*>(p8);
+  s.slackx = p4; p4 += ny;
+  s.alt = p4; p4 += ny;
+  s.yx = p4; p4 += ny;
+  s.xy = p4; p4 += M;
+  s.row_cand = p4; p4 += M;
+  s.row_of_m = p4; p4 += M;
+  s.fw = p4; p4 += M;
+  s.cnt_m = p4; p4 += M;
+  s.col_trk = p4; p4 += N;
+  s.first_m = p4; p4 += N;
+  unsigned char* p1 = reinterpret_cast<unsigned char*>(p4);
+  s.inS = p1; p1 += M;
+  s.seen_m = p1; p1 += M;
+  s.excl = p1; p1 += N;
+  return s;
+}
+
+// block-wide exclusive scan of 0/1 flags over `n` items (n arbitrary), result in out[i], returns total.
+__device__ int block_scan_flags(const unsigned char* flags, int* out, int n, int* s_warp, int* s_carry) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) *s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += VT_THREADS) {
+    int i = base + tid;
+    int v = (i < n && flags[i]) ? 1 : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += t;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += s_warp[w];
+    int carry = *s_carry;
+    if (i < n) out[i] = carry + woff + x - v;
+    __syncthreads();
+    if (tid == VT_THREADS - 1) *s_carry = carry + woff + x;
+    __syncthreads();
+  }
+  return *s_carry;
+}
+
+template <bool VISUAL>
+__global__ void __launch_bounds__(VT_THREADS) voting_kernel(Params p, Frame f, const unsigned int* scene_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ MinPair s_red[2][NWARPS];
+  __shared__ BestPair s_rowc[32][NWARPS];
+  __shared__ int s_warp[NWARPS];
+  __shared__ int s_misc[4];
+  const int sidx = blockIdx.x;
+  const SceneDesc sc = f.scenes[sidx];
+  const int M = sc.m, N = sc.n;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int* winner = f.winner + sc.det_base;
+  unsigned char* cvt = f.c_vt + sc.det_base;
+  if (M == 0) {
+    if (tid == 0) f.new_count[sidx] = 0;
+    return;
+  }
+  VoteSmem s = carve(smem_raw, M, N);
+  const float* pos = f.pos + sc.pos_off;
+
+  for (int m = tid; m < M; m += VT_THREADS) {
+    winner[m] = -1;
+    cvt[m] = (unsigned char)1;  // VotingType::Positional (SortTrack::from default)
+    s.fw[m] = kNone;
+    s.seen_m[m] = 0;
+    s.rmax[m] = (-9223372036854775807LL - 1);
+    s.cnt_m[m] = 0;
+  }
+  for (int n = tid; n < N; n += VT_THREADS) { s.excl[n] = 0; s.first_m[n] = 0x7fffffff; }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ BestFit on the visual matrix
+  if (VISUAL && N > 0) {
+    const int K = p.max_obs;
+    const float maxd = dec_f32(scene_max[sidx]);
+    const float* vis = f.vis + sc.vis_off;
+    // column-owned sweep: thread owns columns n = tid + j*VT_THREADS, rows are walked in order
+    // s.slack / s.slackx double as per-column best (weight bits, row)
+    double* colw = reinterpret_cast<double*>(s.slack);
+    int* colm = s.slackx;
+    for (int n = tid; n < N; n += VT_THREADS) { colm[n] = -1; colw[n] = 0.0; }
+    __syncthreads();
+    for (int m0 = 0; m0 < M; m0 += 32) {
+      const int mend = min(M, m0 + 32);
+      for (int m = m0; m < mend; ++m) {
+        BestPair rb; rb.w = 0.0; rb.i = -1;
+        for (int n = tid; n < N; n += VT_THREADS) {
+          const float* e = vis + ((size_t)m * N + n) * K;
+          int votes = 0;
+          double w = 0.0;
+          for (int k = 0; k < K; ++k) {
+            float d = e[k];
+            if (!is_nan(d)) { ++votes; w += (double)(maxd - d); }
+          }
+          if (votes > 0 && votes >= p.min_votes) {
+            if (colm[n] < 0 || w > colw[n]) { colw[n] = w; colm[n] = m; }  // strict: earliest row wins ties
+            if (rb.i < 0 || w > rb.w) { rb.w = w; rb.i = n; }             // ascending n: earliest column wins
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          BestPair t;
+          t.w = __shfl_xor_sync(0xffffffffu, rb.w, o);
+          t.i = __shfl_xor_sync(0xffffffffu, rb.i, o);
+          rb = best_pair(rb, t);
+        }
+        if (lane == 0) s_rowc[m - m0][wid] = rb;
+      }
+      __syncthreads();
+      if (tid < mend - m0) {
+        BestPair rb = s_rowc[tid][0];
+        for (int w = 1; w < NWARPS; ++w) rb = best_pair(rb, s_rowc[tid][w]);
+        s.fw[m0 + tid] = rb.i;  // provisional: best column, or -1
+      }
+      __syncthreads();
+    }
+    // resolve: a query wins its best track iff it is that track's best query (first element naming the track)
+    for (int m = tid; m < M; m += VT_THREADS) {
+      int n1 = s.fw[m];
+      if (n1 >= 0) {
+        cvt[m] = (unsigned char)0;  // VotingType::Visual
+        if (colm[n1] == m) { winner[m] = n1; s.excl[n1] = 1; }
+        else s.fw[m] = kSelf;       // rewritten to self => new track, still excluded from the positional stage
+      }
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ positional stage: SortVoting
+  const long long thr = weight_i64(p.positional_kind == 0 ? 1.0f : p.iou_threshold) ;
+  // prepass (warp per row): row maxima, row/column "seen" state in stream order
+  if (N > 0) {
+    for (int m = wid; m < M; m += NWARPS) {
+      if (VISUAL && s.fw[m] != kNone) continue;
+      long long mx = (-9223372036854775807LL - 1);
+      int cnt = 0;
+      for (int n = lane; n < N; n += 32) {
+        float v = pos[(size_t)m * N + n];
+        if (!is_nan(v) && !(VISUAL && s.excl[n])) {
+          long long w = weight_i64(v);
+          mx = w > mx ? w : mx;
+          ++cnt;
+          if (m < s.first_m[n]) atomicMin(&s.first_m[n], m);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        long long t = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = t > mx ? t : mx;
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      }
+      if (lane == 0) { s.rmax[m] = mx; s.cnt_m[m] = cnt; s.seen_m[m] = cnt > 0; }
+    }
+  }
+  __syncthreads();
+  // rows: seen candidates in ascending order (first-seen order of the stream), then (Sort only) the unseen ones
+  const int n_seen_rows = block_scan_flags(s.seen_m, s.row_of_m, M, s_warp, &s_misc[0]);
+  for (int m = tid; m < M; m += VT_THREADS)
+    if (s.seen_m[m]) s.row_cand[s.row_of_m[m]] = m;
+  const int nrows = VISUAL ? n_seen_rows : M;
+  // columns: seen tracks ordered by (first row that names them, track index)
+  int n_seen_cols = 0;
+  {
+    // rank by counting; keys are unique
+    for (int n = tid; n < N; n += VT_THREADS) {
+      int fm = s.first_m[n];
+      if (fm == 0x7fffffff) continue;
+      int rank = 0;
+      for (int q = 0; q < N; ++q) {
+        int fq = s.first_m[q];
+        if (fq < fm || (fq == fm && q < n)) ++rank;
+      }
+      s.col_trk[rank] = n;
+    }
+    // count seen columns
+    int c = 0;
+    for (int n = tid; n < N; n += VT_THREADS) c += s.first_m[n] != 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_warp[wid] = c;
+    __syncthreads();
+    for (int w = 0; w < NWARPS; ++w) n_seen_cols += s_warp[w];
+    __syncthreads();
+  }
+  const int ntrk = VISUAL ? n_seen_cols : N;   // SortVoting::new(.., tracks_num)
+  const int ny = nrows + ntrk;
+
+  if (ntrk > 0 && nrows > 0) {   // `if self.track_num == 0 { return HashMap::default() }`
+    // weight accessor
+    auto wgt = [&](int r, int y) -> long long {
+      if (y < nrows) return y == r ? thr : 0;
+      int j = y - nrows;
+      if (j >= n_seen_cols || r >= n_seen_rows) return 0;
+      float v = pos[(size_t)s.row_cand[r] * N + s.col_trk[j]];
+      return is_nan(v) ? 0 : weight_i64(v);
+    };
+    // labels: lx = row maximum over all ny columns, ly = 0
+    for (int r = tid; r < nrows; r += VT_THREADS) {
+      long long mx = thr;
+      if (ny > 1) {
+        int valid = r < n_seen_rows ? s.cnt_m[s.row_cand[r]] : 0;
+        if (ny - 1 > valid) mx = mx > 0 ? mx : 0;           // some implicit zero column exists
+        if (r < n_seen_rows) { long long rm = s.rmax[s.row_cand[r]]; mx = rm > mx ? rm : mx; }
+      }
+      s.lx[r] = mx;
+      s.xy[r] = -1;
+    }
+    for (int y = tid; y < ny; y += VT_THREADS) { s.ly[y] = 0; s.yx[y] = -1; }
+    __syncthreads();
+
+    int parity = 0;
+    for (int root = 0; root < nrows; ++root) {
+      // ---- init search tree at `root`
+      const long long lxr = s.lx[root];
+      MinPair best; best.v = 9223372036854775807LL; best.y = 0x7fffffff;
+      for (int y = tid; y < ny; y += VT_THREADS) {
+        long long sl = lxr + s.ly[y] - wgt(root, y);
+        s.slack[y] = sl; s.slackx[y] = root; s.alt[y] = -1;
+        MinPair c; c.v = sl; c.y = y;
+        best = min_pair(best, c);
+      }
+      for (int x = tid; x < nrows; x += VT_THREADS) s.inS[x] = x == root;
+      best = warp_min(best);
+      if (lane == 0) s_red[parity][wid] = best;
+      __syncthreads();
+      int y_end = -1, x_end = -1;
+      for (;;) {
+        MinPair g = s_red[parity][0];
+#pragma unroll
+        for (int w = 1; w < NWARPS; ++w) g = min_pair(g, s_red[parity][w]);
+        parity ^= 1;
+        const long long delta = g.v;
+        const int ystar = g.y;
+        const int xstar = s.slackx[ystar];
+        const int x2 = s.yx[ystar];
+        // label update of the tree rows; the row's owner also admits x2 (the row matched to ystar) into the tree,
+        // after its own label update so that lx[x2] is not touched by this delta
+        for (int x = tid; x < nrows; x += VT_THREADS) {
+          if (s.inS[x]) { if (delta > 0) s.lx[x] -= delta; }
+          else if (x == x2) s.inS[x] = 1;
+        }
+        if (x2 < 0) {
+          // augmenting path found; still apply the label update to the columns
+          if (delta > 0)
+            for (int y = tid; y < ny; y += VT_THREADS) {
+              if (s.alt[y] >= 0) s.ly[y] += delta;
+              else s.slack[y] -= delta;
+            }
+          y_end = ystar; x_end = xstar;
+          break;
+        }
+        const long long lx2 = s.lx[x2];
+        MinPair nb; nb.v = 9223372036854775807LL; nb.y = 0x7fffffff;
+        for (int y = tid; y < ny; y += VT_THREADS) {
+          if (s.alt[y] >= 0) { if (delta > 0) s.ly[y] += delta; continue; }
+          long long sl = s.slack[y] - delta;
+          if (y == ystar) { s.alt[y] = xstar; s.slack[y] = sl; continue; }
+          long long a = lx2 + s.ly[y] - wgt(x2, y);
+          if (sl > a) { sl = a; s.slackx[y] = x2; }
+          s.slack[y] = sl;
+          MinPair c; c.v = sl; c.y = y;
+          nb = min_pair(nb, c);
+        }
+        nb = warp_min(nb);
+        if (lane == 0) s_red[parity][wid] = nb;
+        __syncthreads();
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int y = y_end, x = x_end;
+        for (;;) {
+          int prec = s.xy[x];
+          s.yx[y] = x;
+          s.xy[x] = y;
+          y = prec;
+          if (y < 0) break;
+          x = s.alt[y];
+        }
+      }
+      __syncthreads();
+    }
+    // emit
+    for (int r = tid; r < n_seen_rows; r += VT_THREADS) {
+      int y = s.xy[r];
+      int m = s.row_cand[r];
+      if (y >= nrows && (y - nrows) < n_seen_cols) {
+        winner[m] = s.col_trk[y - nrows];
+        cvt[m] = (unsigned char)1;
+      }
+    }
+  }
+  __syncthreads();
+  // count new tracks of the scene
+  int c = 0;
+  for (int m = tid; m < M; m += VT_THREADS) c += winner[m] < 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) s_warp[wid] = c;
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int w = 0; w < NWARPS; ++w) t += s_warp[w];
+    f.new_count[sidx] = t;
+  }
+}
+
+static unsigned int* g_scene_max = nullptr;
+static int g_scene_max_cap = 0;
+
+int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                  cudaStream_t st) {
+  (void)ts;
+  if (n_scenes == 0) return 0;
+  size_t smem = vote_smem_bytes(max_m, max_n);
+  if (smem > 200 * 1024) return -3;
+  cudaError_t e;
+  if (p.is_visual) {
+    if (g_scene_max_cap < n_scenes) {
+      if (g_scene_max) cudaFree(g_scene_max);
+      e = cudaMalloc(&g_scene_max, sizeof(unsigned int) * n_scenes);
+      if (e != cudaSuccess) return (int)e;
+      g_scene_max_cap = n_scenes;
+    }
+    vis_max_init_kernel<<<(n_scenes + 255) / 256, 256, 0, st>>>(g_scene_max, n_scenes);
+    if (max_m > 0 && max_n > 0) {
+      dim3 grid(32, n_scenes);
+      vis_max_kernel<<<grid, 256, 0, st>>>(p, f, g_scene_max);
+    }
+    e = cudaFuncSetAttribute(voting_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    voting_kernel<true><<<n_scenes, VT_THREADS, smem, st>>>(p, f, g_scene_max);
+  } else {
+    e = cudaFuncSetAttribute(voting_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    voting_kernel<false><<<n_scenes, VT_THREADS, smem, st>>>(p, f, nullptr);
+  }
+  return 0;
+}
+
+}  // namespace sb

@@ -1,0 +1,354 @@
+// kernels_state.cu -- applying the voting decisions to the device-resident track store.
+//
+// Replaces the per-candidate tail of the reference's predict functions
+//   (src/trackers/sort/simple_api.rs:165-192, sort/batch_api.rs:98-139, visual_sort/simple_api.rs:188-227):
+//   new track   -> TrackStore::add_track of the candidate built by SortMetric::optimize / VisualMetric::optimize
+//   merge       -> TrackStore::merge_external -> Track::merge (src/track.rs:522-588) -> optimize(is_merge = true):
+//                  Kalman predict + update with the candidate box (src/trackers/kalman_prediction.rs:13-32),
+//                  history push, feature-set pruning (src/trackers/visual_sort/metric.rs:129-154,297-374)
+// and the lifecycle sweep TrackerAPI::auto_waste (src/trackers/tracker_api.rs:70-88).
+#include "sb_engine.cuh"
+
+namespace sb {
+
+constexpr int AT = 256;
+
+__device__ __forceinline__ void write_box(float* dst, const Box& b) {
+  dst[0] = b.xc; dst[1] = b.yc; dst[2] = b.angle; dst[3] = b.aspect; dst[4] = b.height; dst[5] = b.conf;
+}
+
+__global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Frame f, int n_scenes,
+                                                   unsigned long long id_base, int* n_tracks) {
+  __shared__ int s_warp[AT / 32];
+  __shared__ int s_carry;
+  __shared__ int s_newbefore;
+  const int sidx = blockIdx.x;
+  const SceneDesc sc = f.scenes[sidx];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int K = p.max_obs;
+  // ids of non-batch trackers are consumed by new tracks only, in request order => prefix over earlier scenes
+  if (!p.is_batch) {
+    int c = 0;
+    for (int s2 = tid; s2 < sidx; s2 += AT) c += f.new_count[s2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_warp[wid] = c;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < AT / 32; ++w) t += s_warp[w];
+      s_newbefore = t;
+    }
+  }
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  const int* winner = f.winner + sc.det_base;
+  for (int base = 0; base < sc.m; base += AT) {
+    const int m = base + tid;
+    const bool active = m < sc.m;
+    const int win = active ? winner[m] : 0;
+    const int isnew = (active && win < 0) ? 1 : 0;
+    // block scan of new flags -> rank among new candidates (candidate order)
+    int x = isnew;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += t;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += s_warp[w];
+    const int carry = s_carry;
+    const int rank = carry + woff + x - isnew;
+    __syncthreads();
+    if (tid == AT - 1) s_carry = carry + woff + x;
+    __syncthreads();
+    if (!active) continue;
+
+    const int g = sc.det_base + m;
+    const float* cbp = f.c_box + (size_t)g * 6;
+    const Box cb{cbp[0], cbp[1], cbp[2], cbp[3], cbp[4], cbp[5]};
+    const long long custom = f.in_custom ? f.in_custom[g] : (-9223372036854775807LL - 1);
+    const unsigned char flags = p.is_visual ? f.c_flags[g] : 0;
+    const float quality = (p.is_visual && f.in_quality) ? f.in_quality[g] : 1.0f;
+    unsigned long long tid64;
+    if (p.is_batch) tid64 = id_base + (unsigned long long)g + 1ull;  // one id per candidate (batch_api.rs:102-106)
+    else tid64 = id_base + (unsigned long long)(s_newbefore + rank) + 1ull;
+    size_t idx;
+    float st[kStateFloats], st2[kStateFloats];
+    Box pred;
+    int fdst = -1;
+    if (isnew) {
+      const int j = sc.n + rank;
+      if (j >= ts.track_cap) { atomicOr(&f.status[sidx], 1); continue; }
+      idx = (size_t)sc.slot * ts.track_cap + j;
+      const float* rb = f.in_boxes + (size_t)g * 6;
+      const Box raw{rb[0], rb[1], rb[2], rb[3], rb[4], rb[5]};
+      kalman_initiate(p.pos_weight, p.vel_weight, raw, st);
+      kalman_predict(p.pos_weight, p.vel_weight, st, st2);
+      kalman_update(p.pos_weight, st2, raw, st);
+      pred = state_box(st, raw.conf);
+      ts.id[idx] = tid64;
+      ts.length[idx] = 1;
+      ts.vt[idx] = -1;
+      write_box(ts.obs + idx * 6, raw);
+      if (p.is_visual) {
+        ts.obs_n[idx] = 1;
+        ts.obs_phys[idx * K] = 0;
+        ts.obs_hasf[idx * K] = flags & 1;
+        ts.obs_q[idx * K] = quality;
+        ts.feat_cnt[idx] = flags & 1;
+        if (flags & 1) fdst = (int)(idx * K);
+      }
+    } else {
+      idx = (size_t)sc.slot * ts.track_cap + win;
+#pragma unroll
+      for (int i = 0; i < kStateFloats; ++i) st2[i] = ts.kst[idx * kStateFloats + i];
+      kalman_predict(p.pos_weight, p.vel_weight, st2, st);
+      kalman_update(p.pos_weight, st, cb, st2);
+#pragma unroll
+      for (int i = 0; i < kStateFloats; ++i) st[i] = st2[i];
+      pred = state_box(st, cb.conf);
+      ts.length[idx] = ts.length[idx] + 1;
+      write_box(ts.obs + idx * 6, cb);
+      if (p.is_visual) {
+        ts.vt[idx] = (signed char)f.c_vt[g];
+        // is_merge && !feature_can_be_used(collect thresholds) => feature dropped (visual_sort/metric.rs:327-337)
+        bool keep = (flags & 1) != 0;
+        if (keep) {
+          bool ok = quality >= p.min_quality_collect;
+          if (p.use_own_area && f.in_own) ok = ok && (f.in_own[g] >= p.min_own_collect);
+          ok = ok && (box_area(cb.aspect, cb.height) >= p.min_area);
+          keep = ok;
+        }
+        // optimize_observations: retain featured, stable sort by quality desc, drop last when len >= max
+        unsigned char phys[kMaxObs]; float q[kMaxObs];
+        int cnt = 0;
+        const int on = ts.obs_n[idx];
+        unsigned int used = 0;
+        for (int k = 0; k < on; ++k) {
+          if (ts.obs_hasf[idx * K + k]) {
+            phys[cnt] = ts.obs_phys[idx * K + k]; q[cnt] = ts.obs_q[idx * K + k];
+            ++cnt;
+          }
+        }
+        for (int a = 1; a < cnt; ++a) {  // stable insertion sort, descending quality
+          unsigned char pa = phys[a]; float qa = q[a];
+          int b = a - 1;
+          while (b >= 0 && q[b] < qa) { phys[b + 1] = phys[b]; q[b + 1] = q[b]; --b; }
+          phys[b + 1] = pa; q[b + 1] = qa;
+        }
+        if (cnt >= K && cnt > 0) --cnt;
+        for (int k = 0; k < cnt; ++k) used |= 1u << phys[k];
+        int freep = 0;
+        while (used & (1u << freep)) ++freep;
+        // push new, swap(0, last)
+        unsigned char hasf_l[kMaxObs];
+        for (int k = 0; k < cnt; ++k) hasf_l[k] = 1;
+        phys[cnt] = (unsigned char)freep; q[cnt] = quality; hasf_l[cnt] = keep ? 1 : 0;
+        ++cnt;
+        { unsigned char tp = phys[0]; phys[0] = phys[cnt - 1]; phys[cnt - 1] = tp;
+          float tq = q[0]; q[0] = q[cnt - 1]; q[cnt - 1] = tq;
+          unsigned char th = hasf_l[0]; hasf_l[0] = hasf_l[cnt - 1]; hasf_l[cnt - 1] = th; }
+        int fc = 0;
+        for (int k = 0; k < cnt; ++k) {
+          ts.obs_phys[idx * K + k] = phys[k]; ts.obs_q[idx * K + k] = q[k]; ts.obs_hasf[idx * K + k] = hasf_l[k];
+          fc += hasf_l[k];
+        }
+        ts.obs_n[idx] = (unsigned char)cnt;
+        ts.feat_cnt[idx] = (unsigned char)fc;
+        if (keep) fdst = (int)(idx * K + freep);
+      }
+    }
+    ts.epoch[idx] = sc.epoch;
+    ts.custom[idx] = custom;
+#pragma unroll
+    for (int i = 0; i < kStateFloats; ++i) ts.kst[idx * kStateFloats + i] = st[i];
+    write_box(ts.pred + idx * 6, pred);
+    ts.radius[idx] = box_radius(pred.aspect, pred.height);
+    if (p.positional_kind == 1) box_vertices(pred.xc, pred.yc, pred.angle, pred.aspect, pred.height, ts.vert + idx * 8);
+    if (f.feat_dst) f.feat_dst[g] = fdst;
+    // SortTrack (src/trackers/sort.rs:286-311)
+    if (f.o_ids) f.o_ids[g] = ts.id[idx];
+    if (f.o_epochs) f.o_epochs[g] = sc.epoch;
+    if (f.o_lengths) f.o_lengths[g] = ts.length[idx];
+    if (f.o_vt) f.o_vt[g] = p.is_visual ? (ts.vt[idx] < 0 ? (unsigned char)1 : (unsigned char)ts.vt[idx]) : (unsigned char)1;
+    if (f.o_pred) write_box(f.o_pred + (size_t)g * 6, pred);
+    if (f.o_obs) {
+      const float* ob = ts.obs + idx * 6;
+      for (int i = 0; i < 6; ++i) f.o_obs[(size_t)g * 6 + i] = ob[i];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) n_tracks[sc.slot] = min(sc.n + s_carry, ts.track_cap);
+}
+
+// copies the features that VisualMetric::optimize keeps into the track's free physical slot (warp per detection)
+__global__ void feat_store_kernel(Params p, TrackStore ts, Frame f) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= f.total) return;
+  int dst = f.feat_dst[w];
+  if (dst < 0) return;
+  const float* src = f.in_feat + (size_t)w * p.feature_dim;
+  float* d = ts.feat + (size_t)dst * p.d8;
+  for (int i = lane; i < p.d8; i += 32) d[i] = i < p.feature_dim ? src[i] : 0.0f;
+  if (lane == 0 && p.visual_kind == 1) ts.fnorm2[dst] = f.c_norm2[w];
+}
+
+void launch_apply(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m,
+                  unsigned long long id_base, int* d_n_tracks, cudaStream_t st) {
+  (void)max_m;
+  if (n_scenes == 0) return;
+  apply_kernel<<<n_scenes, AT, 0, st>>>(p, ts, f, n_scenes, id_base, d_n_tracks);
+  if (p.is_visual && f.in_feat && f.total > 0) {
+    long long threads = (long long)f.total * 32;
+    feat_store_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, ts, f);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// auto_waste: EpochDb::baked (src/trackers/epoch_db.rs:51-66): last_updated + max_idle < current_epoch => Wasted.
+// One CTA per scene slot; stable compaction keeps the store order.
+template <typename T>
+__device__ __forceinline__ void move_rows(T* arr, size_t base, int width, const int* s_dst, int j0, int jn) {
+  // chunk [j0, jn): read all, sync, write (dst <= src, chunks ascend => no clobbering)
+  for (int c = 0; c < width; ++c) {
+    int j = j0 + threadIdx.x;
+    T v{};
+    int d = -1;
+    if (j < jn) { d = s_dst[j - j0]; if (d >= 0 && d != j) v = arr[(base + j) * width + c]; }
+    __syncthreads();
+    if (d >= 0 && d != j) arr[(base + d) * width + c] = v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(AT) waste_kernel(Params p, TrackStore ts, const unsigned int* cur_epoch,
+                                                   const unsigned long long* scene_ids, int* n_tracks, WastedBuf wb) {
+  __shared__ int s_dst[AT];
+  __shared__ int s_warp[AT / 32];
+  __shared__ int s_kept, s_wbase, s_wcount;
+  const int slot = blockIdx.x;
+  const int n = n_tracks[slot];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const size_t base = (size_t)slot * ts.track_cap;
+  const unsigned int cur = cur_epoch[slot];
+  const int K = p.max_obs;
+  if (n == 0) return;
+  // pass 1: count wasted to reserve room in the wasted buffer
+  int wc = 0;
+  for (int j = tid; j < n; j += AT) wc += (ts.epoch[base + j] + (unsigned int)p.max_idle_epochs < cur) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wc += __shfl_xor_sync(0xffffffffu, wc, o);
+  if (lane == 0) s_warp[wid] = wc;
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int w = 0; w < AT / 32; ++w) t += s_warp[w];
+    s_wcount = t;
+    s_wbase = t > 0 ? atomicAdd(wb.count, t) : 0;
+    s_kept = 0;
+  }
+  __syncthreads();
+  if (s_wcount == 0) return;
+  int wasted_seen = 0;  // uniform across threads (recomputed per chunk)
+  for (int j0 = 0; j0 < n; j0 += AT) {
+    const int jn = min(n, j0 + AT);
+    const int j = j0 + tid;
+    int w = 0;
+    if (j < jn) w = (ts.epoch[base + j] + (unsigned int)p.max_idle_epochs < cur) ? 1 : 0;
+    int x = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += t;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    int woff = 0, wtot = 0;
+    for (int q = 0; q < AT / 32; ++q) { if (q < wid) woff += s_warp[q]; wtot += s_warp[q]; }
+    const int wrank = wasted_seen + woff + x - w;  // wasted tracks before j
+    if (j < jn) {
+      if (w) {
+        int o = s_wbase + wrank;
+        if (o < wb.cap) {
+          wb.id[o] = ts.id[base + j]; wb.scene[o] = scene_ids[slot]; wb.epoch[o] = ts.epoch[base + j];
+          wb.length[o] = ts.length[base + j];
+          for (int c = 0; c < 6; ++c) { wb.pred[(size_t)o * 6 + c] = ts.pred[(base + j) * 6 + c]; wb.obs[(size_t)o * 6 + c] = ts.obs[(base + j) * 6 + c]; }
+        }
+        s_dst[tid] = -1;
+      } else s_dst[tid] = j - wrank;
+    }
+    __syncthreads();
+    if (wasted_seen + wtot > 0) {
+      move_rows(ts.id, base, 1, s_dst, j0, jn);
+      move_rows(ts.epoch, base, 1, s_dst, j0, jn);
+      move_rows(ts.length, base, 1, s_dst, j0, jn);
+      move_rows(ts.custom, base, 1, s_dst, j0, jn);
+      move_rows(ts.vt, base, 1, s_dst, j0, jn);
+      move_rows(ts.pred, base, 6, s_dst, j0, jn);
+      move_rows(ts.obs, base, 6, s_dst, j0, jn);
+      move_rows(ts.radius, base, 1, s_dst, j0, jn);
+      move_rows(ts.kst, base, kStateFloats, s_dst, j0, jn);
+      if (p.positional_kind == 1) move_rows(ts.vert, base, 8, s_dst, j0, jn);
+      if (p.is_visual) {
+        move_rows(ts.obs_phys, base, K, s_dst, j0, jn);
+        move_rows(ts.obs_hasf, base, K, s_dst, j0, jn);
+        move_rows(ts.obs_q, base, K, s_dst, j0, jn);
+        move_rows(ts.obs_n, base, 1, s_dst, j0, jn);
+        move_rows(ts.feat_cnt, base, 1, s_dst, j0, jn);
+        move_rows(ts.fnorm2, base, K, s_dst, j0, jn);
+        // feature rows: one track at a time, all threads cooperate (K*d8 floats)
+        const int fw = K * p.d8;
+        for (int jj = j0; jj < jn; ++jj) {
+          int d = s_dst[jj - j0];
+          if (d < 0 || d == jj) continue;
+          for (int c0 = 0; c0 < fw; c0 += AT) {
+            int c = c0 + tid;
+            float v = 0.0f;
+            if (c < fw) v = ts.feat[(base + jj) * fw + c];
+            if (c < fw) ts.feat[(base + d) * fw + c] = v;   // d < jj: rows never overlap
+          }
+        }
+      }
+    }
+    __syncthreads();
+    wasted_seen += wtot;
+  }
+  if (tid == 0) n_tracks[slot] = n - s_wcount;
+}
+
+void launch_waste(const Params& p, const TrackStore& ts, int n_slots, const unsigned int* d_cur_epoch,
+                  const unsigned long long* d_scene_ids, int* d_n_tracks, const WastedBuf& wb, int max_n,
+                  cudaStream_t st) {
+  (void)max_n;
+  if (n_slots == 0) return;
+  waste_kernel<<<n_slots, AT, 0, st>>>(p, ts, d_cur_epoch, d_scene_ids, d_n_tracks, wb);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// stateless Kalman operators (parity tests / callers that keep their own state)
+__global__ void kalman_ops_kernel(int op, float pw, float vw, const float* in30, const float* boxes, int n, float* out30) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a[kStateFloats], b[kStateFloats];
+  Box bx{};
+  if (boxes) { const float* q = boxes + (size_t)i * 6; bx = Box{q[0], q[1], q[2], q[3], q[4], q[5]}; }
+  if (op == 0) kalman_initiate(pw, vw, bx, b);
+  else {
+    for (int k = 0; k < kStateFloats; ++k) a[k] = in30[(size_t)i * kStateFloats + k];
+    if (op == 1) kalman_predict(pw, vw, a, b);
+    else kalman_update(pw, a, bx, b);
+  }
+  for (int k = 0; k < kStateFloats; ++k) out30[(size_t)i * kStateFloats + k] = b[k];
+}
+
+void launch_kalman_ops(int op, float pw, float vw, const float* in30, const float* boxes, int n, float* out30,
+                       cudaStream_t st) {
+  if (n == 0) return;
+  kalman_ops_kernel<<<(n + 127) / 128, 128, 0, st>>>(op, pw, vw, in30, boxes, n, out30);
+}
+
+}  // namespace sb

@@ -1,0 +1,150 @@
+// sb_engine.cuh -- device data layout and kernel launch interfaces of the association engine.
+//
+// HBM layout (all arrays allocated once per tracker and grown by doubling):
+//   track store   : dense per scene slot, index = slot * track_cap + j, j in [0, n_tracks[slot]) in store order
+//                   (insertion order; wasted tracks are removed by a stable compaction).  Array-of-structs rows
+//                   of 6 / 30 floats so that a tile of tracks is one contiguous, fully coalesced block copy.
+//   features      : [slot][track][physical obs slot][D8] f32, D8 = D rounded up to 8 lanes (Feature::from_vec
+//                   zero-padding, src/track/utils.rs:45-71); the logical observation order of
+//                   VisualMetric::optimize (src/trackers/visual_sort/metric.rs:297-374) is a per-track
+//                   permutation (obs_phys) so feature rows never move.
+//   per frame     : candidates in request order; cost matrices packed per scene (row-major m x n, and
+//                   m x n x K for visual distances), NaN == None.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sb_math.cuh"
+
+namespace sb {
+
+constexpr int kMaxConstraints = 8;
+constexpr int kMaxObs = 8;  // visual_max_observations supported on device (reference default 5)
+
+struct Params {  // immutable per tracker, passed by value to kernels
+  int kind, positional_kind, visual_kind;
+  float iou_threshold, min_confidence, pos_weight, vel_weight;
+  int max_idle_epochs;
+  int n_constraints;
+  int constraint_epochs[kMaxConstraints];
+  float constraint_max_dist[kMaxConstraints];
+  float visual_threshold;
+  int feature_dim, d8, max_obs, min_votes, min_track_length;
+  float min_area, min_quality_use, min_quality_collect, min_own_use, min_own_collect;
+  bool is_visual, is_batch, use_own_area;
+};
+
+struct SceneDesc {  // one per scene of the current request
+  int slot;        // scene slot in the track store
+  int m;           // detections of this scene
+  int n;           // stored tracks of this scene before this frame
+  int det_base;    // first detection (row of the request)
+  long long pos_off;  // offset of the m x n positional cost matrix
+  long long vis_off;  // offset of the m x n x K visual matrix
+  unsigned int epoch; // the scene's freshly incremented epoch (candidate epoch)
+  int pad;
+  unsigned long long scene_id;
+};
+
+struct TrackStore {
+  int track_cap;
+  unsigned long long* id;
+  unsigned int* epoch;
+  unsigned int* length;
+  long long* custom;
+  signed char* vt;       // -1 == None
+  float* pred;           // [idx][6] last predicted (posterior) box == observation attr box
+  float* obs;            // [idx][6] last observed box
+  float* radius;         // [idx]
+  float* kst;            // [idx][30]
+  double* vert;          // [idx][8] vertex cache (IoU mode)
+  // visual
+  float* feat;           // [idx][K][d8]
+  float* fnorm2;         // [idx][K] by physical slot (cosine)
+  unsigned char* obs_phys;  // [idx][K] logical -> physical
+  unsigned char* obs_hasf;  // [idx][K] logical: feature present
+  float* obs_q;             // [idx][K] logical: quality
+  unsigned char* obs_n;     // [idx]
+  unsigned char* feat_cnt;  // [idx] visual_features_collected_count
+};
+
+struct Frame {  // per-request transient device buffers
+  int total;               // detections in the request
+  const float* in_boxes;   // [total][6] raw request boxes
+  const float* in_feat;    // [total][D] or null
+  const unsigned char* in_hasf;
+  const float* in_quality;
+  const long long* in_custom;
+  const float* in_own;
+  float* c_box;            // [total][6] candidate (Kalman-normalised) boxes
+  float* c_radius;
+  float* c_conf;           // max(conf, min_confidence)
+  double* c_vert;          // [total][8]
+  unsigned char* c_flags;  // bit0 has feature, bit1 feature usable (feature_can_be_used with *_use thresholds)
+  float* c_norm2;
+  int* winner;             // [total] track index within the scene or -1
+  unsigned char* c_vt;     // voting type of the decision
+  float* pos;              // packed positional cost matrices
+  float* vis;              // packed visual matrices
+  SceneDesc* scenes;       // [n_scenes]
+  int* new_count;          // [n_scenes] new tracks per scene (written by voting)
+  int* status;             // [n_scenes] per-scene status flags (capacity overflow etc.)
+  int* feat_dst;           // [total] destination feature row (idx*K + phys) or -1
+  // outputs (device), any may be null
+  unsigned long long* o_ids;
+  unsigned int* o_epochs;
+  unsigned int* o_lengths;
+  unsigned char* o_vt;
+  float* o_pred;
+  float* o_obs;
+};
+
+// ---- kernel launchers (each in its own .cu) ----
+void launch_prep(const Params& p, const Frame& f, int n_scenes, int max_m, cudaStream_t st);
+void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                     cudaStream_t st);
+void launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                     cudaStream_t st);
+// returns cudaError from configuration (dynamic smem), 0 on success
+int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                  cudaStream_t st);
+void launch_apply(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m,
+                  unsigned long long id_base, int* d_n_tracks, cudaStream_t st);
+// stable compaction of wasted tracks; appends them to the wasted buffers
+struct WastedBuf {
+  int cap;
+  int* count;  // device counter
+  unsigned long long* id;
+  unsigned long long* scene;
+  unsigned int* epoch;
+  unsigned int* length;
+  float* pred;
+  float* obs;
+};
+void launch_waste(const Params& p, const TrackStore& ts, int n_slots, const unsigned int* d_cur_epoch,
+                  const unsigned long long* d_scene_ids, int* d_n_tracks, const WastedBuf& wb, int max_n,
+                  cudaStream_t st);
+
+// stateless operators
+void launch_kalman_ops(int op, float pw, float vw, const float* in30, const float* boxes, int n, float* out30,
+                       cudaStream_t st);
+int launch_nms(const float* d_boxes, const float* d_scores, int n, float nms_thr, float score_thr, int has_score_thr,
+               int* d_out_idx, int* d_out_count, cudaStream_t st);
+
+// shared device helpers
+__device__ __forceinline__ bool compat_ok(const Params& p, unsigned int cand_epoch, unsigned int trk_epoch, float cx,
+                                          float cy, float cr, float tx, float ty, float tr) {
+  // SortAttributes::compatible, src/trackers/sort.rs:250-270 (scene equality is structural here)
+  unsigned int delta = cand_epoch > trk_epoch ? cand_epoch - trk_epoch : trk_epoch - cand_epoch;
+  if ((unsigned int)p.max_idle_epochs < delta) return false;
+  // SpatioTemporalConstraints::validate, src/trackers/spatio_temporal_constraints.rs:48-59
+  for (int i = 0; i < p.n_constraints; ++i) {
+    if ((unsigned int)p.constraint_epochs[i] >= delta) {
+      float d = dist_in_2r(cx, cy, cr, tx, ty, tr);
+      return d <= p.constraint_max_dist[i];
+    }
+  }
+  return true;
+}
+
+}  // namespace sb

@@ -1,0 +1,210 @@
+"""End-to-end parity of the device-resident trackers (through sb200_predict_batch) against the CPU oracle:
+identical ids / epochs / lengths / voting types frame after frame on seeded synthetic workloads, the reference's own
+end-to-end sequences, lifecycle (skip_epochs / wasted / idle), and size-independent properties at BASELINE sizes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import similari_b200.engine as e
+    from similari_b200._lib import lib
+
+    if lib().sb200_device_count() <= 0:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box")
+    return e
+
+
+def both(eng, oracle, **kw):
+    from similari_b200._lib import default_options
+
+    return eng.Tracker(default_options(**kw)), oracle.Tracker(oracle.make_options(**kw))
+
+
+def run_frames(eng, oracle, wl_cfg, frames, opts_kw, exact_boxes=True, check_costs=True):
+    from similari_b200.workload import Workload
+
+    g, o = both(eng, oracle, **opts_kw)
+    wl = Workload(wl_cfg)
+    for fr in range(frames):
+        f = wl.next_frame()
+        quality = None
+        rg = g.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"], quality=quality)
+        ro = o.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"], quality=quality)
+        for key in ("ids", "epochs", "lengths", "voting_types"):
+            assert np.array_equal(rg[key], ro[key]), (fr, key)
+        for key in ("predicted", "observed"):
+            if exact_boxes:
+                assert np.array_equal(np.nan_to_num(rg[key], nan=-7.0), np.nan_to_num(ro[key], nan=-7.0)), (fr, key)
+            else:
+                np.testing.assert_allclose(rg[key], ro[key], rtol=0, atol=1e-4, equal_nan=True)
+        if check_costs:
+            sid = int(f["scene_ids"][0])
+            cg, co = g.last_costs(sid), o.last_costs(sid)
+            assert cg.shape == co.shape
+            if exact_boxes:
+                assert np.array_equal(np.nan_to_num(cg, nan=-7.0), np.nan_to_num(co, nan=-7.0)), fr
+        assert g.active_tracks() == o.active_tracks()
+    return g, o
+
+
+def small(name, **over):
+    import dataclasses
+
+    from similari_b200.workload import CONFIGS
+
+    return dataclasses.replace(CONFIGS[name], **over)
+
+
+@pytest.mark.parametrize("kind_name,kind", [("sort", 0), ("batch_sort", 1)])
+@pytest.mark.parametrize("pos", [0, 1])
+@pytest.mark.parametrize("oriented", [False, True])
+def test_sort_trackers_match_oracle(eng, oracle, kind_name, kind, pos, oriented):
+    cfg = small("cfg2", n_scenes=1 if kind == 0 else 5, n_objects=60, oriented=oriented, canvas=(900.0, 600.0))
+    # oriented IoU passes through device sin/cos: ids must still match, boxes are Kalman outputs (exact)
+    run_frames(eng, oracle, cfg, 8, dict(kind=kind, positional_kind=pos, iou_threshold=0.3, max_idle_epochs=3),
+               exact_boxes=True, check_costs=not (oriented and pos == 1))
+
+
+@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("pos", [0, 1])
+@pytest.mark.parametrize("vis", [0, 1])
+def test_visual_trackers_match_oracle(eng, oracle, kind, pos, vis):
+    cfg = small("cfg5", n_scenes=1 if kind == 2 else 4, n_objects=40, oriented=False, canvas=(700.0, 500.0),
+                feature_dim=64)
+    run_frames(eng, oracle, cfg, 8,
+               dict(kind=kind, positional_kind=pos, iou_threshold=0.3, max_idle_epochs=3, visual_kind=vis,
+                    visual_threshold=0.7 if vis == 0 else 0.2, feature_dim=64, visual_max_observations=3,
+                    visual_min_votes=2, visual_minimal_track_length=1, min_confidence=0.1))
+
+
+def test_constraints_and_custom_ids(eng, oracle):
+    from similari_b200.workload import Workload
+
+    cfg = small("cfg1", n_objects=30)
+    kw = dict(kind=0, positional_kind=1, iou_threshold=0.3, max_idle_epochs=1, constraints=[(1, 1.0)])
+    g, o = both(eng, oracle, **kw)
+    wl = Workload(cfg)
+    for fr in range(5):
+        f = wl.next_frame()
+        cust = np.arange(len(f["boxes"]), dtype=np.int64) + 100 * fr
+        rg = g.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], custom_ids=cust)
+        ro = o.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], custom_ids=cust)
+        for key in ("ids", "epochs", "lengths"):
+            assert np.array_equal(rg[key], ro[key])
+
+
+def test_reference_sort_sequence(eng):
+    # src/trackers/sort/simple_api.rs:280-342 (sort) through the GPU tracker
+    from similari_b200._lib import default_options
+    import oracle as orc
+
+    t = eng.Tracker(default_options(kind=0, positional_kind=1, iou_threshold=0.3, min_confidence=0.05, max_idle_epochs=2,
+                                    history_length=10))
+    assert t.current_epoch() == 0
+    v = t.predict_batch([0], [0, 1], [orc.ltwh(0.0, 0.0, 10.0, 20.0)])
+    assert len(t.wasted()["ids"]) == 0
+    tid = int(v["ids"][0])
+    assert v["lengths"][0] == 1 and v["epochs"][0] == 1 and t.current_epoch() == 1
+    v = t.predict_batch([0], [0, 1], [orc.ltwh(0.1, 0.1, 10.1, 20.0)], custom_ids=[2])
+    assert int(v["ids"][0]) == tid and v["lengths"][0] == 2 and v["epochs"][0] == 2
+    v = t.predict_batch([0], [0, 1], [orc.ltwh(10.1, 10.1, 10.1, 20.0)], custom_ids=[3])
+    assert int(v["ids"][0]) != tid and len(t.wasted()["ids"]) == 0 and t.current_epoch() == 3
+    t.predict_batch([0], [0, 0], np.zeros((0, 6), np.float32))
+    assert len(t.wasted()["ids"]) == 0 and t.current_epoch() == 4
+    t.predict_batch([0], [0, 0], np.zeros((0, 6), np.float32))
+    w = t.wasted()
+    assert list(map(int, w["ids"])) == [tid] and t.current_epoch() == 5
+
+
+def test_reference_visual_sort_sequence(eng):
+    # src/trackers/visual_sort/simple_api.rs:328-666 (visual_sort) through the GPU tracker
+    from similari_b200._lib import default_options
+    import oracle as orc
+
+    V, P = 0, 1
+    t = eng.Tracker(default_options(kind=2, max_idle_epochs=3, history_length=3, visual_kind=0, visual_threshold=1.0,
+                                    positional_kind=0, visual_minimal_track_length=2, visual_minimal_area=5.0,
+                                    visual_minimal_quality_use=0.45, visual_minimal_quality_collect=0.7,
+                                    visual_max_observations=3, visual_min_votes=2, feature_dim=2, min_confidence=0.1))
+
+    def step(scene, feat, q, ltwh, custom):
+        has = np.array([feat is not None], dtype=np.uint8)
+        f = np.array([feat if feat is not None else [0.0, 0.0]], dtype=np.float32)
+        r = t.predict_batch([scene], [0, 1], [orc.ltwh(*ltwh)], features=f, has_feature=has, quality=[q],
+                            custom_ids=[custom])
+        return int(r["ids"][0]), int(r["voting_types"][0]), int(r["epochs"][0]), int(r["lengths"][0])
+
+    def feat_count(scene, tid):
+        st = t.scene_tracks(scene)
+        return int(st["feat_counts"][list(st["ids"]).index(tid)])
+
+    first, vt, ep, ln = step(10, [1.0, 1.0], 0.9, (1.0, 1.0, 3.0, 5.0), 13)
+    assert (vt, ep, ln) == (P, 1, 1) and feat_count(10, first) == 1
+    other_scene, vt, ep, ln = step(1, [1.0, 1.0], 0.9, (1.0, 1.0, 3.0, 5.0), 133)
+    assert (vt, ep, ln) == (P, 1, 1) and other_scene != first
+    assert step(10, [0.95, 0.95], 0.93, (1.1, 1.1, 3.05, 5.01), 15) == (first, P, 2, 2) and feat_count(10, first) == 2
+    assert step(10, None, 0.93, (1.11, 1.15, 3.15, 5.05), 25) == (first, P, 3, 3) and feat_count(10, first) == 2
+    assert step(10, None, 0.93, (1.15, 1.25, 3.10, 5.05), 2) == (first, P, 4, 4) and feat_count(10, first) == 2
+    assert step(10, [0.97, 0.97], 0.44, (1.15, 1.25, 3.10, 5.05), 2)[:2] == (first, P) and feat_count(10, first) == 2
+    assert step(10, [0.97, 0.97], 0.6, (1.15, 1.25, 3.10, 5.05), 2)[:2] == (first, V) and feat_count(10, first) == 2
+    assert step(10, [0.97, 0.97], 0.8, (1.15, 1.25, 3.10, 5.05), 2)[:2] == (first, V) and feat_count(10, first) == 3
+    other, vt, ep, ln = step(10, [0.1, 0.1], 0.9, (10.0, 10.0, 3.0, 5.0), 33)
+    assert (vt, ep, ln) == (P, 8, 1) and other != first and feat_count(10, other) == 1
+    assert step(10, [0.12, 0.15], 0.88, (10.1, 10.1, 3.0, 5.0), 35) == (other, P, 9, 2) and feat_count(10, other) == 2
+    assert step(10, [0.12, 0.14], 0.87, (10.1, 10.1, 3.0, 5.0), 31) == (other, V, 10, 3) and feat_count(10, other) == 3
+    t.skip_epochs(5, scene_id=10)
+    assert sorted(map(int, t.wasted()["ids"])) == sorted([first, other])
+
+
+def test_lifecycle_waste_idle_matches_oracle(eng, oracle):
+    from similari_b200.workload import Workload
+
+    cfg = small("cfg2", n_scenes=3, n_objects=50, canvas=(800.0, 600.0), drop_frac=0.2, fresh_frac=0.2)
+    kw = dict(kind=1, positional_kind=0, max_idle_epochs=1)
+    g, o = both(eng, oracle, **kw)
+    g.set_auto_waste(2)
+    import ctypes as C
+
+    o._L.orc_tracker_skip_epochs(o._h, 99, 0)  # no-op scene to mirror auto-waste cadence
+    wl = Workload(cfg)
+    for fr in range(9):
+        f = wl.next_frame()
+        rg = g.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"])
+        ro = o.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"])
+        assert np.array_equal(rg["ids"], ro["ids"]), fr
+        if fr % 3 == 2:
+            wg, wo = g.wasted(), o.wasted()
+            assert sorted(map(int, wg["ids"])) == sorted(map(int, wo["ids"]))
+            assert g.active_tracks() == o.active_tracks()
+            for sid in f["scene_ids"]:
+                ig, io = g.idle_tracks(int(sid)), o.idle_tracks(int(sid))
+                assert sorted(map(int, ig["ids"])) == sorted(map(int, io["ids"]))
+                sg, so = g.scene_tracks(int(sid)), o.scene_tracks(int(sid))
+                assert list(map(int, sg["ids"])) == list(map(int, so["ids"]))  # store order preserved by compaction
+
+
+def test_full_size_properties_cfg2(eng):
+    """BASELINE cfg2 (64 scenes x 256 x 256, IoU): size-independent properties instead of an oracle run."""
+    from similari_b200._lib import default_options
+    from similari_b200.workload import CONFIGS, Workload, tracker_options_for
+
+    t = eng.Tracker(tracker_options_for("cfg2", default_options))
+    wl = Workload(CONFIGS["cfg2"])
+    prev_ids = None
+    for fr in range(5):
+        f = wl.next_frame()
+        r = t.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"])
+        offs = f["det_offsets"]
+        for s in range(len(f["scene_ids"])):
+            ids = r["ids"][offs[s]:offs[s + 1]]
+            assert len(np.unique(ids)) == len(ids)           # a track id is assigned at most once per scene & frame
+        assert np.all(r["epochs"] == fr + 1)
+        if prev_ids is not None:
+            reused = np.isin(r["ids"], prev_ids).mean()
+            assert reused > 0.8                               # most detections continue an existing track
+            assert np.all(r["lengths"][~np.isin(r["ids"], prev_all)] == 1)
+        prev_ids = r["ids"].copy()
+        prev_all = r["ids"].copy() if fr == 0 else np.union1d(prev_all, r["ids"])

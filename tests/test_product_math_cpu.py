@@ -1,0 +1,149 @@
+"""CPU check of the product's device arithmetic (similari_b200/csrc/sb_math.cuh, host-compiled by tests/host_shim)
+against the oracle: bit-exact Kalman block forms, bit-exact clipped area, IoU.  No GPU needed."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def shim():
+    d = os.path.join(HERE, "host_shim")
+    so = os.path.join(d, "libshim.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-x", "c++",
+                           os.path.join(d, "shim.cpp"), "-o", so])
+    L = C.CDLL(so)
+    f32p, f64p = C.POINTER(C.c_float), C.POINTER(C.c_double)
+    L.shim_vertices.argtypes = [f32p, f64p]
+    L.shim_clip_area.argtypes = [f64p, f64p]
+    L.shim_clip_area.restype = C.c_double
+    L.shim_iou.argtypes = [f32p, f32p]
+    L.shim_iou.restype = C.c_float
+    L.shim_kalman_initiate.argtypes = [C.c_float, C.c_float, f32p, f32p]
+    L.shim_kalman_predict.argtypes = [C.c_float, C.c_float, f32p, f32p]
+    L.shim_kalman_update.argtypes = [C.c_float, f32p, f32p, f32p]
+    L.shim_maha.argtypes = [C.c_float, f32p, f32p]
+    L.shim_maha.restype = C.c_float
+    L.shim_weight.argtypes = [C.c_float]
+    L.shim_weight.restype = C.c_longlong
+    return L
+
+
+def fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def pack30(st110):
+    """oracle mean[10]+cov[10x10] -> product mean[10] + 5 x (Pii, Pi,i+5, Pi+5,i, Pi+5,i+5)."""
+    mean, cov = st110[:10], st110[10:].reshape(10, 10)
+    out = np.zeros(30, np.float32)
+    out[:10] = mean
+    for i in range(5):
+        out[10 + 4 * i: 14 + 4 * i] = [cov[i, i], cov[i, i + 5], cov[i + 5, i], cov[i + 5, i + 5]]
+    return out
+
+
+def offblock_zero(st110):
+    cov = st110[10:].reshape(10, 10).copy()
+    for i in range(5):
+        cov[i, i] = cov[i, i + 5] = cov[i + 5, i] = cov[i + 5, i + 5] = 0
+    return not cov.any()
+
+
+def rand_box(rng, oriented):
+    return np.array([rng.uniform(0, 1920), rng.uniform(0, 1080),
+                     rng.uniform(-1.5, 1.5) if oriented else np.nan,
+                     rng.uniform(0.3, 0.8), rng.uniform(40, 160), rng.uniform(0.3, 1.0)], np.float32)
+
+
+@pytest.mark.parametrize("oriented", [False, True])
+def test_kalman_block_forms_bit_exact(oracle, shim, oriented):
+    rng = np.random.default_rng(7 + oriented)
+    pw, vw = np.float32(1 / 20), np.float32(1 / 160)
+    for trial in range(50):
+        b = rand_box(rng, oriented)
+        ref = oracle.kalman_initiate(b, pw, vw)
+        mine = np.zeros(30, np.float32)
+        shim.shim_kalman_initiate(pw, vw, fp(b), fp(mine))
+        assert np.array_equal(pack30(ref), mine)
+        for step in range(12):
+            ref = oracle.kalman_predict(ref, pw, vw)
+            nxt = np.zeros(30, np.float32)
+            shim.shim_kalman_predict(pw, vw, fp(mine), fp(nxt))
+            mine = nxt
+            assert offblock_zero(ref)
+            assert np.array_equal(pack30(ref), mine), (trial, step, "predict")
+            z = b.copy()
+            z[:2] += rng.normal(0, 2, 2).astype(np.float32)
+            z[3:5] *= rng.uniform(0.98, 1.02, 2).astype(np.float32)
+            if oriented:
+                z[2] += np.float32(rng.normal(0, 0.02))
+            # Mahalanobis distance of the measurement against the *current* state
+            d_ref = oracle.kalman_distance(ref, z, pw, vw)
+            d_mine = shim.shim_maha(pw, fp(mine), fp(z))
+            assert np.float32(d_ref) == np.float32(d_mine), (trial, step, d_ref, d_mine)
+            ref = oracle.kalman_update(ref, z, pw, vw)
+            nxt = np.zeros(30, np.float32)
+            shim.shim_kalman_update(pw, fp(mine), fp(z), fp(nxt))
+            mine = nxt
+            assert offblock_zero(ref)
+            assert np.array_equal(pack30(ref), mine), (trial, step, "update")
+            b = z
+
+
+@pytest.mark.parametrize("oriented", [False, True])
+def test_clip_area_and_iou_bit_exact(oracle, shim, oriented):
+    rng = np.random.default_rng(11 + oriented)
+    n_some = 0
+    for trial in range(3000):
+        l = rand_box(rng, oriented)
+        r = l.copy()
+        r[:2] += rng.normal(0, 30, 2).astype(np.float32)
+        r[3:5] *= rng.uniform(0.7, 1.3, 2).astype(np.float32)
+        if oriented:
+            r[2] += np.float32(rng.normal(0, 0.5))
+        vl, vr = np.zeros(8), np.zeros(8)
+        shim.shim_vertices(fp(l), dp(vl))
+        shim.shim_vertices(fp(r), dp(vr))
+        assert np.array_equal(vl.reshape(4, 2), oracle.vertices(l))
+        a_ref = oracle.polygon_area(oracle.sh_clip(oracle.vertices(l), oracle.vertices(r)))
+        a_mine = shim.shim_clip_area(dp(vl), dp(vr))
+        assert a_ref == a_mine, (trial, a_ref, a_mine)
+        i_ref = oracle.iou(l, r)
+        i_mine = shim.shim_iou(fp(l), fp(r))
+        if i_ref is None:
+            assert np.isnan(i_mine)
+        else:
+            n_some += 1
+            assert np.float32(i_ref) == np.float32(i_mine)
+    assert n_some > 500
+
+
+def test_identical_and_touching_boxes(oracle, shim):
+    b = oracle.ltwh(0.0, 0.0, 3.0, 5.0)
+    assert shim.shim_iou(fp(b), fp(b)) == np.float32(oracle.iou(b, b))
+    c = oracle.ltwh(3.0, 0.0, 3.0, 5.0)  # shares an edge: sliver area from the f32 aspect rounding, or None
+    ref, mine = oracle.iou(b, c), shim.shim_iou(fp(b), fp(c))
+    assert (ref is None and np.isnan(mine)) or np.float32(ref) == np.float32(mine)
+    d = oracle.ltwh(4.0, 0.0, 2.0, 4.0)  # exactly representable, disjoint but within 2R => clip area exactly 0
+    assert oracle.iou(oracle.ltwh(0.0, 0.0, 2.0, 4.0), d) is None
+    assert np.isnan(shim.shim_iou(fp(oracle.ltwh(0.0, 0.0, 2.0, 4.0)), fp(d)))
+
+
+def test_weight_cast(oracle, shim):
+    for v in [0.6, 0.69, 0.3, 100.0 / 0.05, 0.0, float("nan"), 1e30, -1e30]:
+        w = shim.shim_weight(np.float32(v))
+        if np.isnan(v):
+            assert w == 0
+        elif abs(v) > 1e20:
+            assert w in (2**63 - 1, -2**63)
+        else:
+            assert w == int(np.float32(v) * np.float32(1e6))
