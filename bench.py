@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native association engine.
+
+Metric (BASELINE.json): pair-associations/s of BatchVisualSORT on 256 scenes x 512 tracks x 512 detections x 512-dim
+features (cfg5), one `predict` per step.  pair-associations = sum over scenes of N_s * M_s per frame.
+
+  value : device-timed throughput, inputs already resident in HBM (sb200_predict_batch_device)
+  e2e   : the same metric through the host-pointer C-ABI call (sb200_predict_batch): pinned host inputs, H2D inside
+          the timed region, result ids / voting types / epochs / lengths copied back
+  roofline      : the visual cost-matrix kernel (dominant cost kernel), timed live with CUDA events on its stream
+  cpu_baseline  : the CPU oracle (port of the reference's algorithm, all host cores) on a bounded sample
+
+`--impl reference` times the reference's algorithm (the oracle port; the Rust reference cannot be built in this
+image) on the host cores for the same config and prints the same JSON line with "impl": "reference".
+
+Launch: python bench.py --gpus N --steps K --warmup W   (N > 1 under torch.distributed.run, one rank per GPU;
+scenes are sharded by rank -- weak scaling, per-GPU work fixed -- and the assigned track ids are gathered with NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pair_associations_per_sec"
+UNIT = "pair-associations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg5")
+    ap.add_argument("--scenes", type=int, default=0, help="override the scene count (debug)")
+    ap.add_argument("--cpu-sample-scenes", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(name, cfg, extra=None):
+    d = {
+        "workload": f"{name}: {cfg.name}",
+        "scenes_per_gpu": cfg.n_scenes,
+        "tracks_per_scene": cfg.n_objects,
+        "detections_per_scene": f"~{int(cfg.n_objects * 0.95)} (5% dropped, 5% fresh identities per frame)",
+        "feature_dim": cfg.feature_dim,
+        "visual_max_observations": 3,
+        "oriented_boxes": cfg.oriented,
+        "l2": "per-step inputs exceed L2 (features %.0f MB/step)" % (cfg.n_scenes * cfg.n_objects * max(cfg.feature_dim, 6) * 4 / 1e6),
+        "parallelism": "scene-sharded, one process per GPU",
+    }
+    if extra:
+        d.update(extra)
+    return d
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._halt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=5)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_frames(name, n_frames, scene_base, n_scenes_override=0):
+    import dataclasses
+
+    from similari_b200.workload import CONFIGS, Workload
+
+    cfg = CONFIGS[name]
+    if n_scenes_override:
+        cfg = dataclasses.replace(cfg, n_scenes=n_scenes_override)
+    cfg = dataclasses.replace(cfg, seed=cfg.seed + 7919 * scene_base)
+    wl = Workload(cfg, scene_base=scene_base)
+    return cfg, [wl.next_frame() for _ in range(n_frames)]
+
+
+def cpu_port_run(name, frames, warm, steps, threads):
+    """Times the oracle tracker (reference algorithm, reference execution order, `threads` host threads)."""
+    import oracle as orc
+    from similari_b200.workload import tracker_options_for
+
+    t = orc.Tracker(tracker_options_for(name, orc.make_options), threads=threads)
+    units, secs = 0, 0.0
+    prev_n = None
+    for i, f in enumerate(frames[: warm + steps]):
+        m = np.diff(f["det_offsets"]).astype(np.int64)
+        n_before = np.array([len(t.scene_tracks(int(s), cap=1 << 12)["ids"]) for s in f["scene_ids"]], dtype=np.int64) \
+            if i >= warm else None
+        t0 = time.perf_counter()
+        t.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"], want_boxes=False)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            units += int((m * n_before).sum())
+            secs += dt
+    return units, secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle as orc
+
+    orc.build()
+    cores = os.cpu_count() or 1
+    sample_scenes = args.cpu_sample_scenes or max(cores, 8)
+    warm = max(3, min(args.warmup, 4))
+    steps = max(1, min(args.steps, 2))
+    from similari_b200.workload import CONFIGS
+
+    sample_scenes = min(sample_scenes, CONFIGS[args.config].n_scenes)
+    cfg, frames = make_frames(args.config, warm + steps, 0, sample_scenes)
+    units, secs = cpu_port_run(args.config, frames, warm, steps, cores)
+    value = units / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args.config, cfg, {"note": "bounded sample of the full workload: same per-scene shape"}),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample_scenes} of {CONFIGS[args.config].n_scenes} scenes, {steps} timed frame(s) "
+                                   f"after {warm} warm-up frames, {cores} threads (scene-parallel)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} != WORLD_SIZE {world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import similari_b200.engine as eng
+    from similari_b200._lib import default_options, pinned_empty
+    from similari_b200.workload import CONFIGS, tracker_options_for
+
+    name = args.config
+    W, K = max(args.warmup, 3), args.steps
+    base_cfg = CONFIGS[name]
+    n_sc = args.scenes or base_cfg.n_scenes
+    cfg, frames = make_frames(name, W + K, scene_base=rank * n_sc, n_scenes_override=args.scenes)
+    D = cfg.feature_dim
+    visual = D > 0
+
+    def new_tracker():
+        t = eng.Tracker(tracker_options_for(name, default_options, device=local, max_scenes_hint=cfg.n_scenes,
+                                            max_tracks_per_scene_hint=2 * cfg.n_objects + 64))
+        t.set_stream(torch.cuda.current_stream().cuda_stream)
+        return t
+
+    # ---------------------------------------------------------------- e2e: host pointers (pinned), H2D + D2H timed
+    t_e2e = new_tracker()
+    pinned = []
+    for f in frames:
+        b = pinned_empty(f["boxes"].shape, np.float32)
+        b[...] = f["boxes"]
+        ft = None
+        if visual:
+            ft = pinned_empty(f["features"].shape, np.float32)
+            ft[...] = f["features"]
+        pinned.append((b, ft))
+    max_total = max(len(f["boxes"]) for f in frames)
+    out_host = {"ids": pinned_empty((max_total,), np.uint64), "epochs": pinned_empty((max_total,), np.uint32),
+                "lengths": pinned_empty((max_total,), np.uint32), "voting_types": pinned_empty((max_total,), np.uint8)}
+    units_per_step, h2d, d2h = [], [], []
+    e2e_ms = []
+    stage_acc = {}
+    sampler = None
+    for i, f in enumerate(frames):
+        total = len(f["boxes"])
+        n_before = t_e2e.scene_track_counts(f["scene_ids"]).astype(np.int64)
+        m = np.diff(f["det_offsets"]).astype(np.int64)
+        out = {k: v[:total] for k, v in out_host.items()}
+        if i == W:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            sampler = ClockSampler(local)
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        t_e2e.predict_batch(f["scene_ids"], f["det_offsets"], pinned[i][0], features=pinned[i][1], out=out)
+        ev1.record()
+        torch.cuda.synchronize()
+        if i >= W:
+            e2e_ms.append(ev0.elapsed_time(ev1))
+            units_per_step.append(int((m * n_before).sum()))
+            h2d.append(total * 24 + (total * D * 4 if visual else 0))
+            d2h.append(total * (8 + 4 + 4 + 1))
+            for k_, v_ in t_e2e.last_stage_ms().items():
+                stage_acc.setdefault(k_, []).append(v_)
+    e2e_total_ms = float(sum(e2e_ms))
+    ids_e2e_last = out_host["ids"][: len(frames[-1]["boxes"])].copy()
+    t_e2e.close()
+
+    # ---------------------------------------------------------------- value: inputs resident in HBM
+    t_dev = new_tracker()
+    dboxes = [torch.from_numpy(np.ascontiguousarray(f["boxes"])).to(dev) for f in frames]
+    dfeats = [torch.from_numpy(f["features"]).to(dev) if visual else None for f in frames]
+    d_ids = torch.zeros(max_total, dtype=torch.int64, device=dev)
+    d_ep = torch.zeros(max_total, dtype=torch.int32, device=dev)
+    d_len = torch.zeros(max_total, dtype=torch.int32, device=dev)
+    d_vt = torch.zeros(max_total, dtype=torch.uint8, device=dev)
+    gather_buf = torch.zeros(max_total * world, dtype=torch.int64, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+    dev_stage = {}
+    launches = 0
+
+    def step_dev(i):
+        f = frames[i]
+        t_dev.predict_batch_device(f["scene_ids"], f["det_offsets"], dboxes[i].data_ptr(),
+                                   dfeats[i].data_ptr() if visual else 0, d_ids=d_ids.data_ptr(),
+                                   d_epochs=d_ep.data_ptr(), d_lengths=d_len.data_ptr(),
+                                   d_voting_types=d_vt.data_ptr())
+        if world > 1:  # gather the assigned track ids of every shard (north_star: NCCL only to gather track ids)
+            dist.all_gather_into_tensor(gather_buf, d_ids)
+
+    for i in range(W):
+        step_dev(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(W, W + K):
+        step_dev(i)
+        for k_, v_ in t_dev.last_stage_ms().items():
+            dev_stage.setdefault(k_, []).append(v_)
+        launches += 8 if visual else 4
+    ev1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    ids_dev_last = d_ids[: len(frames[-1]["boxes"])].cpu().numpy().astype(np.uint64)
+    assert np.array_equal(ids_dev_last, ids_e2e_last), "device-pointer and host-pointer paths disagree"
+    t_dev.close()
+
+    units = float(sum(units_per_step))
+    # max over ranks of the timed region, sum over ranks of the units
+    if world > 1:
+        tm = torch.tensor([dev_ms, e2e_total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        un = torch.tensor([units], dtype=torch.float64, device=dev)
+        dist.all_reduce(un, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_total_ms = float(tm[0]), float(tm[1])
+        units_all = float(un[0])
+    else:
+        units_all = units
+
+    if rank == 0:
+        value = units_all / (dev_ms * 1e-3)
+        e2e_value = units_all / (e2e_total_ms * 1e-3)
+        # roofline of the cost-matrix kernel (visual distances when the config has features, else positional)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback"
+        Kobs = 3 if visual else 1
+        f_last = frames[-1]
+        m_l = np.diff(f_last["det_offsets"]).astype(np.float64)
+        n_l = float(cfg.n_objects)
+        if visual:
+            kern = "visual_cost"
+            alg_bytes = float(((m_l + n_l * Kobs) * D * 4 + m_l * n_l * Kobs * 4).sum())
+        else:
+            kern = "positional_cost"
+            alg_bytes = float(((m_l + n_l) * 24 + m_l * n_l * 4).sum())
+        kms = float(np.mean(dev_stage[kern])) if dev_stage.get(kern) else float("nan")
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(name, cfg),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(np.mean(h2d)),
+                    "d2h_bytes_per_step": int(np.mean(d2h)), "ms_per_step": e2e_total_ms / K},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "stages_ms": {k_: float(np.mean(v_)) for k_, v_ in dev_stage.items()},
+            "roofline": {"kernel": kern, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kms},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            import oracle as orc
+
+            orc.build()
+            cores = os.cpu_count() or 1
+            sample = args.cpu_sample_scenes or min(cfg.n_scenes, max(cores, 8))
+            ccfg, cframes = make_frames(name, 5, 0, sample)
+            cu, cs = cpu_port_run(name, cframes, 4, 1, cores)
+            line["cpu_baseline"] = {"value": cu / cs, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{sample} of {cfg.n_scenes} scenes x 1 timed frame after 4 warm-up frames, "
+                                              f"{cores} threads (scene-parallel), {cs:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

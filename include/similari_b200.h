@@ -144,6 +144,8 @@ int sb200_predict_batch_device(sb200_tracker* t, int32_t n_scenes, const uint64_
 int sb200_skip_epochs(sb200_tracker* t, uint64_t scene_id, int32_t n);
 int64_t sb200_current_epoch(sb200_tracker* t, uint64_t scene_id);
 int64_t sb200_active_tracks(sb200_tracker* t);                 /* sum(active_shard_stats()) */
+/* stored tracks per scene (0 for unknown scenes): the N of the next frame's N x M cost matrix */
+int sb200_scene_track_counts(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids, int32_t* out);
 int sb200_set_auto_waste(sb200_tracker* t, int32_t periodicity);
 int sb200_clear_wasted(sb200_tracker* t);
 /* wasted(): drains up to `cap` wasted tracks; returns the count (>= 0) or a negative status. */

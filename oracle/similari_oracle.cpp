@@ -803,16 +803,29 @@ struct orc_tracker {
     if (out_obs) store_box(t.last_obs, out_obs + idx * 6);
   }
 
-  void predict_scene(uint64_t scene, int m, const float* boxes, const float* features, const uint8_t* has_feature,
-                     const float* quality, const int64_t* custom_ids, const float* own_area, size_t base,
-                     uint64_t* out_ids, uint32_t* out_epochs, uint32_t* out_lengths, uint8_t* out_vt,
-                     float* out_pred, float* out_obs) {
+  struct SceneWork {
+    uint64_t scene = 0;
+    int m = 0;
+    size_t base = 0;
+    std::vector<Track> cands;
+    std::unordered_map<uint64_t, std::pair<uint64_t, int>> winners;
+    std::vector<float> pos;
+    int n = 0;
+  };
+
+  // distance pass + voting of one scene (read-only on the scene's store: scenes can run on separate threads,
+  // like the reference's distance shards + voting threads)
+  void scene_vote(SceneWork& w, size_t epoch, const float* boxes, const float* features, const uint8_t* has_feature,
+                  const float* quality, const int64_t* custom_ids, const float* own_area, int inner_threads) {
+    const uint64_t scene = w.scene;
+    const int m = w.m;
+    const size_t base = w.base;
+    const int threads = inner_threads;
     const orc_options& o = opts.o;
-    size_t epoch = ++epoch_db[scene];  // next_epoch, epoch_db.rs:35-49
-    std::vector<Track>& tracks = store[scene];
+    std::vector<Track>& tracks = store.find(scene)->second;
     const int n = (int)tracks.size();
     const bool visual = opts.is_visual();
-    std::vector<Track> cands;
+    std::vector<Track>& cands = w.cands;
     cands.reserve(m);
     const bool use_own = visual && (o.visual_minimal_own_area_percentage_collect + o.visual_minimal_own_area_percentage_use > 0.0f);
     for (int i = 0; i < m; ++i) {
@@ -865,8 +878,8 @@ struct orc_tracker {
         }
       }
     });
-    last_costs[scene] = pos;
-    last_shape[scene] = {m, n};
+    w.pos = pos;
+    w.n = n;
     // ---- COO stream in (candidate, track, observation) order; postprocess_distances filters
     std::vector<Ent> ents;
     for (int i = 0; i < m; ++i)
@@ -885,14 +898,26 @@ struct orc_tracker {
       }
     // ---- voting
     float thr = o.positional_kind == ORC_POS_MAHA ? MAHALANOBIS_NEW_TRACK_THRESHOLD : o.iou_threshold;
-    std::unordered_map<uint64_t, std::pair<uint64_t, int>> winners;
+    std::unordered_map<uint64_t, std::pair<uint64_t, int>>& winners = w.winners;
     if (!visual) {
       for (auto& p : sort_voting(thr, (size_t)m, (size_t)n, ents)) winners[p.first] = {p.second, ORC_VOTING_POSITIONAL};
     } else {
       for (auto& w : visual_voting(thr, std::numeric_limits<float>::max(), (size_t)o.visual_min_votes, ents))
         winners[w.from] = {w.to, w.type};
     }
-    // ---- apply in candidate order (sort/simple_api.rs:165-187, batch_api.rs:98-139)
+  }
+
+  // ---- apply in candidate order (sort/simple_api.rs:165-187, batch_api.rs:98-139); sequential over scenes
+  void scene_apply(SceneWork& w, uint64_t* out_ids, uint32_t* out_epochs, uint32_t* out_lengths, uint8_t* out_vt,
+                   float* out_pred, float* out_obs) {
+    const bool visual = opts.is_visual();
+    const int m = w.m;
+    const size_t base = w.base;
+    std::vector<Track>& tracks = store.find(w.scene)->second;
+    std::vector<Track>& cands = w.cands;
+    auto& winners = w.winners;
+    last_costs[w.scene] = w.pos;
+    last_shape[w.scene] = {m, w.n};
     std::unordered_map<uint64_t, size_t> by_id;
     for (size_t j = 0; j < tracks.size(); ++j) by_id[tracks[j].id] = j;
     for (int i = 0; i < m; ++i) {
@@ -1092,11 +1117,23 @@ int orc_tracker_predict_batch(orc_tracker* t, int n_scenes, const uint64_t* scen
     t->auto_waste();
     t->auto_waste_counter = t->auto_waste_periodicity;
   } else t->auto_waste_counter -= 1;
+  std::vector<orc_tracker::SceneWork> work(n_scenes);
+  std::vector<size_t> epochs(n_scenes);
   for (int s = 0; s < n_scenes; ++s) {
-    int base = det_offsets[s], m = det_offsets[s + 1] - det_offsets[s];
-    t->predict_scene(scene_ids[s], m, boxes, features, has_feature, quality, custom_ids, own_area, (size_t)base,
-                     out_ids, out_epochs, out_lengths, out_voting_types, out_predicted, out_observed);
+    work[s].scene = scene_ids[s];
+    work[s].base = (size_t)det_offsets[s];
+    work[s].m = det_offsets[s + 1] - det_offsets[s];
+    epochs[s] = ++t->epoch_db[scene_ids[s]];  // next_epoch, epoch_db.rs:35-49
+    t->store[scene_ids[s]];                    // make sure the scene's store exists before threads read the map
   }
+  const bool scene_parallel = t->threads > 1 && n_scenes > 1;
+  parallel_for(n_scenes, scene_parallel ? t->threads : 1, [&](int b, int e) {
+    for (int s = b; s < e; ++s)
+      t->scene_vote(work[s], epochs[s], boxes, features, has_feature, quality, custom_ids, own_area,
+                    scene_parallel ? 1 : t->threads);
+  });
+  for (int s = 0; s < n_scenes; ++s)
+    t->scene_apply(work[s], out_ids, out_epochs, out_lengths, out_voting_types, out_predicted, out_observed);
   return 0;
 }
 // TrackerAPI::skip_epochs_for_scene, tracker_api.rs:48-51

@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -345,6 +347,10 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
                            const int64_t* custom_ids, const float* own_area, const sb200_predict_out* out,
                            bool device_io) {
   CU(cudaSetDevice(device));
+  static const bool trace = getenv("SB200_TRACE") != nullptr;
+  auto tnow = [] { return std::chrono::steady_clock::now(); };
+  auto t_begin = tnow();
+  auto since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(tnow() - a).count(); };
   if (n_scenes < 0) return fail(SB200_ERR_INVALID, "n_scenes must be >= 0");
   if (n_scenes > 0 && (!scene_ids || !det_offsets)) return fail(SB200_ERR_INVALID, "scene_ids / det_offsets are NULL");
   const int total = n_scenes > 0 ? det_offsets[n_scenes] : 0;
@@ -474,6 +480,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   CU(cudaMemcpyAsync(f_scenes.p, h_scenes.p, sizeof(sb::SceneDesc) * n_scenes, cudaMemcpyHostToDevice, stream));
   CU(cudaMemsetAsync(f_status.p, 0, 4 * (size_t)n_scenes, stream));
 
+  const double ms_setup = since(t_begin);
   CU(cudaEventRecord(ev[0], stream));
   sb::launch_prep(P, f, n_scenes, max_m, stream);
   CU(cudaEventRecord(ev[1], stream));
@@ -503,7 +510,9 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   int* h_status = h_new + n_scenes;
   CU(cudaMemcpyAsync(h_new, f.new_count, 4 * (size_t)n_scenes, cudaMemcpyDeviceToHost, stream));
   CU(cudaMemcpyAsync(h_status, f.status, 4 * (size_t)n_scenes, cudaMemcpyDeviceToHost, stream));
+  const double ms_launch = since(t_begin);
   CU(cudaStreamSynchronize(stream));
+  if (trace) fprintf(stderr, "[sb200] predict: setup %.3f ms, launched at %.3f ms, synced at %.3f ms (total dets %d)\n", ms_setup, ms_launch, since(t_begin), total);
   long long new_total = 0;
   for (int s = 0; s < n_scenes; ++s) {
     if (h_status[s]) return fail(SB200_ERR_INTERNAL, "track store overflow in scene %llu", (unsigned long long)sd[s].scene_id);
@@ -622,6 +631,15 @@ int64_t sb200_active_tracks(sb200_tracker* t) {
   int64_t n = 0;
   for (int v : t->n_tracks) n += v;
   return n;
+}
+
+int sb200_scene_track_counts(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids, int32_t* out) {
+  if (!t || n_scenes < 0 || (n_scenes > 0 && (!scene_ids || !out))) return fail(SB200_ERR_INVALID, "bad arguments");
+  for (int s = 0; s < n_scenes; ++s) {
+    int slot = t->slot_for(scene_ids[s], false);
+    out[s] = slot < 0 ? 0 : t->n_tracks[slot];
+  }
+  return 0;
 }
 
 int sb200_set_auto_waste(sb200_tracker* t, int32_t periodicity) {

@@ -100,6 +100,12 @@ class Tracker:
     def active_tracks(self):
         return int(check(self._L.sb200_active_tracks(self._h)))
 
+    def scene_track_counts(self, scene_ids):
+        scene_ids = np.ascontiguousarray(scene_ids, dtype=np.uint64)
+        out = np.zeros(len(scene_ids), np.int32)
+        check(self._L.sb200_scene_track_counts(self._h, len(scene_ids), ptr(scene_ids), ptr(out)))
+        return out
+
     def set_auto_waste(self, periodicity):
         check(self._L.sb200_set_auto_waste(self._h, periodicity))
 
