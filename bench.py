@@ -197,7 +197,8 @@ def main():
 
     def new_tracker():
         t = eng.Tracker(tracker_options_for(name, default_options, device=local, max_scenes_hint=cfg.n_scenes,
-                                            max_tracks_per_scene_hint=2 * cfg.n_objects + 64))
+                                            max_tracks_per_scene_hint=2 * cfg.n_objects + 64,
+                                            max_dets_per_scene_hint=cfg.n_objects))
         t.set_stream(torch.cuda.current_stream().cuda_stream)
         return t
 
@@ -232,9 +233,13 @@ def main():
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        tw0 = time.perf_counter()
         t_e2e.predict_batch(f["scene_ids"], f["det_offsets"], pinned[i][0], features=pinned[i][1], out=out)
+        tw1 = time.perf_counter()
         ev1.record()
         torch.cuda.synchronize()
+        if os.environ.get("SB200_TRACE"):
+            print(f"[bench] e2e frame {i}: events {ev0.elapsed_time(ev1):.3f} ms, wall {1e3 * (tw1 - tw0):.3f} ms", file=sys.stderr)
         if i >= W:
             e2e_ms.append(ev0.elapsed_time(ev1))
             units_per_step.append(int((m * n_before).sum()))

@@ -161,7 +161,7 @@ struct sb200_tracker {
   int64_t wasted_count = 0;
   // device track store
   sb::TrackStore ts{};
-  DBuf b_id, b_epoch, b_length, b_custom, b_vt, b_pred, b_obs, b_radius, b_kst, b_vert, b_feat, b_fnorm2, b_obs_phys,
+  DBuf b_id, b_epoch, b_length, b_custom, b_vt, b_pred, b_obs, b_radius, b_kst, b_vert, b_feat, b_feat_bf16, b_fnorm2, b_obs_phys,
       b_obs_hasf, b_obs_q, b_obs_n, b_feat_cnt;
   DBuf b_ntracks, b_cur_epoch, b_scene_ids;
   // wasted
@@ -170,7 +170,9 @@ struct sb200_tracker {
   // frame buffers
   DBuf f_in_boxes, f_in_feat, f_in_hasf, f_in_quality, f_in_custom, f_in_own;
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst;
+      f_status, f_featdst, f_cbf16, f_scene_max, f_tiles, f_pairs, f_paircount;
+  HBuf h_tiles;
+  int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
   HBuf h_scenes, h_small;
   // last frame bookkeeping (for sb200_last_costs)
@@ -179,7 +181,7 @@ struct sb200_tracker {
   ~sb200_tracker() {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
-                   &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
+                   &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_paircount, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_in_boxes,
                    &f_in_feat, &f_in_hasf, &f_in_quality, &f_in_custom, &f_in_own, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
@@ -187,6 +189,7 @@ struct sb200_tracker {
     for (DBuf* b : all) b->release();
     h_scenes.release();
     h_small.release();
+    h_tiles.release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
@@ -232,6 +235,11 @@ struct sb200_tracker {
       if ((rc = regrow(b_vert, &ts.vert, 8, ns, nt))) return rc;
     if (P.is_visual) {
       if ((rc = regrow(b_feat, &ts.feat, K * P.d8, ns, nt))) return rc;
+      {
+        unsigned short* tmp = reinterpret_cast<unsigned short*>(ts.feat_bf16);
+        if ((rc = regrow(b_feat_bf16, &tmp, K * P.d8, ns, nt))) return rc;
+        ts.feat_bf16 = tmp;
+      }
       if ((rc = regrow(b_fnorm2, &ts.fnorm2, K, ns, nt))) return rc;
       if ((rc = regrow(b_obs_phys, &ts.obs_phys, K, ns, nt))) return rc;
       if ((rc = regrow(b_obs_hasf, &ts.obs_hasf, K, ns, nt))) return rc;
@@ -403,9 +411,15 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     epoch[sd[s].slot] += 1;
     sd[s].epoch = epoch[sd[s].slot];
   }
-  // frame buffers
+  // frame buffers (sized once from the capacity hints when given, so steady-state frames never reallocate)
   int rc = 0;
-  const size_t T = (size_t)std::max(total, 1);
+  const long long hint_dets = (long long)std::max(opts.max_scenes_hint, n_scenes) * opts.max_dets_per_scene_hint;
+  const size_t T = (size_t)std::max<long long>(std::max(total, 1), hint_dets);
+  {
+    const long long hint_pos = hint_dets * std::max(opts.max_tracks_per_scene_hint, 0);
+    pos_total = std::max(pos_total, hint_pos);
+    if (P.is_visual) vis_total = std::max(vis_total, hint_pos * P.max_obs);
+  }
   if ((rc = f_cbox.ensure(T * 24)) || (rc = f_cradius.ensure(T * 4)) || (rc = f_cconf.ensure(T * 4)) ||
       (rc = f_winner.ensure(T * 4)) || (rc = f_cvt.ensure(T)) || (rc = f_scenes.ensure(sizeof(sb::SceneDesc) * n_scenes)) ||
       (rc = f_newcount.ensure(4 * (size_t)n_scenes)) || (rc = f_status.ensure(4 * (size_t)n_scenes)) ||
@@ -414,8 +428,47 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   if (P.positional_kind == SB200_POS_IOU && (rc = f_cvert.ensure(T * 64))) return rc;
   if (P.is_visual) {
     if ((rc = f_cflags.ensure(T)) || (rc = f_cnorm2.ensure(T * 4)) || (rc = f_featdst.ensure(T * 4)) ||
-        (rc = f_vis.ensure(std::max<size_t>(4, (size_t)vis_total * 4))))
+        (rc = f_vis.ensure(std::max<size_t>(4, (size_t)vis_total * 4))) || (rc = f_scene_max.ensure(4 * (size_t)n_scenes)))
       return rc;
+  }
+  // visual cost kernel selection: tensor-core screen + exact refinement for large frames with a selective threshold,
+  // the dense exact SIMT kernel otherwise (and as the device-side fallback when the survivor list overflows)
+  sb::TcArgs tc;
+  memset(&tc, 0, sizeof(tc));
+  tc.num_sms = num_sms;
+  if (P.is_visual && features != nullptr && total > 0) {
+    long long work = 0;
+    for (int s = 0; s < n_scenes; ++s) work += (long long)sd[s].m * sd[s].n * P.max_obs;
+    const bool selective = P.visual_kind == SB200_VIS_EUCLIDEAN ? (P.visual_threshold < 1e18f) : (P.visual_threshold > -1.0f);
+    tc.use_tc = selective && P.d8 >= 64 && work * P.d8 >= (1ll << 28);
+    if (const char* e = getenv("SB200_VIS_KERNEL")) {
+      if (!strcmp(e, "simt")) tc.use_tc = false;
+      else if (!strcmp(e, "tc")) tc.use_tc = work > 0;
+    }
+    if (tc.use_tc) {
+      std::vector<sb::TcTile> tiles;
+      for (int s = 0; s < n_scenes; ++s) {
+        const int rows = sd[s].n * P.max_obs;
+        for (int m0 = 0; m0 < sd[s].m; m0 += 128)
+          for (int c0 = 0; c0 < rows; c0 += 256) tiles.push_back(sb::TcTile{s, m0, c0, 0});
+      }
+      tc.n_tiles = (int)tiles.size();
+      tc.pair_cap = (int)std::min<long long>(std::max<long long>(4096, (long long)total * 64), 1ll << 27);
+      if (const char* e = getenv("SB200_VIS_PAIR_CAP")) tc.pair_cap = std::max(1, atoi(e));
+      if ((rc = f_cbf16.ensure(T * P.d8 * 2)) || (rc = f_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
+          (rc = h_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
+          (rc = f_pairs.ensure(sizeof(sb::VisPair) * (size_t)tc.pair_cap)) || (rc = f_paircount.ensure(sizeof(int))))
+        return rc;
+      if (tc.n_tiles > 0) {
+        memcpy(h_tiles.p, tiles.data(), sizeof(sb::TcTile) * tc.n_tiles);
+        CU(cudaMemcpyAsync(f_tiles.p, h_tiles.p, sizeof(sb::TcTile) * tc.n_tiles, cudaMemcpyHostToDevice, stream));
+      }
+      tc.d_tiles = f_tiles.as<sb::TcTile>();
+      tc.pairs = f_pairs.as<sb::VisPair>();
+      tc.pair_count = f_paircount.as<int>();
+      tc.a_rows = total;
+      tc.b_rows = (long long)scene_cap * track_cap * P.max_obs;
+    }
   }
   sb::Frame f;
   memset(&f, 0, sizeof(f));
@@ -460,6 +513,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.winner = f_winner.as<int>(); f.c_vt = f_cvt.as<unsigned char>(); f.pos = f_pos.as<float>(); f.vis = f_vis.as<float>();
   f.scenes = f_scenes.as<sb::SceneDesc>(); f.new_count = f_newcount.as<int>(); f.status = f_status.as<int>();
   f.feat_dst = P.is_visual ? f_featdst.as<int>() : nullptr;
+  f.c_bf16 = f_cbf16.p; f.scene_max = f_scene_max.as<unsigned int>();
   // outputs
   sb200_predict_out o{};
   if (out) o = *out;
@@ -486,7 +540,10 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   CU(cudaEventRecord(ev[1], stream));
   sb::launch_pos_cost(P, ts, f, n_scenes, max_m, max_n, stream);
   CU(cudaEventRecord(ev[2], stream));
-  sb::launch_vis_cost(P, ts, f, n_scenes, max_m, max_n, stream);
+  {
+    int vr0 = sb::launch_vis_cost(P, ts, f, n_scenes, max_m, max_n, tc, stream);
+    if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
+  }
   CU(cudaEventRecord(ev[3], stream));
   int vr = sb::launch_voting(P, ts, f, n_scenes, max_m, max_n, stream);
   if (vr == -3) return fail(SB200_ERR_CAPACITY, "scene too large for the on-chip assignment solver (m=%d, n=%d)", max_m, max_n);
@@ -569,6 +626,10 @@ int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out) {
   t->opts = *opts;
   t->P = P;
   t->device = opts->device;
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, opts->device) == cudaSuccess && sms > 0) t->num_sms = sms;
+  }
   cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
   for (auto& ev : t->ev) {

@@ -56,7 +56,8 @@ __device__ __forceinline__ float dec_f32(unsigned int u) {
 }
 
 // per-scene maximum over all valid visual entries ("max_dist" of best.rs:58,72-74), init -1.0
-__global__ void vis_max_kernel(Params p, Frame f, unsigned int* scene_max) {
+__global__ void vis_max_kernel(Params p, Frame f, unsigned int* scene_max, const int* gate, int gate_cap) {
+  if (gate != nullptr && *gate <= gate_cap) return;
   const SceneDesc sc = f.scenes[blockIdx.y];
   const long long cnt = (long long)sc.m * sc.n * p.max_obs;
   const float* v = f.vis + sc.vis_off;
@@ -72,7 +73,8 @@ __global__ void vis_max_kernel(Params p, Frame f, unsigned int* scene_max) {
   }
   if ((threadIdx.x & 31) == 0) atomicMax(scene_max + blockIdx.y, enc_f32(mx));
 }
-__global__ void vis_max_init_kernel(unsigned int* scene_max, int n) {
+__global__ void vis_max_init_kernel(unsigned int* scene_max, int n, const int* gate, int gate_cap) {
+  if (gate != nullptr && *gate <= gate_cap) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) scene_max[i] = enc_f32(-1.0f);
 }
@@ -150,7 +152,8 @@ __device__ int block_scan_flags(const unsigned char* flags, int* out, int n, int
 }
 
 template <bool VISUAL>
-__global__ void __launch_bounds__(VT_THREADS) voting_kernel(Params p, Frame f, const unsigned int* scene_max) {
+__global__ void __launch_bounds__(VT_THREADS) voting_kernel(Params p, Frame f) {
+  const unsigned int* scene_max = f.scene_max;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ MinPair s_red[2][NWARPS];
   __shared__ BestPair s_rowc[32][NWARPS];
@@ -415,8 +418,15 @@ __global__ void __launch_bounds__(VT_THREADS) voting_kernel(Params p, Frame f, c
   }
 }
 
-static unsigned int* g_scene_max = nullptr;
-static int g_scene_max_cap = 0;
+void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_only, const int* gate, int gate_cap,
+                      cudaStream_t st) {
+  if (n_scenes == 0 || !f.scene_max) return;
+  vis_max_init_kernel<<<(n_scenes + 255) / 256, 256, 0, st>>>(f.scene_max, n_scenes, gate, gate_cap);
+  if (!init_only) {
+    dim3 grid(32, n_scenes);
+    vis_max_kernel<<<grid, 256, 0, st>>>(p, f, f.scene_max, gate, gate_cap);
+  }
+}
 
 int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                   cudaStream_t st) {
@@ -426,24 +436,13 @@ int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_s
   if (smem > 200 * 1024) return -3;
   cudaError_t e;
   if (p.is_visual) {
-    if (g_scene_max_cap < n_scenes) {
-      if (g_scene_max) cudaFree(g_scene_max);
-      e = cudaMalloc(&g_scene_max, sizeof(unsigned int) * n_scenes);
-      if (e != cudaSuccess) return (int)e;
-      g_scene_max_cap = n_scenes;
-    }
-    vis_max_init_kernel<<<(n_scenes + 255) / 256, 256, 0, st>>>(g_scene_max, n_scenes);
-    if (max_m > 0 && max_n > 0) {
-      dim3 grid(32, n_scenes);
-      vis_max_kernel<<<grid, 256, 0, st>>>(p, f, g_scene_max);
-    }
     e = cudaFuncSetAttribute(voting_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    voting_kernel<true><<<n_scenes, VT_THREADS, smem, st>>>(p, f, g_scene_max);
+    voting_kernel<true><<<n_scenes, VT_THREADS, smem, st>>>(p, f);
   } else {
     e = cudaFuncSetAttribute(voting_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    voting_kernel<false><<<n_scenes, VT_THREADS, smem, st>>>(p, f, nullptr);
+    voting_kernel<false><<<n_scenes, VT_THREADS, smem, st>>>(p, f);
   }
   return 0;
 }

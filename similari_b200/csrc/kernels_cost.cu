@@ -77,7 +77,7 @@ void launch_prep(const Params& p, const Frame& f, int n_scenes, int max_m, cudaS
   (void)n_scenes; (void)max_m;
   if (f.total == 0) return;
   prep_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f);
-  if (p.is_visual && p.visual_kind == 1 && f.in_feat) {
+  if (p.is_visual && f.in_feat) {  // squared norms (cosine; euclidean on the tensor-core path)
     long long threads = (long long)f.total * 32;
     cand_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, f);
   }
@@ -182,7 +182,8 @@ void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int 
 // gate logic of VisualMetric::metric (src/trackers/visual_sort/metric.rs:200-225,253-295).
 constexpr int VM = 64, VN = 64, VK = 32, VT = 256;  // 4x4 pairs per thread
 
-__global__ void __launch_bounds__(VT) vis_cost_kernel(Params p, TrackStore ts, Frame f) {
+__global__ void __launch_bounds__(VT) vis_cost_kernel(Params p, TrackStore ts, Frame f, const int* gate, int gate_cap) {
+  if (gate != nullptr && *gate <= gate_cap) return;  // fallback switch: only runs when the screen's pair list overflowed
   const SceneDesc sc = f.scenes[blockIdx.z];
   const int K = p.max_obs;
   const int ncols = sc.n * K;  // column c = n*K + k (logical obs)
@@ -309,11 +310,26 @@ __global__ void __launch_bounds__(VT) vis_cost_kernel(Params p, TrackStore ts, F
   }
 }
 
-void launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
-                     cudaStream_t st) {
-  if (!p.is_visual || n_scenes == 0 || max_m == 0 || max_n == 0) return;
-  dim3 grid((max_n * p.max_obs + VN - 1) / VN, (max_m + VM - 1) / VM, n_scenes);
-  vis_cost_kernel<<<grid, VT, 0, st>>>(p, ts, f);
+int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                    const TcArgs& tc, cudaStream_t st) {
+  if (!p.is_visual || n_scenes == 0) return 0;
+  const bool any = max_m > 0 && max_n > 0 && f.in_feat != nullptr;
+  const int* gate = nullptr;
+  if (tc.use_tc && any) {
+    // tensor-core screen + exact refinement; the dense kernel below only runs if the survivor list overflowed
+    launch_scene_max(p, f, n_scenes, /*init_only=*/true, nullptr, 0, st);
+    launch_to_bf16(f.in_feat, p.feature_dim, p.feature_dim, p.d8, f.total, f.c_bf16, st);
+    int rc = launch_vis_cost_tc(p, ts, f, tc.d_tiles, tc.n_tiles, tc.a_rows, tc.b_rows, tc.pairs, tc.pair_count,
+                                tc.pair_cap, tc.num_sms, st);
+    if (rc != 0) return rc;
+    gate = tc.pair_count;
+  }
+  if (max_m > 0 && max_n > 0) {
+    dim3 grid((max_n * p.max_obs + VN - 1) / VN, (max_m + VM - 1) / VM, n_scenes);
+    vis_cost_kernel<<<grid, VT, 0, st>>>(p, ts, f, gate, tc.pair_cap);
+  }
+  launch_scene_max(p, f, n_scenes, /*init_only=*/!(max_m > 0 && max_n > 0), gate, tc.pair_cap, st);
+  return 0;
 }
 
 }  // namespace sb

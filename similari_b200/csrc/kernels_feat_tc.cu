@@ -1,0 +1,456 @@
+// kernels_feat_tc.cu -- visual (ReID feature) cost matrix: tensor-core screen (tcgen05.mma + TMEM + TMA) followed by
+// an exact f32 refinement of the surviving pairs.
+//
+// What the reference computes (src/distance.rs:9-47, src/trackers/visual_sort/metric.rs:200-295): for every
+// (candidate, track-observation) pair the f32 euclidean / cosine distance, kept only if it passes the metric's
+// threshold (euclid d <= thr, cosine cos >= thr).  After thresholding the matrix is sparse: a detection is close to a
+// handful of observations of "its" track and far from everything else.
+//
+// GPU shape:
+//   1. screen  : C~[m][c] = sum_d A[m][d] * B[c][d] with BF16 operand copies on the 5th-gen tensor cores
+//                (one tcgen05.mma.kind::f16 chain, fp32 accumulation in TMEM).  The BF16 rounding error of the dot
+//                product is bounded by E = 2^-8 * ||a|| * ||b|| (Cauchy-Schwarz), so a pair can only pass the
+//                threshold if its screened value is within E of it.  Everything else is written as None (NaN)
+//                straight from the epilogue; survivors are appended to a compact pair list.
+//   2. refine  : one warp per surviving pair recomputes the distance in f32 in the reference's exact summation order
+//                (8-lane blocks, horizontal reduce_add, sequential block accumulation) and applies is_ok /
+//                distance_to_weight.  Every value that reaches the voting stage is therefore bit-identical to the
+//                CPU reference -- the tensor cores only decide which pairs are worth computing.
+//   If the pair list overflows (a non-selective threshold) the caller falls back to the dense exact SIMT kernel.
+//
+// Screen kernel: persistent CTAs (one per SM), 192 threads = TMA producer warp, MMA issuer warp, 4 epilogue warps.
+// Tile 128 (candidates) x 256 (track-observation rows) x 64 (features = one 128-byte swizzle atom of bf16);
+// 4 smem stages of 48 KB; the 512 TMEM columns hold two 128x256 fp32 accumulators so the epilogue of tile i overlaps
+// the MMAs of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sb_engine.cuh"
+
+namespace sb {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64;
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;  // 48 KB
+constexpr int TC_THREADS = 192;
+
+struct TcColMeta {
+  int outcol;     // logical output column (n*K + k) or -1
+  float nb;       // squared norm of the track feature
+  float tx, ty, tr;
+  int row;        // feature row in the store (idx*K + phys), -1 when dead
+  int valid;
+  unsigned int tep;  // track epoch
+};
+
+struct TcSmem {
+  unsigned char stage[TC_STAGES][TC_STAGE_BYTES];  // 1024-byte aligned operand stages first
+  float stg[4][32][33];
+  TcColMeta meta[TC_BN];
+  unsigned long long full_bar[TC_STAGES];
+  unsigned long long empty_bar[TC_STAGES];
+  unsigned long long tmem_full[2];
+  unsigned long long tmem_empty[2];
+  unsigned int tmem_base;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, void* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(void* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 | LBO(=1, ignored for swizzled K-major)<<16 | SBO(8 rows x 128 B = 1024 B)>>4 <<32 | version 1 <<46 | SW128 (2) <<61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = F32 (1<<4), A = B = BF16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+
+// BF16 operand rounding bound on a dot product: each operand carries relative error <= 2^-9, so
+// |dot~ - dot| <= (2^-8 + 2^-18) * sum|a_i b_i| <= ~2^-8 * ||a|| ||b||; 1.5x head-room covers the fp32 accumulation.
+constexpr float kScreenRelErr = 1.5f / 256.0f;
+
+// ------------------------------------------------------------------------------------------------ screen kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p,
+                  TrackStore ts, Frame f, const TcTile* tiles, int n_tiles, VisPair* pairs, int* pair_count, int pair_cap) {
+  extern __shared__ unsigned char smem_raw_[];
+  TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = p.max_obs;
+  const int KB = (p.d8 + TC_BK - 1) / TC_BK;
+
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = S.tmem_base;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapB) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const TcTile tl = tiles[t];
+        const SceneDesc sc = f.scenes[tl.scene];
+        const int rowA = sc.det_base + tl.m0;
+        const int rowB = sc.slot * ts.track_cap * K + tl.c0;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&S.empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&S.full_bar[stage], TC_STAGE_BYTES);
+          unsigned char* base = S.stage[stage];
+          tma_load_2d(base, &mapA, kb * TC_BK, rowA, &S.full_bar[stage]);
+          tma_load_2d(base + TC_A_BYTES, &mapB, kb * TC_BK, rowB, &S.full_bar[stage]);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one elected lane)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&S.tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * TC_BN);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&S.full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(S.stage[stage]);
+          const uint32_t b0 = a0 + TC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint32_t off = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle atom
+            tc_mma_bf16(d_tmem, umma_desc(a0 + off), umma_desc(b0 + off), kIdescBf16, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&S.empty_bar[stage]);  // frees the smem stage once the MMAs above retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&S.tmem_full[buf]);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps 2..5
+    const int q = warp & 3;           // TMEM lane quarter this warp may read
+    const int et = threadIdx.x - 64;  // 0..127
+    const bool cosine = p.visual_kind == 1;
+    const float thr = p.visual_threshold;
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const TcTile tl = tiles[t];
+      const SceneDesc sc = f.scenes[tl.scene];
+      const int ncols = sc.n * K;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of S.meta are done
+      for (int j = et; j < TC_BN; j += 128) {
+        TcColMeta cm;
+        cm.outcol = -1; cm.nb = 0.0f; cm.tx = cm.ty = cm.tr = 0.0f; cm.row = -1; cm.valid = 0; cm.tep = 0;
+        const int prow = tl.c0 + j;
+        const int n = prow / K, ph = prow - n * K;
+        if (n < sc.n) {
+          const size_t ti = (size_t)sc.slot * ts.track_cap + n;
+          const int on = ts.obs_n[ti];
+          // logical <-> physical observation bookkeeping of this track
+          int k_of = -1, dead_rank = 0, live_mask = 0;
+          for (int k = 0; k < K; ++k) {
+            if (k < on && ts.obs_hasf[ti * K + k]) {
+              int pp = ts.obs_phys[ti * K + k];
+              live_mask |= 1 << pp;
+              if (pp == ph) k_of = k;
+            }
+          }
+          if (k_of >= 0) {
+            unsigned int delta = sc.epoch > ts.epoch[ti] ? sc.epoch - ts.epoch[ti] : ts.epoch[ti] - sc.epoch;
+            cm.outcol = n * K + k_of;
+            cm.valid = (ts.feat_cnt[ti] >= p.min_track_length) && ((unsigned int)p.max_idle_epochs >= delta);
+            cm.nb = ts.fnorm2[ti * K + ph];
+            cm.row = (int)(ti * K + ph);
+            cm.tep = ts.epoch[ti];
+            const float* tb = ts.pred + ti * 6;
+            cm.tx = tb[0]; cm.ty = tb[1]; cm.tr = ts.radius[ti];
+          } else {
+            // dead physical slot -> writes None into the dead_rank-th logical column without a feature
+            for (int pp = 0; pp < ph; ++pp) dead_rank += ((live_mask >> pp) & 1) ? 0 : 1;
+            int seen = 0;
+            for (int k = 0; k < K; ++k) {
+              bool lv = k < on && ts.obs_hasf[ti * K + k];
+              if (!lv) { if (seen == dead_rank) { cm.outcol = n * K + k; break; } ++seen; }
+            }
+          }
+        }
+        S.meta[j] = cm;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // row (candidate) state of this thread
+      const int r = q * 32 + lane;
+      const int m = tl.m0 + r;
+      const bool row_in = m < sc.m;
+      const int g = sc.det_base + (row_in ? m : 0);
+      const bool row_ok = row_in && (f.c_flags[g] & 2);
+      const float na = row_in ? f.c_norm2[g] : 0.0f;
+      const float cx = f.c_box[(size_t)g * 6], cy = f.c_box[(size_t)g * 6 + 1], cr = f.c_radius[g];
+      mbar_wait(&S.tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      float* out = f.vis + sc.vis_off;
+      for (int ch = 0; ch < TC_BN / 32; ++ch) {
+        if (tl.c0 + ch * 32 >= ncols) break;  // physical rows >= n*K belong to no track of this scene
+        uint32_t acc[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BN + ch * 32), acc);
+        unsigned int keep = 0;  // bit jj: pair (row, column ch*32+jj) survives the screen
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const TcColMeta cm = S.meta[ch * 32 + jj];
+          if (row_ok && cm.valid) {
+            bool ok = true;  // the idle-epoch part of compatible() is already folded into cm.valid
+            if (p.n_constraints > 0) ok = compat_ok(p, sc.epoch, cm.tep, cx, cy, cr, cm.tx, cm.ty, cm.tr);
+            const float dot = __uint_as_float(acc[jj]);
+            const float nn = sqrtf(na * cm.nb);
+            const float err = kScreenRelErr * nn;
+            bool cand;
+            if (cosine) cand = dot + err >= thr * nn - 1e-5f * nn;                       // cos >= thr possible
+            else cand = (na + cm.nb) - 2.0f * dot - 2.0f * err <= thr * thr + 1e-5f * (na + cm.nb + thr * thr);
+            // NaN / inf anywhere: let the exact pass decide
+            if (!(nn == nn) || !(dot == dot) || isinf(nn) || isinf(dot)) cand = true;
+            if (ok && cand) keep |= 1u << jj;
+          }
+        }
+        // survivors -> pair list (warp-aggregated append), everything else is None
+        {
+          const int cnt = __popc(keep);
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            int tt = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += tt;
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          int base = 0;
+          if (total > 0) {
+            if (lane == 31) base = atomicAdd(pair_count, total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+          }
+          int pos = base + incl - cnt;
+          unsigned int kk = keep;
+          while (kk) {
+            const int jj = __ffs(kk) - 1;
+            kk &= kk - 1;
+            if (pos < pair_cap) {
+              const TcColMeta cm = S.meta[ch * 32 + jj];
+              VisPair vp;
+              vp.g = g; vp.row = cm.row; vp.scene = tl.scene; vp.outcol = cm.outcol;
+              pairs[pos] = vp;
+            }
+            ++pos;
+          }
+        }
+        // coalesced None fill of this 32 x 32 block (the refine pass overwrites the survivors)
+        const int oc = S.meta[ch * 32 + lane].outcol;
+        const float qnan = nanf("");
+        for (int rr = 0; rr < 32; ++rr) {
+          const int mm = tl.m0 + q * 32 + rr;
+          if (mm < sc.m && oc >= 0) out[(size_t)mm * ncols + oc] = qnan;
+        }
+      }
+      // accumulator buffer drained
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ refine kernel
+// One warp per surviving pair: f32 distance in the reference's summation order (src/distance.rs:9-47).
+__device__ __forceinline__ float reduce_add8_tc(const float* t) {
+  float q0 = t[0] + t[4], q1 = t[1] + t[5], q2 = t[2] + t[6], q3 = t[3] + t[7];
+  float d0 = q0 + q2, d1 = q1 + q3;
+  return d0 + d1;
+}
+
+__global__ void __launch_bounds__(256) vis_refine_kernel(Params p, TrackStore ts, Frame f, const VisPair* pairs,
+                                                         const int* pair_count, int pair_cap) {
+  const int lane = threadIdx.x & 31;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  int n_pairs = *pair_count;
+  if (n_pairs > pair_cap) return;  // overflow: the caller falls back to the dense exact kernel
+  const bool cosine = p.visual_kind == 1;
+  const int nblk = p.d8 / 8;
+  const int D = p.feature_dim;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_pairs; i += warps_total) {
+    const VisPair vp = pairs[i];
+    const float* a = f.in_feat + (size_t)vp.g * D;
+    const float* b = ts.feat + (size_t)vp.row * p.d8;
+    float acc = 0.0f;
+    for (int base = 0; base < nblk; base += 32) {
+      const int blk = base + lane;
+      float bs = 0.0f;
+      if (blk < nblk) {
+        float t[8];
+        const float4 b0 = *reinterpret_cast<const float4*>(b + blk * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(b + blk * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+          const int d = blk * 8 + l;
+          const float av = d < D ? a[d] : 0.0f;
+          if (cosine) t[l] = av * bb[l];
+          else { const float df = av - bb[l]; t[l] = df * df; }
+        }
+        bs = reduce_add8_tc(t);
+      }
+      const int cnt = min(32, nblk - base);
+      for (int j = 0; j < cnt; ++j) acc = acc + __shfl_sync(0xffffffffu, bs, j);
+    }
+    if (lane == 0) {
+      const SceneDesc sc = f.scenes[vp.scene];
+      const int m = vp.g - sc.det_base;
+      float v = nanf("");
+      if (cosine) {
+        const float d = acc / sqrtf(f.c_norm2[vp.g] * ts.fnorm2[vp.row]);
+        if (d >= p.visual_threshold) v = 1.0f - d;       // is_ok + distance_to_weight
+      } else {
+        const float d = sqrtf(acc);
+        if (d <= p.visual_threshold) v = d;
+      }
+      f.vis[sc.vis_off + (size_t)m * (sc.n * p.max_obs) + vp.outcol] = v;
+      if (!is_nan(v)) {  // best.rs "max_dist": maximum over the entries that exist
+        unsigned int u = __float_as_uint(v);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        atomicMax(f.scene_max + vp.scene, u);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ bf16 operand copies
+__global__ void to_bf16_kernel(const float* src, int src_pitch, int d, int d8, long long rows, __nv_bfloat16* dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * d8) return;
+  long long r = i / d8;
+  int c = (int)(i - r * d8);
+  float x = c < d ? src[r * src_pitch + c] : 0.0f;
+  dst[i] = __float2bfloat16_rn(x);
+}
+
+void launch_to_bf16(const float* src, int src_pitch, int d, int d8, long long rows, void* dst, cudaStream_t st) {
+  if (rows == 0) return;
+  long long n = rows * d8;
+  to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, src_pitch, d, d8, rows, (__nv_bfloat16*)dst);
+}
+
+// ------------------------------------------------------------------------------------------------ host launcher
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && p) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* base, long long rows, int d8, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[2] = {(cuuint64_t)d8, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d8 * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, const TcTile* d_tiles, int n_tiles,
+                       long long a_rows, long long b_rows, VisPair* pairs, int* pair_count, int pair_cap, int num_sms,
+                       cudaStream_t st) {
+  if (n_tiles == 0) return 0;
+  CUtensorMap mA, mB;
+  if (make_map(&mA, f.c_bf16, a_rows, p.d8, TC_BM) || make_map(&mB, ts.feat_bf16, b_rows, p.d8, TC_BN)) return -1;
+  size_t smem = sizeof(TcSmem) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(vis_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  cudaMemsetAsync(pair_count, 0, sizeof(int), st);
+  int grid = n_tiles < num_sms ? n_tiles : num_sms;
+  vis_screen_kernel<<<grid, TC_THREADS, smem, st>>>(mA, mB, p, ts, f, d_tiles, n_tiles, pairs, pair_count, pair_cap);
+  vis_refine_kernel<<<num_sms * 8, 256, 0, st>>>(p, ts, f, pairs, pair_count, pair_cap);
+  return 0;
+}
+
+}  // namespace sb

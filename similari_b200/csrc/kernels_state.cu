@@ -7,6 +7,8 @@
 //                  Kalman predict + update with the candidate box (src/trackers/kalman_prediction.rs:13-32),
 //                  history push, feature-set pruning (src/trackers/visual_sort/metric.rs:129-154,297-374)
 // and the lifecycle sweep TrackerAPI::auto_waste (src/trackers/tracker_api.rs:70-88).
+#include <cuda_bf16.h>
+
 #include "sb_engine.cuh"
 
 namespace sb {
@@ -193,8 +195,13 @@ __global__ void feat_store_kernel(Params p, TrackStore ts, Frame f) {
   if (dst < 0) return;
   const float* src = f.in_feat + (size_t)w * p.feature_dim;
   float* d = ts.feat + (size_t)dst * p.d8;
-  for (int i = lane; i < p.d8; i += 32) d[i] = i < p.feature_dim ? src[i] : 0.0f;
-  if (lane == 0 && p.visual_kind == 1) ts.fnorm2[dst] = f.c_norm2[w];
+  __nv_bfloat16* db = reinterpret_cast<__nv_bfloat16*>(ts.feat_bf16) + (size_t)dst * p.d8;
+  for (int i = lane; i < p.d8; i += 32) {
+    float x = i < p.feature_dim ? src[i] : 0.0f;
+    d[i] = x;
+    db[i] = __float2bfloat16_rn(x);  // B operand of the tensor-core screen
+  }
+  if (lane == 0) ts.fnorm2[dst] = f.c_norm2[w];
 }
 
 void launch_apply(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m,
@@ -307,9 +314,11 @@ __global__ void __launch_bounds__(AT) waste_kernel(Params p, TrackStore ts, cons
           if (d < 0 || d == jj) continue;
           for (int c0 = 0; c0 < fw; c0 += AT) {
             int c = c0 + tid;
-            float v = 0.0f;
-            if (c < fw) v = ts.feat[(base + jj) * fw + c];
-            if (c < fw) ts.feat[(base + d) * fw + c] = v;   // d < jj: rows never overlap
+            if (c < fw) {  // d < jj: rows never overlap
+              ts.feat[(base + d) * fw + c] = ts.feat[(base + jj) * fw + c];
+              reinterpret_cast<__nv_bfloat16*>(ts.feat_bf16)[(base + d) * fw + c] =
+                  reinterpret_cast<const __nv_bfloat16*>(ts.feat_bf16)[(base + jj) * fw + c];
+            }
           }
         }
       }

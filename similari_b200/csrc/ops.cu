@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -198,7 +199,38 @@ int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* 
   fill_u8_kernel<<<(n + 255) / 256, 256, 0, sc.st>>>(ts.feat_cnt, 1, n);
   sb::launch_prep(p, f, 1, m, sc.st);
   fill_u8_kernel<<<(m + 255) / 256, 256, 0, sc.st>>>(f.c_flags, 3, m);
-  sb::launch_vis_cost(p, ts, f, 1, m, n, sc.st);
+  // same kernel selection rule as the tracker (engine.cu): tensor-core screen + exact refinement for large
+  // contractions with a selective threshold; SB200_VIS_KERNEL=simt|tc overrides
+  sb::TcArgs tc;
+  memset(&tc, 0, sizeof(tc));
+  const bool selective = visual_kind == SB200_VIS_EUCLIDEAN ? (threshold < 1e18f) : (threshold > -1.0f);
+  tc.use_tc = selective && p.d8 >= 64 && (long long)m * n * p.d8 >= (1ll << 28);
+  if (const char* ev = getenv("SB200_VIS_KERNEL")) {
+    if (!strcmp(ev, "simt")) tc.use_tc = false;
+    else if (!strcmp(ev, "tc")) tc.use_tc = true;
+  }
+  f.scene_max = sc.alloc<unsigned int>(1);
+  cudaDeviceGetAttribute(&tc.num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (tc.use_tc) {
+    std::vector<sb::TcTile> tiles;
+    for (int m0 = 0; m0 < m; m0 += 128)
+      for (int c0 = 0; c0 < n; c0 += 256) tiles.push_back(sb::TcTile{0, m0, c0, 0});
+    tc.n_tiles = (int)tiles.size();
+    tc.d_tiles = sc.upload(tiles.data(), tiles.size());
+    tc.pair_cap = std::max(4096, m * 64);
+    if (const char* ev = getenv("SB200_VIS_PAIR_CAP")) tc.pair_cap = std::max(1, atoi(ev));
+    tc.pairs = sc.alloc<sb::VisPair>((size_t)tc.pair_cap);
+    tc.pair_count = sc.alloc<int>(1);
+    tc.a_rows = m;
+    tc.b_rows = n;
+    f.c_bf16 = sc.alloc<unsigned short>((size_t)m * p.d8);
+    ts.feat_bf16 = sc.alloc<unsigned short>((size_t)n * p.d8);
+    if (!tc.d_tiles || !tc.pairs || !tc.pair_count || !f.c_bf16 || !ts.feat_bf16) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
+    sb::launch_to_bf16(ft.in_feat, d, d, p.d8, n, ts.feat_bf16, sc.st);
+  }
+  ts.fnorm2 = ft.c_norm2;
+  int vr = sb::launch_vis_cost(p, ts, f, 1, m, n, tc, sc.st);
+  if (vr != 0) return ops_fail(SB200_ERR_CUDA, "visual cost launch failed");
   cudaMemcpyAsync(out_mn, f.vis, (size_t)m * n * 4, cudaMemcpyDeviceToHost, sc.st);
   return finish(sc);
 }
@@ -232,6 +264,11 @@ static int run_voting(bool visual, float threshold, int min_votes, const float* 
   sd.m = m; sd.n = n; sd.epoch = 1;
   f.scenes = sc.upload(&sd, 1);
   if (!f.pos || (visual && !f.vis) || !f.winner || !f.c_vt || !f.new_count || !f.scenes) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
+  if (visual) {
+    f.scene_max = sc.alloc<unsigned int>(1);
+    if (!f.scene_max) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
+    sb::launch_scene_max(p, f, 1, /*init_only=*/n == 0, nullptr, 0, sc.st);
+  }
   int vr = sb::launch_voting(p, ts, f, 1, m, n, sc.st);
   if (vr == -3) return ops_fail(SB200_ERR_CAPACITY, "scene too large for the on-chip assignment solver");
   if (vr != 0) return ops_fail(SB200_ERR_CUDA, std::string("voting launch failed: ") + cudaGetErrorString((cudaError_t)vr));

@@ -60,7 +60,8 @@ struct TrackStore {
   double* vert;          // [idx][8] vertex cache (IoU mode)
   // visual
   float* feat;           // [idx][K][d8]
-  float* fnorm2;         // [idx][K] by physical slot (cosine)
+  void* feat_bf16;       // [idx][K][d8] bf16 copy of feat: B operand of the tensor-core screen
+  float* fnorm2;         // [idx][K] by physical slot
   unsigned char* obs_phys;  // [idx][K] logical -> physical
   unsigned char* obs_hasf;  // [idx][K] logical: feature present
   float* obs_q;             // [idx][K] logical: quality
@@ -82,6 +83,8 @@ struct Frame {  // per-request transient device buffers
   double* c_vert;          // [total][8]
   unsigned char* c_flags;  // bit0 has feature, bit1 feature usable (feature_can_be_used with *_use thresholds)
   float* c_norm2;
+  void* c_bf16;            // [total][d8] bf16 copy of the candidate features (A operand of the screen)
+  unsigned int* scene_max; // [n_scenes] order-preserving encoding of best.rs "max_dist"
   int* winner;             // [total] track index within the scene or -1
   unsigned char* c_vt;     // voting type of the decision
   float* pos;              // packed positional cost matrices
@@ -99,12 +102,33 @@ struct Frame {  // per-request transient device buffers
   float* o_obs;
 };
 
+struct TcTile { int scene, m0, c0, pad; };  // one 128 x 256 output tile of the tensor-core visual cost kernel
+struct VisPair { int g, row, scene, outcol; };  // screen survivor: detection, feature row, scene, logical column
+
 // ---- kernel launchers (each in its own .cu) ----
 void launch_prep(const Params& p, const Frame& f, int n_scenes, int max_m, cudaStream_t st);
 void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                      cudaStream_t st);
-void launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
-                     cudaStream_t st);
+// visual cost: fp32 SIMT kernel in the reference's summation order (use_tc == false) or the tcgen05 3xTF32 kernel
+struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense exact kernel is used)
+  bool use_tc;
+  const TcTile* d_tiles;
+  int n_tiles;
+  long long a_rows, b_rows;
+  VisPair* pairs;
+  int* pair_count;
+  int pair_cap;
+  int num_sms;
+};
+int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                    const TcArgs& tc, cudaStream_t st);
+int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, const TcTile* d_tiles, int n_tiles,
+                       long long a_rows, long long b_rows, VisPair* pairs, int* pair_count, int pair_cap, int num_sms,
+                       cudaStream_t st);
+void launch_to_bf16(const float* src, int src_pitch, int d, int d8, long long rows, void* dst, cudaStream_t st);
+// gate: run the reduction only if *gate > gate_cap (device-side fallback switch), or always when gate == nullptr
+void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_only, const int* gate, int gate_cap,
+                      cudaStream_t st);
 // returns cudaError from configuration (dynamic smem), 0 on success
 int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                   cudaStream_t st);

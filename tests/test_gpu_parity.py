@@ -262,3 +262,56 @@ def test_nms_matches_oracle(eng, oracle, oriented):
         got = eng.nms_indices(boxes, sc, 0.6, st)
         assert list(ref) == list(got)
     assert len(eng.nms_indices(np.zeros((0, 6), np.float32), None, 0.5)) == 0
+
+
+# --------------------------------------------------------------------------------------------- tensor-core visual cost
+def _tc_inputs(m, n, d, seed):
+    rng = np.random.default_rng(seed)
+    cent = rng.standard_normal((n, d)).astype(np.float32)
+    cent /= np.linalg.norm(cent, axis=1, keepdims=True)
+    tf = cent.copy()
+    src = rng.integers(1, n, m) if n > 1 else np.zeros(m, dtype=np.int64)  # row 0 of the tracks is special below
+    cf = cent[src] + (0.3 / np.sqrt(d)) * rng.standard_normal((m, d)).astype(np.float32)
+    cf = (cf / np.linalg.norm(cf, axis=1, keepdims=True)).astype(np.float32)
+    cf[0] = tf[src[0]]                       # exact duplicate: euclidean 0, cosine 1
+    cf[1] = tf[src[1]] * np.float32(1.0001)  # near duplicate
+    if m > 2:
+        cf[2] = 0.0
+        cf[2, 0] = 1.0                       # one-hot: a single product carries the whole dot
+        tf[0] = 0.0
+        tf[0, 0] = 0.95
+    return cf, tf
+
+
+@pytest.mark.parametrize("kind", ["euclid", "cosine"])
+@pytest.mark.parametrize("m,n,d", [(64, 64, 64), (129, 257, 72), (300, 700, 512), (130, 1000, 2048), (500, 1536, 512)])
+def test_visual_cost_matrix_tensor_core_bit_exact(eng, oracle, kind, m, n, d, monkeypatch):
+    """tcgen05 BF16 screen + exact f32 refinement: every emitted value is bit-identical to the oracle and no pair
+    that passes the threshold is lost by the screen."""
+    monkeypatch.setenv("SB200_VIS_KERNEL", "tc")
+    cf, tf = _tc_inputs(m, n, d, 400 + d + m)
+    if kind == "euclid":
+        ref = oracle.visual_cost_matrix(oracle.VIS_EUCLIDEAN, 0.7, cf, tf)
+        got = eng.visual_cost_matrix(eng._lib.VIS_EUCLIDEAN, 0.7, cf, tf)
+    else:
+        ref = oracle.visual_cost_matrix(oracle.VIS_COSINE, 0.3, cf, tf)
+        got = eng.visual_cost_matrix(eng._lib.VIS_COSINE, 0.3, cf, tf)
+    assert_bits_equal(ref, got)
+    assert np.isfinite(got).sum() >= m - 1
+
+
+def test_visual_cost_matrix_tensor_core_unnormalised_and_overflow(eng, oracle, monkeypatch):
+    """Unnormalised features (the error bound scales with the norms) and the survivor-list overflow fallback."""
+    rng = np.random.default_rng(78)
+    m, n, d = 200, 300, 256
+    tf = (rng.standard_normal((n, d)) * 7.0).astype(np.float32)
+    cf = tf[rng.integers(0, n, m)] + rng.standard_normal((m, d)).astype(np.float32)
+    monkeypatch.setenv("SB200_VIS_KERNEL", "tc")
+    for thr in (20.0, 200.0):   # 200: every pair passes -> dense result
+        ref = oracle.visual_cost_matrix(oracle.VIS_EUCLIDEAN, thr, cf, tf)
+        got = eng.visual_cost_matrix(eng._lib.VIS_EUCLIDEAN, thr, cf, tf)
+        assert_bits_equal(ref, got)
+    monkeypatch.setenv("SB200_VIS_PAIR_CAP", "16")   # force the overflow -> device-side dense fallback
+    ref = oracle.visual_cost_matrix(oracle.VIS_EUCLIDEAN, 20.0, cf, tf)
+    got = eng.visual_cost_matrix(eng._lib.VIS_EUCLIDEAN, 20.0, cf, tf)
+    assert_bits_equal(ref, got)

@@ -80,6 +80,19 @@ def test_visual_trackers_match_oracle(eng, oracle, kind, pos, vis):
                     visual_min_votes=2, visual_minimal_track_length=1, min_confidence=0.1))
 
 
+@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("vis", [0, 1])
+def test_visual_trackers_tensor_core_path_match_oracle(eng, oracle, kind, vis, monkeypatch):
+    """Same end-to-end comparison with the tcgen05 visual-cost kernel forced on (the default for large frames)."""
+    monkeypatch.setenv("SB200_VIS_KERNEL", "tc")
+    cfg = small("cfg5", n_scenes=1 if kind == 2 else 3, n_objects=150, oriented=False, canvas=(1400.0, 900.0),
+                feature_dim=128)
+    run_frames(eng, oracle, cfg, 6,
+               dict(kind=kind, positional_kind=1, iou_threshold=0.3, max_idle_epochs=3, visual_kind=vis,
+                    visual_threshold=0.7 if vis == 0 else 0.2, feature_dim=128, visual_max_observations=3,
+                    visual_min_votes=2, visual_minimal_track_length=1, min_confidence=0.1))
+
+
 def test_constraints_and_custom_ids(eng, oracle):
     from similari_b200.workload import Workload
 
