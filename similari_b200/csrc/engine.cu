@@ -170,7 +170,7 @@ struct sb200_tracker {
   // frame buffers
   DBuf f_in_boxes, f_in_feat, f_in_hasf, f_in_quality, f_in_custom, f_in_own;
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_cbf16, f_scene_max, f_tiles, f_pairs, f_paircount;
+      f_status, f_featdst, f_cbf16, f_scene_max, f_tiles, f_pairs, f_paircount, f_colmeta, f_colgeo, f_rowmeta;
   HBuf h_tiles;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
@@ -181,7 +181,7 @@ struct sb200_tracker {
   ~sb200_tracker() {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
-                   &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_paircount, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
+                   &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_paircount, &f_colmeta, &f_colgeo, &f_rowmeta, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_in_boxes,
                    &f_in_feat, &f_in_hasf, &f_in_quality, &f_in_custom, &f_in_own, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
@@ -383,7 +383,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       if (!seen.emplace(scene_ids[s], s).second) return fail(SB200_ERR_INVALID, "scene %llu appears twice in one request", (unsigned long long)scene_ids[s]);
   }
   int max_m = 0, max_n = 0, need_tracks = 0;
-  long long pos_total = 0, vis_total = 0;
+  long long pos_total = 0, vis_total = 0, col_total = 0;
   for (int s = 0; s < n_scenes; ++s) {
     int slot = slot_for(scene_ids[s], true);
     sb::SceneDesc& d = sd[s];
@@ -394,7 +394,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     d.pos_off = pos_total;
     d.vis_off = vis_total;
     d.scene_id = scene_ids[s];
-    d.pad = 0;
+    d.col_off = (int)col_total;
+    col_total += (long long)d.n * P.max_obs;
     pos_total += (long long)d.m * d.n;
     if (P.is_visual) vis_total += (long long)d.m * d.n * P.max_obs;
     max_m = std::max(max_m, d.m);
@@ -415,6 +416,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   int rc = 0;
   const long long hint_dets = (long long)std::max(opts.max_scenes_hint, n_scenes) * opts.max_dets_per_scene_hint;
   const size_t T = (size_t)std::max<long long>(std::max(total, 1), hint_dets);
+  const long long hint_cols = (long long)std::max(opts.max_scenes_hint, n_scenes) * std::max(opts.max_tracks_per_scene_hint, 0) * P.max_obs;
   {
     const long long hint_pos = hint_dets * std::max(opts.max_tracks_per_scene_hint, 0);
     pos_total = std::max(pos_total, hint_pos);
@@ -457,8 +459,15 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       if (const char* e = getenv("SB200_VIS_PAIR_CAP")) tc.pair_cap = std::max(1, atoi(e));
       if ((rc = f_cbf16.ensure(T * P.d8 * 2)) || (rc = f_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
           (rc = h_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
-          (rc = f_pairs.ensure(sizeof(sb::VisPair) * (size_t)tc.pair_cap)) || (rc = f_paircount.ensure(sizeof(int))))
+          (rc = f_pairs.ensure(sizeof(sb::VisPair) * (size_t)tc.pair_cap)) || (rc = f_paircount.ensure(sizeof(int))) ||
+          (rc = f_colmeta.ensure(sizeof(sb::VisColMeta) * (size_t)std::max<long long>(1, std::max(col_total, hint_cols)))) ||
+          (rc = f_colgeo.ensure(sizeof(sb::VisColGeo) * (size_t)std::max<long long>(1, P.n_constraints > 0 ? std::max(col_total, hint_cols) : 1))) ||
+          (rc = f_rowmeta.ensure(sizeof(sb::VisRowMeta) * T)))
         return rc;
+      tc.colmeta = f_colmeta.as<sb::VisColMeta>();
+      tc.colgeo = f_colgeo.as<sb::VisColGeo>();
+      tc.rowmeta = f_rowmeta.as<sb::VisRowMeta>();
+      tc.total_cols = (int)col_total;
       if (tc.n_tiles > 0) {
         memcpy(h_tiles.p, tiles.data(), sizeof(sb::TcTile) * tc.n_tiles);
         CU(cudaMemcpyAsync(f_tiles.p, h_tiles.p, sizeof(sb::TcTile) * tc.n_tiles, cudaMemcpyHostToDevice, stream));

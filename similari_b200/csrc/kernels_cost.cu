@@ -319,8 +319,7 @@ int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n
     // tensor-core screen + exact refinement; the dense kernel below only runs if the survivor list overflowed
     launch_scene_max(p, f, n_scenes, /*init_only=*/true, nullptr, 0, st);
     launch_to_bf16(f.in_feat, p.feature_dim, p.feature_dim, p.d8, f.total, f.c_bf16, st);
-    int rc = launch_vis_cost_tc(p, ts, f, tc.d_tiles, tc.n_tiles, tc.a_rows, tc.b_rows, tc.pairs, tc.pair_count,
-                                tc.pair_cap, tc.num_sms, st);
+    int rc = launch_vis_cost_tc(p, ts, f, n_scenes, max_n, tc, st);
     if (rc != 0) return rc;
     gate = tc.pair_count;
   }

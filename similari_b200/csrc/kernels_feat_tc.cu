@@ -38,19 +38,10 @@ constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;  // 48 KB
 constexpr int TC_THREADS = 192;
 
-struct TcColMeta {
-  int outcol;     // logical output column (n*K + k) or -1
-  float nb;       // squared norm of the track feature
-  float tx, ty, tr;
-  int row;        // feature row in the store (idx*K + phys), -1 when dead
-  int valid;
-  unsigned int tep;  // track epoch
-};
-
 struct TcSmem {
   unsigned char stage[TC_STAGES][TC_STAGE_BYTES];  // 1024-byte aligned operand stages first
-  float stg[4][32][33];
-  TcColMeta meta[TC_BN];
+  VisColMeta meta[TC_BN];
+  VisColGeo geo[TC_BN];
   unsigned long long full_bar[TC_STAGES];
   unsigned long long empty_bar[TC_STAGES];
   unsigned long long tmem_full[2];
@@ -125,7 +116,8 @@ constexpr float kScreenRelErr = 1.5f / 256.0f;
 // ------------------------------------------------------------------------------------------------ screen kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p,
-                  TrackStore ts, Frame f, const TcTile* tiles, int n_tiles, VisPair* pairs, int* pair_count, int pair_cap) {
+                  TrackStore ts, Frame f, const TcTile* tiles, int n_tiles, VisPair* pairs, int* pair_count, int pair_cap,
+                  const VisColMeta* colmeta, const VisColGeo* colgeo, const VisRowMeta* rowmeta) {
   extern __shared__ unsigned char smem_raw_[];
   TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -200,7 +192,7 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const int q = warp & 3;           // TMEM lane quarter this warp may read
     const int et = threadIdx.x - 64;  // 0..127
     const bool cosine = p.visual_kind == 1;
-    const float thr = p.visual_threshold;
+    const bool geo = p.n_constraints > 0;
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -209,40 +201,12 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int ncols = sc.n * K;
       asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of S.meta are done
       for (int j = et; j < TC_BN; j += 128) {
-        TcColMeta cm;
-        cm.outcol = -1; cm.nb = 0.0f; cm.tx = cm.ty = cm.tr = 0.0f; cm.row = -1; cm.valid = 0; cm.tep = 0;
         const int prow = tl.c0 + j;
-        const int n = prow / K, ph = prow - n * K;
-        if (n < sc.n) {
-          const size_t ti = (size_t)sc.slot * ts.track_cap + n;
-          const int on = ts.obs_n[ti];
-          // logical <-> physical observation bookkeeping of this track
-          int k_of = -1, dead_rank = 0, live_mask = 0;
-          for (int k = 0; k < K; ++k) {
-            if (k < on && ts.obs_hasf[ti * K + k]) {
-              int pp = ts.obs_phys[ti * K + k];
-              live_mask |= 1 << pp;
-              if (pp == ph) k_of = k;
-            }
-          }
-          if (k_of >= 0) {
-            unsigned int delta = sc.epoch > ts.epoch[ti] ? sc.epoch - ts.epoch[ti] : ts.epoch[ti] - sc.epoch;
-            cm.outcol = n * K + k_of;
-            cm.valid = (ts.feat_cnt[ti] >= p.min_track_length) && ((unsigned int)p.max_idle_epochs >= delta);
-            cm.nb = ts.fnorm2[ti * K + ph];
-            cm.row = (int)(ti * K + ph);
-            cm.tep = ts.epoch[ti];
-            const float* tb = ts.pred + ti * 6;
-            cm.tx = tb[0]; cm.ty = tb[1]; cm.tr = ts.radius[ti];
-          } else {
-            // dead physical slot -> writes None into the dead_rank-th logical column without a feature
-            for (int pp = 0; pp < ph; ++pp) dead_rank += ((live_mask >> pp) & 1) ? 0 : 1;
-            int seen = 0;
-            for (int k = 0; k < K; ++k) {
-              bool lv = k < on && ts.obs_hasf[ti * K + k];
-              if (!lv) { if (seen == dead_rank) { cm.outcol = n * K + k; break; } ++seen; }
-            }
-          }
+        VisColMeta cm;
+        cm.snb = 0.0f; cm.colc = 0.0f; cm.outcol = -1; cm.row = -1;
+        if (prow < ncols) {
+          cm = colmeta[sc.col_off + prow];
+          if (geo) S.geo[j] = colgeo[sc.col_off + prow];
         }
         S.meta[j] = cm;
       }
@@ -252,9 +216,10 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       const int m = tl.m0 + r;
       const bool row_in = m < sc.m;
       const int g = sc.det_base + (row_in ? m : 0);
-      const bool row_ok = row_in && (f.c_flags[g] & 2);
-      const float na = row_in ? f.c_norm2[g] : 0.0f;
-      const float cx = f.c_box[(size_t)g * 6], cy = f.c_box[(size_t)g * 6 + 1], cr = f.c_radius[g];
+      const VisRowMeta rm = rowmeta[g];
+      const bool row_ok = row_in && rm.ok;
+      float cx = 0.0f, cy = 0.0f, cr = 0.0f;
+      if (geo) { cx = f.c_box[(size_t)g * 6]; cy = f.c_box[(size_t)g * 6 + 1]; cr = f.c_radius[g]; }
       mbar_wait(&S.tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       float* out = f.vis + sc.vis_off;
@@ -263,25 +228,28 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         uint32_t acc[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BN + ch * 32), acc);
         unsigned int keep = 0;  // bit jj: pair (row, column ch*32+jj) survives the screen
+        if (row_ok) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const TcColMeta cm = S.meta[ch * 32 + jj];
-          if (row_ok && cm.valid) {
-            bool ok = true;  // the idle-epoch part of compatible() is already folded into cm.valid
-            if (p.n_constraints > 0) ok = compat_ok(p, sc.epoch, cm.tep, cx, cy, cr, cm.tx, cm.ty, cm.tr);
+          for (int jj = 0; jj < 32; ++jj) {
+            const VisColMeta cm = S.meta[ch * 32 + jj];
             const float dot = __uint_as_float(acc[jj]);
-            const float nn = sqrtf(na * cm.nb);
-            const float err = kScreenRelErr * nn;
-            bool cand;
-            if (cosine) cand = dot + err >= thr * nn - 1e-5f * nn;                       // cos >= thr possible
-            else cand = (na + cm.nb) - 2.0f * dot - 2.0f * err <= thr * thr + 1e-5f * (na + cm.nb + thr * thr);
-            // NaN / inf anywhere: let the exact pass decide
-            if (!(nn == nn) || !(dot == dot) || isinf(nn) || isinf(dot)) cand = true;
-            if (ok && cand) keep |= 1u << jj;
+            const float nn = rm.sna * cm.snb;
+            // cosine: cos >= thr possible   <=>  dot + E >= (thr - 1e-5) * |a||b|
+            // euclid: d^2 <= thr^2 possible <=>  dot + E >= 0.5 * ((|a|^2 + |b|^2)(1 - 1e-5) - thr^2 (1 + 1e-5))
+            const float lhs = dot + kScreenRelErr * nn;
+            const float rhs = cosine ? rm.rowc * nn : rm.rowc + cm.colc;
+            bool cand = !(lhs < rhs);   // NaN anywhere => let the exact pass decide
+            if (cm.row >= 0 && cand) {
+              if (geo) {
+                const VisColGeo cg = S.geo[ch * 32 + jj];
+                cand = compat_ok(p, sc.epoch, cg.tep, cx, cy, cr, cg.tx, cg.ty, cg.tr);
+              }
+              if (cand) keep |= 1u << jj;
+            }
           }
         }
         // survivors -> pair list (warp-aggregated append), everything else is None
-        {
+        if (__any_sync(0xffffffffu, keep != 0)) {
           const int cnt = __popc(keep);
           int incl = cnt;
 #pragma unroll
@@ -291,17 +259,15 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           }
           const int total = __shfl_sync(0xffffffffu, incl, 31);
           int base = 0;
-          if (total > 0) {
-            if (lane == 31) base = atomicAdd(pair_count, total);
-            base = __shfl_sync(0xffffffffu, base, 31);
-          }
+          if (lane == 31) base = atomicAdd(pair_count, total);
+          base = __shfl_sync(0xffffffffu, base, 31);
           int pos = base + incl - cnt;
           unsigned int kk = keep;
           while (kk) {
             const int jj = __ffs(kk) - 1;
             kk &= kk - 1;
             if (pos < pair_cap) {
-              const TcColMeta cm = S.meta[ch * 32 + jj];
+              const VisColMeta cm = S.meta[ch * 32 + jj];
               VisPair vp;
               vp.g = g; vp.row = cm.row; vp.scene = tl.scene; vp.outcol = cm.outcol;
               pairs[pos] = vp;
@@ -312,9 +278,10 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         // coalesced None fill of this 32 x 32 block (the refine pass overwrites the survivors)
         const int oc = S.meta[ch * 32 + lane].outcol;
         const float qnan = nanf("");
-        for (int rr = 0; rr < 32; ++rr) {
-          const int mm = tl.m0 + q * 32 + rr;
-          if (mm < sc.m && oc >= 0) out[(size_t)mm * ncols + oc] = qnan;
+        const int mlim = min(32, sc.m - (tl.m0 + q * 32));
+        if (oc >= 0) {
+          float* o = out + (size_t)(tl.m0 + q * 32) * ncols + oc;
+          for (int rr = 0; rr < mlim; ++rr) o[(size_t)rr * ncols] = qnan;
         }
       }
       // accumulator buffer drained
@@ -437,19 +404,89 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, int d8, in
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, const TcTile* d_tiles, int n_tiles,
-                       long long a_rows, long long b_rows, VisPair* pairs, int* pair_count, int pair_cap, int num_sms,
+// per-frame metadata: one thread per physical feature row (scene, track n, physical slot p) and per candidate
+__global__ void vis_meta_kernel(Params p, TrackStore ts, Frame f, int n_scenes, int max_rows, VisColMeta* colmeta,
+                                VisColGeo* colgeo) {
+  const int s = blockIdx.y;
+  const SceneDesc sc = f.scenes[s];
+  const int K = p.max_obs;
+  const int prow = blockIdx.x * blockDim.x + threadIdx.x;
+  if (prow >= sc.n * K || prow >= max_rows) return;
+  const int n = prow / K, ph = prow - n * K;
+  const size_t ti = (size_t)sc.slot * ts.track_cap + n;
+  const int on = ts.obs_n[ti];
+  VisColMeta cm;
+  cm.snb = 0.0f; cm.colc = 0.0f; cm.outcol = -1; cm.row = -1;
+  // logical <-> physical observation bookkeeping of this track
+  int k_of = -1, live_mask = 0;
+  for (int k = 0; k < K; ++k) {
+    if (k < on && ts.obs_hasf[ti * K + k]) {
+      int pp = ts.obs_phys[ti * K + k];
+      live_mask |= 1 << pp;
+      if (pp == ph) k_of = k;
+    }
+  }
+  const unsigned int tep = ts.epoch[ti];
+  if (k_of >= 0) {
+    const unsigned int delta = sc.epoch > tep ? sc.epoch - tep : tep - sc.epoch;
+    cm.outcol = n * K + k_of;
+    const bool valid = (ts.feat_cnt[ti] >= p.min_track_length) && ((unsigned int)p.max_idle_epochs >= delta);
+    const float nb = ts.fnorm2[ti * K + ph];
+    cm.snb = sqrtf(nb);
+    cm.colc = 0.5f * nb * (1.0f - 1e-5f);
+    cm.row = valid ? (int)(ti * K + ph) : -1;
+  } else {
+    // dead physical slot -> owns the dead_rank-th logical column without a feature (written as None)
+    int dead_rank = 0;
+    for (int pp = 0; pp < ph; ++pp) dead_rank += ((live_mask >> pp) & 1) ? 0 : 1;
+    int seen = 0;
+    for (int k = 0; k < K; ++k) {
+      bool lv = k < on && ts.obs_hasf[ti * K + k];
+      if (!lv) { if (seen == dead_rank) { cm.outcol = n * K + k; break; } ++seen; }
+    }
+  }
+  colmeta[sc.col_off + prow] = cm;
+  if (p.n_constraints > 0) {
+    const float* tb = ts.pred + ti * 6;
+    VisColGeo cg;
+    cg.tx = tb[0]; cg.ty = tb[1]; cg.tr = ts.radius[ti]; cg.tep = tep;
+    colgeo[sc.col_off + prow] = cg;
+  }
+}
+
+__global__ void vis_rowmeta_kernel(Params p, Frame f, VisRowMeta* rowmeta) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= f.total) return;
+  const float na = f.c_norm2[g];
+  VisRowMeta rm;
+  rm.sna = sqrtf(na);
+  rm.ok = (f.c_flags[g] & 2) ? 1 : 0;
+  rm.pad = 0;
+  const float thr = p.visual_threshold;
+  if (p.visual_kind == 1) rm.rowc = thr - 1e-5f;
+  else rm.rowc = 0.5f * (na * (1.0f - 1e-5f) - thr * thr * (1.0f + 1e-5f));
+  rowmeta[g] = rm;
+}
+
+int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
                        cudaStream_t st) {
-  if (n_tiles == 0) return 0;
+  if (tc.n_tiles == 0) return 0;
   CUtensorMap mA, mB;
-  if (make_map(&mA, f.c_bf16, a_rows, p.d8, TC_BM) || make_map(&mB, ts.feat_bf16, b_rows, p.d8, TC_BN)) return -1;
+  if (make_map(&mA, f.c_bf16, tc.a_rows, p.d8, TC_BM) || make_map(&mB, ts.feat_bf16, tc.b_rows, p.d8, TC_BN)) return -1;
   size_t smem = sizeof(TcSmem) + 1024;
   cudaError_t e = cudaFuncSetAttribute(vis_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  cudaMemsetAsync(pair_count, 0, sizeof(int), st);
-  int grid = n_tiles < num_sms ? n_tiles : num_sms;
-  vis_screen_kernel<<<grid, TC_THREADS, smem, st>>>(mA, mB, p, ts, f, d_tiles, n_tiles, pairs, pair_count, pair_cap);
-  vis_refine_kernel<<<num_sms * 8, 256, 0, st>>>(p, ts, f, pairs, pair_count, pair_cap);
+  cudaMemsetAsync(tc.pair_count, 0, sizeof(int), st);
+  const int max_rows = max_n * p.max_obs;
+  if (max_rows > 0) {
+    dim3 grid((max_rows + 255) / 256, n_scenes);
+    vis_meta_kernel<<<grid, 256, 0, st>>>(p, ts, f, n_scenes, max_rows, tc.colmeta, tc.colgeo);
+  }
+  vis_rowmeta_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f, tc.rowmeta);
+  int grid = tc.n_tiles < tc.num_sms ? tc.n_tiles : tc.num_sms;
+  vis_screen_kernel<<<grid, TC_THREADS, smem, st>>>(mA, mB, p, ts, f, tc.d_tiles, tc.n_tiles, tc.pairs, tc.pair_count,
+                                                     tc.pair_cap, tc.colmeta, tc.colgeo, tc.rowmeta);
+  vis_refine_kernel<<<tc.num_sms * 8, 256, 0, st>>>(p, ts, f, tc.pairs, tc.pair_count, tc.pair_cap);
   return 0;
 }
 

@@ -225,7 +225,12 @@ int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* 
     tc.b_rows = n;
     f.c_bf16 = sc.alloc<unsigned short>((size_t)m * p.d8);
     ts.feat_bf16 = sc.alloc<unsigned short>((size_t)n * p.d8);
-    if (!tc.d_tiles || !tc.pairs || !tc.pair_count || !f.c_bf16 || !ts.feat_bf16) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
+    tc.colmeta = sc.alloc<sb::VisColMeta>(n);
+    tc.colgeo = sc.alloc<sb::VisColGeo>(n);
+    tc.rowmeta = sc.alloc<sb::VisRowMeta>(m);
+    tc.total_cols = n;
+    if (!tc.d_tiles || !tc.pairs || !tc.pair_count || !f.c_bf16 || !ts.feat_bf16 || !tc.colmeta || !tc.colgeo || !tc.rowmeta)
+      return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
     sb::launch_to_bf16(ft.in_feat, d, d, p.d8, n, ts.feat_bf16, sc.st);
   }
   ts.fnorm2 = ft.c_norm2;

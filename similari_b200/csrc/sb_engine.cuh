@@ -42,7 +42,7 @@ struct SceneDesc {  // one per scene of the current request
   long long pos_off;  // offset of the m x n positional cost matrix
   long long vis_off;  // offset of the m x n x K visual matrix
   unsigned int epoch; // the scene's freshly incremented epoch (candidate epoch)
-  int pad;
+  int col_off;        // first entry of this scene in the per-frame column metadata (n * K physical feature rows)
   unsigned long long scene_id;
 };
 
@@ -104,6 +104,15 @@ struct Frame {  // per-request transient device buffers
 
 struct TcTile { int scene, m0, c0, pad; };  // one 128 x 256 output tile of the tensor-core visual cost kernel
 struct VisPair { int g, row, scene, outcol; };  // screen survivor: detection, feature row, scene, logical column
+// per-frame metadata of one physical feature row (track n, physical slot p) of a scene, built once per frame
+struct VisColMeta {
+  float snb;     // sqrt(||b||^2)
+  float colc;    // column part of the screen test
+  int outcol;    // logical output column n*K + k (-1: none)
+  int row;       // feature row idx*K + phys when the observation takes part in the metric, else -1
+};
+struct VisColGeo { float tx, ty, tr; unsigned int tep; };  // only read when spatio-temporal constraints exist
+struct VisRowMeta { float sna, rowc; int ok, pad; };
 
 // ---- kernel launchers (each in its own .cu) ----
 void launch_prep(const Params& p, const Frame& f, int n_scenes, int max_m, cudaStream_t st);
@@ -119,11 +128,14 @@ struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense ex
   int* pair_count;
   int pair_cap;
   int num_sms;
+  VisColMeta* colmeta;   // [sum n_s*K]
+  VisColGeo* colgeo;     // [sum n_s*K]
+  VisRowMeta* rowmeta;   // [total]
+  int total_cols;
 };
 int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                     const TcArgs& tc, cudaStream_t st);
-int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, const TcTile* d_tiles, int n_tiles,
-                       long long a_rows, long long b_rows, VisPair* pairs, int* pair_count, int pair_cap, int num_sms,
+int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
                        cudaStream_t st);
 void launch_to_bf16(const float* src, int src_pitch, int d, int d8, long long rows, void* dst, cudaStream_t st);
 // gate: run the reduction only if *gate > gate_cap (device-side fallback switch), or always when gate == nullptr
