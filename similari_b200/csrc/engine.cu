@@ -170,7 +170,7 @@ struct sb200_tracker {
   // frame buffers
   DBuf f_in_boxes, f_in_feat, f_in_hasf, f_in_quality, f_in_custom, f_in_own;
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_cbf16, f_scene_max, f_tiles, f_pairs, f_paircount, f_colmeta, f_colgeo, f_rowmeta;
+      f_status, f_featdst, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_rowmeta, f_poslist, f_counters, f_visval;
   HBuf h_tiles;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
@@ -181,7 +181,7 @@ struct sb200_tracker {
   ~sb200_tracker() {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
-                   &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_paircount, &f_colmeta, &f_colgeo, &f_rowmeta, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
+                   &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_in_boxes,
                    &f_in_feat, &f_in_hasf, &f_in_quality, &f_in_custom, &f_in_own, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
@@ -383,7 +383,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       if (!seen.emplace(scene_ids[s], s).second) return fail(SB200_ERR_INVALID, "scene %llu appears twice in one request", (unsigned long long)scene_ids[s]);
   }
   int max_m = 0, max_n = 0, need_tracks = 0;
-  long long pos_total = 0, vis_total = 0, col_total = 0;
+  long long pos_total = 0, vis_total = 0, col_total = 0, posl_total = 0, visl_total = 0;
   for (int s = 0; s < n_scenes; ++s) {
     int slot = slot_for(scene_ids[s], true);
     sb::SceneDesc& d = sd[s];
@@ -396,6 +396,12 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     d.scene_id = scene_ids[s];
     d.col_off = (int)col_total;
     col_total += (long long)d.n * P.max_obs;
+    d.pos_lbase = (int)posl_total;
+    d.pos_lcap = (int)std::min<long long>((long long)d.m * 32, (long long)sb::kVotePosCap * 2);
+    posl_total += d.pos_lcap;
+    d.vis_lbase = (int)visl_total;
+    d.vis_lcap = P.is_visual ? (int)std::min<long long>((long long)d.m * 64, (long long)sb::kVoteVisCap * 4) : 0;
+    visl_total += d.vis_lcap;
     pos_total += (long long)d.m * d.n;
     if (P.is_visual) vis_total += (long long)d.m * d.n * P.max_obs;
     max_m = std::max(max_m, d.m);
@@ -455,11 +461,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
           for (int c0 = 0; c0 < rows; c0 += 256) tiles.push_back(sb::TcTile{s, m0, c0, 0});
       }
       tc.n_tiles = (int)tiles.size();
-      tc.pair_cap = (int)std::min<long long>(std::max<long long>(4096, (long long)total * 64), 1ll << 27);
-      if (const char* e = getenv("SB200_VIS_PAIR_CAP")) tc.pair_cap = std::max(1, atoi(e));
       if ((rc = f_cbf16.ensure(T * P.d8 * 2)) || (rc = f_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
           (rc = h_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
-          (rc = f_pairs.ensure(sizeof(sb::VisPair) * (size_t)tc.pair_cap)) || (rc = f_paircount.ensure(sizeof(int))) ||
           (rc = f_colmeta.ensure(sizeof(sb::VisColMeta) * (size_t)std::max<long long>(1, std::max(col_total, hint_cols)))) ||
           (rc = f_colgeo.ensure(sizeof(sb::VisColGeo) * (size_t)std::max<long long>(1, P.n_constraints > 0 ? std::max(col_total, hint_cols) : 1))) ||
           (rc = f_rowmeta.ensure(sizeof(sb::VisRowMeta) * T)))
@@ -473,8 +476,6 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
         CU(cudaMemcpyAsync(f_tiles.p, h_tiles.p, sizeof(sb::TcTile) * tc.n_tiles, cudaMemcpyHostToDevice, stream));
       }
       tc.d_tiles = f_tiles.as<sb::TcTile>();
-      tc.pairs = f_pairs.as<sb::VisPair>();
-      tc.pair_count = f_paircount.as<int>();
       tc.a_rows = total;
       tc.b_rows = (long long)scene_cap * track_cap * P.max_obs;
     }
@@ -523,6 +524,20 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.scenes = f_scenes.as<sb::SceneDesc>(); f.new_count = f_newcount.as<int>(); f.status = f_status.as<int>();
   f.feat_dst = P.is_visual ? f_featdst.as<int>() : nullptr;
   f.c_bf16 = f_cbf16.p; f.scene_max = f_scene_max.as<unsigned int>();
+  // sparse entry lists + per-scene counters (pos_cnt | vis_cnt | scene_mode), zeroed every frame
+  if ((rc = f_poslist.ensure(sizeof(sb::PosEntry) * (size_t)std::max<long long>(1, std::max(posl_total, hint_dets * 32)))) ||
+      (rc = f_counters.ensure(sizeof(int) * 3 * (size_t)n_scenes)))
+    return rc;
+  if (P.is_visual && ((rc = f_pairs.ensure(sizeof(sb::VisPair) * (size_t)std::max<long long>(1, std::max(visl_total, hint_dets * 64)))) ||
+                      (rc = f_visval.ensure(sizeof(float) * (size_t)std::max<long long>(1, std::max(visl_total, hint_dets * 64))))))
+    return rc;
+  f.pos_list = f_poslist.as<sb::PosEntry>();
+  f.pos_cnt = f_counters.as<int>();
+  f.vis_cnt = f.pos_cnt + n_scenes;
+  f.scene_mode = f.pos_cnt + 2 * n_scenes;
+  f.vis_pairs = f_pairs.as<sb::VisPair>();
+  f.vis_val = f_visval.as<float>();
+  CU(cudaMemsetAsync(f_counters.p, 0, sizeof(int) * 3 * (size_t)n_scenes, stream));
   // outputs
   sb200_predict_out o{};
   if (out) o = *out;

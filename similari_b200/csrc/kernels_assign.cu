@@ -56,8 +56,8 @@ __device__ __forceinline__ float dec_f32(unsigned int u) {
 }
 
 // per-scene maximum over all valid visual entries ("max_dist" of best.rs:58,72-74), init -1.0
-__global__ void vis_max_kernel(Params p, Frame f, unsigned int* scene_max, const int* gate, int gate_cap) {
-  if (gate != nullptr && *gate <= gate_cap) return;
+__global__ void vis_max_kernel(Params p, Frame f, unsigned int* scene_max) {
+  if (f.scene_mode[blockIdx.y] == 0) return;  // sparse scenes: the refine kernel already reduced their maximum
   const SceneDesc sc = f.scenes[blockIdx.y];
   const long long cnt = (long long)sc.m * sc.n * p.max_obs;
   const float* v = f.vis + sc.vis_off;
@@ -73,8 +73,7 @@ __global__ void vis_max_kernel(Params p, Frame f, unsigned int* scene_max, const
   }
   if ((threadIdx.x & 31) == 0) atomicMax(scene_max + blockIdx.y, enc_f32(mx));
 }
-__global__ void vis_max_init_kernel(unsigned int* scene_max, int n, const int* gate, int gate_cap) {
-  if (gate != nullptr && *gate <= gate_cap) return;
+__global__ void vis_max_init_kernel(unsigned int* scene_max, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) scene_max[i] = enc_f32(-1.0f);
 }
@@ -160,6 +159,7 @@ __global__ void __launch_bounds__(VT_THREADS) voting_kernel(Params p, Frame f) {
   __shared__ int s_warp[NWARPS];
   __shared__ int s_misc[4];
   const int sidx = blockIdx.x;
+  if (f.scene_mode[sidx] == 0) return;  // handled by voting_sparse_kernel
   const SceneDesc sc = f.scenes[sidx];
   const int M = sc.m, N = sc.n;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -418,13 +418,471 @@ __global__ void __launch_bounds__(VT_THREADS) voting_kernel(Params p, Frame f) {
   }
 }
 
-void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_only, const int* gate, int gate_cap,
-                      cudaStream_t st) {
+// =====================================================================================================
+// Sparse voting: the same algorithms on the sparse views of the cost matrices (valid entries only).
+//
+// After the 2R gate / thresholds both matrices are ~99 % None, so the voting stage works on per-scene entry lists:
+//   BestFit  : sort the scene's valid visual entries by (candidate, track, observation), one thread per (candidate,
+//              track) group accumulates votes and the f64 weight in observation order, row / column argmax with
+//              lowest-index tie-break (see the dense kernel for why that equals the reference's greedy pass).
+//   KM       : CSR (by candidate) and CSC (by track) of the positional entries live in shared memory.  A root whose
+//              tightest column is free is matched by a single warp without touching the other columns -- exactly what
+//              the first iteration of pathfinding's search would do (delta = 0) -- and only the remaining roots run the
+//              block-wide label/slack search, with w(row, col) looked up in the CSC.
+struct SparseSmem {
+  long long* slack; long long* ly; long long* lx; long long* rmax;
+  int* slackx; int* alt; int* yx; int* xy; int* row_cand; int* row_of_m; int* cnt_m; int* col_trk; int* first_m;
+  int* col_rank; int* fw; int* row_ptr; int* col_ptr;
+  float* csr_v; float* csc_v;
+  unsigned short* csr_n; unsigned short* csc_m;
+  unsigned char* inS; unsigned char* seen_m; unsigned char* excl;
+  // BestFit scratch, overlaid on the KM / CSR region (disjoint in time)
+  unsigned long long* vkey; float* vval; unsigned long long* rowW; unsigned long long* colW; int* rown; int* colm;
+};
+
+__host__ __device__ inline size_t sparse_smem_bytes(int M, int N) {
+  size_t ny = (size_t)M + N;
+  size_t km = ny * 8 * 2 + (size_t)M * 8 * 2 + ny * 4 * 3 + (size_t)M * 4 * 4 + (size_t)N * 4 * 3 + (size_t)(M + 1) * 4 +
+              (size_t)(N + 1) * 4 + (size_t)kVotePosCap * 12 + 64;
+  size_t bf = (size_t)kVoteVisCap * 12 + (size_t)M * 12 + (size_t)N * 12 + 64;
+  size_t persist = (size_t)M * 4 + (size_t)M * 2 + N + 64;  // fw, inS, seen_m, excl
+  return (km > bf ? km : bf) + persist;
+}
+
+__device__ inline SparseSmem carve_sparse(unsigned char* base, int M, int N) {
+  SparseSmem s;
+  size_t ny = (size_t)M + N;
+  // persistent part first
+  int* p4 = reinterpret_cast<int*>(base);
+  s.fw = p4; p4 += M;
+  unsigned char* p1 = reinterpret_cast<unsigned char*>(p4);
+  s.inS = p1; p1 += M;
+  s.seen_m = p1; p1 += M;
+  s.excl = p1; p1 += N;
+  unsigned char* scratch = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p1) + 15) & ~(uintptr_t)15);
+  // KM / CSR / CSC view
+  long long* p8 = reinterpret_cast<long long*>(scratch);
+  s.slack = p8; p8 += ny;
+  s.ly = p8; p8 += ny;
+  s.lx = p8; p8 += M;
+  s.rmax = p8; p8 += M;
+  p4 = reinterpret_cast<int*>(p8);
+  s.slackx = p4; p4 += ny;
+  s.alt = p4; p4 += ny;
+  s.yx = p4; p4 += ny;
+  s.xy = p4; p4 += M;
+  s.row_cand = p4; p4 += M;
+  s.row_of_m = p4; p4 += M;
+  s.cnt_m = p4; p4 += M;
+  s.col_trk = p4; p4 += N;
+  s.first_m = p4; p4 += N;
+  s.col_rank = p4; p4 += N;
+  s.row_ptr = p4; p4 += M + 1;
+  s.col_ptr = p4; p4 += N + 1;
+  s.csr_v = reinterpret_cast<float*>(p4); p4 += kVotePosCap;
+  s.csc_v = reinterpret_cast<float*>(p4); p4 += kVotePosCap;
+  unsigned short* p2 = reinterpret_cast<unsigned short*>(p4);
+  s.csr_n = p2; p2 += kVotePosCap;
+  s.csc_m = p2; p2 += kVotePosCap;
+  // BestFit view of the same scratch
+  unsigned long long* q8 = reinterpret_cast<unsigned long long*>(scratch);
+  s.vkey = q8; q8 += kVoteVisCap;
+  s.rowW = q8; q8 += M;
+  s.colW = q8; q8 += N;
+  p4 = reinterpret_cast<int*>(q8);
+  s.vval = reinterpret_cast<float*>(p4); p4 += kVoteVisCap;
+  s.rown = p4; p4 += M;
+  s.colm = p4; p4 += N;
+  return s;
+}
+
+__device__ __forceinline__ unsigned long long enc_f64(double v) {  // order-preserving f64 -> u64
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+
+__device__ int block_exscan_int(int* data, int n, int* s_warp, int* s_carry) {
+  // in-place exclusive scan of data[0..n), returns the total
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) *s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += VT_THREADS) {
+    int i = base + tid;
+    int v = i < n ? data[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += t;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; ++w) woff += s_warp[w];
+    int carry = *s_carry;
+    if (i < n) data[i] = carry + woff + x - v;
+    __syncthreads();
+    if (tid == VT_THREADS - 1) *s_carry = carry + woff + x;
+    __syncthreads();
+  }
+  return *s_carry;
+}
+
+template <bool VISUAL>
+__global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Frame f) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ MinPair s_red[2][NWARPS];
+  __shared__ int s_warp[NWARPS];
+  __shared__ int s_misc[8];
+  const int sidx = blockIdx.x;
+  if (f.scene_mode[sidx] != 0) return;  // handled by the dense voting_kernel
+  const SceneDesc sc = f.scenes[sidx];
+  const int M = sc.m, N = sc.n;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int* winner = f.winner + sc.det_base;
+  unsigned char* cvt = f.c_vt + sc.det_base;
+  if (M == 0) {
+    if (tid == 0) f.new_count[sidx] = 0;
+    return;
+  }
+  SparseSmem s = carve_sparse(smem_raw, M, N);
+  for (int m = tid; m < M; m += VT_THREADS) {
+    winner[m] = -1;
+    cvt[m] = (unsigned char)1;
+    s.fw[m] = kNone;
+    s.seen_m[m] = 0;
+  }
+  for (int n = tid; n < N; n += VT_THREADS) s.excl[n] = 0;
+  __syncthreads();
+
+  // ------------------------------------------------------------------ BestFit on the valid visual entries
+  if (VISUAL && N > 0) {
+    const int K = p.max_obs;
+    const float maxd = dec_f32(f.scene_max[sidx]);
+    const int nraw = min(f.vis_cnt[sidx], sc.vis_lcap);
+    // compact the valid entries (value passed the threshold) into shared memory
+    if (tid == 0) s_misc[0] = 0;
+    __syncthreads();
+    for (int i = tid; i < nraw; i += VT_THREADS) {
+      const float v = f.vis_val[sc.vis_lbase + i];
+      if (!is_nan(v)) {
+        const VisPair vp = f.vis_pairs[sc.vis_lbase + i];
+        const int slot = atomicAdd(&s_misc[0], 1);
+        s.vkey[slot] = ((unsigned long long)(unsigned int)(vp.g - sc.det_base) << 32) | (unsigned int)vp.outcol;
+        s.vval[slot] = v;
+      }
+    }
+    __syncthreads();
+    const int L = s_misc[0];
+    int Lp = 1;
+    while (Lp < L) Lp <<= 1;
+    for (int i = L + tid; i < Lp; i += VT_THREADS) { s.vkey[i] = ~0ull; s.vval[i] = 0.0f; }
+    for (int m = tid; m < M; m += VT_THREADS) { s.rowW[m] = 0ull; s.rown[m] = 0x7fffffff; }
+    for (int n = tid; n < N; n += VT_THREADS) { s.colW[n] = 0ull; s.colm[n] = 0x7fffffff; }
+    __syncthreads();
+    // bitonic sort by (candidate, logical column): groups and their observation order become contiguous
+    for (int k2 = 2; k2 <= Lp; k2 <<= 1) {
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < Lp; i += VT_THREADS) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = s.vkey[i], b = s.vkey[ixj];
+            const bool up = (i & k2) == 0;
+            if ((a > b) == up) {
+              s.vkey[i] = b; s.vkey[ixj] = a;
+              const float t = s.vval[i]; s.vval[i] = s.vval[ixj]; s.vval[ixj] = t;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // group heads: votes and f64 weight sum_k (max_dist - d_k) as f64, best.rs:97
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int i = tid; i < L; i += VT_THREADS) {
+        const unsigned long long key = s.vkey[i];
+        const int m = (int)(key >> 32);
+        const int n = (int)((unsigned int)key) / K;
+        bool head = true;
+        if (i > 0) {
+          const unsigned long long pk = s.vkey[i - 1];
+          head = !((int)(pk >> 32) == m && (int)((unsigned int)pk) / K == n);
+        }
+        if (!head) continue;
+        int votes = 0;
+        double w = 0.0;
+        for (int q = i; q < L; ++q) {
+          const unsigned long long kq = s.vkey[q];
+          if ((int)(kq >> 32) != m || (int)((unsigned int)kq) / K != n) break;
+          ++votes;
+          w += (double)(maxd - s.vval[q]);
+        }
+        if (votes < p.min_votes) continue;
+        const unsigned long long we = enc_f64(w);
+        if (pass == 0) { atomicMax(&s.rowW[m], we); atomicMax(&s.colW[n], we); }
+        else {
+          if (we == s.rowW[m]) atomicMin(&s.rown[m], n);
+          if (we == s.colW[n]) atomicMin(&s.colm[n], m);
+        }
+      }
+      __syncthreads();
+    }
+    // resolve (dense kernel: "a query wins its best track iff it is that track's best query")
+    for (int m = tid; m < M; m += VT_THREADS) {
+      const int n1 = s.rown[m];
+      if (n1 != 0x7fffffff) {
+        cvt[m] = (unsigned char)0;
+        if (s.colm[n1] == m) { winner[m] = n1; s.excl[n1] = 1; s.fw[m] = n1; }
+        else s.fw[m] = kSelf;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ positional stage on the sparse entries
+  const long long thr = weight_i64(p.positional_kind == 0 ? 1.0f : p.iou_threshold);
+  const int nent = min(f.pos_cnt[sidx], sc.pos_lcap);
+  const PosEntry* ents = f.pos_list + sc.pos_lbase;
+  auto ent_ok = [&](const PosEntry& e) -> bool {
+    return !(VISUAL && (s.fw[e.m] != kNone || s.excl[e.n]));
+  };
+  for (int m = tid; m < M; m += VT_THREADS) { s.cnt_m[m] = 0; s.rmax[m] = (-9223372036854775807LL - 1); s.row_ptr[m] = 0; }
+  for (int n = tid; n < N; n += VT_THREADS) { s.first_m[n] = 0x7fffffff; s.col_ptr[n] = 0; }
+  if (tid == 0) { s.row_ptr[M] = 0; s.col_ptr[N] = 0; }
+  __syncthreads();
+  for (int i = tid; i < nent; i += VT_THREADS) {
+    const PosEntry e = ents[i];
+    if (!ent_ok(e)) continue;
+    atomicAdd(&s.row_ptr[e.m], 1);
+    atomicAdd(&s.col_ptr[e.n], 1);
+    atomicMax(&s.rmax[e.m], weight_i64(e.v));
+    atomicMin(&s.first_m[e.n], (int)e.m);
+  }
+  __syncthreads();
+  for (int m = tid; m < M; m += VT_THREADS) { s.cnt_m[m] = s.row_ptr[m]; s.seen_m[m] = s.row_ptr[m] > 0; }
+  __syncthreads();
+  block_exscan_int(s.row_ptr, M + 1, s_warp, &s_misc[1]);
+  block_exscan_int(s.col_ptr, N + 1, s_warp, &s_misc[1]);
+  // scatter into CSR / CSC (slot order inside a row / column is irrelevant); cursors reuse slack / ly as int scratch
+  int* rcur = reinterpret_cast<int*>(s.slack);
+  int* ccur = reinterpret_cast<int*>(s.ly);
+  for (int m = tid; m < M; m += VT_THREADS) rcur[m] = s.row_ptr[m];
+  for (int n = tid; n < N; n += VT_THREADS) ccur[n] = s.col_ptr[n];
+  __syncthreads();
+  for (int i = tid; i < nent; i += VT_THREADS) {
+    const PosEntry e = ents[i];
+    if (!ent_ok(e)) continue;
+    const int a = atomicAdd(&rcur[e.m], 1);
+    s.csr_n[a] = e.n; s.csr_v[a] = e.v;
+    const int b = atomicAdd(&ccur[e.n], 1);
+    s.csc_m[b] = e.m; s.csc_v[b] = e.v;
+  }
+  __syncthreads();
+  // rows: seen candidates ascending, then (Sort only) the unseen ones
+  const int n_seen_rows = block_scan_flags(s.seen_m, s.row_of_m, M, s_warp, &s_misc[0]);
+  for (int m = tid; m < M; m += VT_THREADS)
+    if (s.seen_m[m]) s.row_cand[s.row_of_m[m]] = m;
+  const int nrows = VISUAL ? n_seen_rows : M;
+  int n_seen_cols = 0;
+  {
+    for (int n = tid; n < N; n += VT_THREADS) {
+      const int fm = s.first_m[n];
+      s.col_rank[n] = -1;
+      if (fm == 0x7fffffff) continue;
+      int rank = 0;
+      for (int q = 0; q < N; ++q) {
+        const int fq = s.first_m[q];
+        if (fq < fm || (fq == fm && q < n)) ++rank;
+      }
+      s.col_trk[rank] = n;
+      s.col_rank[n] = rank;
+    }
+    int c = 0;
+    for (int n = tid; n < N; n += VT_THREADS) c += s.first_m[n] != 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) s_warp[wid] = c;
+    __syncthreads();
+    for (int w = 0; w < NWARPS; ++w) n_seen_cols += s_warp[w];
+    __syncthreads();
+  }
+  const int ntrk = VISUAL ? n_seen_cols : N;
+  const int ny = nrows + ntrk;
+
+  if (ntrk > 0 && nrows > 0) {
+    // w(row, col) through the CSC of the column's track
+    auto wgt = [&](int r, int y) -> long long {
+      if (y < nrows) return y == r ? thr : 0;
+      const int j = y - nrows;
+      if (j >= n_seen_cols || r >= n_seen_rows) return 0;
+      const int n = s.col_trk[j];
+      const int m = s.row_cand[r];
+      for (int q = s.col_ptr[n]; q < s.col_ptr[n + 1]; ++q)
+        if (s.csc_m[q] == m) return weight_i64(s.csc_v[q]);
+      return 0;
+    };
+    for (int r = tid; r < nrows; r += VT_THREADS) {
+      long long mx = thr;
+      if (ny > 1) {
+        const int valid = r < n_seen_rows ? s.cnt_m[s.row_cand[r]] : 0;
+        if (ny - 1 > valid) mx = mx > 0 ? mx : 0;
+        if (r < n_seen_rows) { const long long rm = s.rmax[s.row_cand[r]]; mx = rm > mx ? rm : mx; }
+      }
+      s.lx[r] = mx;
+      s.xy[r] = -1;
+    }
+    for (int y = tid; y < ny; y += VT_THREADS) { s.ly[y] = 0; s.yx[y] = -1; }
+    __syncthreads();
+
+    int parity = 0;
+    int root = 0;
+    while (root < nrows) {
+      // ---- fast path (warp 0): roots whose tightest column is free are matched without a block-wide search
+      if (wid == 0) {
+        int r = root;
+        if (thr > 0) {
+          for (; r < nrows; ++r) {
+            const long long lxr = s.lx[r];
+            // candidates for the minimum slack: own diagonal column and the row's valid entries
+            MinPair best; best.v = lxr + s.ly[r] - thr; best.y = r;
+            if (lane != 0) { best.v = 9223372036854775807LL; best.y = 0x7fffffff; }
+            if (r < n_seen_rows) {
+              const int m = s.row_cand[r];
+              for (int q = s.row_ptr[m] + lane; q < s.row_ptr[m + 1]; q += 32) {
+                const int y = nrows + s.col_rank[s.csr_n[q]];
+                MinPair c; c.v = lxr + s.ly[y] - weight_i64(s.csr_v[q]); c.y = y;
+                best = min_pair(best, c);
+              }
+            }
+            best = warp_min(best);
+            // every other column has weight 0 and slack >= lx[r] > 0, so a zero here is the global minimum
+            if (best.v != 0 || s.yx[best.y] >= 0 || lxr <= 0) break;
+            if (lane == 0) { s.xy[r] = best.y; s.yx[best.y] = r; }
+            __syncwarp();
+          }
+        }
+        if (lane == 0) s_misc[2] = r;
+      }
+      __syncthreads();
+      root = s_misc[2];
+      if (root >= nrows) break;
+      // ---- full label / slack search for `root` (same as the dense kernel, weights from the CSC)
+      const long long lxr = s.lx[root];
+      MinPair best; best.v = 9223372036854775807LL; best.y = 0x7fffffff;
+      for (int y = tid; y < ny; y += VT_THREADS) {
+        long long sl = lxr + s.ly[y] - wgt(root, y);
+        s.slack[y] = sl; s.slackx[y] = root; s.alt[y] = -1;
+        MinPair c; c.v = sl; c.y = y;
+        best = min_pair(best, c);
+      }
+      for (int x = tid; x < nrows; x += VT_THREADS) s.inS[x] = x == root;
+      best = warp_min(best);
+      if (lane == 0) s_red[parity][wid] = best;
+      __syncthreads();
+      int y_end = -1, x_end = -1;
+      for (;;) {
+        MinPair g = s_red[parity][0];
+#pragma unroll
+        for (int w = 1; w < NWARPS; ++w) g = min_pair(g, s_red[parity][w]);
+        parity ^= 1;
+        const long long delta = g.v;
+        const int ystar = g.y;
+        const int xstar = s.slackx[ystar];
+        const int x2 = s.yx[ystar];
+        for (int x = tid; x < nrows; x += VT_THREADS) {
+          if (s.inS[x]) { if (delta > 0) s.lx[x] -= delta; }
+          else if (x == x2) s.inS[x] = 1;
+        }
+        if (x2 < 0) {
+          if (delta > 0)
+            for (int y = tid; y < ny; y += VT_THREADS) {
+              if (s.alt[y] >= 0) s.ly[y] += delta;
+              else s.slack[y] -= delta;
+            }
+          y_end = ystar; x_end = xstar;
+          break;
+        }
+        const long long lx2 = s.lx[x2];
+        MinPair nb; nb.v = 9223372036854775807LL; nb.y = 0x7fffffff;
+        for (int y = tid; y < ny; y += VT_THREADS) {
+          if (s.alt[y] >= 0) { if (delta > 0) s.ly[y] += delta; continue; }
+          long long sl = s.slack[y] - delta;
+          if (y == ystar) { s.alt[y] = xstar; s.slack[y] = sl; continue; }
+          long long a = lx2 + s.ly[y] - wgt(x2, y);
+          if (sl > a) { sl = a; s.slackx[y] = x2; }
+          s.slack[y] = sl;
+          MinPair c; c.v = sl; c.y = y;
+          nb = min_pair(nb, c);
+        }
+        nb = warp_min(nb);
+        if (lane == 0) s_red[parity][wid] = nb;
+        __syncthreads();
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int y = y_end, x = x_end;
+        for (;;) {
+          int prec = s.xy[x];
+          s.yx[y] = x;
+          s.xy[x] = y;
+          y = prec;
+          if (y < 0) break;
+          x = s.alt[y];
+        }
+      }
+      __syncthreads();
+      ++root;
+    }
+    for (int r = tid; r < n_seen_rows; r += VT_THREADS) {
+      int y = s.xy[r];
+      int m = s.row_cand[r];
+      if (y >= nrows && (y - nrows) < n_seen_cols) {
+        winner[m] = s.col_trk[y - nrows];
+        cvt[m] = (unsigned char)1;
+      }
+    }
+  }
+  __syncthreads();
+  int c = 0;
+  for (int m = tid; m < M; m += VT_THREADS) c += winner[m] < 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) s_warp[wid] = c;
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int w = 0; w < NWARPS; ++w) t += s_warp[w];
+    f.new_count[sidx] = t;
+  }
+}
+
+// per-scene mode: 0 = the voting stage consumes the sparse lists, 1 = dense matrices
+__global__ void scene_mode_kernel(Params p, Frame f, int n_scenes, int tc_used) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scenes) return;
+  const SceneDesc sc = f.scenes[s];
+  int mode = 0;
+  if (sc.m >= 65535 || sc.n >= 65535) mode = 1;
+  if (f.pos_cnt[s] > sc.pos_lcap || f.pos_cnt[s] > kVotePosCap) mode = 1;
+  if (p.is_visual) {
+    if (!tc_used) mode = 1;
+    else if (f.vis_cnt[s] > sc.vis_lcap || f.vis_cnt[s] > kVoteVisCap) mode = 1;
+  }
+  f.scene_mode[s] = mode;
+}
+
+void launch_scene_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st) {
+  if (n_scenes == 0) return;
+  scene_mode_kernel<<<(n_scenes + 127) / 128, 128, 0, st>>>(p, f, n_scenes, tc_used ? 1 : 0);
+}
+
+void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_only, cudaStream_t st) {
   if (n_scenes == 0 || !f.scene_max) return;
-  vis_max_init_kernel<<<(n_scenes + 255) / 256, 256, 0, st>>>(f.scene_max, n_scenes, gate, gate_cap);
-  if (!init_only) {
+  if (init_only) {
+    vis_max_init_kernel<<<(n_scenes + 255) / 256, 256, 0, st>>>(f.scene_max, n_scenes);
+  } else {
     dim3 grid(32, n_scenes);
-    vis_max_kernel<<<grid, 256, 0, st>>>(p, f, f.scene_max, gate, gate_cap);
+    vis_max_kernel<<<grid, 256, 0, st>>>(p, f, f.scene_max);
   }
 }
 
@@ -432,17 +890,20 @@ int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_s
                   cudaStream_t st) {
   (void)ts;
   if (n_scenes == 0) return 0;
-  size_t smem = vote_smem_bytes(max_m, max_n);
-  if (smem > 200 * 1024) return -3;
+  const size_t smem_d = vote_smem_bytes(max_m, max_n);
+  const size_t smem_s = sparse_smem_bytes(max_m, max_n);
+  if (smem_d > 200 * 1024 || smem_s > 200 * 1024) return -3;
   cudaError_t e;
   if (p.is_visual) {
-    e = cudaFuncSetAttribute(voting_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    voting_kernel<true><<<n_scenes, VT_THREADS, smem, st>>>(p, f);
+    if ((e = cudaFuncSetAttribute(voting_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(voting_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d)) != cudaSuccess) return (int)e;
+    voting_sparse_kernel<true><<<n_scenes, VT_THREADS, smem_s, st>>>(p, f);
+    voting_kernel<true><<<n_scenes, VT_THREADS, smem_d, st>>>(p, f);
   } else {
-    e = cudaFuncSetAttribute(voting_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    voting_kernel<false><<<n_scenes, VT_THREADS, smem, st>>>(p, f);
+    if ((e = cudaFuncSetAttribute(voting_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(voting_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d)) != cudaSuccess) return (int)e;
+    voting_sparse_kernel<false><<<n_scenes, VT_THREADS, smem_s, st>>>(p, f);
+    voting_kernel<false><<<n_scenes, VT_THREADS, smem_d, st>>>(p, f);
   }
   return 0;
 }

@@ -162,6 +162,24 @@ __global__ void __launch_bounds__(TN * TY) pos_cost_kernel(Params p, TrackStore 
       }
     }
     out[(size_t)m * sc.n + n] = v;
+    // sparse view for the voting stage: valid entries are rare (gated by 2R and the threshold), append them
+    const bool valid = !is_nan(v);
+    const unsigned am = __activemask();
+    const unsigned bal = __ballot_sync(am, valid);
+    if (bal) {
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(bal) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&f.pos_cnt[blockIdx.z], __popc(bal));
+      base = __shfl_sync(am, base, leader);
+      if (valid) {
+        const int slot = base + __popc(bal & ((1u << lane) - 1));
+        if (slot < sc.pos_lcap) {
+          PosEntry e; e.m = (unsigned short)m; e.n = (unsigned short)n; e.v = v;
+          f.pos_list[sc.pos_lbase + slot] = e;
+        }
+      }
+    }
   }
 }
 
@@ -182,8 +200,8 @@ void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int 
 // gate logic of VisualMetric::metric (src/trackers/visual_sort/metric.rs:200-225,253-295).
 constexpr int VM = 64, VN = 64, VK = 32, VT = 256;  // 4x4 pairs per thread
 
-__global__ void __launch_bounds__(VT) vis_cost_kernel(Params p, TrackStore ts, Frame f, const int* gate, int gate_cap) {
-  if (gate != nullptr && *gate <= gate_cap) return;  // fallback switch: only runs when the screen's pair list overflowed
+__global__ void __launch_bounds__(VT) vis_cost_kernel(Params p, TrackStore ts, Frame f) {
+  if (f.scene_mode[blockIdx.z] == 0) return;  // this scene's visual entries come from the screen + refine path
   const SceneDesc sc = f.scenes[blockIdx.z];
   const int K = p.max_obs;
   const int ncols = sc.n * K;  // column c = n*K + k (logical obs)
@@ -312,22 +330,30 @@ __global__ void __launch_bounds__(VT) vis_cost_kernel(Params p, TrackStore ts, F
 
 int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                     const TcArgs& tc, cudaStream_t st) {
-  if (!p.is_visual || n_scenes == 0) return 0;
+  if (n_scenes == 0) return 0;
+  if (!p.is_visual) {
+    launch_scene_mode(p, f, n_scenes, false, st);
+    return 0;
+  }
   const bool any = max_m > 0 && max_n > 0 && f.in_feat != nullptr;
-  const int* gate = nullptr;
-  if (tc.use_tc && any) {
-    // tensor-core screen + exact refinement; the dense kernel below only runs if the survivor list overflowed
-    launch_scene_max(p, f, n_scenes, /*init_only=*/true, nullptr, 0, st);
+  const bool use_tc = tc.use_tc && any;
+  launch_scene_max(p, f, n_scenes, /*init_only=*/true, st);
+  if (use_tc) {
+    // tensor-core screen -> per-scene survivor lists
     launch_to_bf16(f.in_feat, p.feature_dim, p.feature_dim, p.d8, f.total, f.c_bf16, st);
-    int rc = launch_vis_cost_tc(p, ts, f, n_scenes, max_n, tc, st);
+    int rc = launch_vis_cost_tc(p, ts, f, n_scenes, max_n, tc, /*phase=*/0, st);
     if (rc != 0) return rc;
-    gate = tc.pair_count;
+  }
+  launch_scene_mode(p, f, n_scenes, use_tc, st);   // which scenes stay sparse, which fall back to the dense kernels
+  if (use_tc) {
+    int rc = launch_vis_cost_tc(p, ts, f, n_scenes, max_n, tc, /*phase=*/1, st);   // exact refinement of the survivors
+    if (rc != 0) return rc;
   }
   if (max_m > 0 && max_n > 0) {
     dim3 grid((max_n * p.max_obs + VN - 1) / VN, (max_m + VM - 1) / VM, n_scenes);
-    vis_cost_kernel<<<grid, VT, 0, st>>>(p, ts, f, gate, tc.pair_cap);
+    vis_cost_kernel<<<grid, VT, 0, st>>>(p, ts, f);
+    launch_scene_max(p, f, n_scenes, /*init_only=*/false, st);
   }
-  launch_scene_max(p, f, n_scenes, /*init_only=*/!(max_m > 0 && max_n > 0), gate, tc.pair_cap, st);
   return 0;
 }
 

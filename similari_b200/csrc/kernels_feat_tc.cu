@@ -116,8 +116,8 @@ constexpr float kScreenRelErr = 1.5f / 256.0f;
 // ------------------------------------------------------------------------------------------------ screen kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p,
-                  TrackStore ts, Frame f, const TcTile* tiles, int n_tiles, VisPair* pairs, int* pair_count, int pair_cap,
-                  const VisColMeta* colmeta, const VisColGeo* colgeo, const VisRowMeta* rowmeta) {
+                  TrackStore ts, Frame f, const TcTile* tiles, int n_tiles, const VisColMeta* colmeta,
+                  const VisColGeo* colgeo, const VisRowMeta* rowmeta) {
   extern __shared__ unsigned char smem_raw_[];
   TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -222,7 +222,6 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       if (geo) { cx = f.c_box[(size_t)g * 6]; cy = f.c_box[(size_t)g * 6 + 1]; cr = f.c_radius[g]; }
       mbar_wait(&S.tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
-      float* out = f.vis + sc.vis_off;
       for (int ch = 0; ch < TC_BN / 32; ++ch) {
         if (tl.c0 + ch * 32 >= ncols) break;  // physical rows >= n*K belong to no track of this scene
         uint32_t acc[32];
@@ -259,29 +258,21 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           }
           const int total = __shfl_sync(0xffffffffu, incl, 31);
           int base = 0;
-          if (lane == 31) base = atomicAdd(pair_count, total);
+          if (lane == 31) base = atomicAdd(&f.vis_cnt[tl.scene], total);
           base = __shfl_sync(0xffffffffu, base, 31);
           int pos = base + incl - cnt;
           unsigned int kk = keep;
           while (kk) {
             const int jj = __ffs(kk) - 1;
             kk &= kk - 1;
-            if (pos < pair_cap) {
+            if (pos < sc.vis_lcap) {
               const VisColMeta cm = S.meta[ch * 32 + jj];
               VisPair vp;
               vp.g = g; vp.row = cm.row; vp.scene = tl.scene; vp.outcol = cm.outcol;
-              pairs[pos] = vp;
+              f.vis_pairs[sc.vis_lbase + pos] = vp;
             }
             ++pos;
           }
-        }
-        // coalesced None fill of this 32 x 32 block (the refine pass overwrites the survivors)
-        const int oc = S.meta[ch * 32 + lane].outcol;
-        const float qnan = nanf("");
-        const int mlim = min(32, sc.m - (tl.m0 + q * 32));
-        if (oc >= 0) {
-          float* o = out + (size_t)(tl.m0 + q * 32) * ncols + oc;
-          for (int rr = 0; rr < mlim; ++rr) o[(size_t)rr * ncols] = qnan;
         }
       }
       // accumulator buffer drained
@@ -306,17 +297,18 @@ __device__ __forceinline__ float reduce_add8_tc(const float* t) {
   return d0 + d1;
 }
 
-__global__ void __launch_bounds__(256) vis_refine_kernel(Params p, TrackStore ts, Frame f, const VisPair* pairs,
-                                                         const int* pair_count, int pair_cap) {
+__global__ void __launch_bounds__(256) vis_refine_kernel(Params p, TrackStore ts, Frame f) {
+  const int scene = blockIdx.y;
+  if (f.scene_mode[scene] != 0) return;  // this scene is computed densely
+  const SceneDesc sc = f.scenes[scene];
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  int n_pairs = *pair_count;
-  if (n_pairs > pair_cap) return;  // overflow: the caller falls back to the dense exact kernel
+  const int n_pairs = min(f.vis_cnt[scene], sc.vis_lcap);
   const bool cosine = p.visual_kind == 1;
   const int nblk = p.d8 / 8;
   const int D = p.feature_dim;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_pairs; i += warps_total) {
-    const VisPair vp = pairs[i];
+    const VisPair vp = f.vis_pairs[sc.vis_lbase + i];
     const float* a = f.in_feat + (size_t)vp.g * D;
     const float* b = ts.feat + (size_t)vp.row * p.d8;
     float acc = 0.0f;
@@ -341,8 +333,6 @@ __global__ void __launch_bounds__(256) vis_refine_kernel(Params p, TrackStore ts
       for (int j = 0; j < cnt; ++j) acc = acc + __shfl_sync(0xffffffffu, bs, j);
     }
     if (lane == 0) {
-      const SceneDesc sc = f.scenes[vp.scene];
-      const int m = vp.g - sc.det_base;
       float v = nanf("");
       if (cosine) {
         const float d = acc / sqrtf(f.c_norm2[vp.g] * ts.fnorm2[vp.row]);
@@ -351,14 +341,42 @@ __global__ void __launch_bounds__(256) vis_refine_kernel(Params p, TrackStore ts
         const float d = sqrtf(acc);
         if (d <= p.visual_threshold) v = d;
       }
-      f.vis[sc.vis_off + (size_t)m * (sc.n * p.max_obs) + vp.outcol] = v;
+      f.vis_val[sc.vis_lbase + i] = v;
       if (!is_nan(v)) {  // best.rs "max_dist": maximum over the entries that exist
         unsigned int u = __float_as_uint(v);
         u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-        atomicMax(f.scene_max + vp.scene, u);
+        atomicMax(f.scene_max + scene, u);
       }
     }
   }
+}
+
+// dense view of the sparse scenes' visual entries (operators / debugging): None everywhere, then the refined survivors
+__global__ void vis_fill_none_kernel(Params p, Frame f) {
+  const int scene = blockIdx.y;
+  if (f.scene_mode[scene] != 0) return;
+  const SceneDesc sc = f.scenes[scene];
+  const long long cnt = (long long)sc.m * sc.n * p.max_obs;
+  float* out = f.vis + sc.vis_off;
+  const float qnan = nanf("");
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x) out[i] = qnan;
+}
+__global__ void vis_scatter_kernel(Params p, Frame f) {
+  const int scene = blockIdx.y;
+  if (f.scene_mode[scene] != 0) return;
+  const SceneDesc sc = f.scenes[scene];
+  const int n_pairs = min(f.vis_cnt[scene], sc.vis_lcap);
+  float* out = f.vis + sc.vis_off;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
+    const VisPair vp = f.vis_pairs[sc.vis_lbase + i];
+    out[(size_t)(vp.g - sc.det_base) * (sc.n * p.max_obs) + vp.outcol] = f.vis_val[sc.vis_lbase + i];
+  }
+}
+void launch_vis_densify(const Params& p, const Frame& f, int n_scenes, cudaStream_t st) {
+  if (n_scenes == 0) return;
+  dim3 grid(64, n_scenes);
+  vis_fill_none_kernel<<<grid, 256, 0, st>>>(p, f);
+  vis_scatter_kernel<<<grid, 256, 0, st>>>(p, f);
 }
 
 // ------------------------------------------------------------------------------------------------ bf16 operand copies
@@ -469,14 +487,18 @@ __global__ void vis_rowmeta_kernel(Params p, Frame f, VisRowMeta* rowmeta) {
 }
 
 int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
-                       cudaStream_t st) {
+                       int phase, cudaStream_t st) {
   if (tc.n_tiles == 0) return 0;
+  if (phase == 1) {
+    dim3 grid(8, n_scenes);
+    vis_refine_kernel<<<grid, 256, 0, st>>>(p, ts, f);
+    return 0;
+  }
   CUtensorMap mA, mB;
   if (make_map(&mA, f.c_bf16, tc.a_rows, p.d8, TC_BM) || make_map(&mB, ts.feat_bf16, tc.b_rows, p.d8, TC_BN)) return -1;
   size_t smem = sizeof(TcSmem) + 1024;
   cudaError_t e = cudaFuncSetAttribute(vis_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  cudaMemsetAsync(tc.pair_count, 0, sizeof(int), st);
   const int max_rows = max_n * p.max_obs;
   if (max_rows > 0) {
     dim3 grid((max_rows + 255) / 256, n_scenes);
@@ -484,9 +506,8 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
   }
   vis_rowmeta_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f, tc.rowmeta);
   int grid = tc.n_tiles < tc.num_sms ? tc.n_tiles : tc.num_sms;
-  vis_screen_kernel<<<grid, TC_THREADS, smem, st>>>(mA, mB, p, ts, f, tc.d_tiles, tc.n_tiles, tc.pairs, tc.pair_count,
-                                                     tc.pair_cap, tc.colmeta, tc.colgeo, tc.rowmeta);
-  vis_refine_kernel<<<tc.num_sms * 8, 256, 0, st>>>(p, ts, f, tc.pairs, tc.pair_count, tc.pair_cap);
+  vis_screen_kernel<<<grid, TC_THREADS, smem, st>>>(mA, mB, p, ts, f, tc.d_tiles, tc.n_tiles, tc.colmeta, tc.colgeo,
+                                                     tc.rowmeta);
   return 0;
 }
 

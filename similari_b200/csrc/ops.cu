@@ -120,6 +120,8 @@ int sb200_sort_cost_matrix(int32_t positional_kind, float iou_threshold, float m
   f.c_conf = sc.alloc<float>(m);
   f.c_vert = sc.alloc<double>((size_t)m * 8);
   f.pos = sc.alloc<float>((size_t)m * n);
+  f.pos_cnt = sc.alloc<int>(4, true);   // sparse list disabled here (capacity 0): only the dense matrix is returned
+  f.pos_list = sc.alloc<sb::PosEntry>(1);
   sb::SceneDesc d;
   memset(&d, 0, sizeof(d));
   d.m = m; d.n = n; d.epoch = 1;
@@ -211,16 +213,25 @@ int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* 
   }
   f.scene_max = sc.alloc<unsigned int>(1);
   cudaDeviceGetAttribute(&tc.num_sms, cudaDevAttrMultiProcessorCount, device);
+  {
+    int lcap = std::max(4096, m * 64);
+    if (const char* ev = getenv("SB200_VIS_PAIR_CAP")) lcap = std::max(1, atoi(ev));
+    sd.vis_lbase = 0; sd.vis_lcap = lcap; sd.pos_lbase = 0; sd.pos_lcap = 0;
+    cudaMemcpyAsync(f.scenes, &sd, sizeof(sd), cudaMemcpyHostToDevice, sc.st);
+    f.vis_pairs = sc.alloc<sb::VisPair>((size_t)lcap);
+    f.vis_val = sc.alloc<float>((size_t)lcap);
+    f.pos_cnt = sc.alloc<int>(4, true);
+    f.vis_cnt = f.pos_cnt + 1;
+    f.scene_mode = f.pos_cnt + 2;
+    f.pos_list = sc.alloc<sb::PosEntry>(1);
+    if (!f.vis_pairs || !f.vis_val || !f.pos_cnt || !f.pos_list) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
+  }
   if (tc.use_tc) {
     std::vector<sb::TcTile> tiles;
     for (int m0 = 0; m0 < m; m0 += 128)
       for (int c0 = 0; c0 < n; c0 += 256) tiles.push_back(sb::TcTile{0, m0, c0, 0});
     tc.n_tiles = (int)tiles.size();
     tc.d_tiles = sc.upload(tiles.data(), tiles.size());
-    tc.pair_cap = std::max(4096, m * 64);
-    if (const char* ev = getenv("SB200_VIS_PAIR_CAP")) tc.pair_cap = std::max(1, atoi(ev));
-    tc.pairs = sc.alloc<sb::VisPair>((size_t)tc.pair_cap);
-    tc.pair_count = sc.alloc<int>(1);
     tc.a_rows = m;
     tc.b_rows = n;
     f.c_bf16 = sc.alloc<unsigned short>((size_t)m * p.d8);
@@ -229,12 +240,13 @@ int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* 
     tc.colgeo = sc.alloc<sb::VisColGeo>(n);
     tc.rowmeta = sc.alloc<sb::VisRowMeta>(m);
     tc.total_cols = n;
-    if (!tc.d_tiles || !tc.pairs || !tc.pair_count || !f.c_bf16 || !ts.feat_bf16 || !tc.colmeta || !tc.colgeo || !tc.rowmeta)
+    if (!tc.d_tiles || !f.c_bf16 || !ts.feat_bf16 || !tc.colmeta || !tc.colgeo || !tc.rowmeta)
       return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
     sb::launch_to_bf16(ft.in_feat, d, d, p.d8, n, ts.feat_bf16, sc.st);
   }
   ts.fnorm2 = ft.c_norm2;
   int vr = sb::launch_vis_cost(p, ts, f, 1, m, n, tc, sc.st);
+  if (vr == 0 && tc.use_tc) sb::launch_vis_densify(p, f, 1, sc.st);
   if (vr != 0) return ops_fail(SB200_ERR_CUDA, "visual cost launch failed");
   cudaMemcpyAsync(out_mn, f.vis, (size_t)m * n * 4, cudaMemcpyDeviceToHost, sc.st);
   return finish(sc);
@@ -264,6 +276,14 @@ static int run_voting(bool visual, float threshold, int min_votes, const float* 
   f.winner = sc.alloc<int>(m);
   f.c_vt = sc.alloc<unsigned char>(m);
   f.new_count = sc.alloc<int>(1);
+  {
+    // operators take dense matrices: scene mode 1 routes the request to the dense voting kernel
+    int hm[4] = {0, 0, 1, 0};
+    f.pos_cnt = sc.upload(hm, 4);
+    if (!f.pos_cnt) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
+    f.vis_cnt = f.pos_cnt + 1;
+    f.scene_mode = f.pos_cnt + 2;
+  }
   sb::SceneDesc sd;
   memset(&sd, 0, sizeof(sd));
   sd.m = m; sd.n = n; sd.epoch = 1;
@@ -272,7 +292,8 @@ static int run_voting(bool visual, float threshold, int min_votes, const float* 
   if (visual) {
     f.scene_max = sc.alloc<unsigned int>(1);
     if (!f.scene_max) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
-    sb::launch_scene_max(p, f, 1, /*init_only=*/n == 0, nullptr, 0, sc.st);
+    sb::launch_scene_max(p, f, 1, /*init_only=*/true, sc.st);
+    if (n > 0) sb::launch_scene_max(p, f, 1, /*init_only=*/false, sc.st);
   }
   int vr = sb::launch_voting(p, ts, f, 1, m, n, sc.st);
   if (vr == -3) return ops_fail(SB200_ERR_CAPACITY, "scene too large for the on-chip assignment solver");

@@ -44,7 +44,14 @@ struct SceneDesc {  // one per scene of the current request
   unsigned int epoch; // the scene's freshly incremented epoch (candidate epoch)
   int col_off;        // first entry of this scene in the per-frame column metadata (n * K physical feature rows)
   unsigned long long scene_id;
+  int pos_lbase, pos_lcap;  // this scene's slice of the sparse positional entry list
+  int vis_lbase, vis_lcap;  // this scene's slice of the visual survivor list
 };
+
+struct VisPair { int g, row, scene, outcol; };  // screen survivor: detection, feature row, scene, logical column
+struct PosEntry { unsigned short m, n; float v; };  // one valid (candidate, track, cost) positional entry
+constexpr int kVotePosCap = 3072;   // sparse entries per scene the voting kernel keeps in shared memory
+constexpr int kVoteVisCap = 3072;
 
 struct TrackStore {
   int track_cap;
@@ -93,6 +100,13 @@ struct Frame {  // per-request transient device buffers
   int* new_count;          // [n_scenes] new tracks per scene (written by voting)
   int* status;             // [n_scenes] per-scene status flags (capacity overflow etc.)
   int* feat_dst;           // [total] destination feature row (idx*K + phys) or -1
+  // sparse views of the (mostly None) cost matrices, consumed by the voting stage
+  PosEntry* pos_list;      // valid positional entries, per-scene slices
+  int* pos_cnt;            // [n_scenes]
+  VisPair* vis_pairs;      // screen survivors, per-scene slices
+  float* vis_val;          // exact value of each survivor (NaN == failed the threshold)
+  int* vis_cnt;            // [n_scenes]
+  int* scene_mode;         // [n_scenes] 0: voting consumes the sparse lists; else bit0 pos dense, bit1 vis dense
   // outputs (device), any may be null
   unsigned long long* o_ids;
   unsigned int* o_epochs;
@@ -103,7 +117,6 @@ struct Frame {  // per-request transient device buffers
 };
 
 struct TcTile { int scene, m0, c0, pad; };  // one 128 x 256 output tile of the tensor-core visual cost kernel
-struct VisPair { int g, row, scene, outcol; };  // screen survivor: detection, feature row, scene, logical column
 // per-frame metadata of one physical feature row (track n, physical slot p) of a scene, built once per frame
 struct VisColMeta {
   float snb;     // sqrt(||b||^2)
@@ -124,9 +137,6 @@ struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense ex
   const TcTile* d_tiles;
   int n_tiles;
   long long a_rows, b_rows;
-  VisPair* pairs;
-  int* pair_count;
-  int pair_cap;
   int num_sms;
   VisColMeta* colmeta;   // [sum n_s*K]
   VisColGeo* colgeo;     // [sum n_s*K]
@@ -135,12 +145,16 @@ struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense ex
 };
 int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                     const TcArgs& tc, cudaStream_t st);
+// phase 0: metadata + tensor-core screen; phase 1: exact refinement of the survivors of the sparse scenes
 int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
-                       cudaStream_t st);
+                       int phase, cudaStream_t st);
+// materialises the dense visual matrix of the sparse scenes (operators / debugging only)
+void launch_vis_densify(const Params& p, const Frame& f, int n_scenes, cudaStream_t st);
 void launch_to_bf16(const float* src, int src_pitch, int d, int d8, long long rows, void* dst, cudaStream_t st);
-// gate: run the reduction only if *gate > gate_cap (device-side fallback switch), or always when gate == nullptr
-void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_only, const int* gate, int gate_cap,
-                      cudaStream_t st);
+// scene_max init (all scenes) and, unless init_only, the dense reduction for the scenes whose mode has bit1 set
+void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_only, cudaStream_t st);
+// per-scene voting mode from the list counters (runs after the cost kernels)
+void launch_scene_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st);
 // returns cudaError from configuration (dynamic smem), 0 on success
 int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                   cudaStream_t st);
