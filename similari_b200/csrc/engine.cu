@@ -418,6 +418,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     epoch[sd[s].slot] += 1;
     sd[s].epoch = epoch[sd[s].slot];
   }
+  const long long pos_used = pos_total;
   // frame buffers (sized once from the capacity hints when given, so steady-state frames never reallocate)
   int rc = 0;
   const long long hint_dets = (long long)std::max(opts.max_scenes_hint, n_scenes) * opts.max_dets_per_scene_hint;
@@ -483,6 +484,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   sb::Frame f;
   memset(&f, 0, sizeof(f));
   f.total = total;
+  f.pos_total = pos_used;
   // inputs
   if (device_io) {
     f.in_boxes = boxes; f.in_feat = features; f.in_hasf = has_feature; f.in_quality = quality;
@@ -523,7 +525,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.winner = f_winner.as<int>(); f.c_vt = f_cvt.as<unsigned char>(); f.pos = f_pos.as<float>(); f.vis = f_vis.as<float>();
   f.scenes = f_scenes.as<sb::SceneDesc>(); f.new_count = f_newcount.as<int>(); f.status = f_status.as<int>();
   f.feat_dst = P.is_visual ? f_featdst.as<int>() : nullptr;
-  f.c_bf16 = f_cbf16.p; f.scene_max = f_scene_max.as<unsigned int>();
+  f.c_bf16 = tc.use_tc ? f_cbf16.p : nullptr; f.scene_max = f_scene_max.as<unsigned int>();
   // sparse entry lists + per-scene counters (pos_cnt | vis_cnt | scene_mode), zeroed every frame
   if ((rc = f_poslist.ensure(sizeof(sb::PosEntry) * (size_t)std::max<long long>(1, std::max(posl_total, hint_dets * 32)))) ||
       (rc = f_counters.ensure(sizeof(int) * 3 * (size_t)n_scenes)))

@@ -5,6 +5,10 @@
 //   -> SortMetric::metric / VisualMetric::positional_metric (src/trackers/sort/metric.rs:38-77,
 //      src/trackers/visual_sort/metric.rs:156-198)
 // Roofline: HBM-write bound -- 4 B of cost per pair-association out, (m + n) small per-box records in.
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
 #include "sb_engine.cuh"
 
 namespace sb {
@@ -43,26 +47,40 @@ __device__ __forceinline__ float reduce_add8(const float* t) {
   return d0 + d1;
 }
 
-__global__ void cand_norm_kernel(Params p, Frame f) {
+// One warp per detection: squared norm in the reference's order (per 8-lane block reduce_add, blocks accumulated
+// sequentially) and, when the tensor-core screen will run, the BF16 operand copy of the row -- the feature row is
+// read from HBM once for both.
+__global__ void cand_norm_kernel(Params p, Frame f, __nv_bfloat16* bf16_out) {
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (w >= f.total) return;
   const int nblk = p.d8 / 8;
   const float* row = f.in_feat + (size_t)w * p.feature_dim;
+  const bool vec = (p.feature_dim % 4 == 0);
   float acc = 0.0f;
-  // blocks are accumulated in order; lanes compute block sums in parallel, lane 0 folds them sequentially
   for (int base = 0; base < nblk; base += 32) {
     int blk = base + lane;
     float bs = 0.0f;
     if (blk < nblk) {
+      float x[8];
+      if (vec && blk * 8 + 8 <= p.feature_dim) {
+        const float4 a = *reinterpret_cast<const float4*>(row + blk * 8);
+        const float4 b = *reinterpret_cast<const float4*>(row + blk * 8 + 4);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      } else {
+#pragma unroll
+        for (int l = 0; l < 8; ++l) { int d = blk * 8 + l; x[l] = d < p.feature_dim ? row[d] : 0.0f; }
+      }
       float t[8];
 #pragma unroll
-      for (int l = 0; l < 8; ++l) {
-        int d = blk * 8 + l;
-        float v = d < p.feature_dim ? row[d] : 0.0f;
-        t[l] = v * v;
-      }
+      for (int l = 0; l < 8; ++l) t[l] = x[l] * x[l];
       bs = reduce_add8(t);
+      if (bf16_out) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) h[l] = __floats2bfloat162_rn(x[2 * l], x[2 * l + 1]);
+        *reinterpret_cast<uint4*>(bf16_out + (size_t)w * p.d8 + blk * 8) = *reinterpret_cast<uint4*>(h);
+      }
     }
     int cnt = min(32, nblk - base);
     for (int j = 0; j < cnt; ++j) {
@@ -77,9 +95,9 @@ void launch_prep(const Params& p, const Frame& f, int n_scenes, int max_m, cudaS
   (void)n_scenes; (void)max_m;
   if (f.total == 0) return;
   prep_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f);
-  if (p.is_visual && f.in_feat) {  // squared norms (cosine; euclidean on the tensor-core path)
+  if (p.is_visual && f.in_feat) {  // squared norms (+ BF16 operand rows when f.c_bf16 is set for this frame)
     long long threads = (long long)f.total * 32;
-    cand_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, f);
+    cand_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, f, reinterpret_cast<__nv_bfloat16*>(f.c_bf16));
   }
 }
 
@@ -183,13 +201,195 @@ __global__ void __launch_bounds__(TN * TY) pos_cost_kernel(Params p, TrackStore 
   }
 }
 
+// --------------------------------------------------------------------------------------------------------
+// Culled positional cost.  Both metrics return None behind the circumscribed-circle gate (too_far), so a candidate
+// can only score against tracks whose centre lies within (r_c + max_t r_t) of its own in x.  One CTA per scene
+// sorts the scene's track centres by x in shared memory; each thread then walks one candidate's x-window, runs the
+// cheap gates on shared-memory copies (x, y, r, epoch) and only touches the heavy per-track record (Kalman state /
+// f64 vertices) for the handful of survivors.  The dense matrix is pre-filled with None by pos_fill_none_kernel.
+// The window is padded by 1e-5 relative so that float rounding in too_far can never keep a culled pair.
+constexpr int PS_THREADS = 512;
+constexpr int PS_MAXN = 4096;   // tracks per scene the culled kernel sorts in shared memory (else dense kernel)
+
+__global__ void pos_fill_none_kernel(Frame f, long long total4, long long total) {
+  const float qnan = nanf("");
+  float4 q4 = make_float4(qnan, qnan, qnan, qnan);
+  float4* o4 = reinterpret_cast<float4*>(f.pos);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) o4[i] = q4;
+  if (blockIdx.x == 0)
+    for (long long i = total4 * 4 + threadIdx.x; i < total; i += blockDim.x) f.pos[i] = qnan;
+}
+
+constexpr int PS_QCAP = 4096;
+
+// exact metric of one gated (candidate, track) pair; valid results go to the dense matrix and the sparse list
+template <int POS>
+__device__ __forceinline__ void pos_eval_pair(const Params& p, const TrackStore& ts, const Frame& f, const SceneDesc& sc,
+                                              int sidx, size_t tbase, int m, int n, float* out) {
+  const int g = sc.det_base + m;
+  const float* cb = f.c_box + (size_t)g * 6;
+  const float cconf = f.c_conf[g];
+  const size_t ti = tbase + n;
+  float v = nanf("");
+  if (POS == 0) {
+    const float* st = ts.kst + ti * kStateFloats;
+    float mean5[5], l5[5];
+    const float hh = st[4];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { mean5[q] = st[q]; l5[q] = sqrtf(kalman_proj_var(p.pos_weight, hh, st[10 + 4 * q], q)); }
+    v = maha_cost(maha_distance(mean5, l5, cb[0], cb[1], angle_or0(cb[2]), cb[3], cb[4])) / cconf;
+  } else {
+    double cv[8], tv[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { cv[q] = f.c_vert[(size_t)g * 8 + q]; tv[q] = ts.vert[ti * 8 + q]; }
+    const float* tb = ts.pred + ti * 6;
+    float iou = iou_from_area(clip_area(cv, tv), cb[4], cb[3], tb[4], tb[3]);
+    if (!is_nan(iou)) {
+      iou = iou * cconf;
+      if (iou >= p.iou_threshold) v = iou;
+    }
+  }
+  if (!is_nan(v)) {
+    out[(size_t)m * sc.n + n] = v;
+    const int slot = atomicAdd(&f.pos_cnt[sidx], 1);
+    if (slot < sc.pos_lcap) {
+      PosEntry e; e.m = (unsigned short)m; e.n = (unsigned short)n; e.v = v;
+      f.pos_list[sc.pos_lbase + slot] = e;
+    }
+  }
+}
+
+template <int POS>
+__global__ void __launch_bounds__(PS_THREADS) pos_scan_kernel(Params p, TrackStore ts, Frame f) {
+  extern __shared__ __align__(16) unsigned char ps_smem[];
+  __shared__ float s_rmax[PS_THREADS / 32];
+  __shared__ int s_bad;
+  __shared__ int s_qn;
+  const int sidx = blockIdx.x;
+  const SceneDesc sc = f.scenes[sidx];
+  const int N = sc.n, M = sc.m;
+  if (N == 0 || M == 0 || N > PS_MAXN) return;   // N > PS_MAXN: the dense kernel handles this scene
+  int Np = 1;
+  while (Np < N) Np <<= 1;
+  float* kx = reinterpret_cast<float*>(ps_smem);           // [Np] sorted x
+  int* kidx = reinterpret_cast<int*>(kx + Np);             // [Np] track index
+  float* sy = reinterpret_cast<float*>(kidx + Np);         // [N] by sorted position
+  float* sr = sy + N;
+  unsigned int* sep = reinterpret_cast<unsigned int*>(sr + N);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const size_t tbase = (size_t)sc.slot * ts.track_cap;
+  if (tid == 0) s_bad = 0;
+  float rmax = 0.0f;
+  for (int n = tid; n < Np; n += PS_THREADS) {
+    if (n < N) {
+      const float x = ts.pred[(tbase + n) * 6];
+      const float r = ts.radius[tbase + n];
+      if (!(x == x) || !(r == r)) s_bad = 1;
+      kx[n] = x; kidx[n] = n;
+      rmax = fmaxf(rmax, r);
+    } else { kx[n] = 3.402823466e+38f; kidx[n] = -1; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+  if (lane == 0) s_rmax[wid] = rmax;
+  __syncthreads();
+  rmax = s_rmax[0];
+  for (int w = 1; w < PS_THREADS / 32; ++w) rmax = fmaxf(rmax, s_rmax[w]);
+  // bitonic sort of (x, index)
+  for (int k2 = 2; k2 <= Np; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < Np; i += PS_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float a = kx[i], b = kx[ixj];
+          const bool up = (i & k2) == 0;
+          if ((a > b) == up) {
+            kx[i] = b; kx[ixj] = a;
+            const int t = kidx[i]; kidx[i] = kidx[ixj]; kidx[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < N; i += PS_THREADS) {
+    const int n = kidx[i];
+    sy[i] = ts.pred[(tbase + n) * 6 + 1];
+    sr[i] = ts.radius[tbase + n];
+    sep[i] = ts.epoch[tbase + n];
+  }
+  __syncthreads();
+  float* out = f.pos + sc.pos_off;
+  const bool bad = s_bad != 0;
+  int2* queue = reinterpret_cast<int2*>(sep + N);   // [PS_QCAP] (candidate, sorted position) pairs that pass the gates
+  for (int m0 = 0; m0 < M; m0 += PS_THREADS) {
+    if (tid == 0) s_qn = 0;
+    __syncthreads();
+    // ---- phase 1: cheap gates over the candidate's x-window; survivors go to the work queue
+    const int m = m0 + tid;
+    if (m < M) {
+      const int g = sc.det_base + m;
+      const float* cb = f.c_box + (size_t)g * 6;
+      const float cx = cb[0], cy = cb[1];
+      const float cr = f.c_radius[g];
+      int lo = 0, hi = N;
+      if (!bad && cx == cx && cr == cr) {
+        const float R = (cr + rmax) * (1.0f + 1e-5f) + 1e-30f;
+        const float xlo = cx - R, xhi = cx + R;
+        int a = 0, b = N;
+        while (a < b) { int mid = (a + b) >> 1; if (kx[mid] < xlo) a = mid + 1; else b = mid; }
+        lo = a;
+        b = N;
+        while (a < b) { int mid = (a + b) >> 1; if (kx[mid] <= xhi) a = mid + 1; else b = mid; }
+        hi = a;
+      }
+      for (int i = lo; i < hi; ++i) {
+        const float tx = kx[i], ty = sy[i], tr = sr[i];
+        if (!compat_ok(p, sc.epoch, sep[i], cx, cy, cr, tx, ty, tr) || too_far(cx, cy, cr, tx, ty, tr)) continue;
+        const int slot = atomicAdd(&s_qn, 1);
+        if (slot < PS_QCAP) queue[slot] = make_int2(m, i);
+        else pos_eval_pair<POS>(p, ts, f, sc, sidx, tbase, m, kidx[i], out);   // queue full: evaluate in place
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: the survivors, one per thread (no divergence on the gate)
+    const int qn = min(s_qn, PS_QCAP);
+    for (int e = tid; e < qn; e += PS_THREADS) {
+      const int2 q = queue[e];
+      pos_eval_pair<POS>(p, ts, f, sc, sidx, tbase, q.x, kidx[q.y], out);
+    }
+    __syncthreads();
+  }
+}
+
 void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                      cudaStream_t st) {
   if (n_scenes == 0 || max_m == 0 || max_n == 0) return;
-  dim3 grid((max_n + TN - 1) / TN, (max_m + TM - 1) / TM, n_scenes);
-  dim3 block(TN, TY);
-  if (p.positional_kind == 0) pos_cost_kernel<0><<<grid, block, 0, st>>>(p, ts, f);
-  else pos_cost_kernel<1><<<grid, block, 0, st>>>(p, ts, f);
+  if (max_n > PS_MAXN || getenv("SB200_POS_DENSE") != nullptr) {
+    // very large scenes: dense tiled kernel
+    dim3 grid((max_n + TN - 1) / TN, (max_m + TM - 1) / TM, n_scenes);
+    dim3 block(TN, TY);
+    if (p.positional_kind == 0) pos_cost_kernel<0><<<grid, block, 0, st>>>(p, ts, f);
+    else pos_cost_kernel<1><<<grid, block, 0, st>>>(p, ts, f);
+    return;
+  }
+  long long total = 0;
+  // pos matrices are packed back to back: total elements = last offset + last size (the host passes it via f.pos_total)
+  total = f.pos_total;
+  if (total > 0) {
+    const long long total4 = total / 4;
+    pos_fill_none_kernel<<<1184, 256, 0, st>>>(f, total4, total);
+  }
+  int Np = 1;
+  while (Np < max_n) Np <<= 1;
+  size_t smem = (size_t)Np * 8 + (size_t)max_n * 12 + (size_t)PS_QCAP * 8 + 64;
+  if (p.positional_kind == 0) {
+    cudaFuncSetAttribute(pos_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pos_scan_kernel<0><<<n_scenes, PS_THREADS, smem, st>>>(p, ts, f);
+  } else {
+    cudaFuncSetAttribute(pos_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pos_scan_kernel<1><<<n_scenes, PS_THREADS, smem, st>>>(p, ts, f);
+  }
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -340,7 +540,7 @@ int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n
   launch_scene_max(p, f, n_scenes, /*init_only=*/true, st);
   if (use_tc) {
     // tensor-core screen -> per-scene survivor lists
-    launch_to_bf16(f.in_feat, p.feature_dim, p.feature_dim, p.d8, f.total, f.c_bf16, st);
+    // (the BF16 operand rows of the candidates were written by cand_norm_kernel in launch_prep)
     int rc = launch_vis_cost_tc(p, ts, f, n_scenes, max_n, tc, /*phase=*/0, st);
     if (rc != 0) return rc;
   }

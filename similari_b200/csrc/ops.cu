@@ -120,6 +120,7 @@ int sb200_sort_cost_matrix(int32_t positional_kind, float iou_threshold, float m
   f.c_conf = sc.alloc<float>(m);
   f.c_vert = sc.alloc<double>((size_t)m * 8);
   f.pos = sc.alloc<float>((size_t)m * n);
+  f.pos_total = (long long)m * n;
   f.pos_cnt = sc.alloc<int>(4, true);   // sparse list disabled here (capacity 0): only the dense matrix is returned
   f.pos_list = sc.alloc<sb::PosEntry>(1);
   sb::SceneDesc d;
@@ -243,6 +244,7 @@ int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* 
     if (!tc.d_tiles || !f.c_bf16 || !ts.feat_bf16 || !tc.colmeta || !tc.colgeo || !tc.rowmeta)
       return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
     sb::launch_to_bf16(ft.in_feat, d, d, p.d8, n, ts.feat_bf16, sc.st);
+    sb::launch_to_bf16(f.in_feat, d, d, p.d8, m, f.c_bf16, sc.st);   // (the tracker fuses this into cand_norm_kernel)
   }
   ts.fnorm2 = ft.c_norm2;
   int vr = sb::launch_vis_cost(p, ts, f, 1, m, n, tc, sc.st);

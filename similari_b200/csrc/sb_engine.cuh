@@ -95,6 +95,7 @@ struct Frame {  // per-request transient device buffers
   int* winner;             // [total] track index within the scene or -1
   unsigned char* c_vt;     // voting type of the decision
   float* pos;              // packed positional cost matrices
+  long long pos_total;     // elements in `pos` this frame
   float* vis;              // packed visual matrices
   SceneDesc* scenes;       // [n_scenes]
   int* new_count;          // [n_scenes] new tracks per scene (written by voting)
