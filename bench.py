@@ -213,7 +213,7 @@ def main():
             ft = pinned_empty(f["features"].shape, np.float32)
             ft[...] = f["features"]
         pinned.append((b, ft))
-    max_total = max(len(f["boxes"]) for f in frames)
+    max_total = cfg.n_scenes * cfg.n_objects   # same on every rank (all_gather needs equal shapes)
     out_host = {"ids": pinned_empty((max_total,), np.uint64), "epochs": pinned_empty((max_total,), np.uint32),
                 "lengths": pinned_empty((max_total,), np.uint32), "voting_types": pinned_empty((max_total,), np.uint8)}
     units_per_step, h2d, d2h = [], [], []
