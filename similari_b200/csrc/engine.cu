@@ -149,6 +149,8 @@ struct sb200_tracker {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaEvent_t ev[6]{};
+  cudaEvent_t ev_copy[8]{};
+  cudaStream_t copy_stream = nullptr;
   float stage_ms[5]{};
   // scene table
   std::unordered_map<uint64_t, int> slot_of;
@@ -191,6 +193,8 @@ struct sb200_tracker {
     h_small.release();
     h_tiles.release();
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_copy) if (e) cudaEventDestroy(e);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 
@@ -445,6 +449,19 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   sb::TcArgs tc;
   memset(&tc, 0, sizeof(tc));
   tc.num_sms = num_sms;
+  std::vector<sb::TcTile> tiles;
+  std::vector<int> tile_first;
+  // scene chunks: with host buffers the H2D copy of chunk c+1 overlaps the kernels of chunk c (scenes are independent)
+  int n_chunks = 1;
+  if (!device_io && n_scenes >= 8 && (long long)total * (24 + (features ? P.feature_dim * 4 : 0)) >= (8ll << 20)) n_chunks = 4;
+  if (const char* e = getenv("SB200_CHUNKS")) n_chunks = std::max(1, std::min(atoi(e), std::max(1, n_scenes)));
+  std::vector<int> chunk_s0(n_chunks + 1);
+  for (int c = 0; c <= n_chunks; ++c) chunk_s0[c] = (int)((long long)n_scenes * c / n_chunks);
+  auto chunk_of_scene_first = [&](int s) -> int {   // first scene of the chunk that owns scene s
+    int c = 0;
+    while (c + 1 < n_chunks && chunk_s0[c + 1] <= s) ++c;
+    return chunk_s0[c];
+  };
   if (P.is_visual && features != nullptr && total > 0) {
     long long work = 0;
     for (int s = 0; s < n_scenes; ++s) work += (long long)sd[s].m * sd[s].n * P.max_obs;
@@ -455,12 +472,14 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       else if (!strcmp(e, "tc")) tc.use_tc = work > 0;
     }
     if (tc.use_tc) {
-      std::vector<sb::TcTile> tiles;
+      tile_first.assign(n_scenes + 1, 0);
       for (int s = 0; s < n_scenes; ++s) {
         const int rows = sd[s].n * P.max_obs;
+        tile_first[s] = (int)tiles.size();
         for (int m0 = 0; m0 < sd[s].m; m0 += 128)
-          for (int c0 = 0; c0 < rows; c0 += 256) tiles.push_back(sb::TcTile{s, m0, c0, 0});
+          for (int c0 = 0; c0 < rows; c0 += 256) tiles.push_back(sb::TcTile{s - chunk_of_scene_first(s), m0, c0, 0});
       }
+      tile_first[n_scenes] = (int)tiles.size();
       tc.n_tiles = (int)tiles.size();
       if ((rc = f_cbf16.ensure(T * P.d8 * 2)) || (rc = f_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
           (rc = h_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
@@ -490,36 +509,35 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     f.in_boxes = boxes; f.in_feat = features; f.in_hasf = has_feature; f.in_quality = quality;
     f.in_custom = reinterpret_cast<const long long*>(custom_ids); f.in_own = own_area;
   } else {
+    // device staging buffers; the H2D copies are issued per scene chunk on the copy stream (see below)
     if ((rc = f_in_boxes.ensure(T * 24))) return rc;
-    if (total > 0) CU(cudaMemcpyAsync(f_in_boxes.p, boxes, (size_t)total * 24, cudaMemcpyHostToDevice, stream));
     f.in_boxes = f_in_boxes.as<float>();
     if (features && total > 0) {
-      size_t fb = (size_t)total * P.feature_dim * 4;
-      if ((rc = f_in_feat.ensure(fb))) return rc;
-      CU(cudaMemcpyAsync(f_in_feat.p, features, fb, cudaMemcpyHostToDevice, stream));
+      if ((rc = f_in_feat.ensure(T * (size_t)P.feature_dim * 4))) return rc;
       f.in_feat = f_in_feat.as<float>();
       if (has_feature) {
         if ((rc = f_in_hasf.ensure(T))) return rc;
-        CU(cudaMemcpyAsync(f_in_hasf.p, has_feature, (size_t)total, cudaMemcpyHostToDevice, stream));
         f.in_hasf = f_in_hasf.as<unsigned char>();
       }
     }
-    if (quality && total > 0) {
-      if ((rc = f_in_quality.ensure(T * 4))) return rc;
-      CU(cudaMemcpyAsync(f_in_quality.p, quality, (size_t)total * 4, cudaMemcpyHostToDevice, stream));
-      f.in_quality = f_in_quality.as<float>();
-    }
-    if (custom_ids && total > 0) {
-      if ((rc = f_in_custom.ensure(T * 8))) return rc;
-      CU(cudaMemcpyAsync(f_in_custom.p, custom_ids, (size_t)total * 8, cudaMemcpyHostToDevice, stream));
-      f.in_custom = f_in_custom.as<long long>();
-    }
-    if (own_area && total > 0) {
-      if ((rc = f_in_own.ensure(T * 4))) return rc;
-      CU(cudaMemcpyAsync(f_in_own.p, own_area, (size_t)total * 4, cudaMemcpyHostToDevice, stream));
-      f.in_own = f_in_own.as<float>();
-    }
+    if (quality && total > 0) { if ((rc = f_in_quality.ensure(T * 4))) return rc; f.in_quality = f_in_quality.as<float>(); }
+    if (custom_ids && total > 0) { if ((rc = f_in_custom.ensure(T * 8))) return rc; f.in_custom = f_in_custom.as<long long>(); }
+    if (own_area && total > 0) { if ((rc = f_in_own.ensure(T * 4))) return rc; f.in_own = f_in_own.as<float>(); }
   }
+  auto h2d_range = [&](int d0, int d1, cudaStream_t cs) -> int {
+    const size_t n = (size_t)(d1 - d0);
+    if (n == 0) return 0;
+    CU(cudaMemcpyAsync(f_in_boxes.as<float>() + (size_t)d0 * 6, boxes + (size_t)d0 * 6, n * 24, cudaMemcpyHostToDevice, cs));
+    if (f.in_feat) {
+      const size_t D = (size_t)P.feature_dim;
+      CU(cudaMemcpyAsync(f_in_feat.as<float>() + d0 * D, features + d0 * D, n * D * 4, cudaMemcpyHostToDevice, cs));
+      if (f.in_hasf) CU(cudaMemcpyAsync(f_in_hasf.as<unsigned char>() + d0, has_feature + d0, n, cudaMemcpyHostToDevice, cs));
+    }
+    if (f.in_quality) CU(cudaMemcpyAsync(f_in_quality.as<float>() + d0, quality + d0, n * 4, cudaMemcpyHostToDevice, cs));
+    if (f.in_custom) CU(cudaMemcpyAsync(f_in_custom.as<long long>() + d0, custom_ids + d0, n * 8, cudaMemcpyHostToDevice, cs));
+    if (f.in_own) CU(cudaMemcpyAsync(f_in_own.as<float>() + d0, own_area + d0, n * 4, cudaMemcpyHostToDevice, cs));
+    return 0;
+  };
   f.c_box = f_cbox.as<float>(); f.c_radius = f_cradius.as<float>(); f.c_conf = f_cconf.as<float>();
   f.c_vert = f_cvert.as<double>(); f.c_flags = f_cflags.as<unsigned char>(); f.c_norm2 = f_cnorm2.as<float>();
   f.winner = f_winner.as<int>(); f.c_vt = f_cvt.as<unsigned char>(); f.pos = f_pos.as<float>(); f.vis = f_vis.as<float>();
@@ -561,22 +579,59 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   CU(cudaMemsetAsync(f_status.p, 0, 4 * (size_t)n_scenes, stream));
 
   const double ms_setup = since(t_begin);
-  CU(cudaEventRecord(ev[0], stream));
-  sb::launch_prep(P, f, n_scenes, max_m, stream);
-  CU(cudaEventRecord(ev[1], stream));
-  sb::launch_pos_cost(P, ts, f, n_scenes, max_m, max_n, stream);
-  CU(cudaEventRecord(ev[2], stream));
-  {
-    int vr0 = sb::launch_vis_cost(P, ts, f, n_scenes, max_m, max_n, tc, stream);
-    if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
+  if (!device_io && !copy_stream) CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+  for (int c = 0; c < n_chunks; ++c) {
+    const int s0 = chunk_s0[c], s1 = chunk_s0[c + 1];
+    if (s1 <= s0) continue;
+    const int d0 = sd[s0].det_base, d1 = s1 < n_scenes ? sd[s1].det_base : total;
+    if (!device_io) {
+      if (n_chunks == 1) {
+        if ((rc = h2d_range(0, total, stream))) return rc;
+      } else {
+        if ((rc = h2d_range(d0, d1, copy_stream))) return rc;
+        CU(cudaEventRecord(ev_copy[c % 8], copy_stream));
+        CU(cudaStreamWaitEvent(stream, ev_copy[c % 8], 0));
+      }
+    }
+    sb::Frame fc = f;
+    fc.total = d1 - d0;
+    fc.det0 = d0;
+    fc.scene0 = s0;
+    fc.new_count_all = f.new_count;
+    fc.scenes = f.scenes + s0;
+    fc.new_count = f.new_count + s0;
+    fc.status = f.status + s0;
+    fc.pos_cnt = f.pos_cnt + s0;
+    fc.vis_cnt = f.vis_cnt + s0;
+    fc.scene_mode = f.scene_mode + s0;
+    fc.scene_max = f.scene_max ? f.scene_max + s0 : nullptr;
+    fc.pos_fill_off = sd[s0].pos_off;
+    fc.pos_total = (s1 < n_scenes ? sd[s1].pos_off : pos_used) - sd[s0].pos_off;
+    int cm = 0, cn = 0;
+    for (int s = s0; s < s1; ++s) { cm = std::max(cm, sd[s].m); cn = std::max(cn, sd[s].n); }
+    sb::TcArgs tcc = tc;
+    if (tc.use_tc) {
+      tcc.d_tiles = tc.d_tiles + tile_first[s0];
+      tcc.n_tiles = tile_first[s1] - tile_first[s0];
+    }
+    const bool timed = c == 0;
+    if (timed) CU(cudaEventRecord(ev[0], stream));
+    sb::launch_prep(P, fc, s1 - s0, cm, stream);
+    if (timed) CU(cudaEventRecord(ev[1], stream));
+    sb::launch_pos_cost(P, ts, fc, s1 - s0, cm, cn, stream);
+    if (timed) CU(cudaEventRecord(ev[2], stream));
+    {
+      int vr0 = sb::launch_vis_cost(P, ts, fc, s1 - s0, cm, cn, tcc, stream);
+      if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
+    }
+    if (timed) CU(cudaEventRecord(ev[3], stream));
+    int vr = sb::launch_voting(P, ts, fc, s1 - s0, cm, cn, stream);
+    if (vr == -3) return fail(SB200_ERR_CAPACITY, "scene too large for the on-chip assignment solver (m=%d, n=%d)", cm, cn);
+    if (vr != 0) return fail(SB200_ERR_CUDA, "voting launch failed: %s", cudaGetErrorString((cudaError_t)vr));
+    if (timed) CU(cudaEventRecord(ev[4], stream));
+    sb::launch_apply(P, ts, fc, s1 - s0, cm, id_counter, b_ntracks.as<int>(), stream);
+    if (timed) CU(cudaEventRecord(ev[5], stream));
   }
-  CU(cudaEventRecord(ev[3], stream));
-  int vr = sb::launch_voting(P, ts, f, n_scenes, max_m, max_n, stream);
-  if (vr == -3) return fail(SB200_ERR_CAPACITY, "scene too large for the on-chip assignment solver (m=%d, n=%d)", max_m, max_n);
-  if (vr != 0) return fail(SB200_ERR_CUDA, "voting launch failed: %s", cudaGetErrorString((cudaError_t)vr));
-  CU(cudaEventRecord(ev[4], stream));
-  sb::launch_apply(P, ts, f, n_scenes, max_m, id_counter, b_ntracks.as<int>(), stream);
-  CU(cudaEventRecord(ev[5], stream));
   CU(cudaGetLastError());
 
   // results back
@@ -603,7 +658,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     new_total += h_new[s];
   }
   id_counter += P.is_batch ? (uint64_t)total : (uint64_t)new_total;
-  for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
+  for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);   // stages of the first chunk
   last_scenes = sd;
   return 0;
 }
@@ -660,6 +715,10 @@ int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out) {
   if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
   for (auto& ev : t->ev) {
     e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
+  }
+  for (auto& ev : t->ev_copy) {
+    e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
   }
   if (opts->max_scenes_hint > 0 || opts->max_tracks_per_scene_hint > 0) {

@@ -20,6 +20,7 @@ namespace sb {
 __global__ void prep_kernel(Params p, Frame f) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= f.total) return;
+  i += f.det0;
   const float* b = f.in_boxes + (size_t)i * 6;
   float xc = b[0], yc = b[1], ang = b[2], asp = b[3], h = b[4], conf = b[5];
   if (ang == 0.0f) ang = nanf("");
@@ -54,6 +55,7 @@ __global__ void cand_norm_kernel(Params p, Frame f, __nv_bfloat16* bf16_out) {
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (w >= f.total) return;
+  w += f.det0;
   const int nblk = p.d8 / 8;
   const float* row = f.in_feat + (size_t)w * p.feature_dim;
   const bool vec = (p.feature_dim % 4 == 0);
@@ -214,10 +216,17 @@ constexpr int PS_MAXN = 4096;   // tracks per scene the culled kernel sorts in s
 __global__ void pos_fill_none_kernel(Frame f, long long total4, long long total) {
   const float qnan = nanf("");
   float4 q4 = make_float4(qnan, qnan, qnan, qnan);
-  float4* o4 = reinterpret_cast<float4*>(f.pos);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) o4[i] = q4;
-  if (blockIdx.x == 0)
-    for (long long i = total4 * 4 + threadIdx.x; i < total; i += blockDim.x) f.pos[i] = qnan;
+  // chunk range [off, off + total): scalar head up to 16-byte alignment, vector body, scalar tail
+  float* base = f.pos + f.pos_fill_off;
+  const long long head = min(total, (long long)((4 - (f.pos_fill_off & 3)) & 3));
+  float4* o4 = reinterpret_cast<float4*>(base + head);
+  const long long n4 = (total - head) / 4;
+  (void)total4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) o4[i] = q4;
+  if (blockIdx.x == 0) {
+    for (long long i = threadIdx.x; i < head; i += blockDim.x) base[i] = qnan;
+    for (long long i = head + n4 * 4 + threadIdx.x; i < total; i += blockDim.x) base[i] = qnan;
+  }
 }
 
 constexpr int PS_QCAP = 4096;
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(PS_THREADS) pos_scan_kernel(Params p, TrackSto
   __syncthreads();
   float* out = f.pos + sc.pos_off;
   const bool bad = s_bad != 0;
-  int2* queue = reinterpret_cast<int2*>(sep + N);   // [PS_QCAP] (candidate, sorted position) pairs that pass the gates
+  int2* queue = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(sep + N) + 7) & ~(uintptr_t)7);   // [PS_QCAP] gated pairs
   for (int m0 = 0; m0 < M; m0 += PS_THREADS) {
     if (tid == 0) s_qn = 0;
     __syncthreads();

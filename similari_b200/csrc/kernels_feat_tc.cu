@@ -475,6 +475,7 @@ __global__ void vis_meta_kernel(Params p, TrackStore ts, Frame f, int n_scenes, 
 __global__ void vis_rowmeta_kernel(Params p, Frame f, VisRowMeta* rowmeta) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= f.total) return;
+  g += f.det0;
   const float na = f.c_norm2[g];
   VisRowMeta rm;
   rm.sna = sqrtf(na);

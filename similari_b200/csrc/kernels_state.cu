@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
   // ids of non-batch trackers are consumed by new tracks only, in request order => prefix over earlier scenes
   if (!p.is_batch) {
     int c = 0;
-    for (int s2 = tid; s2 < sidx; s2 += AT) c += f.new_count[s2];
+    for (int s2 = tid; s2 < f.scene0 + sidx; s2 += AT) c += f.new_count_all[s2];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) s_warp[wid] = c;
@@ -191,6 +191,7 @@ __global__ void feat_store_kernel(Params p, TrackStore ts, Frame f) {
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (w >= f.total) return;
+  w += f.det0;
   int dst = f.feat_dst[w];
   if (dst < 0) return;
   const float* src = f.in_feat + (size_t)w * p.feature_dim;

@@ -76,8 +76,12 @@ struct TrackStore {
   unsigned char* feat_cnt;  // [idx] visual_features_collected_count
 };
 
-struct Frame {  // per-request transient device buffers
-  int total;               // detections in the request
+struct Frame {  // per-request transient device buffers (a request may be processed in scene chunks)
+  int total;               // detections of this chunk
+  int det0;                // first detection of this chunk (global row of the request)
+  int scene0;              // first scene of this chunk (index into the request)
+  const int* new_count_all;  // [all scenes of the request] (ids of non-batch trackers need the global prefix)
+  long long pos_fill_off;  // offset of this chunk's positional matrices inside `pos`
   const float* in_boxes;   // [total][6] raw request boxes
   const float* in_feat;    // [total][D] or null
   const unsigned char* in_hasf;

@@ -93,6 +93,21 @@ def test_visual_trackers_tensor_core_path_match_oracle(eng, oracle, kind, vis, m
                     visual_min_votes=2, visual_minimal_track_length=1, min_confidence=0.1))
 
 
+@pytest.mark.parametrize("kind,chunks", [(1, 3), (3, 2), (2, 4), (0, 5)])
+def test_chunked_requests_match_oracle(eng, oracle, kind, chunks, monkeypatch):
+    """The host-pointer path splits a request into scene chunks (H2D of chunk c+1 overlaps the kernels of chunk c);
+    ids of non-batch trackers need the cross-chunk prefix.  Forced here on small requests."""
+    monkeypatch.setenv("SB200_CHUNKS", str(chunks))
+    visual = kind >= 2
+    cfg = small("cfg5" if visual else "cfg2", n_scenes=7, n_objects=40, oriented=False, canvas=(700.0, 500.0),
+                feature_dim=64 if visual else 0)
+    kw = dict(kind=kind, positional_kind=1, iou_threshold=0.3, max_idle_epochs=3)
+    if visual:
+        kw.update(visual_kind=0, visual_threshold=0.7, feature_dim=64, visual_max_observations=3, visual_min_votes=2,
+                  visual_minimal_track_length=1, min_confidence=0.1)
+    run_frames(eng, oracle, cfg, 6, kw)
+
+
 def test_constraints_and_custom_ids(eng, oracle):
     from similari_b200.workload import Workload
 
