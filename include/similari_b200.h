@@ -132,6 +132,14 @@ int sb200_tracker_set_stream(sb200_tracker* t, void* cuda_stream);
 int sb200_predict_batch(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids, const int32_t* det_offsets,
                         const float* boxes, const float* features, const uint8_t* has_feature, const float* quality,
                         const int64_t* custom_ids, const float* own_area, const sb200_predict_out* out);
+/* Optional input prefetch for pipelined callers (BatchSort::predict is asynchronous in the reference too,
+ * src/trackers/sort/batch_api.rs:222-290): starts the host-to-device copy of a FUTURE request's columns on a copy
+ * stream and returns immediately.  A later sb200_predict_batch() called with the same `boxes` / `features` pointers
+ * and the same detection count uses the prefetched copy instead of copying again, so the copy of frame i+1 overlaps
+ * the kernels of frame i.  The host buffers must stay unchanged until that predict call returns. */
+int sb200_prefetch_inputs(sb200_tracker* t, int32_t total, const float* boxes, const float* features,
+                          const uint8_t* has_feature, const float* quality, const int64_t* custom_ids,
+                          const float* own_area);
 /* Same call with boxes / features / has_feature / quality / custom_ids / own_area and every non-NULL `out` column
  * being DEVICE pointers (inputs already resident in HBM).  scene_ids and det_offsets stay host pointers.
  * The call is asynchronous on the tracker's stream except for one 4-byte-per-scene status read-back. */

@@ -76,7 +76,7 @@ _lib = None
 # every symbol include/similari_b200.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTS = [
     "sb200_options_default", "sb200_last_error", "sb200_device_count", "sb200_tracker_create", "sb200_tracker_destroy",
-    "sb200_tracker_set_stream", "sb200_predict_batch", "sb200_predict_batch_device", "sb200_skip_epochs",
+    "sb200_tracker_set_stream", "sb200_predict_batch", "sb200_prefetch_inputs", "sb200_predict_batch_device", "sb200_skip_epochs",
     "sb200_current_epoch", "sb200_active_tracks", "sb200_scene_track_counts", "sb200_set_auto_waste", "sb200_clear_wasted", "sb200_wasted",
     "sb200_idle_tracks", "sb200_scene_tracks", "sb200_last_costs", "sb200_last_stage_ms", "sb200_sort_cost_matrix",
     "sb200_visual_cost_matrix", "sb200_sort_voting", "sb200_visual_voting", "sb200_kalman_initiate",
@@ -103,6 +103,7 @@ def lib():
         "sb200_tracker_destroy": (None, [vp]),
         "sb200_tracker_set_stream": (C.c_int, [vp, vp]),
         "sb200_predict_batch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PredictOut)]),
+        "sb200_prefetch_inputs": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
         "sb200_predict_batch_device": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PredictOut)]),
         "sb200_skip_epochs": (C.c_int, [vp, u64, i32]),
         "sb200_current_epoch": (i64, [vp, u64]),

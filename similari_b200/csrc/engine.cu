@@ -170,7 +170,16 @@ struct sb200_tracker {
   sb::WastedBuf wb{};
   DBuf w_count, w_id, w_scene, w_epoch, w_length, w_pred, w_obs;
   // frame buffers
-  DBuf f_in_boxes, f_in_feat, f_in_hasf, f_in_quality, f_in_custom, f_in_own;
+  // two input staging sets: sb200_prefetch_inputs() fills one while the kernels of the previous frame read the other
+  struct Staging {
+    DBuf boxes, feat, hasf, quality, custom, own;
+    const void* key_boxes = nullptr;
+    const void* key_feat = nullptr;
+    int total = -1;
+    bool pending = false;   // holds a prefetched request that no predict call has consumed yet
+    cudaEvent_t ev = nullptr;
+  } stg[2];
+  int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
       f_status, f_featdst, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_rowmeta, f_poslist, f_counters, f_visval;
   HBuf h_tiles;
@@ -184,14 +193,17 @@ struct sb200_tracker {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
                    &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
-                   &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_in_boxes,
-                   &f_in_feat, &f_in_hasf, &f_in_quality, &f_in_custom, &f_in_own, &f_cbox, &f_cradius, &f_cconf,
+                   &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
                    &f_featdst, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
     for (DBuf* b : all) b->release();
     h_scenes.release();
     h_small.release();
     h_tiles.release();
+    for (auto& g : stg) {
+      g.boxes.release(); g.feat.release(); g.hasf.release(); g.quality.release(); g.custom.release(); g.own.release();
+      if (g.ev) cudaEventDestroy(g.ev);
+    }
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : ev_copy) if (e) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -453,7 +465,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   std::vector<int> tile_first;
   // scene chunks: with host buffers the H2D copy of chunk c+1 overlaps the kernels of chunk c (scenes are independent)
   int n_chunks = 1;
-  if (!device_io && n_scenes >= 8 && (long long)total * (24 + (features ? P.feature_dim * 4 : 0)) >= (8ll << 20)) n_chunks = 4;
+
   if (const char* e = getenv("SB200_CHUNKS")) n_chunks = std::max(1, std::min(atoi(e), std::max(1, n_scenes)));
   std::vector<int> chunk_s0(n_chunks + 1);
   for (int c = 0; c <= n_chunks; ++c) chunk_s0[c] = (int)((long long)n_scenes * c / n_chunks);
@@ -504,38 +516,59 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   memset(&f, 0, sizeof(f));
   f.total = total;
   f.pos_total = pos_used;
+  bool prefetched = false;
+  Staging* sin = nullptr;
   // inputs
   if (device_io) {
     f.in_boxes = boxes; f.in_feat = features; f.in_hasf = has_feature; f.in_quality = quality;
     f.in_custom = reinterpret_cast<const long long*>(custom_ids); f.in_own = own_area;
   } else {
-    // device staging buffers; the H2D copies are issued per scene chunk on the copy stream (see below)
-    if ((rc = f_in_boxes.ensure(T * 24))) return rc;
-    f.in_boxes = f_in_boxes.as<float>();
+    // device staging: a set already filled by sb200_prefetch_inputs() for exactly these host buffers is used as is;
+    // otherwise the H2D copies are issued per scene chunk below
+    int use = -1;
+    for (int k = 0; k < 2; ++k)
+      if (stg[k].pending && stg[k].key_boxes == boxes && stg[k].key_feat == features && stg[k].total == total) use = k;
+    if (use >= 0) {
+      prefetched = true;
+      stg[use].pending = false;
+      CU(cudaStreamWaitEvent(stream, stg[use].ev, 0));
+    } else {
+      use = stg[0].pending ? 1 : (stg[1].pending ? 0 : 1 - stg_last);
+      stg[use].pending = false;
+    }
+    stg_last = use;
+    Staging& S = stg[use];
+    sin = &S;
+    if (prefetched && (S.boxes.bytes < T * 24 || (features && S.feat.bytes < T * (size_t)P.feature_dim * 4))) {
+      // the filled set is smaller than this frame's sizing rule (hints changed?): re-copy instead of reallocating
+      prefetched = false;
+    }
+    if ((rc = S.boxes.ensure(T * 24))) return rc;
+    f.in_boxes = S.boxes.as<float>();
     if (features && total > 0) {
-      if ((rc = f_in_feat.ensure(T * (size_t)P.feature_dim * 4))) return rc;
-      f.in_feat = f_in_feat.as<float>();
+      if ((rc = S.feat.ensure(T * (size_t)P.feature_dim * 4))) return rc;
+      f.in_feat = S.feat.as<float>();
       if (has_feature) {
-        if ((rc = f_in_hasf.ensure(T))) return rc;
-        f.in_hasf = f_in_hasf.as<unsigned char>();
+        if ((rc = S.hasf.ensure(T))) return rc;
+        f.in_hasf = S.hasf.as<unsigned char>();
       }
     }
-    if (quality && total > 0) { if ((rc = f_in_quality.ensure(T * 4))) return rc; f.in_quality = f_in_quality.as<float>(); }
-    if (custom_ids && total > 0) { if ((rc = f_in_custom.ensure(T * 8))) return rc; f.in_custom = f_in_custom.as<long long>(); }
-    if (own_area && total > 0) { if ((rc = f_in_own.ensure(T * 4))) return rc; f.in_own = f_in_own.as<float>(); }
+    if (quality && total > 0) { if ((rc = S.quality.ensure(T * 4))) return rc; f.in_quality = S.quality.as<float>(); }
+    if (custom_ids && total > 0) { if ((rc = S.custom.ensure(T * 8))) return rc; f.in_custom = S.custom.as<long long>(); }
+    if (own_area && total > 0) { if ((rc = S.own.ensure(T * 4))) return rc; f.in_own = S.own.as<float>(); }
   }
   auto h2d_range = [&](int d0, int d1, cudaStream_t cs) -> int {
     const size_t n = (size_t)(d1 - d0);
-    if (n == 0) return 0;
-    CU(cudaMemcpyAsync(f_in_boxes.as<float>() + (size_t)d0 * 6, boxes + (size_t)d0 * 6, n * 24, cudaMemcpyHostToDevice, cs));
+    if (n == 0 || prefetched) return 0;
+    CU(cudaMemcpyAsync(sin->boxes.as<float>() + (size_t)d0 * 6, boxes + (size_t)d0 * 6, n * 24, cudaMemcpyHostToDevice, cs));
     if (f.in_feat) {
       const size_t D = (size_t)P.feature_dim;
-      CU(cudaMemcpyAsync(f_in_feat.as<float>() + d0 * D, features + d0 * D, n * D * 4, cudaMemcpyHostToDevice, cs));
-      if (f.in_hasf) CU(cudaMemcpyAsync(f_in_hasf.as<unsigned char>() + d0, has_feature + d0, n, cudaMemcpyHostToDevice, cs));
+      CU(cudaMemcpyAsync(sin->feat.as<float>() + d0 * D, features + d0 * D, n * D * 4, cudaMemcpyHostToDevice, cs));
+      if (f.in_hasf) CU(cudaMemcpyAsync(sin->hasf.as<unsigned char>() + d0, has_feature + d0, n, cudaMemcpyHostToDevice, cs));
     }
-    if (f.in_quality) CU(cudaMemcpyAsync(f_in_quality.as<float>() + d0, quality + d0, n * 4, cudaMemcpyHostToDevice, cs));
-    if (f.in_custom) CU(cudaMemcpyAsync(f_in_custom.as<long long>() + d0, custom_ids + d0, n * 8, cudaMemcpyHostToDevice, cs));
-    if (f.in_own) CU(cudaMemcpyAsync(f_in_own.as<float>() + d0, own_area + d0, n * 4, cudaMemcpyHostToDevice, cs));
+    if (f.in_quality) CU(cudaMemcpyAsync(sin->quality.as<float>() + d0, quality + d0, n * 4, cudaMemcpyHostToDevice, cs));
+    if (f.in_custom) CU(cudaMemcpyAsync(sin->custom.as<long long>() + d0, custom_ids + d0, n * 8, cudaMemcpyHostToDevice, cs));
+    if (f.in_own) CU(cudaMemcpyAsync(sin->own.as<float>() + d0, own_area + d0, n * 4, cudaMemcpyHostToDevice, cs));
     return 0;
   };
   f.c_box = f_cbox.as<float>(); f.c_radius = f_cradius.as<float>(); f.c_conf = f_cconf.as<float>();
@@ -717,6 +750,10 @@ int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out) {
     e = cudaEventCreate(&ev);
     if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
   }
+  for (auto& g : t->stg) {
+    e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
+  }
   for (auto& ev : t->ev_copy) {
     e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
@@ -746,6 +783,39 @@ int sb200_predict_batch(sb200_tracker* t, int32_t n_scenes, const uint64_t* scen
                         const int64_t* custom_ids, const float* own_area, const sb200_predict_out* out) {
   if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
   return t->predict(n_scenes, scene_ids, det_offsets, boxes, features, has_feature, quality, custom_ids, own_area, out, false);
+}
+
+int sb200_prefetch_inputs(sb200_tracker* t, int32_t total, const float* boxes, const float* features,
+                          const uint8_t* has_feature, const float* quality, const int64_t* custom_ids,
+                          const float* own_area) {
+  if (!t || total < 0 || (total > 0 && !boxes)) return fail(SB200_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(t->device));
+  if (total == 0) return 0;
+  if (!t->P.is_visual) { features = nullptr; has_feature = nullptr; quality = nullptr; own_area = nullptr; }
+  if (!t->copy_stream) CU(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+  // a free set: not holding an unconsumed prefetch; with nothing pending, the one the last predict did not read
+  if (t->stg[0].pending && t->stg[1].pending)
+    return fail(SB200_ERR_INVALID, "two prefetched requests are already waiting for their predict call");
+  const int k = t->stg[0].pending ? 1 : (t->stg[1].pending ? 0 : 1 - t->stg_last);
+  sb200_tracker::Staging& S = t->stg[k];
+  // capacity exactly as predict() sizes it (hints included), so the predict call never reallocates a filled set
+  const size_t T = (size_t)std::max<long long>(total, (long long)t->opts.max_scenes_hint * t->opts.max_dets_per_scene_hint);
+  const size_t n = (size_t)total;
+  int rc = 0;
+  cudaStream_t cs = t->copy_stream;
+  if ((rc = S.boxes.ensure(T * 24))) return rc;
+  CU(cudaMemcpyAsync(S.boxes.p, boxes, n * 24, cudaMemcpyHostToDevice, cs));
+  if (features) {
+    if ((rc = S.feat.ensure(T * (size_t)t->P.feature_dim * 4))) return rc;
+    CU(cudaMemcpyAsync(S.feat.p, features, n * (size_t)t->P.feature_dim * 4, cudaMemcpyHostToDevice, cs));
+    if (has_feature) { if ((rc = S.hasf.ensure(T))) return rc; CU(cudaMemcpyAsync(S.hasf.p, has_feature, n, cudaMemcpyHostToDevice, cs)); }
+  }
+  if (quality) { if ((rc = S.quality.ensure(T * 4))) return rc; CU(cudaMemcpyAsync(S.quality.p, quality, n * 4, cudaMemcpyHostToDevice, cs)); }
+  if (custom_ids) { if ((rc = S.custom.ensure(T * 8))) return rc; CU(cudaMemcpyAsync(S.custom.p, custom_ids, n * 8, cudaMemcpyHostToDevice, cs)); }
+  if (own_area) { if ((rc = S.own.ensure(T * 4))) return rc; CU(cudaMemcpyAsync(S.own.p, own_area, n * 4, cudaMemcpyHostToDevice, cs)); }
+  CU(cudaEventRecord(S.ev, cs));
+  S.key_boxes = boxes; S.key_feat = features; S.total = total; S.pending = true;
+  return 0;
 }
 
 int sb200_predict_batch_device(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids,

@@ -79,6 +79,17 @@ class Tracker:
                                           ptr(own_area), C.byref(po)))
         return out
 
+    def prefetch_inputs(self, boxes, features=None, has_feature=None, quality=None, custom_ids=None, own_area=None):
+        """sb200_prefetch_inputs: start the H2D copy of a future request.  The arrays must be the very objects later
+        passed to predict_batch (same memory) and C-contiguous with the right dtype (no conversion copies)."""
+        for a, dt in ((boxes, np.float32), (features, np.float32), (has_feature, np.uint8), (quality, np.float32),
+                      (custom_ids, np.int64), (own_area, np.float32)):
+            if a is not None and not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("prefetch_inputs needs C-contiguous numpy arrays of the exact dtype")
+        total = int(np.prod(boxes.shape)) // 6
+        check(self._L.sb200_prefetch_inputs(self._h, total, ptr(boxes), ptr(features), ptr(has_feature), ptr(quality),
+                                            ptr(custom_ids), ptr(own_area)))
+
     def predict_batch_device(self, scene_ids, det_offsets, d_boxes, d_features=0, d_has_feature=0, d_quality=0,
                              d_custom_ids=0, d_own_area=0, d_ids=0, d_epochs=0, d_lengths=0, d_voting_types=0,
                              d_predicted=0, d_observed=0):

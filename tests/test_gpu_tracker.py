@@ -108,6 +108,30 @@ def test_chunked_requests_match_oracle(eng, oracle, kind, chunks, monkeypatch):
     run_frames(eng, oracle, cfg, 6, kw)
 
 
+def test_prefetched_inputs_give_identical_results(eng, oracle):
+    """sb200_prefetch_inputs only moves the H2D copy earlier; results are those of the plain call."""
+    from similari_b200.workload import Workload
+
+    cfg = small("cfg5", n_scenes=3, n_objects=40, oriented=False, canvas=(700.0, 500.0), feature_dim=64)
+    kw = dict(kind=3, positional_kind=1, iou_threshold=0.3, max_idle_epochs=3, visual_kind=0, visual_threshold=0.7,
+              feature_dim=64, visual_max_observations=3, visual_min_votes=2, visual_minimal_track_length=1,
+              min_confidence=0.1)
+    g, o = both(eng, oracle, **kw)
+    wl = Workload(cfg)
+    frames = [wl.next_frame() for _ in range(6)]
+    for f in frames:
+        f["boxes"] = np.ascontiguousarray(f["boxes"], np.float32)
+        f["features"] = np.ascontiguousarray(f["features"], np.float32)
+    g.prefetch_inputs(frames[0]["boxes"], features=frames[0]["features"])
+    for i, f in enumerate(frames):
+        if i + 1 < len(frames) and i != 2:   # frame 3 is deliberately not prefetched
+            g.prefetch_inputs(frames[i + 1]["boxes"], features=frames[i + 1]["features"])
+        rg = g.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"])
+        ro = o.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"])
+        for key in ("ids", "epochs", "lengths", "voting_types"):
+            assert np.array_equal(rg[key], ro[key]), (i, key)
+
+
 def test_constraints_and_custom_ids(eng, oracle):
     from similari_b200.workload import Workload
 
