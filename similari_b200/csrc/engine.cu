@@ -400,6 +400,20 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   }
   int max_m = 0, max_n = 0, need_tracks = 0;
   long long pos_total = 0, vis_total = 0, col_total = 0, posl_total = 0, visl_total = 0;
+  {
+    // The on-chip assignment solver keeps O(m + n) state per scene.  If a store has grown past that (expired tracks
+    // wait up to 100 predicts for the reference's auto-waste tick), collect the expired tracks now instead of failing.
+    int mm = 0, nn = 0;
+    for (int s = 0; s < n_scenes; ++s) {
+      int slot = slot_for(scene_ids[s], false);
+      mm = std::max(mm, det_offsets[s + 1] - det_offsets[s]);
+      if (slot >= 0) nn = std::max(nn, n_tracks[slot]);
+    }
+    if (sb::voting_smem_need(mm, nn) > sb::kVotingSmemLimit) {
+      int rcw = run_waste();
+      if (rcw) return rcw;
+    }
+  }
   for (int s = 0; s < n_scenes; ++s) {
     int slot = slot_for(scene_ids[s], true);
     sb::SceneDesc& d = sd[s];

@@ -16,6 +16,8 @@
 // BestFit needs no sort on a GPU: in the reference's greedy pass over the weight-sorted list an element wins its
 // track iff it is the FIRST element naming that track, i.e. the column-wise argmax of the weight matrix, and a
 // query's decision is its first element, i.e. its row-wise argmax.  Both are plain reductions.
+#include <algorithm>
+
 #include "sb_engine.cuh"
 
 namespace sb {
@@ -884,6 +886,10 @@ void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_o
     dim3 grid(32, n_scenes);
     vis_max_kernel<<<grid, 256, 0, st>>>(p, f, f.scene_max);
   }
+}
+
+size_t voting_smem_need(int max_m, int max_n) {
+  return std::max(vote_smem_bytes(max_m, max_n), sparse_smem_bytes(max_m, max_n));
 }
 
 int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,

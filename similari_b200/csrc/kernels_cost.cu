@@ -7,6 +7,7 @@
 // Roofline: HBM-write bound -- 4 B of cost per pair-association out, (m + n) small per-box records in.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "sb_engine.cuh"
@@ -409,12 +410,27 @@ void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int 
 // gate logic of VisualMetric::metric (src/trackers/visual_sort/metric.rs:200-225,253-295).
 constexpr int VM = 64, VN = 64, VK = 32, VT = 256;  // 4x4 pairs per thread
 
-__global__ void __launch_bounds__(VT) vis_cost_kernel(Params p, TrackStore ts, Frame f) {
-  if (f.scene_mode[blockIdx.z] == 0) return;  // this scene's visual entries come from the screen + refine path
-  const SceneDesc sc = f.scenes[blockIdx.z];
+// tile body; `scene`, `bx`, `by` identify the VM x VN tile
+__device__ void vis_cost_tile(const Params& p, const TrackStore& ts, const Frame& f, int scene, int bx, int by);
+
+// Dense kernel over the scenes in dense mode.  The grid is a fixed number of CTAs that walk (scene, tile) pairs, so
+// when every scene took the screen + refine path (the common case) the launch costs a few microseconds.
+__global__ void __launch_bounds__(VT) vis_cost_kernel(Params p, TrackStore ts, Frame f, int n_scenes, int tiles_x, int tiles_y) {
+  const long long per_scene = (long long)tiles_x * tiles_y;
+  for (int scene = 0; scene < n_scenes; ++scene) {
+    if (f.scene_mode[scene] == 0) continue;  // this scene's visual entries come from the screen + refine path
+    for (long long t = blockIdx.x; t < per_scene; t += gridDim.x) {
+      vis_cost_tile(p, ts, f, scene, (int)(t % tiles_x), (int)(t / tiles_x));
+      __syncthreads();
+    }
+  }
+}
+
+__device__ void vis_cost_tile(const Params& p, const TrackStore& ts, const Frame& f, int scene, int bx, int by) {
+  const SceneDesc sc = f.scenes[scene];
   const int K = p.max_obs;
   const int ncols = sc.n * K;  // column c = n*K + k (logical obs)
-  const int c0 = blockIdx.x * VN, m0 = blockIdx.y * VM;
+  const int c0 = bx * VN, m0 = by * VM;
   if (c0 >= ncols || m0 >= sc.m) return;
   __shared__ float sa[VM][VK + 1];
   __shared__ float sb_[VN][VK + 1];
@@ -559,8 +575,10 @@ int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n
     if (rc != 0) return rc;
   }
   if (max_m > 0 && max_n > 0) {
-    dim3 grid((max_n * p.max_obs + VN - 1) / VN, (max_m + VM - 1) / VM, n_scenes);
-    vis_cost_kernel<<<grid, VT, 0, st>>>(p, ts, f);
+    const int tx = (max_n * p.max_obs + VN - 1) / VN, ty = (max_m + VM - 1) / VM;
+    const long long want = (long long)tx * ty * (use_tc ? 1 : n_scenes);
+    const int grid = (int)std::min<long long>(want, 148 * 8);
+    vis_cost_kernel<<<grid, VT, 0, st>>>(p, ts, f, n_scenes, tx, ty);
     launch_scene_max(p, f, n_scenes, /*init_only=*/false, st);
   }
   return 0;

@@ -160,6 +160,9 @@ void launch_to_bf16(const float* src, int src_pitch, int d, int d8, long long ro
 void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_only, cudaStream_t st);
 // per-scene voting mode from the list counters (runs after the cost kernels)
 void launch_scene_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st);
+// shared memory the voting kernels need for scenes of up to max_m x max_n (limit: kVotingSmemLimit)
+size_t voting_smem_need(int max_m, int max_n);
+constexpr size_t kVotingSmemLimit = 200 * 1024;
 // returns cudaError from configuration (dynamic smem), 0 on success
 int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                   cudaStream_t st);

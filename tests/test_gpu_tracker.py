@@ -108,6 +108,29 @@ def test_chunked_requests_match_oracle(eng, oracle, kind, chunks, monkeypatch):
     run_frames(eng, oracle, cfg, 6, kw)
 
 
+def test_store_growth_triggers_early_collection(eng, oracle):
+    """Every detection is a fresh identity: the store grows by ~400 expired tracks per frame.  When it would exceed
+    the on-chip solver's capacity the engine collects expired tracks ahead of the reference's 100-predict cadence;
+    assignments stay identical to the oracle (which keeps them) and nothing is lost from wasted()."""
+    from similari_b200.workload import Workload
+
+    cfg = small("cfg2", n_scenes=2, n_objects=400, oriented=False, canvas=(4000.0, 3000.0), drop_frac=0.0, fresh_frac=1.0)
+    kw = dict(kind=1, positional_kind=1, iou_threshold=0.3, max_idle_epochs=1)
+    g, o = both(eng, oracle, **kw)
+    wl = Workload(cfg)
+    seen_g, seen_o = set(), set()
+    for fr in range(22):
+        f = wl.next_frame()
+        rg = g.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"])
+        ro = o.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"])
+        for key in ("ids", "epochs", "lengths"):
+            assert np.array_equal(rg[key], ro[key]), (fr, key)
+    assert g.active_tracks() < o.active_tracks()          # the early collection happened
+    seen_g.update(map(int, g.wasted(cap=1 << 17)["ids"]))
+    seen_o.update(map(int, o.wasted(cap=1 << 17)["ids"]))
+    assert seen_g == seen_o and g.active_tracks() == o.active_tracks()
+
+
 def test_prefetched_inputs_give_identical_results(eng, oracle):
     """sb200_prefetch_inputs only moves the H2D copy earlier; results are those of the plain call."""
     from similari_b200.workload import Workload
