@@ -169,6 +169,9 @@ int64_t sb200_scene_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uin
 int64_t sb200_last_costs(sb200_tracker* t, uint64_t scene_id, int64_t cap, float* out, int32_t* m, int32_t* n);
 /* Per-stage device times (ms) of the last predict call: prep, positional cost, visual cost, voting, apply. */
 int sb200_last_stage_ms(sb200_tracker* t, float* out5);
+/* Device times (ms) of the dominant visual-cost kernels of the last predict call: [0] tensor-core screen kernel,
+ * [1] scene-mode + exact refinement kernels; 0 when the tensor-core path was not used. */
+int sb200_last_kernel_ms(sb200_tracker* t, float* out2);
 
 /* ---- stateless operators (host pointers) used by parity tests and by callers that keep their own state ----
  * Positional cost matrix = SortMetric::metric over all pairs (src/trackers/sort/metric.rs:38-77):

@@ -78,7 +78,7 @@ EXPORTS = [
     "sb200_options_default", "sb200_last_error", "sb200_device_count", "sb200_tracker_create", "sb200_tracker_destroy",
     "sb200_tracker_set_stream", "sb200_predict_batch", "sb200_prefetch_inputs", "sb200_predict_batch_device", "sb200_skip_epochs",
     "sb200_current_epoch", "sb200_active_tracks", "sb200_scene_track_counts", "sb200_set_auto_waste", "sb200_clear_wasted", "sb200_wasted",
-    "sb200_idle_tracks", "sb200_scene_tracks", "sb200_last_costs", "sb200_last_stage_ms", "sb200_sort_cost_matrix",
+    "sb200_idle_tracks", "sb200_scene_tracks", "sb200_last_costs", "sb200_last_stage_ms", "sb200_last_kernel_ms", "sb200_sort_cost_matrix",
     "sb200_visual_cost_matrix", "sb200_sort_voting", "sb200_visual_voting", "sb200_kalman_initiate",
     "sb200_kalman_predict", "sb200_kalman_update", "sb200_nms", "sb200_host_alloc", "sb200_host_free",
 ]
@@ -116,6 +116,7 @@ def lib():
         "sb200_scene_tracks": (i64, [vp, u64, i64, vp, vp, vp, vp]),
         "sb200_last_costs": (i64, [vp, u64, i64, vp, C.POINTER(i32), C.POINTER(i32)]),
         "sb200_last_stage_ms": (C.c_int, [vp, vp]),
+        "sb200_last_kernel_ms": (C.c_int, [vp, vp]),
         "sb200_sort_cost_matrix": (C.c_int, [i32, f32, f32, f32, f32, vp, i32, vp, vp, i32, vp, i32]),
         "sb200_visual_cost_matrix": (C.c_int, [i32, f32, vp, i32, vp, i32, i32, vp, i32]),
         "sb200_sort_voting": (C.c_int, [f32, vp, i32, i32, vp, i32]),

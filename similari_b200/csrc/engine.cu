@@ -149,6 +149,9 @@ struct sb200_tracker {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaEvent_t ev[6]{};
+  cudaEvent_t ev_k[3]{};   // screen start / screen end / refine end (first chunk)
+  float kernel_ms[2]{};    // screen, refine(+mode) of the last predict
+  bool tc_timed = false;
   cudaEvent_t ev_copy[8]{};
   cudaStream_t copy_stream = nullptr;
   float stage_ms[5]{};
@@ -205,6 +208,7 @@ struct sb200_tracker {
       if (g.ev) cudaEventDestroy(g.ev);
     }
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_k) if (e) cudaEventDestroy(e);
     for (auto& e : ev_copy) if (e) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -626,6 +630,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   CU(cudaMemsetAsync(f_status.p, 0, 4 * (size_t)n_scenes, stream));
 
   const double ms_setup = since(t_begin);
+  bool tc_timed_now = false;
   if (!device_io && !copy_stream) CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
   for (int c = 0; c < n_chunks; ++c) {
     const int s0 = chunk_s0[c], s1 = chunk_s0[c + 1];
@@ -657,11 +662,12 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     int cm = 0, cn = 0;
     for (int s = s0; s < s1; ++s) { cm = std::max(cm, sd[s].m); cn = std::max(cn, sd[s].n); }
     sb::TcArgs tcc = tc;
+    const bool timed = c == 0;
     if (tc.use_tc) {
       tcc.d_tiles = tc.d_tiles + tile_first[s0];
       tcc.n_tiles = tile_first[s1] - tile_first[s0];
+      if (timed && tcc.n_tiles > 0) { tcc.ev_screen0 = ev_k[0]; tcc.ev_screen1 = ev_k[1]; tcc.ev_refine1 = ev_k[2]; tc_timed_now = true; }
     }
-    const bool timed = c == 0;
     if (timed) CU(cudaEventRecord(ev[0], stream));
     sb::launch_prep(P, fc, s1 - s0, cm, stream);
     if (timed) CU(cudaEventRecord(ev[1], stream));
@@ -706,6 +712,9 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   }
   id_counter += P.is_batch ? (uint64_t)total : (uint64_t)new_total;
   for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);   // stages of the first chunk
+  tc_timed = tc_timed_now;
+  kernel_ms[0] = kernel_ms[1] = 0.0f;
+  if (tc_timed) { cudaEventElapsedTime(&kernel_ms[0], ev_k[0], ev_k[1]); cudaEventElapsedTime(&kernel_ms[1], ev_k[1], ev_k[2]); }
   last_scenes = sd;
   return 0;
 }
@@ -761,6 +770,10 @@ int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out) {
   cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
   for (auto& ev : t->ev) {
+    e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
+  }
+  for (auto& ev : t->ev_k) {
     e = cudaEventCreate(&ev);
     if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
   }
@@ -996,6 +1009,13 @@ int64_t sb200_last_costs(sb200_tracker* t, uint64_t scene_id, int64_t cap, float
 int sb200_last_stage_ms(sb200_tracker* t, float* out5) {
   if (!t || !out5) return fail(SB200_ERR_INVALID, "bad arguments");
   memcpy(out5, t->stage_ms, sizeof(float) * 5);
+  return 0;
+}
+
+int sb200_last_kernel_ms(sb200_tracker* t, float* out2) {
+  if (!t || !out2) return fail(SB200_ERR_INVALID, "bad arguments");
+  out2[0] = t->kernel_ms[0];
+  out2[1] = t->kernel_ms[1];
   return 0;
 }
 

@@ -36,12 +36,12 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;  // 48 KB
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 2 x 4 epilogue warps (the two groups alternate tiles)
 
 struct TcSmem {
   unsigned char stage[TC_STAGES][TC_STAGE_BYTES];  // 1024-byte aligned operand stages first
-  VisColMeta meta[TC_BN];
-  VisColGeo geo[TC_BN];
+  VisColMeta meta[2][TC_BN];   // one copy per epilogue group
+  VisColGeo geo[2][TC_BN];
   unsigned long long full_bar[TC_STAGES];
   unsigned long long empty_bar[TC_STAGES];
   unsigned long long tmem_full[2];
@@ -188,29 +188,34 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
     }
   } else {
-    // ===================================================================== epilogue warps 2..5
+    // ===================================================================== epilogue warps 2..9
+    // Two groups of four warps; group g drains accumulator buffer g, i.e. the tiles with (iteration & 1) == g, so each
+    // group has two tile-times to finish: the per-tile latency (metadata loads, TMEM loads) is off the critical path.
     const int q = warp & 3;           // TMEM lane quarter this warp may read
-    const int et = threadIdx.x - 64;  // 0..127
+    const int grp = (warp - 2) >> 2;  // 0 or 1
+    const int et = (threadIdx.x - 64) & 127;  // 0..127 inside the group
     const bool cosine = p.visual_kind == 1;
     const bool geo = p.n_constraints > 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int buf = it & 1;
+    VisColMeta* gmeta = S.meta[grp];
+    VisColGeo* ggeo = S.geo[grp];
+    int it = grp;
+    for (int t = blockIdx.x + grp * gridDim.x; t < n_tiles; t += 2 * gridDim.x, it += 2) {
+      const int buf = grp;
       const TcTile tl = tiles[t];
       const SceneDesc sc = f.scenes[tl.scene];
       const int ncols = sc.n * K;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers of S.meta are done
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // previous tile's readers of the metadata are done
       for (int j = et; j < TC_BN; j += 128) {
         const int prow = tl.c0 + j;
         VisColMeta cm;
         cm.snb = 0.0f; cm.colc = 0.0f; cm.outcol = -1; cm.row = -1;
         if (prow < ncols) {
           cm = colmeta[sc.col_off + prow];
-          if (geo) S.geo[j] = colgeo[sc.col_off + prow];
+          if (geo) ggeo[j] = colgeo[sc.col_off + prow];
         }
-        S.meta[j] = cm;
+        gmeta[j] = cm;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       // row (candidate) state of this thread
       const int r = q * 32 + lane;
       const int m = tl.m0 + r;
@@ -230,7 +235,7 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         if (row_ok) {
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
-            const VisColMeta cm = S.meta[ch * 32 + jj];
+            const VisColMeta cm = gmeta[ch * 32 + jj];
             const float dot = __uint_as_float(acc[jj]);
             const float nn = rm.sna * cm.snb;
             // cosine: cos >= thr possible   <=>  dot + E >= (thr - 1e-5) * |a||b|
@@ -240,7 +245,7 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             bool cand = !(lhs < rhs);   // NaN anywhere => let the exact pass decide
             if (cm.row >= 0 && cand) {
               if (geo) {
-                const VisColGeo cg = S.geo[ch * 32 + jj];
+                const VisColGeo cg = ggeo[ch * 32 + jj];
                 cand = compat_ok(p, sc.epoch, cg.tep, cx, cy, cr, cg.tx, cg.ty, cg.tr);
               }
               if (cand) keep |= 1u << jj;
@@ -266,7 +271,7 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const int jj = __ffs(kk) - 1;
             kk &= kk - 1;
             if (pos < sc.vis_lcap) {
-              const VisColMeta cm = S.meta[ch * 32 + jj];
+              const VisColMeta cm = gmeta[ch * 32 + jj];
               VisPair vp;
               vp.g = g; vp.row = cm.row; vp.scene = tl.scene; vp.outcol = cm.outcol;
               f.vis_pairs[sc.vis_lbase + pos] = vp;
@@ -493,6 +498,7 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
   if (phase == 1) {
     dim3 grid(8, n_scenes);
     vis_refine_kernel<<<grid, 256, 0, st>>>(p, ts, f);
+    if (tc.ev_refine1) cudaEventRecord(tc.ev_refine1, st);
     return 0;
   }
   CUtensorMap mA, mB;
@@ -507,8 +513,10 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
   }
   vis_rowmeta_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f, tc.rowmeta);
   int grid = tc.n_tiles < tc.num_sms ? tc.n_tiles : tc.num_sms;
+  if (tc.ev_screen0) cudaEventRecord(tc.ev_screen0, st);
   vis_screen_kernel<<<grid, TC_THREADS, smem, st>>>(mA, mB, p, ts, f, tc.d_tiles, tc.n_tiles, tc.colmeta, tc.colgeo,
                                                      tc.rowmeta);
+  if (tc.ev_screen1) cudaEventRecord(tc.ev_screen1, st);
   return 0;
 }
 

@@ -143,6 +143,7 @@ struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense ex
   int n_tiles;
   long long a_rows, b_rows;
   int num_sms;
+  cudaEvent_t ev_screen0, ev_screen1, ev_refine1;  // optional per-kernel timing (null: not timed)
   VisColMeta* colmeta;   // [sum n_s*K]
   VisColGeo* colgeo;     // [sum n_s*K]
   VisRowMeta* rowmeta;   // [total]

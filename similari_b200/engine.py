@@ -157,6 +157,12 @@ class Tracker:
         return dict(zip(("prep", "positional_cost", "visual_cost", "voting", "apply"), map(float, out)))
 
 
+    def last_kernel_ms(self):
+        out = np.zeros(2, np.float32)
+        check(self._L.sb200_last_kernel_ms(self._h, ptr(out)))
+        return {"vis_screen": float(out[0]), "vis_refine": float(out[1])}
+
+
 # ------------------------------------------------------------------------------------------------ stateless operators
 def sort_cost_matrix(positional_kind, cand_boxes, track_boxes, track_states30=None, iou_threshold=0.3,
                      min_confidence=0.05, pos_weight=1 / 20, vel_weight=1 / 160, device=0):
