@@ -502,11 +502,13 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       else if (!strcmp(e, "tc")) tc.use_tc = work > 0;
     }
     if (tc.use_tc) {
+      tc.cluster2 = getenv("SB200_SCREEN_SINGLE") == nullptr;
+      const int mstep = tc.cluster2 ? 256 : 128;   // a cluster covers two 128-row candidate tiles
       tile_first.assign(n_scenes + 1, 0);
       for (int s = 0; s < n_scenes; ++s) {
         const int rows = sd[s].n * P.max_obs;
         tile_first[s] = (int)tiles.size();
-        for (int m0 = 0; m0 < sd[s].m; m0 += 128)
+        for (int m0 = 0; m0 < sd[s].m; m0 += mstep)
           for (int c0 = 0; c0 < rows; c0 += 256) tiles.push_back(sb::TcTile{s - chunk_of_scene_first(s), m0, c0, 0});
       }
       tile_first[n_scenes] = (int)tiles.size();

@@ -27,6 +27,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+#include <cstring>
+
 #include "sb_engine.cuh"
 
 namespace sb {
@@ -76,6 +79,24 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, void* bar, uint16_t mask) {
+  // multicast: the box lands at the same shared-memory offset of every CTA in `mask` and signals each CTA's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(void* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(void* bar) {
@@ -114,6 +135,9 @@ constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 constexpr float kScreenRelErr = 1.5f / 256.0f;
 
 // ------------------------------------------------------------------------------------------------ screen kernel
+// CL == 2: clusters of two CTAs work on two candidate tiles (m0, m0 + 128) of the same track-row tile; each CTA loads
+// its own A tile and HALF of the B tile, multicast into both CTAs' shared memory, so B crosses L2 -> SM once per pair.
+template <int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p,
                   TrackStore ts, Frame f, const TcTile* tiles, int n_tiles, const VisColMeta* colmeta,
@@ -124,8 +148,11 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int K = p.max_obs;
   const int KB = (p.d8 + TC_BK - 1) / TC_BK;
 
+  const uint32_t crank = CL == 2 ? cluster_rank() : 0u;
+  const int cta_first = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // first (cluster) tile of this CTA
+  const int cta_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (threadIdx.x == 32) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], CL); }
     for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -135,6 +162,7 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
 
@@ -145,17 +173,23 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapB) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = cta_first; t < n_tiles; t += cta_step) {
         const TcTile tl = tiles[t];
         const SceneDesc sc = f.scenes[tl.scene];
-        const int rowA = sc.det_base + tl.m0;
+        const int rowA = sc.det_base + tl.m0 + (int)crank * TC_BM;
         const int rowB = sc.slot * ts.track_cap * K + tl.c0;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&S.empty_bar[stage], phase ^ 1);
+          mbar_wait(&S.empty_bar[stage], phase ^ 1);   // CL == 2: both CTAs have released the stage
           mbar_expect_tx(&S.full_bar[stage], TC_STAGE_BYTES);
           unsigned char* base = S.stage[stage];
           tma_load_2d(base, &mapA, kb * TC_BK, rowA, &S.full_bar[stage]);
-          tma_load_2d(base + TC_A_BYTES, &mapB, kb * TC_BK, rowB, &S.full_bar[stage]);
+          if (CL == 2) {
+            // this CTA's half of the B tile (rows rank*128 .. +128), delivered to both CTAs
+            tma_load_2d_mc(base + TC_A_BYTES + crank * (TC_B_BYTES / 2), &mapB, kb * TC_BK, rowB + (int)crank * (TC_BN / 2),
+                           &S.full_bar[stage], (uint16_t)0x3);
+          } else {
+            tma_load_2d(base + TC_A_BYTES, &mapB, kb * TC_BK, rowB, &S.full_bar[stage]);
+          }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -166,7 +200,7 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      for (int t = cta_first; t < n_tiles; t += cta_step, ++it) {
         const int buf = it & 1;
         mbar_wait(&S.tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -181,7 +215,9 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
             const uint32_t off = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle atom
             tc_mma_bf16(d_tmem, umma_desc(a0 + off), umma_desc(b0 + off), kIdescBf16, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(&S.empty_bar[stage]);  // frees the smem stage once the MMAs above retire
+          // frees the smem stage once the MMAs above retire (CL == 2: in both CTAs -- the peer multicasts into it)
+          if (CL == 2) tc_commit_mc(&S.empty_bar[stage], (uint16_t)0x3);
+          else tc_commit(&S.empty_bar[stage]);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(&S.tmem_full[buf]);
@@ -199,9 +235,10 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     VisColMeta* gmeta = S.meta[grp];
     VisColGeo* ggeo = S.geo[grp];
     int it = grp;
-    for (int t = blockIdx.x + grp * gridDim.x; t < n_tiles; t += 2 * gridDim.x, it += 2) {
+    for (int t = cta_first + grp * cta_step; t < n_tiles; t += 2 * cta_step, it += 2) {
       const int buf = grp;
-      const TcTile tl = tiles[t];
+      TcTile tl = tiles[t];
+      tl.m0 += (int)crank * TC_BM;
       const SceneDesc sc = f.scenes[tl.scene];
       const int ncols = sc.n * K;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // previous tile's readers of the metadata are done
@@ -288,6 +325,7 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();   // no CTA leaves while its peer may still multicast into / arrive on its smem
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -501,10 +539,13 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
     if (tc.ev_refine1) cudaEventRecord(tc.ev_refine1, st);
     return 0;
   }
+  const bool cluster = tc.cluster2;
   CUtensorMap mA, mB;
-  if (make_map(&mA, f.c_bf16, tc.a_rows, p.d8, TC_BM) || make_map(&mB, ts.feat_bf16, tc.b_rows, p.d8, TC_BN)) return -1;
+  if (make_map(&mA, f.c_bf16, tc.a_rows, p.d8, TC_BM) || make_map(&mB, ts.feat_bf16, tc.b_rows, p.d8, cluster ? TC_BN / 2 : TC_BN))
+    return -1;
   size_t smem = sizeof(TcSmem) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(vis_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(vis_screen_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(vis_screen_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int max_rows = max_n * p.max_obs;
   if (max_rows > 0) {
@@ -512,10 +553,28 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
     vis_meta_kernel<<<grid, 256, 0, st>>>(p, ts, f, n_scenes, max_rows, tc.colmeta, tc.colgeo);
   }
   vis_rowmeta_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f, tc.rowmeta);
-  int grid = tc.n_tiles < tc.num_sms ? tc.n_tiles : tc.num_sms;
   if (tc.ev_screen0) cudaEventRecord(tc.ev_screen0, st);
-  vis_screen_kernel<<<grid, TC_THREADS, smem, st>>>(mA, mB, p, ts, f, tc.d_tiles, tc.n_tiles, tc.colmeta, tc.colgeo,
-                                                     tc.rowmeta);
+  if (!cluster) {
+    int grid = tc.n_tiles < tc.num_sms ? tc.n_tiles : tc.num_sms;
+    vis_screen_kernel<1><<<grid, TC_THREADS, smem, st>>>(mA, mB, p, ts, f, tc.d_tiles, tc.n_tiles, tc.colmeta, tc.colgeo,
+                                                          tc.rowmeta);
+  } else {
+    int nclusters = std::min(tc.n_tiles, tc.num_sms / 2);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(nclusters * 2);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, vis_screen_kernel<2>, mA, mB, p, ts, f, tc.d_tiles, tc.n_tiles, tc.colmeta, tc.colgeo,
+                           tc.rowmeta);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (tc.ev_screen1) cudaEventRecord(tc.ev_screen1, st);
   return 0;
 }

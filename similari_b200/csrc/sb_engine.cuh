@@ -51,7 +51,7 @@ struct SceneDesc {  // one per scene of the current request
 struct VisPair { int g, row, scene, outcol; };  // screen survivor: detection, feature row, scene, logical column
 struct PosEntry { unsigned short m, n; float v; };  // one valid (candidate, track, cost) positional entry
 constexpr int kVotePosCap = 3072;   // sparse entries per scene the voting kernel keeps in shared memory
-constexpr int kVoteVisCap = 3072;
+constexpr int kVoteVisCap = 4096;   // power of two: the BestFit bitonic sort pads the list up to the next power of two
 
 struct TrackStore {
   int track_cap;
@@ -139,6 +139,7 @@ void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int 
 // visual cost: fp32 SIMT kernel in the reference's summation order (use_tc == false) or the tcgen05 3xTF32 kernel
 struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense exact kernel is used)
   bool use_tc;
+  bool cluster2;   // tiles describe candidate-tile PAIRS processed by 2-CTA clusters with multicast B loads
   const TcTile* d_tiles;
   int n_tiles;
   long long a_rows, b_rows;
