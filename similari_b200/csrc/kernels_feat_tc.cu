@@ -45,6 +45,8 @@ struct TcSmem {
   unsigned char stage[TC_STAGES][TC_STAGE_BYTES];  // 1024-byte aligned operand stages first
   VisColMeta meta[2][TC_BN];   // one copy per epilogue group
   VisColGeo geo[2][TC_BN];
+  float2 scr[2][TC_BN];          // (E * |b|, column constant) read by the screen loop
+  unsigned int colvalid[2][TC_BN / 32];
   unsigned long long full_bar[TC_STAGES];
   unsigned long long empty_bar[TC_STAGES];
   unsigned long long tmem_full[2];
@@ -234,12 +236,20 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     const bool geo = p.n_constraints > 0;
     VisColMeta* gmeta = S.meta[grp];
     VisColGeo* ggeo = S.geo[grp];
+    float2* gscr = S.scr[grp];
+    unsigned int* gvalid = S.colvalid[grp];
     int it = grp;
-    for (int t = cta_first + grp * cta_step; t < n_tiles; t += 2 * cta_step, it += 2) {
+    int t = cta_first + grp * cta_step;
+    // software-pipelined tile header: the (tile, scene) pair of the NEXT tile is fetched while this one is drained
+    TcTile tl_n;
+    SceneDesc sc_n;
+    if (t < n_tiles) { tl_n = tiles[t]; sc_n = f.scenes[tl_n.scene]; }
+    for (; t < n_tiles; t += 2 * cta_step, it += 2) {
       const int buf = grp;
-      TcTile tl = tiles[t];
+      TcTile tl = tl_n;
+      const SceneDesc sc = sc_n;
+      if (t + 2 * cta_step < n_tiles) { tl_n = tiles[t + 2 * cta_step]; sc_n = f.scenes[tl_n.scene]; }
       tl.m0 += (int)crank * TC_BM;
-      const SceneDesc sc = f.scenes[tl.scene];
       const int ncols = sc.n * K;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // previous tile's readers of the metadata are done
       for (int j = et; j < TC_BN; j += 128) {
@@ -251,6 +261,10 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           if (geo) ggeo[j] = colgeo[sc.col_off + prow];
         }
         gmeta[j] = cm;
+        // the screen reads (snb * E, colc) as one float2; columns that hold no observation are masked by gvalid
+        gscr[j] = make_float2(kScreenRelErr * cm.snb, cm.colc);
+        const unsigned int vb = __ballot_sync(0xffffffffu, cm.row >= 0);
+        if (lane == 0) gvalid[j >> 5] = vb;
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       // row (candidate) state of this thread
@@ -264,46 +278,60 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       if (geo) { cx = f.c_box[(size_t)g * 6]; cy = f.c_box[(size_t)g * 6 + 1]; cr = f.c_radius[g]; }
       mbar_wait(&S.tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
+      // ---- phase A: drain the accumulator into per-thread survivor masks, then hand the TMEM buffer back at once
+      unsigned int keep[TC_BN / 32];
+#pragma unroll
       for (int ch = 0; ch < TC_BN / 32; ++ch) {
-        if (tl.c0 + ch * 32 >= ncols) break;  // physical rows >= n*K belong to no track of this scene
-        uint32_t acc[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BN + ch * 32), acc);
-        unsigned int keep = 0;  // bit jj: pair (row, column ch*32+jj) survives the screen
-        if (row_ok) {
+        keep[ch] = 0;
+        if (tl.c0 + ch * 32 < ncols) {  // physical rows >= n*K belong to no track of this scene (warp-uniform)
+          uint32_t acc[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BN + ch * 32), acc);
+          unsigned int kb = 0;  // bit jj: pair (row, column ch*32+jj) survives the screen
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) {
-            const VisColMeta cm = gmeta[ch * 32 + jj];
-            const float dot = __uint_as_float(acc[jj]);
-            const float nn = rm.sna * cm.snb;
-            // cosine: cos >= thr possible   <=>  dot + E >= (thr - 1e-5) * |a||b|
-            // euclid: d^2 <= thr^2 possible <=>  dot + E >= 0.5 * ((|a|^2 + |b|^2)(1 - 1e-5) - thr^2 (1 + 1e-5))
-            const float lhs = dot + kScreenRelErr * nn;
-            const float rhs = cosine ? rm.rowc * nn : rm.rowc + cm.colc;
-            bool cand = !(lhs < rhs);   // NaN anywhere => let the exact pass decide
-            if (cm.row >= 0 && cand) {
-              if (geo) {
-                const VisColGeo cg = ggeo[ch * 32 + jj];
-                cand = compat_ok(p, sc.epoch, cg.tep, cx, cy, cr, cg.tx, cg.ty, cg.tr);
-              }
-              if (cand) keep |= 1u << jj;
+            const float2 cs = gscr[ch * 32 + jj];
+            // cosine: cos >= thr possible   <=>  dot + E|a||b| >= (thr - 1e-5) * |a||b|
+            // euclid: d^2 <= thr^2 possible <=>  dot + E|a||b| >= 0.5 * ((|a|^2 + |b|^2)(1 - 1e-5) - thr^2 (1 + 1e-5))
+            const float lhs = __uint_as_float(acc[jj]) + rm.sna * cs.x;
+            const float rhs = cosine ? rm.rowc * (rm.sna * gmeta[ch * 32 + jj].snb) : rm.rowc + cs.y;
+            if (!(lhs < rhs)) kb |= 1u << jj;   // NaN anywhere => let the exact pass decide
+          }
+          kb &= gvalid[ch];
+          if (!row_ok) kb = 0;
+          if (geo && kb) {
+            unsigned int kk = kb;
+            while (kk) {
+              const int jj = __ffs(kk) - 1;
+              kk &= kk - 1;
+              const VisColGeo cg = ggeo[ch * 32 + jj];
+              if (!compat_ok(p, sc.epoch, cg.tep, cx, cy, cr, cg.tx, cg.ty, cg.tr)) kb &= ~(1u << jj);
             }
           }
+          keep[ch] = kb;
         }
-        // survivors -> pair list (warp-aggregated append), everything else is None
-        if (__any_sync(0xffffffffu, keep != 0)) {
-          const int cnt = __popc(keep);
-          int incl = cnt;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);   // accumulator buffer drained: the next MMA may start
+      // ---- phase B: survivors -> pair list, ONE warp-aggregated append per tile; everything else is None
+      int cnt = 0;
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            int tt = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += tt;
-          }
-          const int total = __shfl_sync(0xffffffffu, incl, 31);
-          int base = 0;
-          if (lane == 31) base = atomicAdd(&f.vis_cnt[tl.scene], total);
-          base = __shfl_sync(0xffffffffu, base, 31);
-          int pos = base + incl - cnt;
-          unsigned int kk = keep;
+      for (int ch = 0; ch < TC_BN / 32; ++ch) cnt += __popc(keep[ch]);
+      if (__any_sync(0xffffffffu, cnt != 0)) {
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int tt = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += tt;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&f.vis_cnt[tl.scene], total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int pos = base + incl - cnt;
+#pragma unroll
+        for (int ch = 0; ch < TC_BN / 32; ++ch) {
+          unsigned int kk = keep[ch];
           while (kk) {
             const int jj = __ffs(kk) - 1;
             kk &= kk - 1;
@@ -317,10 +345,6 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           }
         }
       }
-      // accumulator buffer drained
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);
     }
   }
   tc_fence_before();
