@@ -184,7 +184,7 @@ struct sb200_tracker {
   } stg[2];
   int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_rowmeta, f_poslist, f_counters, f_visval;
+      f_status, f_featdst, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
   HBuf h_tiles;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
@@ -195,7 +195,7 @@ struct sb200_tracker {
   ~sb200_tracker() {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
-                   &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
+                   &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_colb, &f_colvalid, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
                    &f_featdst, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
@@ -428,8 +428,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     d.pos_off = pos_total;
     d.vis_off = vis_total;
     d.scene_id = scene_ids[s];
-    d.col_off = (int)col_total;
-    col_total += (long long)d.n * P.max_obs;
+    d.col_off = (int)col_total;   // multiple of 128: the screen kernel bulk-copies 16-byte aligned slabs of column metadata
+    col_total += ((long long)d.n * P.max_obs + 127) / 128 * 128;
     d.pos_lbase = (int)posl_total;
     d.pos_lcap = (int)std::min<long long>((long long)d.m * 32, (long long)sb::kVotePosCap * 2);
     posl_total += d.pos_lcap;
@@ -457,7 +457,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   int rc = 0;
   const long long hint_dets = (long long)std::max(opts.max_scenes_hint, n_scenes) * opts.max_dets_per_scene_hint;
   const size_t T = (size_t)std::max<long long>(std::max(total, 1), hint_dets);
-  const long long hint_cols = (long long)std::max(opts.max_scenes_hint, n_scenes) * std::max(opts.max_tracks_per_scene_hint, 0) * P.max_obs;
+  const long long hint_cols = (long long)std::max(opts.max_scenes_hint, n_scenes) *
+                              (((long long)std::max(opts.max_tracks_per_scene_hint, 0) * P.max_obs + 127) / 128 * 128);
   {
     const long long hint_pos = hint_dets * std::max(opts.max_tracks_per_scene_hint, 0);
     pos_total = std::max(pos_total, hint_pos);
@@ -515,12 +516,16 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       tc.n_tiles = (int)tiles.size();
       if ((rc = f_cbf16.ensure(T * P.d8 * 2)) || (rc = f_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
           (rc = h_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
-          (rc = f_colmeta.ensure(sizeof(sb::VisColMeta) * (size_t)std::max<long long>(1, std::max(col_total, hint_cols)))) ||
+          (rc = f_colmeta.ensure(sizeof(sb::VisColMeta) * (size_t)(std::max(col_total, hint_cols) + 256))) ||
+          (rc = f_colb.ensure(4 * (size_t)(std::max(col_total, hint_cols) + 256))) ||
+          (rc = f_colvalid.ensure((size_t)(std::max(col_total, hint_cols) + 256) / 8 + 16)) ||
           (rc = f_colgeo.ensure(sizeof(sb::VisColGeo) * (size_t)std::max<long long>(1, P.n_constraints > 0 ? std::max(col_total, hint_cols) : 1))) ||
-          (rc = f_rowmeta.ensure(sizeof(sb::VisRowMeta) * T)))
+          (rc = f_rowmeta.ensure(sizeof(sb::VisRowMeta) * (T + 256))))
         return rc;
       tc.colmeta = f_colmeta.as<sb::VisColMeta>();
       tc.colgeo = f_colgeo.as<sb::VisColGeo>();
+      tc.colb = f_colb.as<float>();
+      tc.colvalid = f_colvalid.as<unsigned int>();
       tc.rowmeta = f_rowmeta.as<sb::VisRowMeta>();
       tc.total_cols = (int)col_total;
       if (tc.n_tiles > 0) {

@@ -41,16 +41,22 @@ constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;  // 48 KB
 constexpr int TC_THREADS = 320;  // TMA warp, MMA warp, 2 x 4 epilogue warps (the two groups alternate tiles)
 
+struct TcHdr { int scene, m0, ncols_left, m, det_base, col0, epoch, vis_lbase, vis_lcap, pad; };
 struct TcSmem {
   unsigned char stage[TC_STAGES][TC_STAGE_BYTES];  // 1024-byte aligned operand stages first
-  VisColMeta meta[2][TC_BN];   // one copy per epilogue group
-  VisColGeo geo[2][TC_BN];
-  float2 scr[2][TC_BN];          // (E * |b|, column constant) read by the screen loop
-  unsigned int colvalid[2][TC_BN / 32];
+  // per epilogue group: the metadata slabs of its current tile, bulk-copied by the producer warp
+  // four slab sets (two per group): the producer runs up to two tile pairs ahead of the epilogue
+  VisColMeta meta[4][TC_BN];
+  VisRowMeta rowm[4][TC_BM];
+  float colb[4][TC_BN];
+  unsigned int colvalid[4][TC_BN / 32];
+  TcHdr hdr[4];
   unsigned long long full_bar[TC_STAGES];
   unsigned long long empty_bar[TC_STAGES];
   unsigned long long tmem_full[2];
   unsigned long long tmem_empty[2];
+  unsigned long long meta_full[4];
+  unsigned long long meta_empty[4];
   unsigned int tmem_base;
 };
 
@@ -99,6 +105,10 @@ __device__ __forceinline__ uint32_t cluster_rank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(void* bar) {
@@ -124,6 +134,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Asynchronous TMEM load split in two: the issue, and a wait that names the destination registers as in/out operands so the
+// compiler cannot move a consumer of r[] above it.
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait32(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 | LBO(=1, ignored for swizzled K-major)<<16 | SBO(8 rows x 128 B = 1024 B)>>4 <<32 | version 1 <<46 | SW128 (2) <<61
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
@@ -139,13 +163,14 @@ constexpr float kScreenRelErr = 1.5f / 256.0f;
 // ------------------------------------------------------------------------------------------------ screen kernel
 // CL == 2: clusters of two CTAs work on two candidate tiles (m0, m0 + 128) of the same track-row tile; each CTA loads
 // its own A tile and HALF of the B tile, multicast into both CTAs' shared memory, so B crosses L2 -> SM once per pair.
-template <int CL>
+template <int CL, bool COSINE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p,
                   TrackStore ts, Frame f, const TcTile* tiles, int n_tiles, const VisColMeta* colmeta,
-                  const VisColGeo* colgeo, const VisRowMeta* rowmeta) {
+                  const VisColGeo* colgeo, const VisRowMeta* rowmeta, const float* colb, const unsigned int* colvalid) {
   extern __shared__ unsigned char smem_raw_[];
-  TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
+  // offset arithmetic on the __shared__ array (not on an integer) keeps the accesses in the shared address space
+  TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw_ + ((1024u - (smem_u32(smem_raw_) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = p.max_obs;
   const int KB = (p.d8 + TC_BK - 1) / TC_BK;
@@ -155,7 +180,10 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int cta_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (threadIdx.x == 32) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], CL); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4);
+    }
+    for (int b = 0; b < 4; ++b) { mbar_init(&S.meta_full[b], 1); mbar_init(&S.meta_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -175,11 +203,32 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&mapB) : "memory");
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cta_first; t < n_tiles; t += cta_step) {
-        const TcTile tl = tiles[t];
-        const SceneDesc sc = f.scenes[tl.scene];
-        const int rowA = sc.det_base + tl.m0 + (int)crank * TC_BM;
+      int it = 0;
+      TcTile tl_n = tiles[cta_first < n_tiles ? cta_first : 0];
+      SceneDesc sc_n = f.scenes[tl_n.scene];
+      for (int t = cta_first; t < n_tiles; t += cta_step, ++it) {
+        const TcTile tl = tl_n;
+        const SceneDesc sc = sc_n;
+        if (t + cta_step < n_tiles) { tl_n = tiles[t + cta_step]; sc_n = f.scenes[tl_n.scene]; }
+        const int m0 = tl.m0 + (int)crank * TC_BM;
+        const int rowA = sc.det_base + m0;
         const int rowB = sc.slot * ts.track_cap * K + tl.c0;
+        {
+          // metadata of this tile for the epilogue group that will drain it: header by plain stores (published by the
+          // release of the arrive below), column / row slabs by bulk copies that complete on the same barrier
+          const int g = it & 3;   // slab set: tile parity picks the group, bit 1 alternates the group's two sets
+          mbar_wait(&S.meta_empty[g], ((it >> 2) & 1) ^ 1);
+          TcHdr h;
+          h.scene = tl.scene; h.m0 = m0; h.ncols_left = sc.n * K - tl.c0; h.m = sc.m; h.det_base = sc.det_base;
+          h.col0 = sc.col_off + tl.c0; h.epoch = (int)sc.epoch; h.vis_lbase = sc.vis_lbase; h.vis_lcap = sc.vis_lcap; h.pad = 0;
+          S.hdr[g] = h;
+          mbar_expect_tx(&S.meta_full[g], (uint32_t)(sizeof(VisColMeta) * TC_BN + sizeof(VisRowMeta) * TC_BM +
+                                                    4 * TC_BN + TC_BN / 8));
+          bulk_load(S.meta[g], colmeta + h.col0, (uint32_t)(sizeof(VisColMeta) * TC_BN), &S.meta_full[g]);
+          bulk_load(S.rowm[g], rowmeta + rowA, (uint32_t)(sizeof(VisRowMeta) * TC_BM), &S.meta_full[g]);
+          bulk_load(S.colb[g], colb + h.col0, 4 * TC_BN, &S.meta_full[g]);
+          bulk_load(S.colvalid[g], colvalid + (h.col0 >> 5), TC_BN / 8, &S.meta_full[g]);   // col0 is a multiple of 128
+        }
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&S.empty_bar[stage], phase ^ 1);   // CL == 2: both CTAs have released the stage
           mbar_expect_tx(&S.full_bar[stage], TC_STAGE_BYTES);
@@ -228,83 +277,67 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   } else {
     // ===================================================================== epilogue warps 2..9
     // Two groups of four warps; group g drains accumulator buffer g, i.e. the tiles with (iteration & 1) == g, so each
-    // group has two tile-times to finish: the per-tile latency (metadata loads, TMEM loads) is off the critical path.
+    // group has two tile-times per tile.  All per-tile metadata arrives in shared memory through the producer warp's
+    // bulk copies: the epilogue issues no global load between the TMEM drain and the survivor append.
     const int q = warp & 3;           // TMEM lane quarter this warp may read
     const int grp = (warp - 2) >> 2;  // 0 or 1
-    const int et = (threadIdx.x - 64) & 127;  // 0..127 inside the group
-    const bool cosine = p.visual_kind == 1;
     const bool geo = p.n_constraints > 0;
-    VisColMeta* gmeta = S.meta[grp];
-    VisColGeo* ggeo = S.geo[grp];
-    float2* gscr = S.scr[grp];
-    unsigned int* gvalid = S.colvalid[grp];
+    const int r = q * 32 + lane;      // accumulator row (candidate) of this thread
     int it = grp;
-    int t = cta_first + grp * cta_step;
-    // software-pipelined tile header: the (tile, scene) pair of the NEXT tile is fetched while this one is drained
-    TcTile tl_n;
-    SceneDesc sc_n;
-    if (t < n_tiles) { tl_n = tiles[t]; sc_n = f.scenes[tl_n.scene]; }
-    for (; t < n_tiles; t += 2 * cta_step, it += 2) {
+    for (int t = cta_first + grp * cta_step; t < n_tiles; t += 2 * cta_step, it += 2) {
       const int buf = grp;
-      TcTile tl = tl_n;
-      const SceneDesc sc = sc_n;
-      if (t + 2 * cta_step < n_tiles) { tl_n = tiles[t + 2 * cta_step]; sc_n = f.scenes[tl_n.scene]; }
-      tl.m0 += (int)crank * TC_BM;
-      const int ncols = sc.n * K;
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // previous tile's readers of the metadata are done
-      for (int j = et; j < TC_BN; j += 128) {
-        const int prow = tl.c0 + j;
-        VisColMeta cm;
-        cm.snb = 0.0f; cm.colc = 0.0f; cm.outcol = -1; cm.row = -1;
-        if (prow < ncols) {
-          cm = colmeta[sc.col_off + prow];
-          if (geo) ggeo[j] = colgeo[sc.col_off + prow];
-        }
-        gmeta[j] = cm;
-        // the screen reads (snb * E, colc) as one float2; columns that hold no observation are masked by gvalid
-        gscr[j] = make_float2(kScreenRelErr * cm.snb, cm.colc);
-        const unsigned int vb = __ballot_sync(0xffffffffu, cm.row >= 0);
-        if (lane == 0) gvalid[j >> 5] = vb;
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-      // row (candidate) state of this thread
-      const int r = q * 32 + lane;
-      const int m = tl.m0 + r;
-      const bool row_in = m < sc.m;
-      const int g = sc.det_base + (row_in ? m : 0);
-      const VisRowMeta rm = rowmeta[g];
-      const bool row_ok = row_in && rm.ok;
+      const int ms = it & 3;   // slab set of this tile (same rule as the producer)
+      mbar_wait(&S.meta_full[ms], (it >> 2) & 1);
+      const VisColMeta* gmeta = S.meta[ms];
+      const TcHdr h = S.hdr[ms];
+      const VisRowMeta rm = S.rowm[ms][r];
+      const int m = h.m0 + r;
+      const bool row_ok = m < h.m && rm.ok;
+      const int g = h.det_base + m;
       float cx = 0.0f, cy = 0.0f, cr = 0.0f;
-      if (geo) { cx = f.c_box[(size_t)g * 6]; cy = f.c_box[(size_t)g * 6 + 1]; cr = f.c_radius[g]; }
+      if (geo && row_ok) { cx = f.c_box[(size_t)g * 6]; cy = f.c_box[(size_t)g * 6 + 1]; cr = f.c_radius[g]; }
+      // Screen test, E = kScreenRelErr bounds the BF16 operand rounding (|dot~ - dot| <= E |a||b| <= E (|a|^2 + |b|^2) / 2):
+      //   cosine: cos >= thr possible   <=>  dot~ >= (thr - 1e-5 - E) |a| * |b|                                = rowk * colb
+      //   euclid: d^2 <= thr^2 possible <=>  dot~ >= 0.5 ((1 - 1e-5 - E)(|a|^2 + |b|^2) - thr^2 (1 + 1e-5))   = rowk + colb
+      const float rowk = rm.rowk;
+      const float* gcolb = S.colb[ms];
       mbar_wait(&S.tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       // ---- phase A: drain the accumulator into per-thread survivor masks, then hand the TMEM buffer back at once
       unsigned int keep[TC_BN / 32];
+      uint32_t acc[2][32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BN);
+      const int nch = min(TC_BN / 32, (h.ncols_left + 31) / 32);   // chunks that hold tracks of this scene
+      tc_ld32_issue(taddr, acc[0]);
 #pragma unroll
       for (int ch = 0; ch < TC_BN / 32; ++ch) {
         keep[ch] = 0;
-        if (tl.c0 + ch * 32 < ncols) {  // physical rows >= n*K belong to no track of this scene (warp-uniform)
-          uint32_t acc[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BN + ch * 32), acc);
+        if (ch < nch) {  // warp-uniform
+          tc_ld_wait32(acc[ch & 1]);                                     // chunk ch has landed
+          if (ch + 1 < nch) tc_ld32_issue(taddr + (ch + 1) * 32, acc[(ch + 1) & 1]);   // in flight while ch is screened
           unsigned int kb = 0;  // bit jj: pair (row, column ch*32+jj) survives the screen
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) {
-            const float2 cs = gscr[ch * 32 + jj];
-            // cosine: cos >= thr possible   <=>  dot + E|a||b| >= (thr - 1e-5) * |a||b|
-            // euclid: d^2 <= thr^2 possible <=>  dot + E|a||b| >= 0.5 * ((|a|^2 + |b|^2)(1 - 1e-5) - thr^2 (1 + 1e-5))
-            const float lhs = __uint_as_float(acc[jj]) + rm.sna * cs.x;
-            const float rhs = cosine ? rm.rowc * (rm.sna * gmeta[ch * 32 + jj].snb) : rm.rowc + cs.y;
-            if (!(lhs < rhs)) kb |= 1u << jj;   // NaN anywhere => let the exact pass decide
+          for (int jj = 0; jj < 32; jj += 4) {
+            const float4 cb = *reinterpret_cast<const float4*>(gcolb + ch * 32 + jj);
+            const float b0 = COSINE ? rowk * cb.x : rowk + cb.x, b1 = COSINE ? rowk * cb.y : rowk + cb.y;
+            const float b2 = COSINE ? rowk * cb.z : rowk + cb.z, b3 = COSINE ? rowk * cb.w : rowk + cb.w;
+            // a NaN anywhere keeps the pair: the exact pass decides
+            if (!(__uint_as_float(acc[ch & 1][jj]) < b0)) kb |= 1u << jj;
+            if (!(__uint_as_float(acc[ch & 1][jj + 1]) < b1)) kb |= 2u << jj;
+            if (!(__uint_as_float(acc[ch & 1][jj + 2]) < b2)) kb |= 4u << jj;
+            if (!(__uint_as_float(acc[ch & 1][jj + 3]) < b3)) kb |= 8u << jj;
           }
-          kb &= gvalid[ch];
+          kb &= S.colvalid[ms][ch];   // columns without a usable observation never survive
+          const int left = h.ncols_left - ch * 32;   // columns past the scene's last track row hold foreign metadata
+          if (left < 32) kb &= (1u << left) - 1u;
           if (!row_ok) kb = 0;
           if (geo && kb) {
             unsigned int kk = kb;
             while (kk) {
               const int jj = __ffs(kk) - 1;
               kk &= kk - 1;
-              const VisColGeo cg = ggeo[ch * 32 + jj];
-              if (!compat_ok(p, sc.epoch, cg.tep, cx, cy, cr, cg.tx, cg.ty, cg.tr)) kb &= ~(1u << jj);
+              const VisColGeo cg = colgeo[h.col0 + ch * 32 + jj];   // rare path: straight from global memory
+              if (!compat_ok(p, (unsigned int)h.epoch, cg.tep, cx, cy, cr, cg.tx, cg.ty, cg.tr)) kb &= ~(1u << jj);
             }
           }
           keep[ch] = kb;
@@ -326,7 +359,7 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         int base = 0;
-        if (lane == 31) base = atomicAdd(&f.vis_cnt[tl.scene], total);
+        if (lane == 31) base = atomicAdd(&f.vis_cnt[h.scene], total);
         base = __shfl_sync(0xffffffffu, base, 31);
         int pos = base + incl - cnt;
 #pragma unroll
@@ -335,16 +368,18 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           while (kk) {
             const int jj = __ffs(kk) - 1;
             kk &= kk - 1;
-            if (pos < sc.vis_lcap) {
+            if (pos < h.vis_lcap) {
               const VisColMeta cm = gmeta[ch * 32 + jj];
               VisPair vp;
-              vp.g = g; vp.row = cm.row; vp.scene = tl.scene; vp.outcol = cm.outcol;
-              f.vis_pairs[sc.vis_lbase + pos] = vp;
+              vp.g = g; vp.row = cm.row; vp.scene = h.scene; vp.outcol = cm.outcol;
+              f.vis_pairs[h.vis_lbase + pos] = vp;
             }
             ++pos;
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&S.meta_empty[ms]);   // the slabs of this tile may be overwritten
     }
   }
   tc_fence_before();
@@ -491,52 +526,58 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, int d8, in
 
 // per-frame metadata: one thread per physical feature row (scene, track n, physical slot p) and per candidate
 __global__ void vis_meta_kernel(Params p, TrackStore ts, Frame f, int n_scenes, int max_rows, VisColMeta* colmeta,
-                                VisColGeo* colgeo) {
+                                VisColGeo* colgeo, float* colb, unsigned int* colvalid) {
   const int s = blockIdx.y;
   const SceneDesc sc = f.scenes[s];
   const int K = p.max_obs;
   const int prow = blockIdx.x * blockDim.x + threadIdx.x;
-  if (prow >= sc.n * K || prow >= max_rows) return;
-  const int n = prow / K, ph = prow - n * K;
-  const size_t ti = (size_t)sc.slot * ts.track_cap + n;
-  const int on = ts.obs_n[ti];
+  const bool in = prow < sc.n * K && prow < max_rows;
   VisColMeta cm;
-  cm.snb = 0.0f; cm.colc = 0.0f; cm.outcol = -1; cm.row = -1;
-  // logical <-> physical observation bookkeeping of this track
-  int k_of = -1, live_mask = 0;
-  for (int k = 0; k < K; ++k) {
-    if (k < on && ts.obs_hasf[ti * K + k]) {
-      int pp = ts.obs_phys[ti * K + k];
-      live_mask |= 1 << pp;
-      if (pp == ph) k_of = k;
-    }
-  }
-  const unsigned int tep = ts.epoch[ti];
-  if (k_of >= 0) {
-    const unsigned int delta = sc.epoch > tep ? sc.epoch - tep : tep - sc.epoch;
-    cm.outcol = n * K + k_of;
-    const bool valid = (ts.feat_cnt[ti] >= p.min_track_length) && ((unsigned int)p.max_idle_epochs >= delta);
-    const float nb = ts.fnorm2[ti * K + ph];
-    cm.snb = sqrtf(nb);
-    cm.colc = 0.5f * nb * (1.0f - 1e-5f);
-    cm.row = valid ? (int)(ti * K + ph) : -1;
-  } else {
-    // dead physical slot -> owns the dead_rank-th logical column without a feature (written as None)
-    int dead_rank = 0;
-    for (int pp = 0; pp < ph; ++pp) dead_rank += ((live_mask >> pp) & 1) ? 0 : 1;
-    int seen = 0;
+  cm.colb = 0.0f; cm.colc = 0.0f; cm.outcol = -1; cm.row = -1;
+  if (in) {
+    const int n = prow / K, ph = prow - n * K;
+    const size_t ti = (size_t)sc.slot * ts.track_cap + n;
+    const int on = ts.obs_n[ti];
+    // logical <-> physical observation bookkeeping of this track
+    int k_of = -1, live_mask = 0;
     for (int k = 0; k < K; ++k) {
-      bool lv = k < on && ts.obs_hasf[ti * K + k];
-      if (!lv) { if (seen == dead_rank) { cm.outcol = n * K + k; break; } ++seen; }
+      if (k < on && ts.obs_hasf[ti * K + k]) {
+        int pp = ts.obs_phys[ti * K + k];
+        live_mask |= 1 << pp;
+        if (pp == ph) k_of = k;
+      }
+    }
+    const unsigned int tep = ts.epoch[ti];
+    if (k_of >= 0) {
+      const unsigned int delta = sc.epoch > tep ? sc.epoch - tep : tep - sc.epoch;
+      cm.outcol = n * K + k_of;
+      const bool valid = (ts.feat_cnt[ti] >= p.min_track_length) && ((unsigned int)p.max_idle_epochs >= delta);
+      const float nb = ts.fnorm2[ti * K + ph];
+      cm.colb = p.visual_kind == 1 ? sqrtf(nb) : 0.5f * nb * (1.0f - 1e-5f - kScreenRelErr);
+      cm.row = valid ? (int)(ti * K + ph) : -1;
+    } else {
+      // dead physical slot -> owns the dead_rank-th logical column without a feature (written as None)
+      int dead_rank = 0;
+      for (int pp = 0; pp < ph; ++pp) dead_rank += ((live_mask >> pp) & 1) ? 0 : 1;
+      int seen = 0;
+      for (int k = 0; k < K; ++k) {
+        bool lv = k < on && ts.obs_hasf[ti * K + k];
+        if (!lv) { if (seen == dead_rank) { cm.outcol = n * K + k; break; } ++seen; }
+      }
+    }
+    colmeta[sc.col_off + prow] = cm;
+    colb[sc.col_off + prow] = cm.colb;
+    if (p.n_constraints > 0) {
+      const float* tb = ts.pred + ti * 6;
+      VisColGeo cg;
+      cg.tx = tb[0]; cg.ty = tb[1]; cg.tr = ts.radius[ti]; cg.tep = tep;
+      colgeo[sc.col_off + prow] = cg;
     }
   }
-  colmeta[sc.col_off + prow] = cm;
-  if (p.n_constraints > 0) {
-    const float* tb = ts.pred + ti * 6;
-    VisColGeo cg;
-    cg.tx = tb[0]; cg.ty = tb[1]; cg.tr = ts.radius[ti]; cg.tep = tep;
-    colgeo[sc.col_off + prow] = cg;
-  }
+  // col_off is a multiple of 128, so the 32 columns of a warp are exactly one word of the validity mask
+  const unsigned int vb = __ballot_sync(0xffffffffu, cm.row >= 0);
+  if ((threadIdx.x & 31) == 0 && vb != 0) colvalid[(sc.col_off + prow) >> 5] = vb;
+  else if ((threadIdx.x & 31) == 0 && in) colvalid[(sc.col_off + prow) >> 5] = 0u;
 }
 
 __global__ void vis_rowmeta_kernel(Params p, Frame f, VisRowMeta* rowmeta) {
@@ -545,12 +586,10 @@ __global__ void vis_rowmeta_kernel(Params p, Frame f, VisRowMeta* rowmeta) {
   g += f.det0;
   const float na = f.c_norm2[g];
   VisRowMeta rm;
-  rm.sna = sqrtf(na);
   rm.ok = (f.c_flags[g] & 2) ? 1 : 0;
-  rm.pad = 0;
   const float thr = p.visual_threshold;
-  if (p.visual_kind == 1) rm.rowc = thr - 1e-5f;
-  else rm.rowc = 0.5f * (na * (1.0f - 1e-5f) - thr * thr * (1.0f + 1e-5f));
+  if (p.visual_kind == 1) rm.rowk = (thr - 1e-5f - kScreenRelErr) * sqrtf(na);
+  else rm.rowk = 0.5f * (na * (1.0f - 1e-5f - kScreenRelErr) - thr * thr * (1.0f + 1e-5f));
   rowmeta[g] = rm;
 }
 
@@ -568,35 +607,42 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
   if (make_map(&mA, f.c_bf16, tc.a_rows, p.d8, TC_BM) || make_map(&mB, ts.feat_bf16, tc.b_rows, p.d8, cluster ? TC_BN / 2 : TC_BN))
     return -1;
   size_t smem = sizeof(TcSmem) + 1024;
-  cudaError_t e = cudaFuncSetAttribute(vis_screen_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(vis_screen_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool cosine = p.visual_kind == 1;
+  cudaError_t e = cudaSuccess;
+  const void* fn = cluster ? (cosine ? (const void*)vis_screen_kernel<2, true> : (const void*)vis_screen_kernel<2, false>)
+                           : (cosine ? (const void*)vis_screen_kernel<1, true> : (const void*)vis_screen_kernel<1, false>);
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int max_rows = max_n * p.max_obs;
   if (max_rows > 0) {
     dim3 grid((max_rows + 255) / 256, n_scenes);
-    vis_meta_kernel<<<grid, 256, 0, st>>>(p, ts, f, n_scenes, max_rows, tc.colmeta, tc.colgeo);
+    vis_meta_kernel<<<grid, 256, 0, st>>>(p, ts, f, n_scenes, max_rows, tc.colmeta, tc.colgeo, tc.colb, tc.colvalid);
   }
   vis_rowmeta_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f, tc.rowmeta);
   if (tc.ev_screen0) cudaEventRecord(tc.ev_screen0, st);
-  if (!cluster) {
-    int grid = tc.n_tiles < tc.num_sms ? tc.n_tiles : tc.num_sms;
-    vis_screen_kernel<1><<<grid, TC_THREADS, smem, st>>>(mA, mB, p, ts, f, tc.d_tiles, tc.n_tiles, tc.colmeta, tc.colgeo,
-                                                          tc.rowmeta);
-  } else {
-    int nclusters = std::min(tc.n_tiles, tc.num_sms / 2);
+  {
+    const int ncta = cluster ? 2 * std::min(tc.n_tiles, tc.num_sms / 2) : std::min(tc.n_tiles, tc.num_sms);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(nclusters * 2);
+    cfg.gridDim = dim3(ncta);
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = cluster ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, vis_screen_kernel<2>, mA, mB, p, ts, f, tc.d_tiles, tc.n_tiles, tc.colmeta, tc.colgeo,
-                           tc.rowmeta);
+    const TcTile* d_tiles = tc.d_tiles;
+    int n_tiles = tc.n_tiles;
+    const VisColMeta* cmeta = tc.colmeta;
+    const VisColGeo* cgeo = tc.colgeo;
+    const VisRowMeta* rmeta = tc.rowmeta;
+    const float* cb = tc.colb;
+    const unsigned int* cv = tc.colvalid;
+    void* args[] = {(void*)&mA, (void*)&mB, (void*)&p, (void*)&ts, (void*)&f, (void*)&d_tiles, (void*)&n_tiles,
+                    (void*)&cmeta, (void*)&cgeo, (void*)&rmeta, (void*)&cb, (void*)&cv};
+    e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) return (int)e;
   }
   if (tc.ev_screen1) cudaEventRecord(tc.ev_screen1, st);

@@ -238,11 +238,13 @@ int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* 
     tc.b_rows = n;
     f.c_bf16 = sc.alloc<unsigned short>((size_t)m * p.d8);
     ts.feat_bf16 = sc.alloc<unsigned short>((size_t)n * p.d8);
-    tc.colmeta = sc.alloc<sb::VisColMeta>(n);
+    tc.colmeta = sc.alloc<sb::VisColMeta>(n + 256);   // the screen kernel bulk-copies whole 256-column slabs
     tc.colgeo = sc.alloc<sb::VisColGeo>(n);
-    tc.rowmeta = sc.alloc<sb::VisRowMeta>(m);
+    tc.colb = sc.alloc<float>(n + 256);
+    tc.colvalid = sc.alloc<unsigned int>((n + 256) / 32 + 4);
+    tc.rowmeta = sc.alloc<sb::VisRowMeta>(m + 256);
     tc.total_cols = n;
-    if (!tc.d_tiles || !f.c_bf16 || !ts.feat_bf16 || !tc.colmeta || !tc.colgeo || !tc.rowmeta)
+    if (!tc.d_tiles || !f.c_bf16 || !ts.feat_bf16 || !tc.colmeta || !tc.colgeo || !tc.rowmeta || !tc.colb || !tc.colvalid)
       return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
     sb::launch_to_bf16(ft.in_feat, d, d, p.d8, n, ts.feat_bf16, sc.st);
     sb::launch_to_bf16(f.in_feat, d, d, p.d8, m, f.c_bf16, sc.st);   // (the tracker fuses this into cand_norm_kernel)

@@ -124,13 +124,13 @@ struct Frame {  // per-request transient device buffers (a request may be proces
 struct TcTile { int scene, m0, c0, pad; };  // one 128 x 256 output tile of the tensor-core visual cost kernel
 // per-frame metadata of one physical feature row (track n, physical slot p) of a scene, built once per frame
 struct VisColMeta {
-  float snb;     // sqrt(||b||^2)
+  float colb;    // column constant of the screen test (copy of TcArgs::colb)
   float colc;    // column part of the screen test
   int outcol;    // logical output column n*K + k (-1: none)
   int row;       // feature row idx*K + phys when the observation takes part in the metric, else -1
 };
 struct VisColGeo { float tx, ty, tr; unsigned int tep; };  // only read when spatio-temporal constraints exist
-struct VisRowMeta { float sna, rowc; int ok, pad; };
+struct VisRowMeta { float rowk; int ok, pad0, pad1; };   // row constant of the screen test, candidate may vote visually
 
 // ---- kernel launchers (each in its own .cu) ----
 void launch_prep(const Params& p, const Frame& f, int n_scenes, int max_m, cudaStream_t st);
@@ -147,6 +147,8 @@ struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense ex
   cudaEvent_t ev_screen0, ev_screen1, ev_refine1;  // optional per-kernel timing (null: not timed)
   VisColMeta* colmeta;   // [sum n_s*K]
   VisColGeo* colgeo;     // [sum n_s*K]
+  float* colb;                // [sum n_s*K (+pad)] column constant of the screen test
+  unsigned int* colvalid;     // bit per column: the observation takes part in the metric
   VisRowMeta* rowmeta;   // [total]
   int total_cols;
 };
