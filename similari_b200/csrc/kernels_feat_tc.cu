@@ -399,58 +399,97 @@ __device__ __forceinline__ float reduce_add8_tc(const float* t) {
   return d0 + d1;
 }
 
-__global__ void __launch_bounds__(256) vis_refine_kernel(Params p, TrackStore ts, Frame f) {
+// A warp takes 32 pairs at a time.  Phase 1 (cooperative, coalesced): for every pair the lanes compute the 8-element
+// block sums s_blk = reduce_add8(...) of up to 64 blocks and park them in shared memory.  Phase 2: lane p owns pair p and
+// adds its block sums strictly in block order, acc = (..((0 + s_0) + s_1) + ..), which is the reference's order; the 32
+// serial chains run side by side instead of one 64-step shuffle chain per pair.
+constexpr int RF_WARPS = 4;
+constexpr int RF_SEG = 64;             // blocks per segment
+constexpr int RF_PITCH = RF_SEG + 1;   // +1: lane p reads row p, rows must start in different banks
+
+template <bool COSINE, bool TAIL>
+__device__ __forceinline__ float refine_block_sum(const float* __restrict__ a, const float* __restrict__ b, int blk, int D) {
+  const float4 b0 = *reinterpret_cast<const float4*>(b + blk * 8);
+  const float4 b1 = *reinterpret_cast<const float4*>(b + blk * 8 + 4);
+  float av[8];
+  if (!TAIL) {
+    const float4 a0 = *reinterpret_cast<const float4*>(a + blk * 8);
+    const float4 a1 = *reinterpret_cast<const float4*>(a + blk * 8 + 4);
+    av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+  } else {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) av[l] = blk * 8 + l < D ? a[blk * 8 + l] : 0.0f;   // the input row has D, not d8, floats
+  }
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float t[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) {
+    if (COSINE) t[l] = av[l] * bb[l];
+    else { const float df = av[l] - bb[l]; t[l] = df * df; }
+  }
+  return reduce_add8_tc(t);
+}
+
+template <bool COSINE, bool TAIL>
+__global__ void __launch_bounds__(RF_WARPS * 32) vis_refine_kernel(Params p, TrackStore ts, Frame f) {
+  __shared__ float s_bs[RF_WARPS][32][RF_PITCH];
   const int scene = blockIdx.y;
   if (f.scene_mode[scene] != 0) return;  // this scene is computed densely
   const SceneDesc sc = f.scenes[scene];
-  const int lane = threadIdx.x & 31;
-  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int warps_total = gridDim.x * RF_WARPS;
   const int n_pairs = min(f.vis_cnt[scene], sc.vis_lcap);
-  const bool cosine = p.visual_kind == 1;
   const int nblk = p.d8 / 8;
   const int D = p.feature_dim;
-  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_pairs; i += warps_total) {
-    const VisPair vp = f.vis_pairs[sc.vis_lbase + i];
-    const float* a = f.in_feat + (size_t)vp.g * D;
-    const float* b = ts.feat + (size_t)vp.row * p.d8;
+  float (*bs)[RF_PITCH] = s_bs[w];
+  float vmax = nanf("");
+  for (int i0 = (blockIdx.x * RF_WARPS + w) * 32; i0 < n_pairs; i0 += warps_total * 32) {
+    const int npair = min(32, n_pairs - i0);
+    VisPair mine;
+    mine.g = 0; mine.row = 0; mine.scene = 0; mine.outcol = 0;
+    if (lane < npair) mine = f.vis_pairs[sc.vis_lbase + i0 + lane];
     float acc = 0.0f;
-    for (int base = 0; base < nblk; base += 32) {
-      const int blk = base + lane;
-      float bs = 0.0f;
-      if (blk < nblk) {
-        float t[8];
-        const float4 b0 = *reinterpret_cast<const float4*>(b + blk * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(b + blk * 8 + 4);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int seg0 = 0; seg0 < nblk; seg0 += RF_SEG) {
+      const int segn = min(RF_SEG, nblk - seg0);
+#pragma unroll 4
+      for (int pp = 0; pp < npair; ++pp) {
+        const int g = __shfl_sync(0xffffffffu, mine.g, pp);
+        const int row = __shfl_sync(0xffffffffu, mine.row, pp);
+        const float* a = f.in_feat + (size_t)g * D;
+        const float* b = ts.feat + (size_t)row * p.d8;
 #pragma unroll
-        for (int l = 0; l < 8; ++l) {
-          const int d = blk * 8 + l;
-          const float av = d < D ? a[d] : 0.0f;
-          if (cosine) t[l] = av * bb[l];
-          else { const float df = av - bb[l]; t[l] = df * df; }
+        for (int h = 0; h < RF_SEG / 32; ++h) {
+          const int j = h * 32 + lane;
+          if (j < segn) bs[pp][j] = refine_block_sum<COSINE, TAIL>(a, b, seg0 + j, D);
         }
-        bs = reduce_add8_tc(t);
       }
-      const int cnt = min(32, nblk - base);
-      for (int j = 0; j < cnt; ++j) acc = acc + __shfl_sync(0xffffffffu, bs, j);
+      __syncwarp();
+      if (lane < npair)
+        for (int j = 0; j < segn; ++j) acc = acc + bs[lane][j];
+      __syncwarp();
     }
-    if (lane == 0) {
+    if (lane < npair) {
       float v = nanf("");
-      if (cosine) {
-        const float d = acc / sqrtf(f.c_norm2[vp.g] * ts.fnorm2[vp.row]);
+      if (COSINE) {
+        const float d = acc / sqrtf(f.c_norm2[mine.g] * ts.fnorm2[mine.row]);
         if (d >= p.visual_threshold) v = 1.0f - d;       // is_ok + distance_to_weight
       } else {
         const float d = sqrtf(acc);
         if (d <= p.visual_threshold) v = d;
       }
-      f.vis_val[sc.vis_lbase + i] = v;
-      if (!is_nan(v)) {  // best.rs "max_dist": maximum over the entries that exist
-        unsigned int u = __float_as_uint(v);
-        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-        atomicMax(f.scene_max + scene, u);
-      }
+      f.vis_val[sc.vis_lbase + i0 + lane] = v;
+      if (!is_nan(v) && !(v <= vmax)) vmax = v;   // best.rs "max_dist": maximum over the entries that exist
     }
   }
+  // one atomic per warp
+  unsigned int u = 0u;
+  if (!is_nan(vmax)) {
+    u = __float_as_uint(vmax);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) u = max(u, __shfl_xor_sync(0xffffffffu, u, o));
+  if (lane == 0 && u != 0u) atomicMax(f.scene_max + scene, u);
 }
 
 // dense view of the sparse scenes' visual entries (operators / debugging): None everywhere, then the refined survivors
@@ -597,8 +636,15 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
                        int phase, cudaStream_t st) {
   if (tc.n_tiles == 0) return 0;
   if (phase == 1) {
-    dim3 grid(8, n_scenes);
-    vis_refine_kernel<<<grid, 256, 0, st>>>(p, ts, f);
+    dim3 grid(10, n_scenes);
+    const bool tail = p.feature_dim != p.d8;
+    if (p.visual_kind == 1) {
+      if (tail) vis_refine_kernel<true, true><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
+      else vis_refine_kernel<true, false><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
+    } else {
+      if (tail) vis_refine_kernel<false, true><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
+      else vis_refine_kernel<false, false><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
+    }
     if (tc.ev_refine1) cudaEventRecord(tc.ev_refine1, st);
     return 0;
   }
