@@ -218,14 +218,16 @@ def main():
     out_host = {"ids": pinned_empty((max_total,), np.uint64), "epochs": pinned_empty((max_total,), np.uint32),
                 "lengths": pinned_empty((max_total,), np.uint32), "voting_types": pinned_empty((max_total,), np.uint8)}
     units_per_step, h2d, d2h = [], [], []
-    e2e_ms = []
     stage_acc = {}
     sampler = None
+    # Whole-span timing: one event before the first timed step (after a device-wide sync, so nothing is in flight) and
+    # one after a device-wide sync behind the last one.  Software pipeline: each step starts the H2D copy of the NEXT
+    # frame and then runs this frame (whose copy was started one step earlier); the K timed steps therefore issue
+    # exactly K input copies, all of which complete inside the span, and K result read-backs.
     t_e2e.prefetch_inputs(pinned[0][0], features=pinned[0][1])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i, f in enumerate(frames[: W + K]):
         total = len(f["boxes"])
-        n_before = t_e2e.scene_track_counts(f["scene_ids"]).astype(np.int64)
-        m = np.diff(f["det_offsets"]).astype(np.int64)
         out = {k: v[:total] for k, v in out_host.items()}
         if i == W:
             if world > 1:
@@ -233,26 +235,21 @@ def main():
             torch.cuda.synchronize()
             sampler = ClockSampler(local)
             sampler.start()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
+            ev0.record()
         tw0 = time.perf_counter()
-        # software pipeline: start the H2D copy of the NEXT frame, then run this frame (whose copy was started one
-        # step earlier); every timed step therefore contains one full input copy and one full result read-back
         t_e2e.prefetch_inputs(pinned[i + 1][0], features=pinned[i + 1][1])
         t_e2e.predict_batch(f["scene_ids"], f["det_offsets"], pinned[i][0], features=pinned[i][1], out=out)
-        tw1 = time.perf_counter()
-        ev1.record()
-        ev1.synchronize()   # (not a device-wide sync: the prefetch of the next frame keeps running on the copy stream)
         if os.environ.get("SB200_TRACE"):
-            print(f"[bench] e2e frame {i}: events {ev0.elapsed_time(ev1):.3f} ms, wall {1e3 * (tw1 - tw0):.3f} ms", file=sys.stderr)
+            print(f"[bench] e2e frame {i}: wall {1e3 * (time.perf_counter() - tw0):.3f} ms", file=sys.stderr)
         if i >= W:
-            e2e_ms.append(ev0.elapsed_time(ev1))
-            units_per_step.append(int((m * n_before).sum()))
             h2d.append(total * 24 + (total * D * 4 if visual else 0))
             d2h.append(total * (8 + 4 + 4 + 1))
             for k_, v_ in t_e2e.last_stage_ms().items():
                 stage_acc.setdefault(k_, []).append(v_)
-    e2e_total_ms = float(sum(e2e_ms))
+    torch.cuda.synchronize()   # the prefetch issued by the last timed step has landed too
+    ev1.record()
+    ev1.synchronize()
+    e2e_total_ms = float(ev0.elapsed_time(ev1))
     ids_e2e_last = out_host["ids"][: len(frames[W + K - 1]["boxes"])].copy()
     t_e2e.close()
 
@@ -287,13 +284,15 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(W, W + K):
+        n_before = t_dev.scene_track_counts(frames[i]["scene_ids"]).astype(np.int64)   # host-side mirror, no GPU work
+        units_per_step.append(int((np.diff(frames[i]["det_offsets"]).astype(np.int64) * n_before).sum()))
         step_dev(i)
         for k_, v_ in t_dev.last_stage_ms().items():
             dev_stage.setdefault(k_, []).append(v_)
         for k_, v_ in t_dev.last_kernel_ms().items():
             dev_stage.setdefault(k_, []).append(v_)
         n_tracks_steps.append(t_dev.scene_track_counts(frames[i]["scene_ids"]).astype(np.float64))
-        launches += 16 if visual else 8   # kernels per predict (see profiles/: launch list)
+        launches += 18 if visual else 9   # kernels per predict (see profiles/: launch list)
     ev1.record()
     if world > 1:
         dist.barrier()

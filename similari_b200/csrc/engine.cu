@@ -62,23 +62,29 @@ struct DBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct HBuf {  // grow-only pinned host buffer
+struct HBuf {  // grow-only pinned host buffer, mapped into the device address space (dp)
   void* p = nullptr;
+  void* dp = nullptr;   // device-side alias: kernels can read the buffer over PCIe without a copy-engine transfer
   size_t bytes = 0;
   int ensure(size_t need) {
     if (need <= bytes) return 0;
     size_t nb = std::max(need, bytes + bytes / 2);
     void* np = nullptr;
-    cudaError_t e = cudaMallocHost(&np, nb);
-    if (e != cudaSuccess) return fail(SB200_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", nb, cudaGetErrorString(e));
+    cudaError_t e = cudaHostAlloc(&np, nb, cudaHostAllocMapped);
+    if (e != cudaSuccess) return fail(SB200_ERR_CUDA, "cudaHostAlloc(%zu) failed: %s", nb, cudaGetErrorString(e));
+    void* ndp = nullptr;
+    e = cudaHostGetDevicePointer(&ndp, np, 0);
+    if (e != cudaSuccess) { cudaFreeHost(np); return fail(SB200_ERR_CUDA, "cudaHostGetDevicePointer failed: %s", cudaGetErrorString(e)); }
     if (p) cudaFreeHost(p);
     p = np;
+    dp = ndp;
     bytes = nb;
     return 0;
   }
   void release() {
     if (p) cudaFreeHost(p);
     p = nullptr;
+    dp = nullptr;
     bytes = 0;
   }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -181,6 +187,7 @@ struct sb200_tracker {
     int total = -1;
     bool pending = false;   // holds a prefetched request that no predict call has consumed yet
     cudaEvent_t ev = nullptr;
+    cudaEvent_t ev0 = nullptr;   // start of the set's prefetch copy (SB200_TRACE timing)
   } stg[2];
   int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
@@ -206,6 +213,7 @@ struct sb200_tracker {
     for (auto& g : stg) {
       g.boxes.release(); g.feat.release(); g.hasf.release(); g.quality.release(); g.custom.release(); g.own.release();
       if (g.ev) cudaEventDestroy(g.ev);
+      if (g.ev0) cudaEventDestroy(g.ev0);
     }
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : ev_k) if (e) cudaEventDestroy(e);
@@ -530,7 +538,9 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       tc.total_cols = (int)col_total;
       if (tc.n_tiles > 0) {
         memcpy(h_tiles.p, tiles.data(), sizeof(sb::TcTile) * tc.n_tiles);
-        CU(cudaMemcpyAsync(f_tiles.p, h_tiles.p, sizeof(sb::TcTile) * tc.n_tiles, cudaMemcpyHostToDevice, stream));
+        // pulled by a kernel, not by the H2D copy engine: that engine may be busy for milliseconds with the prefetch of
+        // the next frame (sb200_prefetch_inputs), and a DMA queued behind it would stall this frame's kernels
+        sb::launch_pull(f_tiles.p, h_tiles.dp, sizeof(sb::TcTile) * tc.n_tiles, stream);
       }
       tc.d_tiles = f_tiles.as<sb::TcTile>();
       tc.a_rows = total;
@@ -633,7 +643,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   // scene descriptors
   if ((rc = h_scenes.ensure(sizeof(sb::SceneDesc) * n_scenes))) return rc;
   memcpy(h_scenes.p, sd.data(), sizeof(sb::SceneDesc) * n_scenes);
-  CU(cudaMemcpyAsync(f_scenes.p, h_scenes.p, sizeof(sb::SceneDesc) * n_scenes, cudaMemcpyHostToDevice, stream));
+  sb::launch_pull(f_scenes.p, h_scenes.dp, sizeof(sb::SceneDesc) * n_scenes, stream);
   CU(cudaMemsetAsync(f_status.p, 0, 4 * (size_t)n_scenes, stream));
 
   const double ms_setup = since(t_begin);
@@ -710,6 +720,11 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   CU(cudaMemcpyAsync(h_status, f.status, 4 * (size_t)n_scenes, cudaMemcpyDeviceToHost, stream));
   const double ms_launch = since(t_begin);
   CU(cudaStreamSynchronize(stream));
+  if (trace && prefetched && sin) {
+    float cms = 0.0f;
+    if (cudaEventElapsedTime(&cms, sin->ev0, sin->ev) == cudaSuccess)
+      fprintf(stderr, "[sb200] prefetch copy of this frame took %.3f ms on the copy stream\n", cms);
+  }
   if (trace) fprintf(stderr, "[sb200] predict: setup %.3f ms, launched at %.3f ms, synced at %.3f ms (total dets %d)\n", ms_setup, ms_launch, since(t_begin), total);
   long long new_total = 0;
   for (int s = 0; s < n_scenes; ++s) {
@@ -785,7 +800,8 @@ int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out) {
     if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
   }
   for (auto& g : t->stg) {
-    e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+    e = cudaEventCreate(&g.ev);
+    if (e == cudaSuccess) e = cudaEventCreate(&g.ev0);
     if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
   }
   for (auto& ev : t->ev_copy) {
@@ -838,6 +854,7 @@ int sb200_prefetch_inputs(sb200_tracker* t, int32_t total, const float* boxes, c
   int rc = 0;
   cudaStream_t cs = t->copy_stream;
   if ((rc = S.boxes.ensure(T * 24))) return rc;
+  CU(cudaEventRecord(S.ev0, cs));
   CU(cudaMemcpyAsync(S.boxes.p, boxes, n * 24, cudaMemcpyHostToDevice, cs));
   if (features) {
     if ((rc = S.feat.ensure(T * (size_t)t->P.feature_dim * 4))) return rc;

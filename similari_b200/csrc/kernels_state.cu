@@ -361,4 +361,20 @@ void launch_kalman_ops(int op, float pw, float vw, const float* in30, const floa
   kalman_ops_kernel<<<(n + 127) / 128, 128, 0, st>>>(op, pw, vw, in30, boxes, n, out30);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Small per-frame tables (scene descriptors, tile list) are read straight from mapped pinned host memory.
+__global__ void pull_kernel(unsigned int* __restrict__ dst, const unsigned int* __restrict__ src, size_t n4, size_t n1) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+  if (i < n1) dst[n4 * 4 + i] = src[n4 * 4 + i];
+}
+
+void launch_pull(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return;
+  const size_t words = bytes / 4, n4 = words / 4, n1 = words - n4 * 4;
+  const size_t threads = n4 > n1 ? n4 : n1;
+  pull_kernel<<<(unsigned int)((threads + 255) / 256), 256, 0, st>>>(reinterpret_cast<unsigned int*>(dst),
+                                                                    reinterpret_cast<const unsigned int*>(src), n4, n1);
+}
+
 }  // namespace sb
