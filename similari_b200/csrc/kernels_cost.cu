@@ -59,7 +59,7 @@ __global__ void cand_norm_kernel(Params p, Frame f, __nv_bfloat16* bf16_out) {
   w += f.det0;
   const int nblk = p.d8 / 8;
   const float* row = f.in_feat + (size_t)w * p.feature_dim;
-  const bool vec = (p.feature_dim % 4 == 0);
+  const bool vec = (p.feature_dim % 4 == 0) && (reinterpret_cast<uintptr_t>(f.in_feat) & 15) == 0;
   float acc = 0.0f;
   for (int base = 0; base < nblk; base += 32) {
     int blk = base + lane;

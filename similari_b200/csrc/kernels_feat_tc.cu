@@ -637,7 +637,8 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
   if (tc.n_tiles == 0) return 0;
   if (phase == 1) {
     dim3 grid(10, n_scenes);
-    const bool tail = p.feature_dim != p.d8;
+    // the vector path needs 16-byte aligned input rows (a caller-owned device pointer on the device-io path)
+    const bool tail = p.feature_dim != p.d8 || (reinterpret_cast<uintptr_t>(f.in_feat) & 15) != 0;
     if (p.visual_kind == 1) {
       if (tail) vis_refine_kernel<true, true><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
       else vis_refine_kernel<true, false><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);

@@ -197,10 +197,38 @@ __global__ void feat_store_kernel(Params p, TrackStore ts, Frame f) {
   const float* src = f.in_feat + (size_t)w * p.feature_dim;
   float* d = ts.feat + (size_t)dst * p.d8;
   __nv_bfloat16* db = reinterpret_cast<__nv_bfloat16*>(ts.feat_bf16) + (size_t)dst * p.d8;
-  for (int i = lane; i < p.d8; i += 32) {
-    float x = i < p.feature_dim ? src[i] : 0.0f;
-    d[i] = x;
-    db[i] = __float2bfloat16_rn(x);  // B operand of the tensor-core screen
+  if (p.feature_dim == p.d8 && (reinterpret_cast<uintptr_t>(f.in_feat) & 15) == 0) {
+    // rows are 32-byte multiples: 16-byte vectors, four in flight per lane
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(d);
+    uint2* b4 = reinterpret_cast<uint2*>(db);
+    const int n4 = p.d8 >> 2;
+    for (int i0 = 0; i0 < n4; i0 += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        if (i < n4) v[u] = __ldcs(s4 + i);   // the input row is dead after this kernel
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        if (i < n4) {
+          d4[i] = v[u];
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(v[u].x, v[u].y), hi = __floats2bfloat162_rn(v[u].z, v[u].w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const unsigned int*>(&lo);
+          pk.y = *reinterpret_cast<const unsigned int*>(&hi);
+          b4[i] = pk;   // B operand of the tensor-core screen
+        }
+      }
+    }
+  } else {
+    for (int i = lane; i < p.d8; i += 32) {
+      float x = i < p.feature_dim ? src[i] : 0.0f;
+      d[i] = x;
+      db[i] = __float2bfloat16_rn(x);
+    }
   }
   if (lane == 0) ts.fnorm2[dst] = f.c_norm2[w];
 }
