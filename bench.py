@@ -291,7 +291,7 @@ def main():
             dev_stage.setdefault(k_, []).append(v_)
         for k_, v_ in t_dev.last_kernel_ms().items():
             dev_stage.setdefault(k_, []).append(v_)
-        n_tracks_steps.append(t_dev.scene_track_counts(frames[i]["scene_ids"]).astype(np.float64))
+        n_tracks_steps.append(n_before.astype(np.float64))   # the cost matrices of this step are built on the store BEFORE it
         launches += 18 if visual else 9   # kernels per predict (see profiles/: launch list)
     ev1.record()
     if world > 1:
@@ -339,8 +339,7 @@ def main():
             fl, by = [], []
             for i in range(W, W + K):
                 m_l = np.diff(frames[i]["det_offsets"]).astype(np.float64)
-                n_l = n_tracks_steps[i - W] - 0.0   # tracks after the step; the screen ran on the store before it
-                n_l = np.maximum(n_l - (m_l * 0.055), 1.0) if False else n_l
+                n_l = n_tracks_steps[i - W]
                 fl.append(float((2.0 * m_l * n_l * Kobs * D).sum()))
                 by.append(float(((m_l + n_l * Kobs) * D * 4 + m_l * n_l * Kobs * 4).sum()))
             kms = float(np.mean(dev_stage["vis_screen"]))
@@ -361,7 +360,7 @@ def main():
             kms = float(np.mean(dev_stage["positional_cost"]))
             achieved = alg_bytes / (kms * 1e-3) / 1e9
             roof = {"kernel": "positional_cost stage", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kms}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
