@@ -511,7 +511,12 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       else if (!strcmp(e, "tc")) tc.use_tc = work > 0;
     }
     if (tc.use_tc) {
-      tc.cluster2 = getenv("SB200_SCREEN_SINGLE") == nullptr;
+      {
+        // SB200_SCREEN = single | multicast | pair (default): CTA organisation of the screen kernel
+        const char* e = getenv("SB200_SCREEN");
+        tc.cluster2 = !(e && !strcmp(e, "single")) && getenv("SB200_SCREEN_SINGLE") == nullptr;
+        tc.pair = tc.cluster2 && !(e && !strcmp(e, "multicast"));
+      }
       const int mstep = tc.cluster2 ? 256 : 128;   // a cluster covers two 128-row candidate tiles
       tile_first.assign(n_scenes + 1, 0);
       for (int s = 0; s < n_scenes; ++s) {

@@ -35,7 +35,9 @@
 namespace sb {
 
 constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 64;
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 4;          // 48 KB stages (A tile + whole B tile)
+constexpr int TC_STAGES_PAIR = 6;     // 32 KB stages of the cta_group::2 variant (A tile + half of the B tile)
+constexpr int TC_STAGE_BYTES_PAIR = 32768;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;  // 32 KB
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;  // 48 KB
@@ -51,8 +53,8 @@ struct TcSmem {
   float colb[4][TC_BN];
   unsigned int colvalid[4][TC_BN / 32];
   TcHdr hdr[4];
-  unsigned long long full_bar[TC_STAGES];
-  unsigned long long empty_bar[TC_STAGES];
+  unsigned long long full_bar[TC_STAGES_PAIR];
+  unsigned long long empty_bar[TC_STAGES_PAIR];
   unsigned long long tmem_full[2];
   unsigned long long tmem_empty[2];
   unsigned long long meta_full[4];
@@ -96,6 +98,33 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_commit_mc(void* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// ---- cta_group::2 (CTA pair) helpers.  leader_addr(): the shared::cluster address of the same variable in CTA rank 0.
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(smem_u32(p)));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  // the bytes land in THIS CTA's shared memory, the transaction count on the LEADER's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair_mc(void* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -156,6 +185,9 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // instruction descriptor: D = F32 (1<<4), A = B = BF16 (1<<7, 1<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
+// cta_group::2: one MMA spans the CTA pair, M = 256 (128 accumulator rows in each CTA's TMEM), N = 256
+constexpr uint32_t kIdescBf16Pair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
 // BF16 operand rounding bound on a dot product: each operand carries relative error <= 2^-9, so
 // |dot~ - dot| <= (2^-8 + 2^-18) * sum|a_i b_i| <= ~2^-8 * ||a|| ||b||; 1.5x head-room covers the fp32 accumulation.
 constexpr float kScreenRelErr = 1.5f / 256.0f;
@@ -163,6 +195,10 @@ constexpr float kScreenRelErr = 1.5f / 256.0f;
 // ------------------------------------------------------------------------------------------------ screen kernel
 // CL == 2: clusters of two CTAs work on two candidate tiles (m0, m0 + 128) of the same track-row tile; each CTA loads
 // its own A tile and HALF of the B tile, multicast into both CTAs' shared memory, so B crosses L2 -> SM once per pair.
+// CL == 3: the two CTAs form a cta_group::2 pair: one 256 x 256 x 16 MMA per instruction, issued by the leader CTA only.
+// Each CTA stages its own A tile and HALF of the B tile (no multicast: the tensor cores read the peer's half), which
+// halves the shared-memory bytes written and read per MMA -- with 128 x 256 single-CTA tiles every operand byte is
+// written once by TMA and read once by the MMA, 192 B/clk against the 128 B/clk an SM's shared memory delivers.
 template <int CL, bool COSINE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p,
@@ -175,24 +211,34 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int K = p.max_obs;
   const int KB = (p.d8 + TC_BK - 1) / TC_BK;
 
-  const uint32_t crank = CL == 2 ? cluster_rank() : 0u;
-  const int cta_first = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // first (cluster) tile of this CTA
-  const int cta_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr bool PAIR = CL == 3;
+  constexpr int NST = PAIR ? TC_STAGES_PAIR : TC_STAGES;
+  constexpr int STAGE_B = PAIR ? TC_STAGE_BYTES_PAIR : TC_STAGE_BYTES;
+  unsigned char* const stage_base = &S.stage[0][0];   // NST stages of STAGE_B bytes (192 KB either way)
+  const uint32_t crank = CL >= 2 ? cluster_rank() : 0u;
+  const int cta_first = CL >= 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // first (cluster) tile of this CTA
+  const int cta_step = CL >= 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   if (threadIdx.x == 32) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], CL); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&S.full_bar[s], 1); mbar_init(&S.empty_bar[s], CL == 2 ? 2 : 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], 4);
+      // PAIR: the leader's tmem_empty collects the epilogue warps of both CTAs
+      mbar_init(&S.tmem_full[b], 1); mbar_init(&S.tmem_empty[b], PAIR ? 8 : 4);
     }
     for (int b = 0; b < 4; ++b) { mbar_init(&S.meta_full[b], 1); mbar_init(&S.meta_empty[b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (PAIR) {   // both CTAs of the pair allocate, same warp, same destination
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into them
+  if (CL >= 2) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast into them
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
 
@@ -231,23 +277,31 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         }
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&S.empty_bar[stage], phase ^ 1);   // CL == 2: both CTAs have released the stage
-          mbar_expect_tx(&S.full_bar[stage], TC_STAGE_BYTES);
-          unsigned char* base = S.stage[stage];
-          tma_load_2d(base, &mapA, kb * TC_BK, rowA, &S.full_bar[stage]);
-          if (CL == 2) {
-            // this CTA's half of the B tile (rows rank*128 .. +128), delivered to both CTAs
-            tma_load_2d_mc(base + TC_A_BYTES + crank * (TC_B_BYTES / 2), &mapB, kb * TC_BK, rowB + (int)crank * (TC_BN / 2),
-                           &S.full_bar[stage], (uint16_t)0x3);
+          unsigned char* base = stage_base + stage * STAGE_B;
+          if (PAIR) {
+            // both CTAs' bytes are counted on the leader's barrier, which the leader arms for the whole pair
+            const uint32_t lbar = leader_addr(&S.full_bar[stage]);
+            if (crank == 0) mbar_expect_tx(&S.full_bar[stage], 2 * TC_STAGE_BYTES_PAIR);
+            tma_load_2d_pair(base, &mapA, kb * TC_BK, rowA, lbar);
+            tma_load_2d_pair(base + TC_A_BYTES, &mapB, kb * TC_BK, rowB + (int)crank * (TC_BN / 2), lbar);
           } else {
-            tma_load_2d(base + TC_A_BYTES, &mapB, kb * TC_BK, rowB, &S.full_bar[stage]);
+            mbar_expect_tx(&S.full_bar[stage], TC_STAGE_BYTES);
+            tma_load_2d(base, &mapA, kb * TC_BK, rowA, &S.full_bar[stage]);
+            if (CL == 2) {
+              // this CTA's half of the B tile (rows rank*128 .. +128), delivered to both CTAs
+              tma_load_2d_mc(base + TC_A_BYTES + crank * (TC_B_BYTES / 2), &mapB, kb * TC_BK, rowB + (int)crank * (TC_BN / 2),
+                             &S.full_bar[stage], (uint16_t)0x3);
+            } else {
+              tma_load_2d(base + TC_A_BYTES, &mapB, kb * TC_BK, rowB, &S.full_bar[stage]);
+            }
           }
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one elected lane)
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (one elected lane; PAIR: leader CTA)
+    if (lane == 0 && (!PAIR || crank == 0)) {
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -259,19 +313,22 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&S.full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(S.stage[stage]);
+          const uint32_t a0 = smem_u32(stage_base + stage * STAGE_B);
           const uint32_t b0 = a0 + TC_A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             const uint32_t off = k * 32;  // 16 bf16 = 32 bytes inside the 128-byte swizzle atom
-            tc_mma_bf16(d_tmem, umma_desc(a0 + off), umma_desc(b0 + off), kIdescBf16, (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) tc_mma_bf16_pair(d_tmem, umma_desc(a0 + off), umma_desc(b0 + off), kIdescBf16Pair, (kb | k) != 0 ? 1u : 0u);
+            else tc_mma_bf16(d_tmem, umma_desc(a0 + off), umma_desc(b0 + off), kIdescBf16, (kb | k) != 0 ? 1u : 0u);
           }
-          // frees the smem stage once the MMAs above retire (CL == 2: in both CTAs -- the peer multicasts into it)
-          if (CL == 2) tc_commit_mc(&S.empty_bar[stage], (uint16_t)0x3);
+          // frees the smem stage once the MMAs above retire, in both CTAs when they share the stage's data
+          if (PAIR) tc_commit_pair_mc(&S.empty_bar[stage], (uint16_t)0x3);
+          else if (CL == 2) tc_commit_mc(&S.empty_bar[stage], (uint16_t)0x3);
           else tc_commit(&S.empty_bar[stage]);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&S.tmem_full[buf]);
+        if (PAIR) tc_commit_pair_mc(&S.tmem_full[buf], (uint16_t)0x3);   // both CTAs' epilogues drain their half
+        else tc_commit(&S.tmem_full[buf]);
       }
     }
   } else {
@@ -345,7 +402,10 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&S.tmem_empty[buf]);   // accumulator buffer drained: the next MMA may start
+      if (lane == 0) {   // accumulator buffer drained: the next MMA may start
+        if (PAIR) mbar_arrive_cluster(leader_addr(&S.tmem_empty[buf]));
+        else mbar_arrive(&S.tmem_empty[buf]);
+      }
       // ---- phase B: survivors -> pair list, ONE warp-aggregated append per tile; everything else is None
       int cnt = 0;
 #pragma unroll
@@ -384,10 +444,11 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();   // no CTA leaves while its peer may still multicast into / arrive on its smem
+  if (CL >= 2) cluster_sync_all();   // no CTA leaves while its peer may still multicast into / arrive on its smem
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -656,8 +717,9 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
   size_t smem = sizeof(TcSmem) + 1024;
   const bool cosine = p.visual_kind == 1;
   cudaError_t e = cudaSuccess;
-  const void* fn = cluster ? (cosine ? (const void*)vis_screen_kernel<2, true> : (const void*)vis_screen_kernel<2, false>)
-                           : (cosine ? (const void*)vis_screen_kernel<1, true> : (const void*)vis_screen_kernel<1, false>);
+  const void* fn = tc.pair ? (cosine ? (const void*)vis_screen_kernel<3, true> : (const void*)vis_screen_kernel<3, false>)
+                   : cluster ? (cosine ? (const void*)vis_screen_kernel<2, true> : (const void*)vis_screen_kernel<2, false>)
+                             : (cosine ? (const void*)vis_screen_kernel<1, true> : (const void*)vis_screen_kernel<1, false>);
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int max_rows = max_n * p.max_obs;

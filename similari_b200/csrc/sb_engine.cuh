@@ -141,7 +141,8 @@ void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int 
 // visual cost: fp32 SIMT kernel in the reference's summation order (use_tc == false) or the tcgen05 3xTF32 kernel
 struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense exact kernel is used)
   bool use_tc;
-  bool cluster2;   // tiles describe candidate-tile PAIRS processed by 2-CTA clusters with multicast B loads
+  bool cluster2;   // tiles describe candidate-tile PAIRS processed by 2-CTA clusters (multicast B loads, or pair MMAs)
+  bool pair;       // with cluster2: cta_group::2 MMAs (256 x 256 x 16 across the CTA pair)
   const TcTile* d_tiles;
   int n_tiles;
   long long a_rows, b_rows;

@@ -93,6 +93,21 @@ def test_visual_trackers_tensor_core_path_match_oracle(eng, oracle, kind, vis, m
                     visual_min_votes=2, visual_minimal_track_length=1, min_confidence=0.1))
 
 
+@pytest.mark.parametrize("mode", ["single", "multicast", "pair"])
+@pytest.mark.parametrize("vis", [0, 1])
+def test_screen_kernel_cta_organisations_match_oracle(eng, oracle, mode, vis, monkeypatch):
+    """The three CTA organisations of the screen kernel (one CTA per tile, 2-CTA cluster with multicast B loads,
+    cta_group::2 pair MMAs -- the default) against the oracle; 300 candidates per scene exercise the ragged second
+    candidate tile of a pair (rows 256..299 valid, the rest masked) and D = 96 the zero-filled K tail."""
+    monkeypatch.setenv("SB200_VIS_KERNEL", "tc")
+    monkeypatch.setenv("SB200_SCREEN", mode)
+    cfg = small("cfg5", n_scenes=3, n_objects=300, oriented=False, canvas=(2200.0, 1400.0), feature_dim=96)
+    run_frames(eng, oracle, cfg, 5,
+               dict(kind=3, positional_kind=1, iou_threshold=0.3, max_idle_epochs=3, visual_kind=vis,
+                    visual_threshold=0.7 if vis == 0 else 0.2, feature_dim=96, visual_max_observations=3,
+                    visual_min_votes=2, visual_minimal_track_length=1, min_confidence=0.1))
+
+
 @pytest.mark.parametrize("kind,chunks", [(1, 3), (3, 2), (2, 4), (0, 5)])
 def test_chunked_requests_match_oracle(eng, oracle, kind, chunks, monkeypatch):
     """The host-pointer path splits a request into scene chunks (H2D of chunk c+1 overlaps the kernels of chunk c);
