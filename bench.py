@@ -59,6 +59,8 @@ def config_dict(name, cfg, extra=None):
         "oriented_boxes": cfg.oriented,
         "l2": "per-step inputs exceed L2 (features %.0f MB/step)" % (cfg.n_scenes * cfg.n_objects * max(cfg.feature_dim, 6) * 4 / 1e6),
         "parallelism": "scene-sharded, one process per GPU",
+        "units": "pair-associations = sum over scenes of M detections x N stored tracks that can still match "
+                 "(expired tracks awaiting collection are not counted)",
     }
     if extra:
         d.update(extra)
@@ -118,13 +120,20 @@ def cpu_port_run(name, frames, warm, steps, threads):
     import oracle as orc
     from similari_b200.workload import tracker_options_for
 
-    t = orc.Tracker(tracker_options_for(name, orc.make_options), threads=threads)
+    opts = tracker_options_for(name, orc.make_options)
+    t = orc.Tracker(opts, threads=threads)
     units, secs = 0, 0.0
-    prev_n = None
+
+    def live_tracks(scene):
+        # N of the metric = stored tracks that can still match (the reference keeps expired tracks in its store until
+        # its next auto-waste tick and rejects them pair by pair in `compatible`; they are not counted as work)
+        stored = len(t.scene_tracks(scene, cap=1 << 14)["ids"])
+        idle = t.idle_tracks(scene, cap=1 << 14)["epochs"].astype(np.int64)
+        return stored - int((idle + int(opts.max_idle_epochs) < int(t.current_epoch(scene))).sum())
+
     for i, f in enumerate(frames[: warm + steps]):
         m = np.diff(f["det_offsets"]).astype(np.int64)
-        n_before = np.array([len(t.scene_tracks(int(s), cap=1 << 12)["ids"]) for s in f["scene_ids"]], dtype=np.int64) \
-            if i >= warm else None
+        n_before = np.array([live_tracks(int(s)) for s in f["scene_ids"]], dtype=np.int64) if i >= warm else None
         t0 = time.perf_counter()
         t.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"], want_boxes=False)
         dt = time.perf_counter() - t0
@@ -198,7 +207,7 @@ def main():
 
     def new_tracker():
         t = eng.Tracker(tracker_options_for(name, default_options, device=local, max_scenes_hint=cfg.n_scenes,
-                                            max_tracks_per_scene_hint=2 * cfg.n_objects + 64,
+                                            max_tracks_per_scene_hint=3 * cfg.n_objects,
                                             max_dets_per_scene_hint=cfg.n_objects))
         t.set_stream(torch.cuda.current_stream().cuda_stream)
         return t
@@ -284,7 +293,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for i in range(W, W + K):
-        n_before = t_dev.scene_track_counts(frames[i]["scene_ids"]).astype(np.int64)   # host-side mirror, no GPU work
+        n_before = t_dev.scene_live_counts(frames[i]["scene_ids"])[0].astype(np.int64)   # host-side mirror, no GPU work
         units_per_step.append(int((np.diff(frames[i]["det_offsets"]).astype(np.int64) * n_before).sum()))
         step_dev(i)
         for k_, v_ in t_dev.last_stage_ms().items():

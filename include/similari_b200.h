@@ -152,8 +152,14 @@ int sb200_predict_batch_device(sb200_tracker* t, int32_t n_scenes, const uint64_
 int sb200_skip_epochs(sb200_tracker* t, uint64_t scene_id, int32_t n);
 int64_t sb200_current_epoch(sb200_tracker* t, uint64_t scene_id);
 int64_t sb200_active_tracks(sb200_tracker* t);                 /* sum(active_shard_stats()) */
-/* stored tracks per scene (0 for unknown scenes): the N of the next frame's N x M cost matrix */
+/* stored tracks per scene (0 for unknown scenes) as the reference's store would count them: the N of the next frame's
+ * N x M cost matrix, expired tracks that the reference has not collected yet included */
 int sb200_scene_track_counts(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids, int32_t* out);
+/* what the device actually holds and scans per scene: `live` = tracks that can still match (expired tracks leave the
+ * device store at the end of the frame in which they expire and wait, hidden, for the reference's collection point:
+ * auto-waste tick, wasted(), skip_epochs), `blocks` = feature blocks of the scene's arena (rows scanned by the visual
+ * cost kernel = blocks * visual_max_observations).  Either output may be NULL. */
+int sb200_scene_live_counts(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids, int32_t* live, int32_t* blocks);
 int sb200_set_auto_waste(sb200_tracker* t, int32_t periodicity);
 int sb200_clear_wasted(sb200_tracker* t);
 /* wasted(): drains up to `cap` wasted tracks; returns the count (>= 0) or a negative status. */

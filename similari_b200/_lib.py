@@ -77,7 +77,7 @@ _lib = None
 EXPORTS = [
     "sb200_options_default", "sb200_last_error", "sb200_device_count", "sb200_tracker_create", "sb200_tracker_destroy",
     "sb200_tracker_set_stream", "sb200_predict_batch", "sb200_prefetch_inputs", "sb200_predict_batch_device", "sb200_skip_epochs",
-    "sb200_current_epoch", "sb200_active_tracks", "sb200_scene_track_counts", "sb200_set_auto_waste", "sb200_clear_wasted", "sb200_wasted",
+    "sb200_current_epoch", "sb200_active_tracks", "sb200_scene_track_counts", "sb200_scene_live_counts", "sb200_set_auto_waste", "sb200_clear_wasted", "sb200_wasted",
     "sb200_idle_tracks", "sb200_scene_tracks", "sb200_last_costs", "sb200_last_stage_ms", "sb200_last_kernel_ms", "sb200_sort_cost_matrix",
     "sb200_visual_cost_matrix", "sb200_sort_voting", "sb200_visual_voting", "sb200_kalman_initiate",
     "sb200_kalman_predict", "sb200_kalman_update", "sb200_nms", "sb200_host_alloc", "sb200_host_free",
@@ -109,6 +109,7 @@ def lib():
         "sb200_current_epoch": (i64, [vp, u64]),
         "sb200_active_tracks": (i64, [vp]),
         "sb200_scene_track_counts": (C.c_int, [vp, i32, vp, vp]),
+        "sb200_scene_live_counts": (C.c_int, [vp, i32, vp, vp, vp]),
         "sb200_set_auto_waste": (C.c_int, [vp, i32]),
         "sb200_clear_wasted": (C.c_int, [vp]),
         "sb200_wasted": (i64, [vp, i64, vp, vp, vp, vp, vp, vp]),

@@ -160,12 +160,21 @@ struct sb200_tracker {
   bool tc_timed = false;
   cudaEvent_t ev_copy[8]{};
   cudaStream_t copy_stream = nullptr;
+  // side stream of the positional stage (visual trackers): the culled scan runs next to the refinement of the visual
+  // survivors instead of in front of the screen
+  cudaStream_t pos_stream = nullptr;
+  cudaEvent_t ev_fork[2]{}, ev_join = nullptr, ev_pos[2]{};
   float stage_ms[5]{};
   // scene table
   std::unordered_map<uint64_t, int> slot_of;
   std::vector<uint64_t> scene_of_slot;
   std::vector<uint32_t> epoch;      // host epoch db
-  std::vector<int> n_tracks;        // host mirror
+  std::vector<int> n_tracks;        // host mirror: live tracks per slot (expired tracks leave the device store every frame)
+  std::vector<int> n_hidden;        // expired tracks per slot swept early and not yet collected in the reference's sense
+  std::vector<int> arena_top;       // host mirror: feature blocks handed out per slot (rows the screen scans = top * K)
+  std::vector<uint64_t> last_req_scenes;   // scene ids of the previous request and their slots (steady-state fast path)
+  std::vector<int> last_req_slots;
+  int64_t revealed = 0;             // wasted-buffer records [0, revealed) are collected; [revealed, wasted_count) hidden
   int scene_cap = 0, track_cap = 0;
   uint64_t id_counter = 0;
   int auto_waste_counter = 100, auto_waste_periodicity = 100;
@@ -173,8 +182,8 @@ struct sb200_tracker {
   // device track store
   sb::TrackStore ts{};
   DBuf b_id, b_epoch, b_length, b_custom, b_vt, b_pred, b_obs, b_radius, b_kst, b_vert, b_feat, b_feat_bf16, b_fnorm2, b_obs_phys,
-      b_obs_hasf, b_obs_q, b_obs_n, b_feat_cnt;
-  DBuf b_ntracks, b_cur_epoch, b_scene_ids;
+      b_obs_hasf, b_obs_q, b_obs_n, b_feat_cnt, b_fblk, b_blk_owner, b_blk_free;
+  DBuf b_ntracks, b_cur_epoch, b_scene_ids, b_nfree, b_atop;
   // wasted
   sb::WastedBuf wb{};
   DBuf w_count, w_id, w_scene, w_epoch, w_length, w_pred, w_obs;
@@ -191,7 +200,7 @@ struct sb200_tracker {
   } stg[2];
   int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
+      f_status, f_featdst, f_frameout, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
   HBuf h_tiles;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
@@ -203,6 +212,7 @@ struct sb200_tracker {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
                    &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_colb, &f_colvalid, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
+                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
                    &f_featdst, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
@@ -219,6 +229,10 @@ struct sb200_tracker {
     for (auto& e : ev_k) if (e) cudaEventDestroy(e);
     for (auto& e : ev_copy) if (e) cudaEventDestroy(e);
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (pos_stream) cudaStreamDestroy(pos_stream);
+    for (auto& e : ev_fork) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_pos) if (e) cudaEventDestroy(e);
+    if (ev_join) cudaEventDestroy(ev_join);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 
@@ -274,19 +288,31 @@ struct sb200_tracker {
       if ((rc = regrow(b_obs_q, &ts.obs_q, K, ns, nt))) return rc;
       if ((rc = regrow(b_obs_n, &ts.obs_n, 1, ns, nt))) return rc;
       if ((rc = regrow(b_feat_cnt, &ts.feat_cnt, 1, ns, nt))) return rc;
+      if ((rc = regrow(b_fblk, &ts.fblk, 1, ns, nt))) return rc;
+      if ((rc = regrow(b_blk_owner, &ts.blk_owner, 1, ns, nt))) return rc;
+      if ((rc = regrow(b_blk_free, &ts.blk_free, 1, ns, nt))) return rc;
     }
     if (ns != scene_cap) {
       // per-slot small arrays
-      DBuf n1, n2, n3;
+      DBuf n1, n2, n3, n4, n5;
       if ((rc = n1.ensure(sizeof(int) * ns))) return rc;
       if ((rc = n2.ensure(sizeof(unsigned int) * ns))) return rc;
       if ((rc = n3.ensure(sizeof(unsigned long long) * ns))) return rc;
+      if ((rc = n4.ensure(sizeof(int) * ns))) return rc;
+      if ((rc = n5.ensure(sizeof(int) * ns))) return rc;
       CU(cudaMemsetAsync(n1.p, 0, sizeof(int) * ns, stream));
-      if (b_ntracks.p && scene_cap > 0)
+      CU(cudaMemsetAsync(n4.p, 0, sizeof(int) * ns, stream));
+      CU(cudaMemsetAsync(n5.p, 0, sizeof(int) * ns, stream));
+      if (b_ntracks.p && scene_cap > 0) {
         CU(cudaMemcpyAsync(n1.p, b_ntracks.p, sizeof(int) * scene_cap, cudaMemcpyDeviceToDevice, stream));
+        CU(cudaMemcpyAsync(n4.p, b_nfree.p, sizeof(int) * scene_cap, cudaMemcpyDeviceToDevice, stream));
+        CU(cudaMemcpyAsync(n5.p, b_atop.p, sizeof(int) * scene_cap, cudaMemcpyDeviceToDevice, stream));
+      }
       CU(cudaStreamSynchronize(stream));
-      b_ntracks.release(); b_cur_epoch.release(); b_scene_ids.release();
-      b_ntracks = n1; b_cur_epoch = n2; b_scene_ids = n3;
+      b_ntracks.release(); b_cur_epoch.release(); b_scene_ids.release(); b_nfree.release(); b_atop.release();
+      b_ntracks = n1; b_cur_epoch = n2; b_scene_ids = n3; b_nfree = n4; b_atop = n5;
+      ts.n_free = b_nfree.as<int>();
+      ts.arena_top = b_atop.as<int>();
     }
     scene_cap = ns;
     track_cap = nt;
@@ -303,6 +329,8 @@ struct sb200_tracker {
     scene_of_slot.push_back(scene_id);
     epoch.push_back(0);
     n_tracks.push_back(0);
+    n_hidden.push_back(0);
+    arena_top.push_back(0);
     return s;
   }
 
@@ -348,7 +376,11 @@ struct sb200_tracker {
     int64_t active = 0;
     int max_n = 0;
     for (int v : n_tracks) { active += v; max_n = std::max(max_n, v); }
-    if (active == 0) return 0;
+    if (active == 0) {
+      revealed = wasted_count;
+      std::fill(n_hidden.begin(), n_hidden.end(), 0);
+      return 0;
+    }
     int rc = ensure_wasted(wasted_count + active);
     if (rc) return rc;
     if ((rc = h_small.ensure((size_t)n_slots * 16))) return rc;
@@ -370,6 +402,38 @@ struct sb200_tracker {
     CU(cudaStreamSynchronize(stream));
     for (int s = 0; s < n_slots; ++s) n_tracks[s] = hn[s];
     wasted_count = hc;
+    // this is one of the reference's collection points: everything swept early becomes visible now
+    revealed = wasted_count;
+    std::fill(n_hidden.begin(), n_hidden.end(), 0);
+    return 0;
+  }
+
+  // removes the first n records of the wasted buffer (the rest, hidden ones included, shift to the front)
+  int drop_wasted_front(int64_t n) {
+    if (n <= 0 || !w_count.p) return 0;
+    n = std::min(n, wasted_count);
+    const int64_t rest = wasted_count - n;
+    cudaStream_t st = stream;
+    int rc = 0;
+    if (rest > 0) {
+      DBuf tmp;   // overlapping device-to-device moves are done through a temporary
+      if ((rc = tmp.ensure((size_t)rest * 24))) return rc;
+      auto shift = [&](void* base, size_t el) -> int {
+        CU(cudaMemcpyAsync(tmp.p, (char*)base + n * el, rest * el, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(base, tmp.p, rest * el, cudaMemcpyDeviceToDevice, st));
+        return 0;
+      };
+      if ((rc = shift(wb.id, 8)) || (rc = shift(wb.scene, 8)) || (rc = shift(wb.epoch, 4)) || (rc = shift(wb.length, 4)) ||
+          (rc = shift(wb.pred, 24)) || (rc = shift(wb.obs, 24)))
+        return rc;
+      CU(cudaStreamSynchronize(st));
+      tmp.release();
+    }
+    int newc = (int)rest;
+    CU(cudaMemcpyAsync(w_count.p, &newc, sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    wasted_count = rest;
+    revealed = std::max<int64_t>(0, revealed - n);
     return 0;
   }
 
@@ -405,39 +469,35 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
 
   // scene slots, epochs (EpochDb::next_epoch, src/trackers/epoch_db.rs:35-49)
   std::vector<sb::SceneDesc> sd(n_scenes);
-  {
+  // same scene list as the previous request (the steady state of a batch tracker): validated slots are reused
+  const bool same_req = (int)last_req_scenes.size() == n_scenes &&
+                        memcmp(last_req_scenes.data(), scene_ids, sizeof(uint64_t) * (size_t)n_scenes) == 0;
+  if (!same_req) {
     std::unordered_map<uint64_t, int> seen;
     for (int s = 0; s < n_scenes; ++s)
       if (!seen.emplace(scene_ids[s], s).second) return fail(SB200_ERR_INVALID, "scene %llu appears twice in one request", (unsigned long long)scene_ids[s]);
+    last_req_slots.resize(n_scenes);
+    for (int s = 0; s < n_scenes; ++s) last_req_slots[s] = slot_for(scene_ids[s], true);
+    last_req_scenes.assign(scene_ids, scene_ids + n_scenes);
   }
-  int max_m = 0, max_n = 0, need_tracks = 0;
+  int max_m = 0, max_n = 0, max_nb = 0, need_tracks = 0;
+  long long live_total = 0;
   long long pos_total = 0, vis_total = 0, col_total = 0, posl_total = 0, visl_total = 0;
-  {
-    // The on-chip assignment solver keeps O(m + n) state per scene.  If a store has grown past that (expired tracks
-    // wait up to 100 predicts for the reference's auto-waste tick), collect the expired tracks now instead of failing.
-    int mm = 0, nn = 0;
-    for (int s = 0; s < n_scenes; ++s) {
-      int slot = slot_for(scene_ids[s], false);
-      mm = std::max(mm, det_offsets[s + 1] - det_offsets[s]);
-      if (slot >= 0) nn = std::max(nn, n_tracks[slot]);
-    }
-    if (sb::voting_smem_need(mm, nn) > sb::kVotingSmemLimit) {
-      int rcw = run_waste();
-      if (rcw) return rcw;
-    }
-  }
   for (int s = 0; s < n_scenes; ++s) {
-    int slot = slot_for(scene_ids[s], true);
+    const int slot = last_req_slots[s];
     sb::SceneDesc& d = sd[s];
     d.slot = slot;
     d.m = det_offsets[s + 1] - det_offsets[s];
     d.n = n_tracks[slot];
+    d.nb = P.is_visual ? arena_top[slot] : 0;
+    d.pad0 = 0;
+    live_total += d.n;
     d.det_base = det_offsets[s];
     d.pos_off = pos_total;
     d.vis_off = vis_total;
     d.scene_id = scene_ids[s];
     d.col_off = (int)col_total;   // multiple of 128: the screen kernel bulk-copies 16-byte aligned slabs of column metadata
-    col_total += ((long long)d.n * P.max_obs + 127) / 128 * 128;
+    col_total += ((long long)d.nb * P.max_obs + 127) / 128 * 128;
     d.pos_lbase = (int)posl_total;
     d.pos_lcap = (int)std::min<long long>((long long)d.m * 32, (long long)sb::kVotePosCap * 2);
     posl_total += d.pos_lcap;
@@ -448,6 +508,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     if (P.is_visual) vis_total += (long long)d.m * d.n * P.max_obs;
     max_m = std::max(max_m, d.m);
     max_n = std::max(max_n, d.n);
+    max_nb = std::max(max_nb, d.nb);
     need_tracks = std::max(need_tracks, d.n + d.m);
   }
   {
@@ -455,6 +516,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     int hint_s = std::max((int)scene_of_slot.size(), opts.max_scenes_hint);
     int rc = ensure_store(hint_s, hint_t);
     if (rc) return rc;
+    // room for every live track of the request in the wasted buffer: the end-of-frame sweep appends without a host check
+    if ((rc = ensure_wasted(wasted_count + live_total + 1))) return rc;
   }
   for (int s = 0; s < n_scenes; ++s) {
     epoch[sd[s].slot] += 1;
@@ -488,7 +551,6 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   sb::TcArgs tc;
   memset(&tc, 0, sizeof(tc));
   tc.num_sms = num_sms;
-  std::vector<sb::TcTile> tiles;
   std::vector<int> tile_first;
   // scene chunks: with host buffers the H2D copy of chunk c+1 overlaps the kernels of chunk c (scenes are independent)
   int n_chunks = 1;
@@ -518,15 +580,14 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
         tc.pair = tc.cluster2 && !(e && !strcmp(e, "multicast"));
       }
       const int mstep = tc.cluster2 ? 256 : 128;   // a cluster covers two 128-row candidate tiles
+      // tile counts now (buffer sizes, launch geometry); the list itself is written after the first kernels of the frame
+      // have been launched, so building it overlaps prep + positional cost instead of delaying them
       tile_first.assign(n_scenes + 1, 0);
       for (int s = 0; s < n_scenes; ++s) {
-        const int rows = sd[s].n * P.max_obs;
-        tile_first[s] = (int)tiles.size();
-        for (int m0 = 0; m0 < sd[s].m; m0 += mstep)
-          for (int c0 = 0; c0 < rows; c0 += 256) tiles.push_back(sb::TcTile{s - chunk_of_scene_first(s), m0, c0, 0});
+        const int rows = sd[s].nb * P.max_obs;   // physical feature rows of the scene's arena (free blocks included)
+        tile_first[s + 1] = tile_first[s] + ((sd[s].m + mstep - 1) / mstep) * ((rows + 255) / 256);
       }
-      tile_first[n_scenes] = (int)tiles.size();
-      tc.n_tiles = (int)tiles.size();
+      tc.n_tiles = tile_first[n_scenes];
       if ((rc = f_cbf16.ensure(T * P.d8 * 2)) || (rc = f_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
           (rc = h_tiles.ensure(sizeof(sb::TcTile) * std::max(1, tc.n_tiles))) ||
           (rc = f_colmeta.ensure(sizeof(sb::VisColMeta) * (size_t)(std::max(col_total, hint_cols) + 256))) ||
@@ -541,12 +602,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       tc.colvalid = f_colvalid.as<unsigned int>();
       tc.rowmeta = f_rowmeta.as<sb::VisRowMeta>();
       tc.total_cols = (int)col_total;
-      if (tc.n_tiles > 0) {
-        memcpy(h_tiles.p, tiles.data(), sizeof(sb::TcTile) * tc.n_tiles);
-        // pulled by a kernel, not by the H2D copy engine: that engine may be busy for milliseconds with the prefetch of
-        // the next frame (sb200_prefetch_inputs), and a DMA queued behind it would stall this frame's kernels
-        sb::launch_pull(f_tiles.p, h_tiles.dp, sizeof(sb::TcTile) * tc.n_tiles, stream);
-      }
+      tc.max_rows = max_nb * P.max_obs;
       tc.d_tiles = f_tiles.as<sb::TcTile>();
       tc.a_rows = total;
       tc.b_rows = (long long)scene_cap * track_cap * P.max_obs;
@@ -616,10 +672,12 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.winner = f_winner.as<int>(); f.c_vt = f_cvt.as<unsigned char>(); f.pos = f_pos.as<float>(); f.vis = f_vis.as<float>();
   f.scenes = f_scenes.as<sb::SceneDesc>(); f.new_count = f_newcount.as<int>(); f.status = f_status.as<int>();
   f.feat_dst = P.is_visual ? f_featdst.as<int>() : nullptr;
+  if ((rc = f_frameout.ensure(sizeof(int) * 3 * (size_t)n_scenes))) return rc;
+  f.frame_out = f_frameout.as<int>();
   f.c_bf16 = tc.use_tc ? f_cbf16.p : nullptr; f.scene_max = f_scene_max.as<unsigned int>();
   // sparse entry lists + per-scene counters (pos_cnt | vis_cnt | scene_mode), zeroed every frame
   if ((rc = f_poslist.ensure(sizeof(sb::PosEntry) * (size_t)std::max<long long>(1, std::max(posl_total, hint_dets * 32)))) ||
-      (rc = f_counters.ensure(sizeof(int) * 3 * (size_t)n_scenes)))
+      (rc = f_counters.ensure(sizeof(int) * 4 * (size_t)n_scenes)))
     return rc;
   if (P.is_visual && ((rc = f_pairs.ensure(sizeof(sb::VisPair) * (size_t)std::max<long long>(1, std::max(visl_total, hint_dets * 64)))) ||
                       (rc = f_visval.ensure(sizeof(float) * (size_t)std::max<long long>(1, std::max(visl_total, hint_dets * 64))))))
@@ -628,9 +686,10 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.pos_cnt = f_counters.as<int>();
   f.vis_cnt = f.pos_cnt + n_scenes;
   f.scene_mode = f.pos_cnt + 2 * n_scenes;
+  f.vis_mode = f.pos_cnt + 3 * n_scenes;
   f.vis_pairs = f_pairs.as<sb::VisPair>();
   f.vis_val = f_visval.as<float>();
-  CU(cudaMemsetAsync(f_counters.p, 0, sizeof(int) * 3 * (size_t)n_scenes, stream));
+  CU(cudaMemsetAsync(f_counters.p, 0, sizeof(int) * 4 * (size_t)n_scenes, stream));
   // outputs
   sb200_predict_out o{};
   if (out) o = *out;
@@ -653,6 +712,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
 
   const double ms_setup = since(t_begin);
   bool tc_timed_now = false;
+  bool pos_forked = false;
   if (!device_io && !copy_stream) CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
   for (int c = 0; c < n_chunks; ++c) {
     const int s0 = chunk_s0[c], s1 = chunk_s0[c + 1];
@@ -675,9 +735,11 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     fc.scenes = f.scenes + s0;
     fc.new_count = f.new_count + s0;
     fc.status = f.status + s0;
+    fc.frame_out = f.frame_out + 3 * s0;
     fc.pos_cnt = f.pos_cnt + s0;
     fc.vis_cnt = f.vis_cnt + s0;
     fc.scene_mode = f.scene_mode + s0;
+    fc.vis_mode = f.vis_mode + s0;
     fc.scene_max = f.scene_max ? f.scene_max + s0 : nullptr;
     fc.pos_fill_off = sd[s0].pos_off;
     fc.pos_total = (s1 < n_scenes ? sd[s1].pos_off : pos_used) - sd[s0].pos_off;
@@ -690,14 +752,73 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       tcc.n_tiles = tile_first[s1] - tile_first[s0];
       if (timed && tcc.n_tiles > 0) { tcc.ev_screen0 = ev_k[0]; tcc.ev_screen1 = ev_k[1]; tcc.ev_refine1 = ev_k[2]; tc_timed_now = true; }
     }
+    // Visual trackers on the tensor-core path fork the positional stage onto a side stream: the dense None fill runs
+    // next to the candidate norms / screen, the culled scan (latency bound, shared memory) next to the refinement of the
+    // survivors (HBM bound).  Both join in front of the final scene mode.  SB200_NO_FORK=1 keeps everything in order.
+    static const bool no_fork = getenv("SB200_NO_FORK") != nullptr;
+    const bool fork = P.is_visual && tc.use_tc && tcc.n_tiles > 0 && !no_fork;
+    if (fork && !pos_stream) {
+      CU(cudaStreamCreateWithFlags(&pos_stream, cudaStreamNonBlocking));
+      for (auto& e : ev_fork) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      for (auto& e : ev_pos) CU(cudaEventCreate(&e));
+    }
     if (timed) CU(cudaEventRecord(ev[0], stream));
     sb::launch_prep(P, fc, s1 - s0, cm, stream);
     if (timed) CU(cudaEventRecord(ev[1], stream));
-    sb::launch_pos_cost(P, ts, fc, s1 - s0, cm, cn, stream);
-    if (timed) CU(cudaEventRecord(ev[2], stream));
-    {
+    auto fill_tiles = [&]() -> int {
+      if (!(c == 0 && tc.use_tc && tc.n_tiles > 0)) return 0;
+      // tile list of the whole request, straight into mapped pinned memory, while the kernels above run.  It is pulled
+      // by a kernel, not by the H2D copy engine: that engine may be busy for milliseconds with the prefetch of the next
+      // frame (sb200_prefetch_inputs), and a DMA queued behind it would stall this frame's kernels.
+      const int mstep = tc.cluster2 ? 256 : 128;
+      sb::TcTile* ht = h_tiles.as<sb::TcTile>();
+      int k = 0;
+      for (int s = 0; s < n_scenes; ++s) {
+        const int rows = sd[s].nb * P.max_obs;
+        const int sc_local = s - chunk_of_scene_first(s);
+        for (int m0 = 0; m0 < sd[s].m; m0 += mstep)
+          for (int c0 = 0; c0 < rows; c0 += 256) ht[k++] = sb::TcTile{sc_local, m0, c0, 0};
+      }
+      sb::launch_pull(f_tiles.p, h_tiles.dp, sizeof(sb::TcTile) * tc.n_tiles, stream);
+      return 0;
+    };
+    if (!fork) {
+      sb::launch_pos_cost(P, ts, fc, s1 - s0, cm, cn, stream);
+      if (timed) CU(cudaEventRecord(ev[2], stream));
+      if ((rc = fill_tiles())) return rc;
       int vr0 = sb::launch_vis_cost(P, ts, fc, s1 - s0, cm, cn, tcc, stream);
       if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
+    } else {
+      CU(cudaEventRecord(ev_fork[0], stream));                  // candidate boxes ready (prep), counters zeroed
+      CU(cudaStreamWaitEvent(pos_stream, ev_fork[0], 0));
+      sb::launch_pos_fill(P, fc, s1 - s0, cm, cn, pos_stream);
+      if (timed) CU(cudaEventRecord(ev[2], stream));
+      if ((rc = fill_tiles())) return rc;
+      // first half of the visual stage up to the screen; the refinement is launched after the fork point
+      sb::TcArgs tca = tcc;
+      cudaEvent_t ev_refine_end = tca.ev_refine1;
+      tca.ev_refine1 = nullptr;
+      {
+        // screen (phase 0) + vis_mode, then the fork event, then refine (phase 1)
+        sb::launch_scene_max(P, fc, s1 - s0, /*init_only=*/true, stream);
+        int vr0 = sb::launch_vis_cost_tc(P, ts, fc, s1 - s0, cn, tca, /*phase=*/0, stream);
+        if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
+        sb::launch_vis_mode(P, fc, s1 - s0, true, stream);
+        CU(cudaEventRecord(ev_fork[1], stream));                // the screen has drained: SMs are free for the scan
+        CU(cudaStreamWaitEvent(pos_stream, ev_fork[1], 0));
+        if (timed) CU(cudaEventRecord(ev_pos[0], pos_stream));
+        sb::launch_pos_scan(P, ts, fc, s1 - s0, cm, cn, pos_stream);
+        if (timed) CU(cudaEventRecord(ev_pos[1], pos_stream));
+        CU(cudaEventRecord(ev_join, pos_stream));
+        tca.ev_refine1 = ev_refine_end;
+        vr0 = sb::launch_vis_cost_tc(P, ts, fc, s1 - s0, cn, tca, /*phase=*/1, stream);
+        if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
+      }
+      CU(cudaStreamWaitEvent(stream, ev_join, 0));
+      int vr1 = sb::launch_vis_cost_b(P, ts, fc, s1 - s0, cm, cn, tcc, stream);
+      if (vr1 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr1);
+      if (timed) pos_forked = true;
     }
     if (timed) CU(cudaEventRecord(ev[3], stream));
     int vr = sb::launch_voting(P, ts, fc, s1 - s0, cm, cn, stream);
@@ -705,6 +826,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     if (vr != 0) return fail(SB200_ERR_CUDA, "voting launch failed: %s", cudaGetErrorString((cudaError_t)vr));
     if (timed) CU(cudaEventRecord(ev[4], stream));
     sb::launch_apply(P, ts, fc, s1 - s0, cm, id_counter, b_ntracks.as<int>(), stream);
+    sb::launch_frame_sweep(P, ts, fc, s1 - s0, b_ntracks.as<int>(), wb, stream);
     if (timed) CU(cudaEventRecord(ev[5], stream));
   }
   CU(cudaGetLastError());
@@ -718,10 +840,10 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     if (o.predicted_boxes) CU(cudaMemcpyAsync(o.predicted_boxes, f.o_pred, (size_t)total * 24, cudaMemcpyDeviceToHost, stream));
     if (o.observed_boxes) CU(cudaMemcpyAsync(o.observed_boxes, f.o_obs, (size_t)total * 24, cudaMemcpyDeviceToHost, stream));
   }
-  if ((rc = h_small.ensure((size_t)n_scenes * 8 + 64))) return rc;
-  int* h_new = h_small.as<int>();
-  int* h_status = h_new + n_scenes;
-  CU(cudaMemcpyAsync(h_new, f.new_count, 4 * (size_t)n_scenes, cudaMemcpyDeviceToHost, stream));
+  if ((rc = h_small.ensure((size_t)n_scenes * 16 + 64))) return rc;
+  int* h_fo = h_small.as<int>();            // [n_scenes][3] live tracks, arena blocks, newly expired
+  int* h_status = h_fo + 3 * n_scenes;
+  CU(cudaMemcpyAsync(h_fo, f.frame_out, 12 * (size_t)n_scenes, cudaMemcpyDeviceToHost, stream));
   CU(cudaMemcpyAsync(h_status, f.status, 4 * (size_t)n_scenes, cudaMemcpyDeviceToHost, stream));
   const double ms_launch = since(t_begin);
   CU(cudaStreamSynchronize(stream));
@@ -734,11 +856,21 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   long long new_total = 0;
   for (int s = 0; s < n_scenes; ++s) {
     if (h_status[s]) return fail(SB200_ERR_INTERNAL, "track store overflow in scene %llu", (unsigned long long)sd[s].scene_id);
-    n_tracks[sd[s].slot] = sd[s].n + h_new[s];
-    new_total += h_new[s];
+    const int live = h_fo[3 * s], expired = h_fo[3 * s + 2];
+    n_tracks[sd[s].slot] = live;
+    arena_top[sd[s].slot] = h_fo[3 * s + 1];
+    n_hidden[sd[s].slot] += expired;   // swept from the device store, not yet collected in the reference's sense
+    wasted_count += expired;
+    new_total += live + expired - sd[s].n;
   }
   id_counter += P.is_batch ? (uint64_t)total : (uint64_t)new_total;
   for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);   // stages of the first chunk
+  if (pos_forked) {
+    // forked frame: [1] = the culled scan on the side stream (it overlaps the visual stage), [2] = prep end -> visual end
+    float fill_ms = stage_ms[1];
+    cudaEventElapsedTime(&stage_ms[1], ev_pos[0], ev_pos[1]);
+    stage_ms[2] += fill_ms;
+  }
   tc_timed = tc_timed_now;
   kernel_ms[0] = kernel_ms[1] = 0.0f;
   if (tc_timed) { cudaEventElapsedTime(&kernel_ms[0], ev_k[0], ev_k[1]); cudaEventElapsedTime(&kernel_ms[1], ev_k[1], ev_k[2]); }
@@ -900,8 +1032,9 @@ int64_t sb200_current_epoch(sb200_tracker* t, uint64_t scene_id) {
 
 int64_t sb200_active_tracks(sb200_tracker* t) {
   if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
-  int64_t n = 0;
+  int64_t n = 0;   // the reference's store still holds the expired tracks it has not collected yet
   for (int v : t->n_tracks) n += v;
+  for (int v : t->n_hidden) n += v;
   return n;
 }
 
@@ -909,7 +1042,17 @@ int sb200_scene_track_counts(sb200_tracker* t, int32_t n_scenes, const uint64_t*
   if (!t || n_scenes < 0 || (n_scenes > 0 && (!scene_ids || !out))) return fail(SB200_ERR_INVALID, "bad arguments");
   for (int s = 0; s < n_scenes; ++s) {
     int slot = t->slot_for(scene_ids[s], false);
-    out[s] = slot < 0 ? 0 : t->n_tracks[slot];
+    out[s] = slot < 0 ? 0 : t->n_tracks[slot] + t->n_hidden[slot];
+  }
+  return 0;
+}
+
+int sb200_scene_live_counts(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids, int32_t* live, int32_t* blocks) {
+  if (!t || n_scenes < 0 || (n_scenes > 0 && !scene_ids)) return fail(SB200_ERR_INVALID, "bad arguments");
+  for (int s = 0; s < n_scenes; ++s) {
+    int slot = t->slot_for(scene_ids[s], false);
+    if (live) live[s] = slot < 0 ? 0 : t->n_tracks[slot];
+    if (blocks) blocks[s] = slot < 0 ? 0 : (t->P.is_visual ? t->arena_top[slot] : t->n_tracks[slot]);
   }
   return 0;
 }
@@ -924,10 +1067,9 @@ int sb200_set_auto_waste(sb200_tracker* t, int32_t periodicity) {
 int sb200_clear_wasted(sb200_tracker* t) {
   if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
   CU(cudaSetDevice(t->device));
-  if (t->w_count.p) CU(cudaMemsetAsync(t->w_count.p, 0, sizeof(int), t->stream));
-  CU(cudaStreamSynchronize(t->stream));
-  t->wasted_count = 0;
-  return 0;
+  // TrackerAPI::clear_wasted (src/trackers/tracker_api.rs:94-100) empties the wasted store; tracks swept early that the
+  // reference has not collected yet are not in it and stay pending
+  return t->drop_wasted_front(t->revealed);
 }
 
 int64_t sb200_wasted(sb200_tracker* t, int64_t cap, uint64_t* ids, uint64_t* scene_ids, uint32_t* epochs,
@@ -945,27 +1087,8 @@ int64_t sb200_wasted(sb200_tracker* t, int64_t cap, uint64_t* ids, uint64_t* sce
   if (lengths) CU(cudaMemcpyAsync(lengths, t->wb.length, 4 * n, cudaMemcpyDeviceToHost, st));
   if (predicted_boxes) CU(cudaMemcpyAsync(predicted_boxes, t->wb.pred, 24 * n, cudaMemcpyDeviceToHost, st));
   if (observed_boxes) CU(cudaMemcpyAsync(observed_boxes, t->wb.obs, 24 * n, cudaMemcpyDeviceToHost, st));
-  // drain: shift the remaining records to the front
-  int64_t rest = t->wasted_count - n;
-  if (rest > 0) {
-    // overlapping device-to-device moves are done through a temporary
-    DBuf tmp;
-    if ((rc = tmp.ensure((size_t)rest * 24))) return rc;
-    auto shift = [&](void* base, size_t el) -> int {
-      CU(cudaMemcpyAsync(tmp.p, (char*)base + n * el, rest * el, cudaMemcpyDeviceToDevice, st));
-      CU(cudaMemcpyAsync(base, tmp.p, rest * el, cudaMemcpyDeviceToDevice, st));
-      return 0;
-    };
-    if ((rc = shift(t->wb.id, 8)) || (rc = shift(t->wb.scene, 8)) || (rc = shift(t->wb.epoch, 4)) ||
-        (rc = shift(t->wb.length, 4)) || (rc = shift(t->wb.pred, 24)) || (rc = shift(t->wb.obs, 24)))
-      return rc;
-    CU(cudaStreamSynchronize(st));
-    tmp.release();
-  }
-  int newc = (int)rest;
-  CU(cudaMemcpyAsync(t->w_count.p, &newc, sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));
-  t->wasted_count = rest;
+  if ((rc = t->drop_wasted_front(n))) return rc;   // drain
   return n;
 }
 
@@ -1008,9 +1131,39 @@ static int64_t dump_scene(sb200_tracker* t, uint64_t scene_id, int64_t cap, bool
   return k;
 }
 
+// expired tracks of `scene_id` swept early: the reference's store still holds them (they are idle by definition)
+static int64_t append_hidden(sb200_tracker* t, uint64_t scene_id, int64_t k, int64_t cap, uint64_t* ids, uint32_t* epochs,
+                             uint32_t* lengths, float* pred, float* obs) {
+  const int64_t h0 = t->revealed, hn = t->wasted_count - t->revealed;
+  if (hn <= 0 || k >= cap) return k;
+  std::vector<uint64_t> hid(hn), hsc(hn);
+  std::vector<uint32_t> hep(hn), hle(hn);
+  std::vector<float> hpr((size_t)hn * 6), hob((size_t)hn * 6);
+  cudaStream_t st = t->stream;
+  CU(cudaMemcpyAsync(hid.data(), t->wb.id + h0, 8 * (size_t)hn, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hsc.data(), t->wb.scene + h0, 8 * (size_t)hn, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hep.data(), t->wb.epoch + h0, 4 * (size_t)hn, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hle.data(), t->wb.length + h0, 4 * (size_t)hn, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hpr.data(), t->wb.pred + h0 * 6, 24 * (size_t)hn, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hob.data(), t->wb.obs + h0 * 6, 24 * (size_t)hn, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int64_t j = 0; j < hn && k < cap; ++j) {
+    if (hsc[j] != scene_id) continue;
+    if (ids) ids[k] = hid[j];
+    if (epochs) epochs[k] = hep[j];
+    if (lengths) lengths[k] = hle[j];
+    if (pred) memcpy(pred + k * 6, &hpr[(size_t)j * 6], 24);
+    if (obs) memcpy(obs + k * 6, &hob[(size_t)j * 6], 24);
+    ++k;
+  }
+  return k;
+}
+
 int64_t sb200_idle_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uint64_t* ids, uint32_t* epochs,
                           uint32_t* lengths, float* predicted_boxes, float* observed_boxes) {
-  return dump_scene(t, scene_id, cap, true, ids, epochs, lengths, predicted_boxes, observed_boxes, nullptr, nullptr);
+  int64_t k = dump_scene(t, scene_id, cap, true, ids, epochs, lengths, predicted_boxes, observed_boxes, nullptr, nullptr);
+  if (k < 0) return k;
+  return append_hidden(t, scene_id, k, cap, ids, epochs, lengths, predicted_boxes, observed_boxes);
 }
 
 int64_t sb200_scene_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uint64_t* ids, float* boxes,

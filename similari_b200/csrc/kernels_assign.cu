@@ -859,23 +859,37 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Fra
 }
 
 // per-scene mode: 0 = the voting stage consumes the sparse lists, 1 = dense matrices
+__device__ __forceinline__ int vis_side_mode(const Params& p, const Frame& f, const SceneDesc& sc, int s, int tc_used) {
+  if (sc.m >= 65535 || sc.n >= 65535) return 1;
+  if (p.is_visual) {
+    if (!tc_used) return 1;
+    if (f.vis_cnt[s] > sc.vis_lcap || f.vis_cnt[s] > kVoteVisCap) return 1;
+  }
+  return 0;
+}
 __global__ void scene_mode_kernel(Params p, Frame f, int n_scenes, int tc_used) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_scenes) return;
   const SceneDesc sc = f.scenes[s];
-  int mode = 0;
-  if (sc.m >= 65535 || sc.n >= 65535) mode = 1;
+  int mode = vis_side_mode(p, f, sc, s, tc_used);
   if (f.pos_cnt[s] > sc.pos_lcap || f.pos_cnt[s] > kVotePosCap) mode = 1;
-  if (p.is_visual) {
-    if (!tc_used) mode = 1;
-    else if (f.vis_cnt[s] > sc.vis_lcap || f.vis_cnt[s] > kVoteVisCap) mode = 1;
-  }
   f.scene_mode[s] = mode;
+}
+// the visual half alone: decided right after the screen, so the refinement does not wait for the positional stage
+__global__ void vis_mode_kernel(Params p, Frame f, int n_scenes, int tc_used) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scenes) return;
+  f.vis_mode[s] = vis_side_mode(p, f, f.scenes[s], s, tc_used);
 }
 
 void launch_scene_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st) {
   if (n_scenes == 0) return;
   scene_mode_kernel<<<(n_scenes + 127) / 128, 128, 0, st>>>(p, f, n_scenes, tc_used ? 1 : 0);
+}
+
+void launch_vis_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st) {
+  if (n_scenes == 0 || !f.vis_mode) return;
+  vis_mode_kernel<<<(n_scenes + 127) / 128, 128, 0, st>>>(p, f, n_scenes, tc_used ? 1 : 0);
 }
 
 void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_only, cudaStream_t st) {

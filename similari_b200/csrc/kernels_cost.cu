@@ -279,6 +279,10 @@ __global__ void __launch_bounds__(PS_THREADS) pos_scan_kernel(Params p, TrackSto
   const SceneDesc sc = f.scenes[sidx];
   const int N = sc.n, M = sc.m;
   if (N == 0 || M == 0 || N > PS_MAXN) return;   // N > PS_MAXN: the dense kernel handles this scene
+  // gridDim.y CTAs share a scene (few scenes, many SMs): each sorts the tracks for itself and takes a slice of candidates
+  const int mchunk = (M + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int m_begin = (int)blockIdx.y * mchunk, m_end = min(M, m_begin + mchunk);
+  if (m_begin >= M) return;
   int Np = 1;
   while (Np < N) Np <<= 1;
   float* kx = reinterpret_cast<float*>(ps_smem);           // [Np] sorted x
@@ -332,12 +336,12 @@ __global__ void __launch_bounds__(PS_THREADS) pos_scan_kernel(Params p, TrackSto
   float* out = f.pos + sc.pos_off;
   const bool bad = s_bad != 0;
   int2* queue = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(sep + N) + 7) & ~(uintptr_t)7);   // [PS_QCAP] gated pairs
-  for (int m0 = 0; m0 < M; m0 += PS_THREADS) {
+  for (int m0 = m_begin; m0 < m_end; m0 += PS_THREADS) {
     if (tid == 0) s_qn = 0;
     __syncthreads();
     // ---- phase 1: cheap gates over the candidate's x-window; survivors go to the work queue
     const int m = m0 + tid;
-    if (m < M) {
+    if (m < m_end) {
       const int g = sc.det_base + m;
       const float* cb = f.c_box + (size_t)g * 6;
       const float cx = cb[0], cy = cb[1];
@@ -372,10 +376,20 @@ __global__ void __launch_bounds__(PS_THREADS) pos_scan_kernel(Params p, TrackSto
   }
 }
 
-void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+static bool pos_use_dense(int max_n) { return max_n > PS_MAXN || getenv("SB200_POS_DENSE") != nullptr; }
+
+void launch_pos_fill(const Params& p, const Frame& f, int n_scenes, int max_m, int max_n, cudaStream_t st) {
+  (void)p;
+  if (n_scenes == 0 || max_m == 0 || max_n == 0 || pos_use_dense(max_n)) return;   // the dense kernel writes every element
+  // pos matrices are packed back to back: total elements = last offset + last size (the host passes it via f.pos_total)
+  const long long total = f.pos_total;
+  if (total > 0) pos_fill_none_kernel<<<1184, 256, 0, st>>>(f, total / 4, total);
+}
+
+void launch_pos_scan(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                      cudaStream_t st) {
   if (n_scenes == 0 || max_m == 0 || max_n == 0) return;
-  if (max_n > PS_MAXN || getenv("SB200_POS_DENSE") != nullptr) {
+  if (pos_use_dense(max_n)) {
     // very large scenes: dense tiled kernel
     dim3 grid((max_n + TN - 1) / TN, (max_m + TM - 1) / TM, n_scenes);
     dim3 block(TN, TY);
@@ -383,23 +397,25 @@ void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int 
     else pos_cost_kernel<1><<<grid, block, 0, st>>>(p, ts, f);
     return;
   }
-  long long total = 0;
-  // pos matrices are packed back to back: total elements = last offset + last size (the host passes it via f.pos_total)
-  total = f.pos_total;
-  if (total > 0) {
-    const long long total4 = total / 4;
-    pos_fill_none_kernel<<<1184, 256, 0, st>>>(f, total4, total);
-  }
   int Np = 1;
   while (Np < max_n) Np <<= 1;
   size_t smem = (size_t)Np * 8 + (size_t)max_n * 12 + (size_t)PS_QCAP * 8 + 64;
+  // with fewer scenes than SMs, several CTAs per scene (each at least 64 candidates)
+  int nsplit = std::max(1, std::min(std::min(16, (max_m + 63) / 64), (2 * 148) / std::max(1, n_scenes)));
+  dim3 grid(n_scenes, nsplit);
   if (p.positional_kind == 0) {
     cudaFuncSetAttribute(pos_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pos_scan_kernel<0><<<n_scenes, PS_THREADS, smem, st>>>(p, ts, f);
+    pos_scan_kernel<0><<<grid, PS_THREADS, smem, st>>>(p, ts, f);
   } else {
     cudaFuncSetAttribute(pos_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pos_scan_kernel<1><<<n_scenes, PS_THREADS, smem, st>>>(p, ts, f);
+    pos_scan_kernel<1><<<grid, PS_THREADS, smem, st>>>(p, ts, f);
   }
+}
+
+void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                     cudaStream_t st) {
+  launch_pos_fill(p, f, n_scenes, max_m, max_n, st);
+  launch_pos_scan(p, ts, f, n_scenes, max_m, max_n, st);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -449,8 +465,8 @@ __device__ void vis_cost_tile(const Params& p, const TrackStore& ts, const Frame
       size_t ti = (size_t)sc.slot * ts.track_cap + n;
       if (k < ts.obs_n[ti] && ts.obs_hasf[ti * K + k] && ts.feat_cnt[ti] >= p.min_track_length) {
         int phys = ts.obs_phys[ti * K + k];
-        row = (int)(ti * K + phys);
-        nrm = cosine ? ts.fnorm2[ti * K + phys] : 0.0f;
+        row = (int)(feat_block(ts, sc.slot, ti) * K + phys);
+        nrm = cosine ? ts.fnorm2[row] : 0.0f;
         ok = 1;
       }
     }
@@ -553,13 +569,9 @@ __device__ void vis_cost_tile(const Params& p, const TrackStore& ts, const Frame
   }
 }
 
-int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
-                    const TcArgs& tc, cudaStream_t st) {
-  if (n_scenes == 0) return 0;
-  if (!p.is_visual) {
-    launch_scene_mode(p, f, n_scenes, false, st);
-    return 0;
-  }
+int launch_vis_cost_a(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                      const TcArgs& tc, cudaStream_t st) {
+  if (n_scenes == 0 || !p.is_visual) return 0;
   const bool any = max_m > 0 && max_n > 0 && f.in_feat != nullptr;
   const bool use_tc = tc.use_tc && any;
   launch_scene_max(p, f, n_scenes, /*init_only=*/true, st);
@@ -569,12 +581,26 @@ int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n
     int rc = launch_vis_cost_tc(p, ts, f, n_scenes, max_n, tc, /*phase=*/0, st);
     if (rc != 0) return rc;
   }
-  launch_scene_mode(p, f, n_scenes, use_tc, st);   // which scenes stay sparse, which fall back to the dense kernels
+  launch_vis_mode(p, f, n_scenes, use_tc, st);   // which scenes' survivor lists are complete
   if (use_tc) {
     int rc = launch_vis_cost_tc(p, ts, f, n_scenes, max_n, tc, /*phase=*/1, st);   // exact refinement of the survivors
     if (rc != 0) return rc;
   }
+  return 0;
+}
+
+int launch_vis_cost_b(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                      const TcArgs& tc, cudaStream_t st) {
+  if (n_scenes == 0) return 0;
+  if (!p.is_visual) {
+    launch_scene_mode(p, f, n_scenes, false, st);
+    return 0;
+  }
+  const bool any = max_m > 0 && max_n > 0 && f.in_feat != nullptr;
+  const bool use_tc = tc.use_tc && any;
+  launch_scene_mode(p, f, n_scenes, use_tc, st);   // which scenes stay sparse, which fall back to the dense kernels
   if (max_m > 0 && max_n > 0) {
+    // a scene in dense mode is recomputed whole by the exact kernel (whatever the refinement did for it before)
     const int tx = (max_n * p.max_obs + VN - 1) / VN, ty = (max_m + VM - 1) / VM;
     const long long want = (long long)tx * ty * (use_tc ? 1 : n_scenes);
     const int grid = (int)std::min<long long>(want, 148 * 8);
@@ -582,6 +608,13 @@ int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n
     launch_scene_max(p, f, n_scenes, /*init_only=*/false, st);
   }
   return 0;
+}
+
+int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                    const TcArgs& tc, cudaStream_t st) {
+  int rc = launch_vis_cost_a(p, ts, f, n_scenes, max_m, max_n, tc, st);
+  if (rc != 0) return rc;
+  return launch_vis_cost_b(p, ts, f, n_scenes, max_m, max_n, tc, st);
 }
 
 }  // namespace sb

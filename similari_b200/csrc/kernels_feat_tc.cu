@@ -265,7 +265,7 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
           const int g = it & 3;   // slab set: tile parity picks the group, bit 1 alternates the group's two sets
           mbar_wait(&S.meta_empty[g], ((it >> 2) & 1) ^ 1);
           TcHdr h;
-          h.scene = tl.scene; h.m0 = m0; h.ncols_left = sc.n * K - tl.c0; h.m = sc.m; h.det_base = sc.det_base;
+          h.scene = tl.scene; h.m0 = m0; h.ncols_left = sc.nb * K - tl.c0; h.m = sc.m; h.det_base = sc.det_base;
           h.col0 = sc.col_off + tl.c0; h.epoch = (int)sc.epoch; h.vis_lbase = sc.vis_lbase; h.vis_lcap = sc.vis_lcap; h.pad = 0;
           S.hdr[g] = h;
           mbar_expect_tx(&S.meta_full[g], (uint32_t)(sizeof(VisColMeta) * TC_BN + sizeof(VisRowMeta) * TC_BM +
@@ -495,7 +495,7 @@ template <bool COSINE, bool TAIL>
 __global__ void __launch_bounds__(RF_WARPS * 32) vis_refine_kernel(Params p, TrackStore ts, Frame f) {
   __shared__ float s_bs[RF_WARPS][32][RF_PITCH];
   const int scene = blockIdx.y;
-  if (f.scene_mode[scene] != 0) return;  // this scene is computed densely
+  if (f.vis_mode[scene] != 0) return;  // survivor list overflowed: this scene is computed densely
   const SceneDesc sc = f.scenes[scene];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int warps_total = gridDim.x * RF_WARPS;
@@ -624,53 +624,60 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, int d8, in
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-// per-frame metadata: one thread per physical feature row (scene, track n, physical slot p) and per candidate
+// per-frame metadata: one thread per physical feature row (scene, arena block b, physical slot p) and per candidate.
+// A block without an owner (free list) is an invalid column; otherwise the row belongs to track n = blk_owner[b].
 __global__ void vis_meta_kernel(Params p, TrackStore ts, Frame f, int n_scenes, int max_rows, VisColMeta* colmeta,
                                 VisColGeo* colgeo, float* colb, unsigned int* colvalid) {
   const int s = blockIdx.y;
   const SceneDesc sc = f.scenes[s];
   const int K = p.max_obs;
   const int prow = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in = prow < sc.n * K && prow < max_rows;
+  const bool in = prow < sc.nb * K && prow < max_rows;
   VisColMeta cm;
   cm.colb = 0.0f; cm.colc = 0.0f; cm.outcol = -1; cm.row = -1;
   if (in) {
-    const int n = prow / K, ph = prow - n * K;
-    const size_t ti = (size_t)sc.slot * ts.track_cap + n;
-    const int on = ts.obs_n[ti];
-    // logical <-> physical observation bookkeeping of this track
-    int k_of = -1, live_mask = 0;
-    for (int k = 0; k < K; ++k) {
-      if (k < on && ts.obs_hasf[ti * K + k]) {
-        int pp = ts.obs_phys[ti * K + k];
-        live_mask |= 1 << pp;
-        if (pp == ph) k_of = k;
-      }
-    }
-    const unsigned int tep = ts.epoch[ti];
-    if (k_of >= 0) {
-      const unsigned int delta = sc.epoch > tep ? sc.epoch - tep : tep - sc.epoch;
-      cm.outcol = n * K + k_of;
-      const bool valid = (ts.feat_cnt[ti] >= p.min_track_length) && ((unsigned int)p.max_idle_epochs >= delta);
-      const float nb = ts.fnorm2[ti * K + ph];
-      cm.colb = p.visual_kind == 1 ? sqrtf(nb) : 0.5f * nb * (1.0f - 1e-5f - kScreenRelErr);
-      cm.row = valid ? (int)(ti * K + ph) : -1;
-    } else {
-      // dead physical slot -> owns the dead_rank-th logical column without a feature (written as None)
-      int dead_rank = 0;
-      for (int pp = 0; pp < ph; ++pp) dead_rank += ((live_mask >> pp) & 1) ? 0 : 1;
-      int seen = 0;
+    const int b = prow / K, ph = prow - b * K;
+    const size_t sbase = (size_t)sc.slot * ts.track_cap;
+    const int n = ts.blk_owner ? ts.blk_owner[sbase + b] : b;
+    const size_t ti = sbase + (n >= 0 ? n : 0);
+    const size_t frow = (sbase + b) * K + ph;   // feature row of this column
+    unsigned int tep = 0u;
+    if (n >= 0) {
+      const int on = ts.obs_n[ti];
+      // logical <-> physical observation bookkeeping of this track
+      int k_of = -1, live_mask = 0;
       for (int k = 0; k < K; ++k) {
-        bool lv = k < on && ts.obs_hasf[ti * K + k];
-        if (!lv) { if (seen == dead_rank) { cm.outcol = n * K + k; break; } ++seen; }
+        if (k < on && ts.obs_hasf[ti * K + k]) {
+          int pp = ts.obs_phys[ti * K + k];
+          live_mask |= 1 << pp;
+          if (pp == ph) k_of = k;
+        }
+      }
+      tep = ts.epoch[ti];
+      if (k_of >= 0) {
+        const unsigned int delta = sc.epoch > tep ? sc.epoch - tep : tep - sc.epoch;
+        cm.outcol = n * K + k_of;
+        const bool valid = (ts.feat_cnt[ti] >= p.min_track_length) && ((unsigned int)p.max_idle_epochs >= delta);
+        const float nb = ts.fnorm2[frow];
+        cm.colb = p.visual_kind == 1 ? sqrtf(nb) : 0.5f * nb * (1.0f - 1e-5f - kScreenRelErr);
+        cm.row = valid ? (int)frow : -1;
+      } else {
+        // dead physical slot -> owns the dead_rank-th logical column without a feature (written as None)
+        int dead_rank = 0;
+        for (int pp = 0; pp < ph; ++pp) dead_rank += ((live_mask >> pp) & 1) ? 0 : 1;
+        int seen = 0;
+        for (int k = 0; k < K; ++k) {
+          bool lv = k < on && ts.obs_hasf[ti * K + k];
+          if (!lv) { if (seen == dead_rank) { cm.outcol = n * K + k; break; } ++seen; }
+        }
       }
     }
     colmeta[sc.col_off + prow] = cm;
     colb[sc.col_off + prow] = cm.colb;
     if (p.n_constraints > 0) {
-      const float* tb = ts.pred + ti * 6;
       VisColGeo cg;
-      cg.tx = tb[0]; cg.ty = tb[1]; cg.tr = ts.radius[ti]; cg.tep = tep;
+      cg.tx = 0.0f; cg.ty = 0.0f; cg.tr = 0.0f; cg.tep = tep;
+      if (n >= 0) { const float* tb = ts.pred + ti * 6; cg.tx = tb[0]; cg.ty = tb[1]; cg.tr = ts.radius[ti]; }
       colgeo[sc.col_off + prow] = cg;
     }
   }
@@ -722,7 +729,7 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
                              : (cosine ? (const void*)vis_screen_kernel<1, true> : (const void*)vis_screen_kernel<1, false>);
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const int max_rows = max_n * p.max_obs;
+  const int max_rows = tc.max_rows > 0 ? tc.max_rows : max_n * p.max_obs;
   if (max_rows > 0) {
     dim3 grid((max_rows + 255) / 256, n_scenes);
     vis_meta_kernel<<<grid, 256, 0, st>>>(p, ts, f, n_scenes, max_rows, tc.colmeta, tc.colgeo, tc.colb, tc.colvalid);

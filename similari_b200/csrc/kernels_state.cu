@@ -9,6 +9,8 @@
 // and the lifecycle sweep TrackerAPI::auto_waste (src/trackers/tracker_api.rs:70-88).
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "sb_engine.cuh"
 
 namespace sb {
@@ -44,6 +46,10 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
   }
   if (tid == 0) s_carry = 0;
   __syncthreads();
+  // feature arena of this scene (visual trackers): new tracks take blocks from the free list first, then fresh ones
+  const size_t sbase = (size_t)sc.slot * ts.track_cap;
+  const int nfree0 = ts.fblk ? ts.n_free[sc.slot] : 0;
+  const int top0 = ts.fblk ? ts.arena_top[sc.slot] : 0;
   const int* winner = f.winner + sc.det_base;
   for (int base = 0; base < sc.m; base += AT) {
     const int m = base + tid;
@@ -101,7 +107,14 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
         ts.obs_hasf[idx * K] = flags & 1;
         ts.obs_q[idx * K] = quality;
         ts.feat_cnt[idx] = flags & 1;
-        if (flags & 1) fdst = (int)(idx * K);
+        size_t blk = idx;
+        if (ts.fblk) {
+          const int b = rank < nfree0 ? ts.blk_free[sbase + (nfree0 - 1 - rank)] : top0 + (rank - nfree0);
+          ts.fblk[idx] = b;
+          ts.blk_owner[sbase + b] = j;
+          blk = sbase + b;
+        }
+        if (flags & 1) fdst = (int)(blk * K);
       }
     } else {
       idx = (size_t)sc.slot * ts.track_cap + win;
@@ -160,7 +173,7 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
         }
         ts.obs_n[idx] = (unsigned char)cnt;
         ts.feat_cnt[idx] = (unsigned char)fc;
-        if (keep) fdst = (int)(idx * K + freep);
+        if (keep) fdst = (int)(feat_block(ts, sc.slot, idx) * K + freep);
       }
     }
     ts.epoch[idx] = sc.epoch;
@@ -183,7 +196,14 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
     }
   }
   __syncthreads();
-  if (tid == 0) n_tracks[sc.slot] = min(sc.n + s_carry, ts.track_cap);
+  if (tid == 0) {
+    const int added = min(sc.n + s_carry, ts.track_cap) - sc.n;
+    n_tracks[sc.slot] = sc.n + added;
+    if (ts.fblk) {
+      ts.n_free[sc.slot] = nfree0 - min(nfree0, added);
+      ts.arena_top[sc.slot] = top0 + max(0, added - nfree0);
+    }
+  }
 }
 
 // copies the features that VisualMetric::optimize keeps into the track's free physical slot (warp per detection)
@@ -246,55 +266,68 @@ void launch_apply(const Params& p, const TrackStore& ts, const Frame& f, int n_s
 
 // --------------------------------------------------------------------------------------------------------
 // auto_waste: EpochDb::baked (src/trackers/epoch_db.rs:51-66): last_updated + max_idle < current_epoch => Wasted.
-// One CTA per scene slot; stable compaction keeps the store order.
+// One CTA per scene; a stable compaction keeps the store order.
+//
+// Two callers: the reference's collection points (auto-waste tick, wasted(), skip_epochs: all scene slots, epochs from the
+// host's epoch db) and the end-of-frame sweep (the scenes of the request, `scenes` != null, epoch = the scene's new epoch).
+// Only the small per-track arrays move (about 300 B per track).  Feature rows never do: an expired track's block of the
+// scene's feature arena goes to the free list and is handed to the next new track.
+constexpr int WR = 8;   // elements in flight per thread and round of compact_rows
+
+// Moves row j to row s_dst[j] (<= j; -1: dropped) for j in [first, n).  The flattened (row, column) elements are taken in
+// ascending rounds of AT * WR: a round reads all its elements, synchronises, then writes them.  Destinations never lie
+// above sources, so a round can only overwrite elements it has already read or that an earlier round has moved away.
 template <typename T>
-__device__ __forceinline__ void move_rows(T* arr, size_t base, int width, const int* s_dst, int j0, int jn) {
-  // chunk [j0, jn): read all, sync, write (dst <= src, chunks ascend => no clobbering)
-  for (int c = 0; c < width; ++c) {
-    int j = j0 + threadIdx.x;
-    T v{};
-    int d = -1;
-    if (j < jn) { d = s_dst[j - j0]; if (d >= 0 && d != j) v = arr[(base + j) * width + c]; }
+__device__ __forceinline__ void compact_rows(T* arr, size_t base, int width, const int* s_dst, int first, int n) {
+  T* a = arr + base * width;
+  const int total = n * width;
+  for (int e0 = first * width; e0 < total; e0 += AT * WR) {
+    T v[WR];
+    int de[WR];
+#pragma unroll
+    for (int r = 0; r < WR; ++r) {
+      const int e = e0 + r * AT + (int)threadIdx.x;
+      de[r] = -1;
+      if (e < total) {
+        const int j = e / width, c = e - j * width;
+        const int d = s_dst[j];
+        if (d >= 0 && d != j) { v[r] = a[e]; de[r] = d * width + c; }
+      }
+    }
     __syncthreads();
-    if (d >= 0 && d != j) arr[(base + d) * width + c] = v;
+#pragma unroll
+    for (int r = 0; r < WR; ++r)
+      if (de[r] >= 0) a[de[r]] = v[r];
     __syncthreads();
   }
 }
 
 __global__ void __launch_bounds__(AT) waste_kernel(Params p, TrackStore ts, const unsigned int* cur_epoch,
-                                                   const unsigned long long* scene_ids, int* n_tracks, WastedBuf wb) {
-  __shared__ int s_dst[AT];
+                                                   const unsigned long long* scene_ids, int* n_tracks, WastedBuf wb,
+                                                   const SceneDesc* scenes, int* frame_out) {
+  extern __shared__ int s_dst[];   // [n] destination row of every track (-1: expired)
   __shared__ int s_warp[AT / 32];
-  __shared__ int s_kept, s_wbase, s_wcount;
-  const int slot = blockIdx.x;
+  __shared__ int s_wbase, s_wcount, s_first;
+  const int slot = scenes ? scenes[blockIdx.x].slot : (int)blockIdx.x;
   const int n = n_tracks[slot];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const size_t base = (size_t)slot * ts.track_cap;
-  const unsigned int cur = cur_epoch[slot];
+  const unsigned int cur = scenes ? scenes[blockIdx.x].epoch : cur_epoch[slot];
+  const unsigned long long scene_id = scenes ? scenes[blockIdx.x].scene_id : scene_ids[slot];
   const int K = p.max_obs;
-  if (n == 0) return;
-  // pass 1: count wasted to reserve room in the wasted buffer
-  int wc = 0;
-  for (int j = tid; j < n; j += AT) wc += (ts.epoch[base + j] + (unsigned int)p.max_idle_epochs < cur) ? 1 : 0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wc += __shfl_xor_sync(0xffffffffu, wc, o);
-  if (lane == 0) s_warp[wid] = wc;
-  __syncthreads();
-  if (tid == 0) {
-    int t = 0;
-    for (int w = 0; w < AT / 32; ++w) t += s_warp[w];
-    s_wcount = t;
-    s_wbase = t > 0 ? atomicAdd(wb.count, t) : 0;
-    s_kept = 0;
+  const bool arena = ts.fblk != nullptr;
+  if (n == 0) {
+    if (frame_out && tid == 0) {
+      frame_out[blockIdx.x * 3] = 0; frame_out[blockIdx.x * 3 + 1] = arena ? ts.arena_top[slot] : 0; frame_out[blockIdx.x * 3 + 2] = 0;
+    }
+    return;
   }
-  __syncthreads();
-  if (s_wcount == 0) return;
-  int wasted_seen = 0;  // uniform across threads (recomputed per chunk)
+  // pass 1: destination of every track = index minus the expired tracks before it
+  if (tid == 0) s_first = n;
+  int seen = 0;   // expired tracks in the chunks before (uniform)
   for (int j0 = 0; j0 < n; j0 += AT) {
-    const int jn = min(n, j0 + AT);
     const int j = j0 + tid;
-    int w = 0;
-    if (j < jn) w = (ts.epoch[base + j] + (unsigned int)p.max_idle_epochs < cur) ? 1 : 0;
+    const int w = (j < n && ts.epoch[base + j] + (unsigned int)p.max_idle_epochs < cur) ? 1 : 0;
     int x = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -305,57 +338,79 @@ __global__ void __launch_bounds__(AT) waste_kernel(Params p, TrackStore ts, cons
     __syncthreads();
     int woff = 0, wtot = 0;
     for (int q = 0; q < AT / 32; ++q) { if (q < wid) woff += s_warp[q]; wtot += s_warp[q]; }
-    const int wrank = wasted_seen + woff + x - w;  // wasted tracks before j
-    if (j < jn) {
-      if (w) {
-        int o = s_wbase + wrank;
-        if (o < wb.cap) {
-          wb.id[o] = ts.id[base + j]; wb.scene[o] = scene_ids[slot]; wb.epoch[o] = ts.epoch[base + j];
-          wb.length[o] = ts.length[base + j];
-          for (int c = 0; c < 6; ++c) { wb.pred[(size_t)o * 6 + c] = ts.pred[(base + j) * 6 + c]; wb.obs[(size_t)o * 6 + c] = ts.obs[(base + j) * 6 + c]; }
-        }
-        s_dst[tid] = -1;
-      } else s_dst[tid] = j - wrank;
+    const int before = seen + woff + x - w;
+    if (j < n) {
+      s_dst[j] = w ? -1 - before : j - before;   // expired: -(rank among the expired) - 1
+      if (w) atomicMin(&s_first, j);
     }
+    seen += wtot;
     __syncthreads();
-    if (wasted_seen + wtot > 0) {
-      move_rows(ts.id, base, 1, s_dst, j0, jn);
-      move_rows(ts.epoch, base, 1, s_dst, j0, jn);
-      move_rows(ts.length, base, 1, s_dst, j0, jn);
-      move_rows(ts.custom, base, 1, s_dst, j0, jn);
-      move_rows(ts.vt, base, 1, s_dst, j0, jn);
-      move_rows(ts.pred, base, 6, s_dst, j0, jn);
-      move_rows(ts.obs, base, 6, s_dst, j0, jn);
-      move_rows(ts.radius, base, 1, s_dst, j0, jn);
-      move_rows(ts.kst, base, kStateFloats, s_dst, j0, jn);
-      if (p.positional_kind == 1) move_rows(ts.vert, base, 8, s_dst, j0, jn);
-      if (p.is_visual) {
-        move_rows(ts.obs_phys, base, K, s_dst, j0, jn);
-        move_rows(ts.obs_hasf, base, K, s_dst, j0, jn);
-        move_rows(ts.obs_q, base, K, s_dst, j0, jn);
-        move_rows(ts.obs_n, base, 1, s_dst, j0, jn);
-        move_rows(ts.feat_cnt, base, 1, s_dst, j0, jn);
-        move_rows(ts.fnorm2, base, K, s_dst, j0, jn);
-        // feature rows: one track at a time, all threads cooperate (K*d8 floats)
-        const int fw = K * p.d8;
-        for (int jj = j0; jj < jn; ++jj) {
-          int d = s_dst[jj - j0];
-          if (d < 0 || d == jj) continue;
-          for (int c0 = 0; c0 < fw; c0 += AT) {
-            int c = c0 + tid;
-            if (c < fw) {  // d < jj: rows never overlap
-              ts.feat[(base + d) * fw + c] = ts.feat[(base + jj) * fw + c];
-              reinterpret_cast<__nv_bfloat16*>(ts.feat_bf16)[(base + d) * fw + c] =
-                  reinterpret_cast<const __nv_bfloat16*>(ts.feat_bf16)[(base + jj) * fw + c];
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-    wasted_seen += wtot;
   }
-  if (tid == 0) n_tracks[slot] = n - s_wcount;
+  if (tid == 0) {
+    s_wcount = seen;
+    s_wbase = seen > 0 ? atomicAdd(wb.count, seen) : 0;
+  }
+  __syncthreads();
+  const int wcount = s_wcount;
+  if (frame_out && tid == 0) {
+    frame_out[blockIdx.x * 3] = n - wcount;
+    frame_out[blockIdx.x * 3 + 1] = arena ? ts.arena_top[slot] : 0;
+    frame_out[blockIdx.x * 3 + 2] = wcount;
+  }
+  if (wcount == 0) return;
+  const int first = s_first;
+  const int nfree0 = arena ? ts.n_free[slot] : 0;
+  // pass 2: records of the expired tracks -> wasted buffer, their feature blocks -> free list (store order)
+  for (int j = first + tid; j < n; j += AT) {
+    const int d = s_dst[j];
+    if (d >= 0) continue;
+    const int wrank = -1 - d;
+    const int o = s_wbase + wrank;
+    if (o < wb.cap) {
+      wb.id[o] = ts.id[base + j]; wb.scene[o] = scene_id; wb.epoch[o] = ts.epoch[base + j];
+      wb.length[o] = ts.length[base + j];
+      for (int c = 0; c < 6; ++c) { wb.pred[(size_t)o * 6 + c] = ts.pred[(base + j) * 6 + c]; wb.obs[(size_t)o * 6 + c] = ts.obs[(base + j) * 6 + c]; }
+    }
+    if (arena) {
+      const int b = ts.fblk[base + j];
+      ts.blk_free[base + nfree0 + wrank] = b;
+      ts.blk_owner[base + b] = -1;
+    }
+  }
+  __syncthreads();
+  // pass 3: stable compaction of the per-track arrays
+  compact_rows(ts.id, base, 1, s_dst, first, n);
+  compact_rows(ts.epoch, base, 1, s_dst, first, n);
+  compact_rows(ts.length, base, 1, s_dst, first, n);
+  compact_rows(ts.custom, base, 1, s_dst, first, n);
+  compact_rows(ts.vt, base, 1, s_dst, first, n);
+  compact_rows(ts.pred, base, 6, s_dst, first, n);
+  compact_rows(ts.obs, base, 6, s_dst, first, n);
+  compact_rows(ts.radius, base, 1, s_dst, first, n);
+  compact_rows(ts.kst, base, kStateFloats, s_dst, first, n);
+  if (p.positional_kind == 1) compact_rows(ts.vert, base, 8, s_dst, first, n);
+  if (p.is_visual) {
+    compact_rows(ts.obs_phys, base, K, s_dst, first, n);
+    compact_rows(ts.obs_hasf, base, K, s_dst, first, n);
+    compact_rows(ts.obs_q, base, K, s_dst, first, n);
+    compact_rows(ts.obs_n, base, 1, s_dst, first, n);
+    compact_rows(ts.feat_cnt, base, 1, s_dst, first, n);
+    if (arena) compact_rows(ts.fblk, base, 1, s_dst, first, n);
+  }
+  const int kept = n - wcount;
+  if (arena) {   // owners follow the compaction
+    for (int j = first + tid; j < kept; j += AT) ts.blk_owner[base + ts.fblk[base + j]] = j;
+    if (tid == 0) ts.n_free[slot] = nfree0 + wcount;
+  }
+  if (tid == 0) n_tracks[slot] = kept;
+}
+
+static void launch_waste_kernel(const Params& p, const TrackStore& ts, int n_ctas, const unsigned int* d_cur_epoch,
+                                const unsigned long long* d_scene_ids, int* d_n_tracks, const WastedBuf& wb,
+                                const SceneDesc* scenes, int* frame_out, cudaStream_t st) {
+  const size_t smem = (size_t)std::max(1, ts.track_cap) * sizeof(int);   // s_dst for the largest possible scene
+  if (smem > 48 * 1024) cudaFuncSetAttribute(waste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  waste_kernel<<<n_ctas, AT, smem, st>>>(p, ts, d_cur_epoch, d_scene_ids, d_n_tracks, wb, scenes, frame_out);
 }
 
 void launch_waste(const Params& p, const TrackStore& ts, int n_slots, const unsigned int* d_cur_epoch,
@@ -363,7 +418,13 @@ void launch_waste(const Params& p, const TrackStore& ts, int n_slots, const unsi
                   cudaStream_t st) {
   (void)max_n;
   if (n_slots == 0) return;
-  waste_kernel<<<n_slots, AT, 0, st>>>(p, ts, d_cur_epoch, d_scene_ids, d_n_tracks, wb);
+  launch_waste_kernel(p, ts, n_slots, d_cur_epoch, d_scene_ids, d_n_tracks, wb, nullptr, nullptr, st);
+}
+
+void launch_frame_sweep(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int* d_n_tracks,
+                        const WastedBuf& wb, cudaStream_t st) {
+  if (n_scenes == 0) return;
+  launch_waste_kernel(p, ts, n_scenes, nullptr, nullptr, d_n_tracks, wb, f.scenes, f.frame_out, st);
 }
 
 // --------------------------------------------------------------------------------------------------------

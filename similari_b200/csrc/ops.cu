@@ -188,7 +188,7 @@ int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* 
   f.vis = sc.alloc<float>((size_t)m * n);
   sb::SceneDesc sd;
   memset(&sd, 0, sizeof(sd));
-  sd.m = m; sd.n = n; sd.epoch = 1;
+  sd.m = m; sd.n = n; sd.nb = n; sd.epoch = 1;   // stateless operator: one observation per track, block == track
   f.scenes = sc.upload(&sd, 1);
   if (!ft.in_feat || !ft.in_boxes || !ft.c_box || !ft.c_radius || !ft.c_conf || !ft.c_flags || !ft.c_norm2 || !ts.pred ||
       !ts.radius || !ts.epoch || !ts.feat || !ts.obs_phys || !ts.obs_hasf || !ts.obs_n || !ts.feat_cnt || !f.in_feat ||
@@ -224,6 +224,7 @@ int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* 
     f.pos_cnt = sc.alloc<int>(4, true);
     f.vis_cnt = f.pos_cnt + 1;
     f.scene_mode = f.pos_cnt + 2;
+    f.vis_mode = f.pos_cnt + 3;
     f.pos_list = sc.alloc<sb::PosEntry>(1);
     if (!f.vis_pairs || !f.vis_val || !f.pos_cnt || !f.pos_list) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
   }
@@ -293,6 +294,7 @@ static int run_voting(bool visual, float threshold, int min_votes, const float* 
     if (!f.pos_cnt) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
     f.vis_cnt = f.pos_cnt + 1;
     f.scene_mode = f.pos_cnt + 2;
+    f.vis_mode = f.pos_cnt + 3;
   }
   sb::SceneDesc sd;
   memset(&sd, 0, sizeof(sd));

@@ -46,6 +46,8 @@ struct SceneDesc {  // one per scene of the current request
   unsigned long long scene_id;
   int pos_lbase, pos_lcap;  // this scene's slice of the sparse positional entry list
   int vis_lbase, vis_lcap;  // this scene's slice of the visual survivor list
+  int nb;             // feature blocks of this scene's arena in use (physical rows scanned by the screen = nb * K)
+  int pad0;
 };
 
 struct VisPair { int g, row, scene, outcol; };  // screen survivor: detection, feature row, scene, logical column
@@ -74,7 +76,21 @@ struct TrackStore {
   float* obs_q;             // [idx][K] logical: quality
   unsigned char* obs_n;     // [idx]
   unsigned char* feat_cnt;  // [idx] visual_features_collected_count
+  // Feature arena (tracker stores; null in the stateless operators, where block == track index).  A track owns one block
+  // of K feature rows inside its scene's arena, feature row = (slot * track_cap + fblk[idx]) * K + physical slot.  The
+  // small per-track arrays above are compacted (stably) whenever tracks expire; the feature rows never move: an expired
+  // track's block goes to the scene's free list and is handed to the next new track.
+  int* fblk;        // [idx] block of the track
+  int* blk_owner;   // [slot * track_cap + block] track index j of the owner in current store order, -1: free
+  int* blk_free;    // [slot * track_cap + i] free-list stack
+  int* n_free;      // [slot]
+  int* arena_top;   // [slot] blocks ever handed out (== live tracks + free blocks)
 };
+
+// first feature row of track `ti` (absolute store index) of scene slot `slot`, divided by K
+__device__ __forceinline__ size_t feat_block(const TrackStore& ts, int slot, size_t ti) {
+  return ts.fblk ? (size_t)slot * ts.track_cap + (size_t)ts.fblk[ti] : ti;
+}
 
 struct Frame {  // per-request transient device buffers (a request may be processed in scene chunks)
   int total;               // detections of this chunk
@@ -104,14 +120,16 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   SceneDesc* scenes;       // [n_scenes]
   int* new_count;          // [n_scenes] new tracks per scene (written by voting)
   int* status;             // [n_scenes] per-scene status flags (capacity overflow etc.)
-  int* feat_dst;           // [total] destination feature row (idx*K + phys) or -1
+  int* feat_dst;           // [total] destination feature row (block*K + phys) or -1
+  int* frame_out;          // [n_scenes][3] written by the end-of-frame sweep: live tracks, arena blocks, newly expired
   // sparse views of the (mostly None) cost matrices, consumed by the voting stage
   PosEntry* pos_list;      // valid positional entries, per-scene slices
   int* pos_cnt;            // [n_scenes]
   VisPair* vis_pairs;      // screen survivors, per-scene slices
   float* vis_val;          // exact value of each survivor (NaN == failed the threshold)
   int* vis_cnt;            // [n_scenes]
-  int* scene_mode;         // [n_scenes] 0: voting consumes the sparse lists; else bit0 pos dense, bit1 vis dense
+  int* scene_mode;         // [n_scenes] 0: voting consumes the sparse lists; 1: dense matrices (a list overflowed)
+  int* vis_mode;           // [n_scenes] visual side alone (set right after the screen): 0 = the survivors get refined
   // outputs (device), any may be null
   unsigned long long* o_ids;
   unsigned int* o_epochs;
@@ -154,9 +172,21 @@ struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense ex
   unsigned int* colvalid;     // bit per column: the observation takes part in the metric
   VisRowMeta* rowmeta;   // [total]
   int total_cols;
+  int max_rows;          // max over the scenes of nb * K
 };
 int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                     const TcArgs& tc, cudaStream_t st);
+// The same in two halves, so that the positional cost can run on a second stream next to the refinement:
+//   _a: metadata, tensor-core screen, vis_mode, exact refinement of the survivors (needs nothing from the positional stage)
+//   _b: final scene_mode (needs the positional list counters), dense exact kernel for the scenes in dense mode
+int launch_vis_cost_a(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                      const TcArgs& tc, cudaStream_t st);
+int launch_vis_cost_b(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                      const TcArgs& tc, cudaStream_t st);
+// positional cost in two launches (dense None fill, culled scan) for callers that place them on a side stream
+void launch_pos_fill(const Params& p, const Frame& f, int n_scenes, int max_m, int max_n, cudaStream_t st);
+void launch_pos_scan(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                     cudaStream_t st);
 // phase 0: metadata + tensor-core screen; phase 1: exact refinement of the survivors of the sparse scenes
 int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
                        int phase, cudaStream_t st);
@@ -165,8 +195,9 @@ void launch_vis_densify(const Params& p, const Frame& f, int n_scenes, cudaStrea
 void launch_to_bf16(const float* src, int src_pitch, int d, int d8, long long rows, void* dst, cudaStream_t st);
 // scene_max init (all scenes) and, unless init_only, the dense reduction for the scenes whose mode has bit1 set
 void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_only, cudaStream_t st);
-// per-scene voting mode from the list counters (runs after the cost kernels)
+// per-scene voting mode from the list counters (runs after the cost kernels); launch_vis_mode: the visual half of it
 void launch_scene_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st);
+void launch_vis_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st);
 // shared memory the voting kernels need for scenes of up to max_m x max_n (limit: kVotingSmemLimit)
 size_t voting_smem_need(int max_m, int max_n);
 constexpr size_t kVotingSmemLimit = 200 * 1024;
@@ -189,6 +220,12 @@ struct WastedBuf {
 void launch_waste(const Params& p, const TrackStore& ts, int n_slots, const unsigned int* d_cur_epoch,
                   const unsigned long long* d_scene_ids, int* d_n_tracks, const WastedBuf& wb, int max_n,
                   cudaStream_t st);
+// end-of-frame sweep over the scenes of the request: tracks that can never match again (EpochDb::baked,
+// src/trackers/epoch_db.rs:51-66, evaluated at the scene's new epoch) leave the device store at once -- their records go
+// to the wasted buffer, where the host keeps them hidden until the reference's own collection point -- and
+// frame_out[s] = {live tracks, arena blocks, newly expired} is written for the host mirror.
+void launch_frame_sweep(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int* d_n_tracks,
+                        const WastedBuf& wb, cudaStream_t st);
 
 // stateless operators
 void launch_kalman_ops(int op, float pw, float vw, const float* in30, const float* boxes, int n, float* out30,

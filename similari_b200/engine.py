@@ -117,6 +117,14 @@ class Tracker:
         check(self._L.sb200_scene_track_counts(self._h, len(scene_ids), ptr(scene_ids), ptr(out)))
         return out
 
+    def scene_live_counts(self, scene_ids):
+        """(live tracks, feature blocks) per scene: what the device store holds / the visual cost kernel scans."""
+        scene_ids = np.ascontiguousarray(scene_ids, dtype=np.uint64)
+        live = np.zeros(len(scene_ids), np.int32)
+        blocks = np.zeros(len(scene_ids), np.int32)
+        check(self._L.sb200_scene_live_counts(self._h, len(scene_ids), ptr(scene_ids), ptr(live), ptr(blocks)))
+        return live, blocks
+
     def set_auto_waste(self, periodicity):
         check(self._L.sb200_set_auto_waste(self._h, periodicity))
 
