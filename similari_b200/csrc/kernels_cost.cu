@@ -249,10 +249,14 @@ __device__ __forceinline__ void pos_eval_pair(const Params& p, const TrackStore&
     for (int q = 0; q < 5; ++q) { mean5[q] = st[q]; l5[q] = sqrtf(kalman_proj_var(p.pos_weight, hh, st[10 + 4 * q], q)); }
     v = maha_cost(maha_distance(mean5, l5, cb[0], cb[1], angle_or0(cb[2]), cb[3], cb[4])) / cconf;
   } else {
+    const float* tb = ts.pred + ti * 6;
+    // cheap certain-None gates first (any threshold a tracker would use; tiny thresholds take the exact path)
+    const bool pregate = p.iou_threshold > 1e-4f;
+    if (pregate && iou_bound_fails(cb[4], cb[3], tb[4], tb[3], cconf, p.iou_threshold)) return;
     double cv[8], tv[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) { cv[q] = f.c_vert[(size_t)g * 8 + q]; tv[q] = ts.vert[ti * 8 + q]; }
-    const float* tb = ts.pred + ti * 6;
+    if (pregate && rects_apart(cv, tv)) return;
     float iou = iou_from_area(clip_area(cv, tv), cb[4], cb[3], tb[4], tb[3]);
     if (!is_nan(iou)) {
       iou = iou * cconf;
@@ -270,7 +274,7 @@ __device__ __forceinline__ void pos_eval_pair(const Params& p, const TrackStore&
 }
 
 template <int POS>
-__global__ void __launch_bounds__(PS_THREADS) pos_scan_kernel(Params p, TrackStore ts, Frame f) {
+__global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, TrackStore ts, Frame f) {
   extern __shared__ __align__(16) unsigned char ps_smem[];
   __shared__ float s_rmax[PS_THREADS / 32];
   __shared__ int s_bad;
@@ -400,7 +404,7 @@ void launch_pos_scan(const Params& p, const TrackStore& ts, const Frame& f, int 
   int Np = 1;
   while (Np < max_n) Np <<= 1;
   size_t smem = (size_t)Np * 8 + (size_t)max_n * 12 + (size_t)PS_QCAP * 8 + 64;
-  // with fewer scenes than SMs, several CTAs per scene (each at least 64 candidates)
+  // two CTAs fit an SM: with fewer scenes than that, several CTAs per scene (each at least 64 candidates)
   int nsplit = std::max(1, std::min(std::min(16, (max_m + 63) / 64), (2 * 148) / std::max(1, n_scenes)));
   dim3 grid(n_scenes, nsplit);
   if (p.positional_kind == 0) {

@@ -498,13 +498,17 @@ __global__ void __launch_bounds__(RF_WARPS * 32) vis_refine_kernel(Params p, Tra
   if (f.vis_mode[scene] != 0) return;  // survivor list overflowed: this scene is computed densely
   const SceneDesc sc = f.scenes[scene];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int warps_total = gridDim.x * RF_WARPS;
   const int n_pairs = min(f.vis_cnt[scene], sc.vis_lcap);
   const int nblk = p.d8 / 8;
   const int D = p.feature_dim;
   float (*bs)[RF_PITCH] = s_bs[w];
   float vmax = nanf("");
-  for (int i0 = (blockIdx.x * RF_WARPS + w) * 32; i0 < n_pairs; i0 += warps_total * 32) {
+  // warps claim 32 survivors at a time from the scene's counter: however many survive, the scene's warps finish together
+  for (;;) {
+    int i0 = 0;
+    if (lane == 0) i0 = atomicAdd(f.refine_next + scene, 32);
+    i0 = __shfl_sync(0xffffffffu, i0, 0);
+    if (i0 >= n_pairs) break;
     const int npair = min(32, n_pairs - i0);
     VisPair mine;
     mine.g = 0; mine.row = 0; mine.scene = 0; mine.outcol = 0;
@@ -704,7 +708,7 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
                        int phase, cudaStream_t st) {
   if (tc.n_tiles == 0) return 0;
   if (phase == 1) {
-    dim3 grid(10, n_scenes);
+    dim3 grid(16, n_scenes);   // 64 warps x 32 survivors per scene in flight; more survivors are claimed in further rounds
     // the vector path needs 16-byte aligned input rows (a caller-owned device pointer on the device-io path)
     const bool tail = p.feature_dim != p.d8 || (reinterpret_cast<uintptr_t>(f.in_feat) & 15) != 0;
     if (p.visual_kind == 1) {

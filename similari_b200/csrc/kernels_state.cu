@@ -272,7 +272,8 @@ void launch_apply(const Params& p, const TrackStore& ts, const Frame& f, int n_s
 // host's epoch db) and the end-of-frame sweep (the scenes of the request, `scenes` != null, epoch = the scene's new epoch).
 // Only the small per-track arrays move (about 300 B per track).  Feature rows never do: an expired track's block of the
 // scene's feature arena goes to the free list and is handed to the next new track.
-constexpr int WR = 8;   // elements in flight per thread and round of compact_rows
+constexpr int WT = 1024;   // threads of the sweep kernel
+constexpr int WR = 8;      // elements in flight per thread and round of compact_rows
 
 // Moves row j to row s_dst[j] (<= j; -1: dropped) for j in [first, n).  The flattened (row, column) elements are taken in
 // ascending rounds of AT * WR: a round reads all its elements, synchronises, then writes them.  Destinations never lie
@@ -281,12 +282,12 @@ template <typename T>
 __device__ __forceinline__ void compact_rows(T* arr, size_t base, int width, const int* s_dst, int first, int n) {
   T* a = arr + base * width;
   const int total = n * width;
-  for (int e0 = first * width; e0 < total; e0 += AT * WR) {
+  for (int e0 = first * width; e0 < total; e0 += WT * WR) {
     T v[WR];
     int de[WR];
 #pragma unroll
     for (int r = 0; r < WR; ++r) {
-      const int e = e0 + r * AT + (int)threadIdx.x;
+      const int e = e0 + r * WT + (int)threadIdx.x;
       de[r] = -1;
       if (e < total) {
         const int j = e / width, c = e - j * width;
@@ -302,11 +303,11 @@ __device__ __forceinline__ void compact_rows(T* arr, size_t base, int width, con
   }
 }
 
-__global__ void __launch_bounds__(AT) waste_kernel(Params p, TrackStore ts, const unsigned int* cur_epoch,
+__global__ void __launch_bounds__(WT) waste_kernel(Params p, TrackStore ts, const unsigned int* cur_epoch,
                                                    const unsigned long long* scene_ids, int* n_tracks, WastedBuf wb,
                                                    const SceneDesc* scenes, int* frame_out) {
   extern __shared__ int s_dst[];   // [n] destination row of every track (-1: expired)
-  __shared__ int s_warp[AT / 32];
+  __shared__ int s_warp[WT / 32];
   __shared__ int s_wbase, s_wcount, s_first;
   const int slot = scenes ? scenes[blockIdx.x].slot : (int)blockIdx.x;
   const int n = n_tracks[slot];
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(AT) waste_kernel(Params p, TrackStore ts, cons
   // pass 1: destination of every track = index minus the expired tracks before it
   if (tid == 0) s_first = n;
   int seen = 0;   // expired tracks in the chunks before (uniform)
-  for (int j0 = 0; j0 < n; j0 += AT) {
+  for (int j0 = 0; j0 < n; j0 += WT) {
     const int j = j0 + tid;
     const int w = (j < n && ts.epoch[base + j] + (unsigned int)p.max_idle_epochs < cur) ? 1 : 0;
     int x = w;
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(AT) waste_kernel(Params p, TrackStore ts, cons
     if (lane == 31) s_warp[wid] = x;
     __syncthreads();
     int woff = 0, wtot = 0;
-    for (int q = 0; q < AT / 32; ++q) { if (q < wid) woff += s_warp[q]; wtot += s_warp[q]; }
+    for (int q = 0; q < WT / 32; ++q) { if (q < wid) woff += s_warp[q]; wtot += s_warp[q]; }
     const int before = seen + woff + x - w;
     if (j < n) {
       s_dst[j] = w ? -1 - before : j - before;   // expired: -(rank among the expired) - 1
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(AT) waste_kernel(Params p, TrackStore ts, cons
   const int first = s_first;
   const int nfree0 = arena ? ts.n_free[slot] : 0;
   // pass 2: records of the expired tracks -> wasted buffer, their feature blocks -> free list (store order)
-  for (int j = first + tid; j < n; j += AT) {
+  for (int j = first + tid; j < n; j += WT) {
     const int d = s_dst[j];
     if (d >= 0) continue;
     const int wrank = -1 - d;
@@ -378,28 +379,44 @@ __global__ void __launch_bounds__(AT) waste_kernel(Params p, TrackStore ts, cons
     }
   }
   __syncthreads();
-  // pass 3: stable compaction of the per-track arrays
-  compact_rows(ts.id, base, 1, s_dst, first, n);
-  compact_rows(ts.epoch, base, 1, s_dst, first, n);
-  compact_rows(ts.length, base, 1, s_dst, first, n);
-  compact_rows(ts.custom, base, 1, s_dst, first, n);
-  compact_rows(ts.vt, base, 1, s_dst, first, n);
+  // pass 3: stable compaction of the per-track arrays.  The narrow columns of a track travel together (one thread per
+  // track, one read / write round per WT tracks); the wide rows go through compact_rows.
+  for (int j0 = first; j0 < n; j0 += WT) {
+    const int j = j0 + tid;
+    int d = -1;
+    unsigned long long v_id = 0; unsigned int v_ep = 0, v_len = 0; long long v_cu = 0; signed char v_vt = 0; float v_r = 0.0f;
+    unsigned char v_on = 0, v_fc = 0, v_ph[kMaxObs], v_hf[kMaxObs]; float v_q[kMaxObs]; int v_fb = 0;
+    if (j < n) {
+      d = s_dst[j];
+      if (d >= 0 && d != j) {
+        const size_t t = base + j;
+        v_id = ts.id[t]; v_ep = ts.epoch[t]; v_len = ts.length[t]; v_cu = ts.custom[t]; v_vt = ts.vt[t]; v_r = ts.radius[t];
+        if (p.is_visual) {
+          v_on = ts.obs_n[t]; v_fc = ts.feat_cnt[t];
+          if (arena) v_fb = ts.fblk[t];
+          for (int k = 0; k < K; ++k) { v_ph[k] = ts.obs_phys[t * K + k]; v_hf[k] = ts.obs_hasf[t * K + k]; v_q[k] = ts.obs_q[t * K + k]; }
+        }
+      } else d = -1;
+    }
+    __syncthreads();
+    if (d >= 0) {
+      const size_t t = base + d;
+      ts.id[t] = v_id; ts.epoch[t] = v_ep; ts.length[t] = v_len; ts.custom[t] = v_cu; ts.vt[t] = v_vt; ts.radius[t] = v_r;
+      if (p.is_visual) {
+        ts.obs_n[t] = v_on; ts.feat_cnt[t] = v_fc;
+        if (arena) ts.fblk[t] = v_fb;
+        for (int k = 0; k < K; ++k) { ts.obs_phys[t * K + k] = v_ph[k]; ts.obs_hasf[t * K + k] = v_hf[k]; ts.obs_q[t * K + k] = v_q[k]; }
+      }
+    }
+    __syncthreads();
+  }
   compact_rows(ts.pred, base, 6, s_dst, first, n);
   compact_rows(ts.obs, base, 6, s_dst, first, n);
-  compact_rows(ts.radius, base, 1, s_dst, first, n);
   compact_rows(ts.kst, base, kStateFloats, s_dst, first, n);
   if (p.positional_kind == 1) compact_rows(ts.vert, base, 8, s_dst, first, n);
-  if (p.is_visual) {
-    compact_rows(ts.obs_phys, base, K, s_dst, first, n);
-    compact_rows(ts.obs_hasf, base, K, s_dst, first, n);
-    compact_rows(ts.obs_q, base, K, s_dst, first, n);
-    compact_rows(ts.obs_n, base, 1, s_dst, first, n);
-    compact_rows(ts.feat_cnt, base, 1, s_dst, first, n);
-    if (arena) compact_rows(ts.fblk, base, 1, s_dst, first, n);
-  }
   const int kept = n - wcount;
   if (arena) {   // owners follow the compaction
-    for (int j = first + tid; j < kept; j += AT) ts.blk_owner[base + ts.fblk[base + j]] = j;
+    for (int j = first + tid; j < kept; j += WT) ts.blk_owner[base + ts.fblk[base + j]] = j;
     if (tid == 0) ts.n_free[slot] = nfree0 + wcount;
   }
   if (tid == 0) n_tracks[slot] = kept;
@@ -410,7 +427,7 @@ static void launch_waste_kernel(const Params& p, const TrackStore& ts, int n_cta
                                 const SceneDesc* scenes, int* frame_out, cudaStream_t st) {
   const size_t smem = (size_t)std::max(1, ts.track_cap) * sizeof(int);   // s_dst for the largest possible scene
   if (smem > 48 * 1024) cudaFuncSetAttribute(waste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  waste_kernel<<<n_ctas, AT, smem, st>>>(p, ts, d_cur_epoch, d_scene_ids, d_n_tracks, wb, scenes, frame_out);
+  waste_kernel<<<n_ctas, WT, smem, st>>>(p, ts, d_cur_epoch, d_scene_ids, d_n_tracks, wb, scenes, frame_out);
 }
 
 void launch_waste(const Params& p, const TrackStore& ts, int n_slots, const unsigned int* d_cur_epoch,

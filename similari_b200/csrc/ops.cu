@@ -221,10 +221,11 @@ int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* 
     cudaMemcpyAsync(f.scenes, &sd, sizeof(sd), cudaMemcpyHostToDevice, sc.st);
     f.vis_pairs = sc.alloc<sb::VisPair>((size_t)lcap);
     f.vis_val = sc.alloc<float>((size_t)lcap);
-    f.pos_cnt = sc.alloc<int>(4, true);
+    f.pos_cnt = sc.alloc<int>(8, true);
     f.vis_cnt = f.pos_cnt + 1;
     f.scene_mode = f.pos_cnt + 2;
     f.vis_mode = f.pos_cnt + 3;
+    f.refine_next = f.pos_cnt + 4;
     f.pos_list = sc.alloc<sb::PosEntry>(1);
     if (!f.vis_pairs || !f.vis_val || !f.pos_cnt || !f.pos_list) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
   }

@@ -130,6 +130,7 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   int* vis_cnt;            // [n_scenes]
   int* scene_mode;         // [n_scenes] 0: voting consumes the sparse lists; 1: dense matrices (a list overflowed)
   int* vis_mode;           // [n_scenes] visual side alone (set right after the screen): 0 = the survivors get refined
+  int* refine_next;        // [n_scenes] next unclaimed survivor of the scene (the refinement's warps claim 32 at a time)
   // outputs (device), any may be null
   unsigned long long* o_ids;
   unsigned int* o_epochs;

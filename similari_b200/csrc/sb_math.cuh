@@ -139,6 +139,45 @@ SB_HD double clip_area(const double* subj, const double* clp) {
   return fabs(tmp / 2.0);
 }
 
+// Conservative pre-gates of the IoU metric: both return true only when the reference's result is certainly None for any
+// threshold above ~1e-6, so the f64 clip can be skipped.  Pairs they cannot decide go through clip_area unchanged.
+//   * rects_apart: separating-axis test of the two (convex) quadrilaterals on their own edge normals, in f64 on the very
+//     vertices the clip uses, with a margin nine orders of magnitude above the rounding of a dot product.  Separated
+//     polygons have an empty intersection; Sutherland-Hodgman returns either nothing or a rounding sliver whose IoU
+//     (~1e-12) no positive threshold accepts.
+//   * iou_bound_fails: intersection <= min(area), union >= max(area)  =>  IoU <= min / max.
+SB_HD bool rects_apart(const double* a, const double* b) {
+  double scale = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { scale = fmax(scale, fabs(a[i])); scale = fmax(scale, fabs(b[i])); }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const double* q = pass == 0 ? a : b;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      // edge e of the quadrilateral: vertices e -> e + 1; axis = the edge direction of the adjacent side's normal
+      const double ux = q[2 * (e + 1)] - q[2 * e], uy = q[2 * (e + 1) + 1] - q[2 * e + 1];
+      double amin = 1e300, amax = -1e300, bmin = 1e300, bmax = -1e300;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const double pa = a[2 * v] * ux + a[2 * v + 1] * uy;
+        const double pb = b[2 * v] * ux + b[2 * v + 1] * uy;
+        amin = fmin(amin, pa); amax = fmax(amax, pa);
+        bmin = fmin(bmin, pb); bmax = fmax(bmax, pb);
+      }
+      const double tol = 1e-7 * (fabs(ux) + fabs(uy)) * (scale + 1.0);
+      if (bmin - amax > tol || amin - bmax > tol) return true;
+    }
+  }
+  return false;
+}
+SB_HD bool iou_bound_fails(float h_l, float a_l, float h_r, float a_r, float conf, float threshold) {
+  const float al = h_l * h_l * a_l, ar = h_r * h_r * a_r;
+  if (!(al > 0.0f) || !(ar > 0.0f) || !(conf == conf)) return false;   // degenerate / NaN boxes: let the exact path decide
+  const float lo = fminf(al, ar), hi = fmaxf(al, ar);
+  return lo * conf * 1.0001f < threshold * hi;
+}
+
 // Universal2DBox::calculate_metric_object (src/utils/bbox.rs:512-535) given the clipped area.
 // Returns NaN for None (intersection == 0).
 SB_HD float iou_from_area(double inter, float h_l, float a_l, float h_r, float a_r) {
