@@ -171,7 +171,11 @@ int64_t sb200_idle_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uint
 /* Debug / parity: dense dump of one scene's store in store order.  states: [n][30] = mean[10] + 5 x (Pxx,Pxv,Pvx,Pvv). */
 int64_t sb200_scene_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uint64_t* ids, float* boxes,
                            float* states30, int32_t* feature_counts);
-/* Debug / parity: last frame's positional cost matrix of a scene ([m][n] f32, NaN == None). */
+/* Debug / parity: last frame's positional cost matrix of a scene ([m][n] f32, NaN == None), n = the scene's live tracks
+ * in store order.  Visual trackers on the tensor-core path evaluate the positional metric lazily -- only for candidates
+ * the visual BestFit pass left undecided against tracks it did not claim, the pairs VisualVoting::winners
+ * (src/trackers/visual_sort/voting.rs:45-100) can still consult -- so the other entries read None; with the environment
+ * variable SB200_FULL_COSTS=1 every pair is evaluated as the reference does. */
 int64_t sb200_last_costs(sb200_tracker* t, uint64_t scene_id, int64_t cap, float* out, int32_t* m, int32_t* n);
 /* Per-stage device times (ms) of the last predict call: prep, positional cost, visual cost, voting, apply. */
 int sb200_last_stage_ms(sb200_tracker* t, float* out5);

@@ -200,7 +200,7 @@ struct sb200_tracker {
   } stg[2];
   int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_frameout, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
+      f_status, f_featdst, f_frameout, f_decided, f_excl, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
   HBuf h_tiles;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
@@ -212,7 +212,7 @@ struct sb200_tracker {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
                    &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_colb, &f_colvalid, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
-                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout,
+                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
                    &f_featdst, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
@@ -754,16 +754,24 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       tcc.n_tiles = tile_first[s1] - tile_first[s0];
       if (timed && tcc.n_tiles > 0) { tcc.ev_screen0 = ev_k[0]; tcc.ev_screen1 = ev_k[1]; tcc.ev_refine1 = ev_k[2]; tc_timed_now = true; }
     }
-    // Visual trackers on the tensor-core path fork the positional stage onto a side stream: the dense None fill runs
-    // next to the candidate norms / screen, the culled scan (latency bound, shared memory) next to the refinement of the
-    // survivors (HBM bound).  Both join in front of the final scene mode.  SB200_NO_FORK=1 keeps everything in order.
-    static const bool no_fork = getenv("SB200_NO_FORK") != nullptr;
-    const bool fork = P.is_visual && tc.use_tc && tcc.n_tiles > 0 && !no_fork;
+    // Visual trackers on the tensor-core path evaluate the positional metric lazily: VisualVoting only consults it for
+    // candidates the visual BestFit pass left undecided, against tracks that pass did not claim, so the order is
+    // screen -> refine -> BestFit pre-pass (masks) -> culled scan of what is still open -> full voting.  The dense None
+    // fill of the positional matrices runs on a side stream next to the screen.  SB200_FULL_COSTS=1 (every pair is
+    // evaluated, sb200_last_costs is complete) and SB200_NO_FORK=1 keep the plain order.
+    const bool full_costs = getenv("SB200_FULL_COSTS") != nullptr || getenv("SB200_NO_FORK") != nullptr;
+    const bool fork = P.is_visual && tc.use_tc && tcc.n_tiles > 0 && !full_costs;
     if (fork && !pos_stream) {
       CU(cudaStreamCreateWithFlags(&pos_stream, cudaStreamNonBlocking));
       for (auto& e : ev_fork) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
       for (auto& e : ev_pos) CU(cudaEventCreate(&e));
+    }
+    if (fork) {
+      if ((rc = f_decided.ensure(T)) || (rc = f_excl.ensure((size_t)scene_cap * track_cap + 16))) return rc;
+      fc.decided = f_decided.as<unsigned char>();
+      fc.excl = f_excl.as<unsigned char>();
+      if (c == 0) CU(cudaMemsetAsync(f_decided.p, 0, (size_t)std::max(total, 1), stream));
     }
     if (timed) CU(cudaEventRecord(ev[0], stream));
     sb::launch_prep(P, fc, s1 - s0, cm, stream);
@@ -792,34 +800,26 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       int vr0 = sb::launch_vis_cost(P, ts, fc, s1 - s0, cm, cn, tcc, stream);
       if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
     } else {
-      CU(cudaEventRecord(ev_fork[0], stream));                  // candidate boxes ready (prep), counters zeroed
+      CU(cudaEventRecord(ev_fork[0], stream));                  // counters zeroed, scene table pulled
       CU(cudaStreamWaitEvent(pos_stream, ev_fork[0], 0));
       sb::launch_pos_fill(P, fc, s1 - s0, cm, cn, pos_stream);
+      CU(cudaEventRecord(ev_join, pos_stream));
       if (timed) CU(cudaEventRecord(ev[2], stream));
       if ((rc = fill_tiles())) return rc;
-      // first half of the visual stage up to the screen; the refinement is launched after the fork point
-      sb::TcArgs tca = tcc;
-      cudaEvent_t ev_refine_end = tca.ev_refine1;
-      tca.ev_refine1 = nullptr;
       {
-        // screen (phase 0) + vis_mode, then the fork event, then refine (phase 1)
-        sb::launch_scene_max(P, fc, s1 - s0, /*init_only=*/true, stream);
-        int vr0 = sb::launch_vis_cost_tc(P, ts, fc, s1 - s0, cn, tca, /*phase=*/0, stream);
+        int vr0 = sb::launch_vis_cost_a(P, ts, fc, s1 - s0, cm, cn, tcc, stream);   // metadata, screen, vis_mode, refinement
         if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
-        sb::launch_vis_mode(P, fc, s1 - s0, true, stream);
-        CU(cudaEventRecord(ev_fork[1], stream));                // the screen has drained: SMs are free for the scan
-        CU(cudaStreamWaitEvent(pos_stream, ev_fork[1], 0));
-        if (timed) CU(cudaEventRecord(ev_pos[0], pos_stream));
-        sb::launch_pos_scan(P, ts, fc, s1 - s0, cm, cn, pos_stream);
-        if (timed) CU(cudaEventRecord(ev_pos[1], pos_stream));
-        CU(cudaEventRecord(ev_join, pos_stream));
-        tca.ev_refine1 = ev_refine_end;
-        vr0 = sb::launch_vis_cost_tc(P, ts, fc, s1 - s0, cn, tca, /*phase=*/1, stream);
-        if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
+        vr0 = sb::launch_vote_masks(P, ts, fc, s1 - s0, cm, cn, stream);            // who is still open positionally
+        if (vr0 == -3) return fail(SB200_ERR_CAPACITY, "scene too large for the on-chip assignment solver (m=%d, n=%d)", cm, cn);
+        if (vr0 != 0) return fail(SB200_ERR_CUDA, "voting launch failed: %s", cudaGetErrorString((cudaError_t)vr0));
       }
-      CU(cudaStreamWaitEvent(stream, ev_join, 0));
-      int vr1 = sb::launch_vis_cost_b(P, ts, fc, s1 - s0, cm, cn, tcc, stream);
+      CU(cudaStreamWaitEvent(stream, ev_join, 0));                // the None fill has landed
+      if (timed) CU(cudaEventRecord(ev_pos[0], stream));
+      sb::launch_pos_scan_lazy(P, ts, fc, s1 - s0, cm, cn, /*pass=*/0, stream);
+      if (timed) CU(cudaEventRecord(ev_pos[1], stream));
+      int vr1 = sb::launch_vis_cost_b(P, ts, fc, s1 - s0, cm, cn, tcc, stream);     // final scene mode, dense fallbacks
       if (vr1 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr1);
+      sb::launch_pos_scan_lazy(P, ts, fc, s1 - s0, cm, cn, /*pass=*/1, stream);     // scenes that fell back to dense voting
       if (timed) pos_forked = true;
     }
     if (timed) CU(cudaEventRecord(ev[3], stream));
@@ -868,10 +868,11 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   id_counter += P.is_batch ? (uint64_t)total : (uint64_t)new_total;
   for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);   // stages of the first chunk
   if (pos_forked) {
-    // forked frame: [1] = the culled scan on the side stream (it overlaps the visual stage), [2] = prep end -> visual end
-    float fill_ms = stage_ms[1];
-    cudaEventElapsedTime(&stage_ms[1], ev_pos[0], ev_pos[1]);
-    stage_ms[2] += fill_ms;
+    // lazy frame: the culled scan sits inside the visual span (after the BestFit pre-pass): report it on its own
+    float fill_ms = stage_ms[1], scan_ms = 0.0f;
+    cudaEventElapsedTime(&scan_ms, ev_pos[0], ev_pos[1]);
+    stage_ms[1] = scan_ms;
+    stage_ms[2] += fill_ms - scan_ms;
   }
   tc_timed = tc_timed_now;
   kernel_ms[0] = kernel_ms[1] = 0.0f;

@@ -440,13 +440,14 @@ struct SparseSmem {
   unsigned char* inS; unsigned char* seen_m; unsigned char* excl;
   // BestFit scratch, overlaid on the KM / CSR region (disjoint in time)
   unsigned long long* vkey; float* vval; unsigned long long* rowW; unsigned long long* colW; int* rown; int* colm;
+  int* bstart; int* bcur;   // per-candidate buckets of the valid visual entries (bucket path of BestFit)
 };
 
 __host__ __device__ inline size_t sparse_smem_bytes(int M, int N) {
   size_t ny = (size_t)M + N;
   size_t km = ny * 8 * 2 + (size_t)M * 8 * 2 + ny * 4 * 3 + (size_t)M * 4 * 4 + (size_t)N * 4 * 3 + (size_t)(M + 1) * 4 +
               (size_t)(N + 1) * 4 + (size_t)kVotePosCap * 12 + 64;
-  size_t bf = (size_t)kVoteVisCap * 12 + (size_t)M * 12 + (size_t)N * 12 + 64;
+  size_t bf = (size_t)kVoteVisCap * 12 + (size_t)M * 12 + (size_t)N * 12 + (size_t)(2 * M + 2) * 4 + 64;
   size_t persist = (size_t)M * 4 + (size_t)M * 2 + N + 64;  // fw, inS, seen_m, excl
   return (km > bf ? km : bf) + persist;
 }
@@ -495,6 +496,8 @@ __device__ inline SparseSmem carve_sparse(unsigned char* base, int M, int N) {
   s.vval = reinterpret_cast<float*>(p4); p4 += kVoteVisCap;
   s.rown = p4; p4 += M;
   s.colm = p4; p4 += N;
+  s.bstart = p4; p4 += M + 1;
+  s.bcur = p4; p4 += M + 1;
   return s;
 }
 
@@ -530,21 +533,22 @@ __device__ int block_exscan_int(int* data, int n, int* s_warp, int* s_carry) {
   return *s_carry;
 }
 
-template <bool VISUAL>
-__global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Frame f) {
+template <bool VISUAL, bool MASK_ONLY>
+__global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, TrackStore ts, Frame f) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ MinPair s_red[2][NWARPS];
   __shared__ int s_warp[NWARPS];
   __shared__ int s_misc[8];
   const int sidx = blockIdx.x;
-  if (f.scene_mode[sidx] != 0) return;  // handled by the dense voting_kernel
+  if (MASK_ONLY) { if (f.vis_mode[sidx] != 0) return; }  // the scan takes such a scene in full
+  else if (f.scene_mode[sidx] != 0) return;  // handled by the dense voting_kernel
   const SceneDesc sc = f.scenes[sidx];
   const int M = sc.m, N = sc.n;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   int* winner = f.winner + sc.det_base;
   unsigned char* cvt = f.c_vt + sc.det_base;
   if (M == 0) {
-    if (tid == 0) f.new_count[sidx] = 0;
+    if (!MASK_ONLY && tid == 0) f.new_count[sidx] = 0;
     return;
   }
   SparseSmem s = carve_sparse(smem_raw, M, N);
@@ -562,9 +566,81 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Fra
     const int K = p.max_obs;
     const float maxd = dec_f32(f.scene_max[sidx]);
     const int nraw = min(f.vis_cnt[sidx], sc.vis_lcap);
-    // compact the valid entries (value passed the threshold) into shared memory
+    // The valid entries (value passed the threshold) are grouped per candidate by a counting sort; a candidate's
+    // handful of entries is then ordered by logical column by the one thread that owns the candidate, which also
+    // walks its (candidate, track) groups: votes and the f64 weight sum_k (max_dist - d_k) in observation order
+    // (best.rs:97).  Row maxima need no atomics (a thread owns its row), column maxima are order-preserving
+    // atomicMax / atomicMin.  A pathological bucket (> kBucketMax entries of one candidate) takes the whole-list
+    // bitonic sort instead.
+    constexpr int kBucketMax = 32;
+    for (int m = tid; m <= M; m += VT_THREADS) s.bstart[m] = 0;
+    for (int m = tid; m < M; m += VT_THREADS) { s.rowW[m] = 0ull; s.rown[m] = 0x7fffffff; }
+    for (int n = tid; n < N; n += VT_THREADS) { s.colW[n] = 0ull; s.colm[n] = 0x7fffffff; }
+    if (tid == 0) { s_misc[0] = 0; s_misc[3] = 0; }
+    __syncthreads();
+    for (int i = tid; i < nraw; i += VT_THREADS) {
+      const float v = f.vis_val[sc.vis_lbase + i];
+      if (!is_nan(v)) {
+        const int m = f.vis_pairs[sc.vis_lbase + i].g - sc.det_base;
+        const int c = atomicAdd(&s.bstart[m], 1);
+        if (c + 1 > kBucketMax) s_misc[3] = 1;
+      }
+    }
+    __syncthreads();
+    const bool buckets = s_misc[3] == 0;
+    __syncthreads();
+    if (buckets) {
+      int* ecol = reinterpret_cast<int*>(s.vkey);   // [L] logical column of the entry (the u64 key array is free here)
+      float* eval = s.vval;                         // [L]
+      const int L = block_exscan_int(s.bstart, M + 1, s_warp, &s_misc[1]);
+      (void)L;
+      for (int m = tid; m < M; m += VT_THREADS) s.bcur[m] = s.bstart[m];
+      __syncthreads();
+      for (int i = tid; i < nraw; i += VT_THREADS) {
+        const float v = f.vis_val[sc.vis_lbase + i];
+        if (!is_nan(v)) {
+          const VisPair vp = f.vis_pairs[sc.vis_lbase + i];
+          const int slot = atomicAdd(&s.bcur[vp.g - sc.det_base], 1);
+          ecol[slot] = vp.outcol;
+          eval[slot] = v;
+        }
+      }
+      __syncthreads();
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int m = tid; m < M; m += VT_THREADS) {
+          const int b0 = s.bstart[m], b1 = s.bstart[m + 1];
+          if (b1 == b0) continue;
+          if (pass == 0) {   // insertion sort of the bucket by logical column (keys are unique)
+            for (int a = b0 + 1; a < b1; ++a) {
+              const int ca = ecol[a]; const float va = eval[a];
+              int b = a - 1;
+              while (b >= b0 && ecol[b] > ca) { ecol[b + 1] = ecol[b]; eval[b + 1] = eval[b]; --b; }
+              ecol[b + 1] = ca; eval[b + 1] = va;
+            }
+          }
+          unsigned long long best_w = 0ull;
+          int best_n = 0x7fffffff;
+          int q = b0;
+          while (q < b1) {
+            const int n = ecol[q] / K;
+            int votes = 0;
+            double w = 0.0;
+            for (; q < b1 && ecol[q] / K == n; ++q) { ++votes; w += (double)(maxd - eval[q]); }
+            if (votes < p.min_votes) continue;
+            const unsigned long long we = enc_f64(w);
+            if (pass == 0) {
+              atomicMax(&s.colW[n], we);
+              if (we > best_w) { best_w = we; best_n = n; }   // groups ascend in n: the first maximum is the lowest n
+            } else if (we == s.colW[n]) atomicMin(&s.colm[n], m);
+          }
+          if (pass == 0) { s.rowW[m] = best_w; s.rown[m] = best_n; }
+        }
+        __syncthreads();
+      }
+    } else {
     if (tid == 0) s_misc[0] = 0;
     __syncthreads();
+    // compact the valid entries into shared memory
     for (int i = tid; i < nraw; i += VT_THREADS) {
       const float v = f.vis_val[sc.vis_lbase + i];
       if (!is_nan(v)) {
@@ -579,8 +655,6 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Fra
     int Lp = 1;
     while (Lp < L) Lp <<= 1;
     for (int i = L + tid; i < Lp; i += VT_THREADS) { s.vkey[i] = ~0ull; s.vval[i] = 0.0f; }
-    for (int m = tid; m < M; m += VT_THREADS) { s.rowW[m] = 0ull; s.rown[m] = 0x7fffffff; }
-    for (int n = tid; n < N; n += VT_THREADS) { s.colW[n] = 0ull; s.colm[n] = 0x7fffffff; }
     __syncthreads();
     // bitonic sort by (candidate, logical column): groups and their observation order become contiguous
     for (int k2 = 2; k2 <= Lp; k2 <<= 1) {
@@ -629,6 +703,7 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Fra
       }
       __syncthreads();
     }
+    }
     // resolve (dense kernel: "a query wins its best track iff it is that track's best query")
     for (int m = tid; m < M; m += VT_THREADS) {
       const int n1 = s.rown[m];
@@ -639,6 +714,14 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Fra
       }
     }
     __syncthreads();
+  }
+  if (MASK_ONLY) {
+    // pre-pass: publish who is still open for the positional stage (the full pass recomputes the same decisions)
+    unsigned char* dec = f.decided + sc.det_base;
+    unsigned char* ex = f.excl + (size_t)sc.slot * ts.track_cap;
+    for (int m = tid; m < M; m += VT_THREADS) dec[m] = s.fw[m] != kNone;
+    for (int n = tid; n < N; n += VT_THREADS) ex[n] = s.excl[n];
+    return;
   }
 
   // ------------------------------------------------------------------ positional stage on the sparse entries
@@ -687,25 +770,31 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Fra
   const int nrows = VISUAL ? n_seen_rows : M;
   int n_seen_cols = 0;
   {
+    // Columns in first-seen order (voting.rs:61-75 with entries visited by candidate, then store order): rank of track
+    // n = tracks first touched by an earlier candidate + tracks of the same first candidate with a lower index.  A
+    // histogram over the first candidates gives the former; the latter are among the (few) entries of that candidate's
+    // CSR row.
+    int* hist = s.alt;   // [M + 1]; the alternating-tree array is not in use before the search starts
+    for (int m = tid; m <= M; m += VT_THREADS) hist[m] = 0;
+    __syncthreads();
     for (int n = tid; n < N; n += VT_THREADS) {
       const int fm = s.first_m[n];
       s.col_rank[n] = -1;
+      if (fm != 0x7fffffff) atomicAdd(&hist[fm], 1);
+    }
+    __syncthreads();
+    n_seen_cols = block_exscan_int(hist, M + 1, s_warp, &s_misc[1]);
+    for (int n = tid; n < N; n += VT_THREADS) {
+      const int fm = s.first_m[n];
       if (fm == 0x7fffffff) continue;
-      int rank = 0;
-      for (int q = 0; q < N; ++q) {
-        const int fq = s.first_m[q];
-        if (fq < fm || (fq == fm && q < n)) ++rank;
+      int rank = hist[fm];
+      for (int q = s.row_ptr[fm]; q < s.row_ptr[fm + 1]; ++q) {
+        const int n2 = s.csr_n[q];
+        if (n2 < n && s.first_m[n2] == fm) ++rank;
       }
       s.col_trk[rank] = n;
       s.col_rank[n] = rank;
     }
-    int c = 0;
-    for (int n = tid; n < N; n += VT_THREADS) c += s.first_m[n] != 0x7fffffff;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) s_warp[wid] = c;
-    __syncthreads();
-    for (int w = 0; w < NWARPS; ++w) n_seen_cols += s_warp[w];
     __syncthreads();
   }
   const int ntrk = VISUAL ? n_seen_cols : N;
@@ -908,23 +997,33 @@ size_t voting_smem_need(int max_m, int max_n) {
 
 int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                   cudaStream_t st) {
-  (void)ts;
   if (n_scenes == 0) return 0;
   const size_t smem_d = vote_smem_bytes(max_m, max_n);
   const size_t smem_s = sparse_smem_bytes(max_m, max_n);
   if (smem_d > 200 * 1024 || smem_s > 200 * 1024) return -3;
   cudaError_t e;
   if (p.is_visual) {
-    if ((e = cudaFuncSetAttribute(voting_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(voting_sparse_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(voting_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d)) != cudaSuccess) return (int)e;
-    voting_sparse_kernel<true><<<n_scenes, VT_THREADS, smem_s, st>>>(p, f);
+    voting_sparse_kernel<true, false><<<n_scenes, VT_THREADS, smem_s, st>>>(p, ts, f);
     voting_kernel<true><<<n_scenes, VT_THREADS, smem_d, st>>>(p, f);
   } else {
-    if ((e = cudaFuncSetAttribute(voting_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)) != cudaSuccess) return (int)e;
+    if ((e = cudaFuncSetAttribute(voting_sparse_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(voting_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d)) != cudaSuccess) return (int)e;
-    voting_sparse_kernel<false><<<n_scenes, VT_THREADS, smem_s, st>>>(p, f);
+    voting_sparse_kernel<false, false><<<n_scenes, VT_THREADS, smem_s, st>>>(p, ts, f);
     voting_kernel<false><<<n_scenes, VT_THREADS, smem_d, st>>>(p, f);
   }
+  return 0;
+}
+
+int launch_vote_masks(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                      cudaStream_t st) {
+  if (n_scenes == 0 || !p.is_visual || !f.decided || !f.excl) return 0;
+  const size_t smem_s = sparse_smem_bytes(max_m, max_n);
+  if (smem_s > 200 * 1024) return -3;
+  cudaError_t e = cudaFuncSetAttribute(voting_sparse_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
+  if (e != cudaSuccess) return (int)e;
+  voting_sparse_kernel<true, true><<<n_scenes, VT_THREADS, smem_s, st>>>(p, ts, f);
   return 0;
 }
 

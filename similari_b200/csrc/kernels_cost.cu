@@ -256,7 +256,13 @@ __device__ __forceinline__ void pos_eval_pair(const Params& p, const TrackStore&
     double cv[8], tv[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) { cv[q] = f.c_vert[(size_t)g * 8 + q]; tv[q] = ts.vert[ti * 8 + q]; }
-    if (pregate && rects_apart(cv, tv)) return;
+    if (pregate) {
+      // upper bound of the intersection area -> upper bound of IoU = ub / (sum - ub), increasing in ub
+      const double ub = rect_overlap_bound(cv, tv);
+      if (ub == 0.0) return;
+      const double sum = (double)(cb[4] * cb[4] * cb[3] + tb[4] * tb[4] * tb[3]);
+      if (ub < 0.5 * sum && ub * (double)cconf * 1.0001 < (double)p.iou_threshold * (sum - ub)) return;
+    }
     float iou = iou_from_area(clip_area(cv, tv), cb[4], cb[3], tb[4], tb[3]);
     if (!is_nan(iou)) {
       iou = iou * cconf;
@@ -273,8 +279,11 @@ __device__ __forceinline__ void pos_eval_pair(const Params& p, const TrackStore&
   }
 }
 
+// lazy_pass < 0: plain scan.  0: lazy (visual trackers) -- in scenes whose visual lists are complete only candidates the
+// visual pass left undecided and tracks it did not claim take part; 1: full scan of the scenes that ended in dense mode
+// although their visual lists were complete (their first scan was a lazy one).
 template <int POS>
-__global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, TrackStore ts, Frame f) {
+__global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, TrackStore ts, Frame f, int lazy_pass) {
   extern __shared__ __align__(16) unsigned char ps_smem[];
   __shared__ float s_rmax[PS_THREADS / 32];
   __shared__ int s_bad;
@@ -283,6 +292,9 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
   const SceneDesc sc = f.scenes[sidx];
   const int N = sc.n, M = sc.m;
   if (N == 0 || M == 0 || N > PS_MAXN) return;   // N > PS_MAXN: the dense kernel handles this scene
+  if (lazy_pass == 1 && !(f.scene_mode[sidx] != 0 && f.vis_mode[sidx] == 0)) return;
+  const bool lazy = lazy_pass == 0 && f.vis_mode[sidx] == 0;
+  const unsigned char* excl = lazy ? f.excl + (size_t)sc.slot * ts.track_cap : nullptr;
   // gridDim.y CTAs share a scene (few scenes, many SMs): each sorts the tracks for itself and takes a slice of candidates
   const int mchunk = (M + (int)gridDim.y - 1) / (int)gridDim.y;
   const int m_begin = (int)blockIdx.y * mchunk, m_end = min(M, m_begin + mchunk);
@@ -303,7 +315,8 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
       const float x = ts.pred[(tbase + n) * 6];
       const float r = ts.radius[tbase + n];
       if (!(x == x) || !(r == r)) s_bad = 1;
-      kx[n] = x; kidx[n] = n;
+      // a track the visual pass claimed sorts behind every window, like the padding
+      kx[n] = (excl && excl[n]) ? 3.402823466e+38f : x; kidx[n] = n;
       rmax = fmaxf(rmax, r);
     } else { kx[n] = 3.402823466e+38f; kidx[n] = -1; }
   }
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
     __syncthreads();
     // ---- phase 1: cheap gates over the candidate's x-window; survivors go to the work queue
     const int m = m0 + tid;
-    if (m < m_end) {
+    if (m < m_end && !(lazy && f.decided[sc.det_base + m])) {
       const int g = sc.det_base + m;
       const float* cb = f.c_box + (size_t)g * 6;
       const float cx = cb[0], cy = cb[1];
@@ -362,6 +375,7 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
         hi = a;
       }
       for (int i = lo; i < hi; ++i) {
+        if (excl && excl[kidx[i]]) continue;   // (only reachable on the unsorted NaN path; sorted windows never hold them)
         const float tx = kx[i], ty = sy[i], tr = sr[i];
         if (!compat_ok(p, sc.epoch, sep[i], cx, cy, cr, tx, ty, tr) || too_far(cx, cy, cr, tx, ty, tr)) continue;
         const int slot = atomicAdd(&s_qn, 1);
@@ -390,10 +404,11 @@ void launch_pos_fill(const Params& p, const Frame& f, int n_scenes, int max_m, i
   if (total > 0) pos_fill_none_kernel<<<1184, 256, 0, st>>>(f, total / 4, total);
 }
 
-void launch_pos_scan(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
-                     cudaStream_t st) {
+static void pos_scan_impl(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                          int lazy_pass, cudaStream_t st) {
   if (n_scenes == 0 || max_m == 0 || max_n == 0) return;
   if (pos_use_dense(max_n)) {
+    if (lazy_pass == 1) return;   // the dense kernel has already written every element
     // very large scenes: dense tiled kernel
     dim3 grid((max_n + TN - 1) / TN, (max_m + TM - 1) / TM, n_scenes);
     dim3 block(TN, TY);
@@ -409,11 +424,20 @@ void launch_pos_scan(const Params& p, const TrackStore& ts, const Frame& f, int 
   dim3 grid(n_scenes, nsplit);
   if (p.positional_kind == 0) {
     cudaFuncSetAttribute(pos_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pos_scan_kernel<0><<<grid, PS_THREADS, smem, st>>>(p, ts, f);
+    pos_scan_kernel<0><<<grid, PS_THREADS, smem, st>>>(p, ts, f, lazy_pass);
   } else {
     cudaFuncSetAttribute(pos_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pos_scan_kernel<1><<<grid, PS_THREADS, smem, st>>>(p, ts, f);
+    pos_scan_kernel<1><<<grid, PS_THREADS, smem, st>>>(p, ts, f, lazy_pass);
   }
+}
+
+void launch_pos_scan(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                     cudaStream_t st) {
+  pos_scan_impl(p, ts, f, n_scenes, max_m, max_n, -1, st);
+}
+void launch_pos_scan_lazy(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                          int pass, cudaStream_t st) {
+  pos_scan_impl(p, ts, f, n_scenes, max_m, max_n, (f.decided && f.excl) ? pass : (pass == 0 ? -1 : 1), st);
 }
 
 void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,

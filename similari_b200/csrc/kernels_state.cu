@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
     float st[kStateFloats], st2[kStateFloats];
     Box pred;
     int fdst = -1;
+    unsigned long long o_id = 0; unsigned int o_len = 0; signed char o_vt = -1;   // SortTrack columns of this detection
     if (isnew) {
       const int j = sc.n + rank;
       if (j >= ts.track_cap) { atomicOr(&f.status[sidx], 1); continue; }
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
       ts.id[idx] = tid64;
       ts.length[idx] = 1;
       ts.vt[idx] = -1;
+      o_id = tid64; o_len = 1; o_vt = -1;
       write_box(ts.obs + idx * 6, raw);
       if (p.is_visual) {
         ts.obs_n[idx] = 1;
@@ -118,17 +120,32 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
       }
     } else {
       idx = (size_t)sc.slot * ts.track_cap + win;
+      // every load of the merge first (one round trip to memory), then the arithmetic, then the stores
 #pragma unroll
       for (int i = 0; i < kStateFloats; ++i) st2[i] = ts.kst[idx * kStateFloats + i];
+      const unsigned int len0 = ts.length[idx];
+      o_id = ts.id[idx];
+      int on = 0;
+      unsigned char l_hasf[kMaxObs], l_phys[kMaxObs]; float l_q[kMaxObs];
+      size_t blk = idx;
+      if (p.is_visual) {
+        on = ts.obs_n[idx];
+        for (int k = 0; k < K; ++k) {
+          l_hasf[k] = ts.obs_hasf[idx * K + k]; l_phys[k] = ts.obs_phys[idx * K + k]; l_q[k] = ts.obs_q[idx * K + k];
+        }
+        blk = feat_block(ts, sc.slot, idx);
+      }
       kalman_predict(p.pos_weight, p.vel_weight, st2, st);
       kalman_update(p.pos_weight, st, cb, st2);
 #pragma unroll
       for (int i = 0; i < kStateFloats; ++i) st[i] = st2[i];
       pred = state_box(st, cb.conf);
-      ts.length[idx] = ts.length[idx] + 1;
+      o_len = len0 + 1;
+      ts.length[idx] = o_len;
       write_box(ts.obs + idx * 6, cb);
       if (p.is_visual) {
-        ts.vt[idx] = (signed char)f.c_vt[g];
+        o_vt = (signed char)f.c_vt[g];
+        ts.vt[idx] = o_vt;
         // is_merge && !feature_can_be_used(collect thresholds) => feature dropped (visual_sort/metric.rs:327-337)
         bool keep = (flags & 1) != 0;
         if (keep) {
@@ -140,11 +157,10 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
         // optimize_observations: retain featured, stable sort by quality desc, drop last when len >= max
         unsigned char phys[kMaxObs]; float q[kMaxObs];
         int cnt = 0;
-        const int on = ts.obs_n[idx];
         unsigned int used = 0;
-        for (int k = 0; k < on; ++k) {
-          if (ts.obs_hasf[idx * K + k]) {
-            phys[cnt] = ts.obs_phys[idx * K + k]; q[cnt] = ts.obs_q[idx * K + k];
+        for (int k = 0; k < K; ++k) {
+          if (k < on && l_hasf[k]) {
+            phys[cnt] = l_phys[k]; q[cnt] = l_q[k];
             ++cnt;
           }
         }
@@ -173,7 +189,7 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
         }
         ts.obs_n[idx] = (unsigned char)cnt;
         ts.feat_cnt[idx] = (unsigned char)fc;
-        if (keep) fdst = (int)(feat_block(ts, sc.slot, idx) * K + freep);
+        if (keep) fdst = (int)(blk * K + freep);
       }
     }
     ts.epoch[idx] = sc.epoch;
@@ -185,15 +201,12 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
     if (p.positional_kind == 1) box_vertices(pred.xc, pred.yc, pred.angle, pred.aspect, pred.height, ts.vert + idx * 8);
     if (f.feat_dst) f.feat_dst[g] = fdst;
     // SortTrack (src/trackers/sort.rs:286-311)
-    if (f.o_ids) f.o_ids[g] = ts.id[idx];
+    if (f.o_ids) f.o_ids[g] = o_id;
     if (f.o_epochs) f.o_epochs[g] = sc.epoch;
-    if (f.o_lengths) f.o_lengths[g] = ts.length[idx];
-    if (f.o_vt) f.o_vt[g] = p.is_visual ? (ts.vt[idx] < 0 ? (unsigned char)1 : (unsigned char)ts.vt[idx]) : (unsigned char)1;
+    if (f.o_lengths) f.o_lengths[g] = o_len;
+    if (f.o_vt) f.o_vt[g] = p.is_visual ? (o_vt < 0 ? (unsigned char)1 : (unsigned char)o_vt) : (unsigned char)1;
     if (f.o_pred) write_box(f.o_pred + (size_t)g * 6, pred);
-    if (f.o_obs) {
-      const float* ob = ts.obs + idx * 6;
-      for (int i = 0; i < 6; ++i) f.o_obs[(size_t)g * 6 + i] = ob[i];
-    }
+    if (f.o_obs) write_box(f.o_obs + (size_t)g * 6, isnew ? Box{f.in_boxes[(size_t)g * 6], f.in_boxes[(size_t)g * 6 + 1], f.in_boxes[(size_t)g * 6 + 2], f.in_boxes[(size_t)g * 6 + 3], f.in_boxes[(size_t)g * 6 + 4], f.in_boxes[(size_t)g * 6 + 5]} : cb);
   }
   __syncthreads();
   if (tid == 0) {

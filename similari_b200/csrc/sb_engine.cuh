@@ -130,6 +130,11 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   int* vis_cnt;            // [n_scenes]
   int* scene_mode;         // [n_scenes] 0: voting consumes the sparse lists; 1: dense matrices (a list overflowed)
   int* vis_mode;           // [n_scenes] visual side alone (set right after the screen): 0 = the survivors get refined
+  // Lazy positional stage of the visual trackers (null: every pair is evaluated).  VisualVoting (visual_sort/voting.rs:
+  // 45-100) only lets the positional metric decide candidates the visual BestFit pass left undecided, against tracks it
+  // did not claim; a BestFit pre-pass publishes both sets and the culled scan skips everything else.
+  unsigned char* decided;  // [total] candidate was decided by the visual pass
+  unsigned char* excl;     // [slot * track_cap + n] track was claimed by the visual pass
   int* refine_next;        // [n_scenes] next unclaimed survivor of the scene (the refinement's warps claim 32 at a time)
   // outputs (device), any may be null
   unsigned long long* o_ids;
@@ -188,6 +193,13 @@ int launch_vis_cost_b(const Params& p, const TrackStore& ts, const Frame& f, int
 void launch_pos_fill(const Params& p, const Frame& f, int n_scenes, int max_m, int max_n, cudaStream_t st);
 void launch_pos_scan(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                      cudaStream_t st);
+// pass 0: scenes whose visual lists are complete (vis_mode == 0) skip decided candidates / claimed tracks, the others are
+// scanned in full; pass 1 (after scene_mode): full scan of the scenes that fell back to dense voting only then
+void launch_pos_scan_lazy(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                          int pass, cudaStream_t st);
+// BestFit pre-pass of the sparse voting kernel: writes Frame::decided / Frame::excl for the scenes with vis_mode == 0
+int launch_vote_masks(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
+                      cudaStream_t st);
 // phase 0: metadata + tensor-core screen; phase 1: exact refinement of the survivors of the sparse scenes
 int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
                        int phase, cudaStream_t st);

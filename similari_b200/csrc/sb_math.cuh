@@ -139,23 +139,28 @@ SB_HD double clip_area(const double* subj, const double* clp) {
   return fabs(tmp / 2.0);
 }
 
-// Conservative pre-gates of the IoU metric: both return true only when the reference's result is certainly None for any
-// threshold above ~1e-6, so the f64 clip can be skipped.  Pairs they cannot decide go through clip_area unchanged.
-//   * rects_apart: separating-axis test of the two (convex) quadrilaterals on their own edge normals, in f64 on the very
-//     vertices the clip uses, with a margin nine orders of magnitude above the rounding of a dot product.  Separated
-//     polygons have an empty intersection; Sutherland-Hodgman returns either nothing or a rounding sliver whose IoU
-//     (~1e-12) no positive threshold accepts.
+// Conservative pre-gates of the IoU metric: they decide "certainly None" for any threshold above ~1e-6, so that the f64
+// clip can be skipped.  Pairs they cannot decide go through clip_area unchanged.
+//   * rect_overlap_bound: both quadrilaterals are projected on the edge directions of each of them (f64, the very
+//     vertices the clip uses).  A gap on any axis (with a margin nine orders of magnitude above the rounding of a dot
+//     product) separates them: the intersection is empty and Sutherland-Hodgman returns either nothing or a rounding
+//     sliver whose IoU (~1e-12) no positive threshold accepts -> the bound is 0.  Otherwise the intersection lies inside
+//     the axis-aligned (in that rectangle's frame) box spanned by the overlap intervals, whose area bounds it from
+//     above; the smaller of the two frames' bounds is returned (1e300: no bound, e.g. a degenerate edge).
 //   * iou_bound_fails: intersection <= min(area), union >= max(area)  =>  IoU <= min / max.
-SB_HD bool rects_apart(const double* a, const double* b) {
+SB_HD double rect_overlap_bound(const double* a, const double* b) {
   double scale = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { scale = fmax(scale, fabs(a[i])); scale = fmax(scale, fabs(b[i])); }
+  double bound = 1e300;
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
     const double* q = pass == 0 ? a : b;
+    double area = 1.0;
+    bool usable = true;
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      // edge e of the quadrilateral: vertices e -> e + 1; axis = the edge direction of the adjacent side's normal
+      // edge e of the quadrilateral: vertices e -> e + 1 (the two edge directions of a rectangle are its two axes)
       const double ux = q[2 * (e + 1)] - q[2 * e], uy = q[2 * (e + 1) + 1] - q[2 * e + 1];
       double amin = 1e300, amax = -1e300, bmin = 1e300, bmax = -1e300;
 #pragma unroll
@@ -166,10 +171,15 @@ SB_HD bool rects_apart(const double* a, const double* b) {
         bmin = fmin(bmin, pb); bmax = fmax(bmax, pb);
       }
       const double tol = 1e-7 * (fabs(ux) + fabs(uy)) * (scale + 1.0);
-      if (bmin - amax > tol || amin - bmax > tol) return true;
+      if (bmin - amax > tol || amin - bmax > tol) return 0.0;
+      const double len2 = ux * ux + uy * uy;
+      if (!(len2 > 0.0)) { usable = false; continue; }
+      const double ov = fmin(amax, bmax) - fmax(amin, bmin) + tol;   // in units of |u| * length
+      area *= fmax(ov, 0.0) / len2 * sqrt(len2);                      // -> length along this axis
     }
+    if (usable) bound = fmin(bound, area);
   }
-  return false;
+  return bound;
 }
 SB_HD bool iou_bound_fails(float h_l, float a_l, float h_r, float a_r, float conf, float threshold) {
   const float al = h_l * h_l * a_l, ar = h_r * h_r * a_r;

@@ -27,4 +27,8 @@ float shim_maha(float pw, const float* st, const float* b) {
   return sb::maha_distance(st, l5, b[0], b[1], sb::angle_or0(b[2]), b[3], b[4]);
 }
 long long shim_weight(float v) { return sb::weight_i64(v); }
+double shim_overlap_bound(const double* a8, const double* b8) { return sb::rect_overlap_bound(a8, b8); }
+int shim_iou_bound_fails(const float* l, const float* r, float conf, float thr) {
+  return sb::iou_bound_fails(l[4], l[3], r[4], r[3], conf, thr) ? 1 : 0;
+}
 }

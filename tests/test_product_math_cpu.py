@@ -30,6 +30,10 @@ def shim():
     L.shim_maha.restype = C.c_float
     L.shim_weight.argtypes = [C.c_float]
     L.shim_weight.restype = C.c_longlong
+    L.shim_overlap_bound.argtypes = [f64p, f64p]
+    L.shim_overlap_bound.restype = C.c_double
+    L.shim_iou_bound_fails.argtypes = [f32p, f32p, C.c_float, C.c_float]
+    L.shim_iou_bound_fails.restype = C.c_int
     return L
 
 
@@ -147,3 +151,50 @@ def test_weight_cast(oracle, shim):
             assert w in (2**63 - 1, -2**63)
         else:
             assert w == int(np.float32(v) * np.float32(1e6))
+
+
+@pytest.mark.parametrize("oriented", [False, True])
+def test_iou_pregates_never_reject_a_pair_the_reference_keeps(shim, oriented):
+    """The culled positional kernel skips the f64 clip when a pre-gate proves the reference's result is None
+    (rect_overlap_bound == 0: separated; IoU upper bounds below the threshold).  Properties on 40k random pairs,
+    incl. near-duplicates, touching and nested boxes: the bound is never below the clipped area, a zero bound means
+    an (at most rounding-sliver) empty clip, and no pair whose exact IoU * conf reaches the threshold is rejected."""
+    r = np.random.default_rng(77 + oriented)
+    n = 40000
+    thr = 0.3
+    rejected = kept = 0
+    for i in range(n):
+        l = np.array([r.uniform(0, 400), r.uniform(0, 400), r.uniform(-1.6, 1.6) if oriented else np.nan,
+                      r.uniform(0.3, 0.8), r.uniform(40, 160), 1.0], np.float32)
+        mode = i % 4
+        if mode == 0:      # near duplicate
+            q = l.copy()
+            q[:2] += r.normal(0, 3, 2).astype(np.float32)
+            q[4] *= np.float32(r.uniform(0.9, 1.1))
+            if oriented:
+                q[2] += np.float32(r.normal(0, 0.05))
+        elif mode == 1:    # neighbour
+            q = np.array([l[0] + r.uniform(-150, 150), l[1] + r.uniform(-150, 150),
+                          r.uniform(-1.6, 1.6) if oriented else np.nan, r.uniform(0.3, 0.8), r.uniform(40, 160), 1.0], np.float32)
+        elif mode == 2:    # exactly touching / shifted by its own width
+            q = l.copy()
+            q[0] += l[3] * l[4]
+        else:              # nested
+            q = l.copy()
+            q[4] *= np.float32(0.5)
+        conf = np.float32(r.uniform(0.1, 1.0))
+        vl, vq = np.zeros(8), np.zeros(8)
+        shim.shim_vertices(fp(l), dp(vl))
+        shim.shim_vertices(fp(q), dp(vq))
+        area = shim.shim_clip_area(dp(vl), dp(vq))
+        ub = shim.shim_overlap_bound(dp(vl), dp(vq))
+        s_ = float(np.float32(l[4] * l[4] * l[3] + q[4] * q[4] * q[3]))
+        assert ub >= area * (1 - 1e-12) or (ub == 0.0 and area <= 1e-6 * s_), (i, ub, area)
+        iou = area / (s_ - area) if area > 0 else 0.0
+        passes = (np.float32(iou) * conf) >= np.float32(thr) and area != 0.0
+        gate = ub == 0.0 or (ub < 0.5 * s_ and ub * float(conf) * 1.0001 < thr * (s_ - ub)) or \
+            bool(shim.shim_iou_bound_fails(fp(l), fp(q), conf, np.float32(thr)))
+        assert not (gate and passes), (i, iou, conf, ub, area)
+        rejected += gate
+        kept += (not gate)
+    assert rejected > n // 4 and kept > n // 8     # both branches are exercised
