@@ -315,8 +315,9 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
       const float x = ts.pred[(tbase + n) * 6];
       const float r = ts.radius[tbase + n];
       if (!(x == x) || !(r == r)) s_bad = 1;
-      // a track the visual pass claimed sorts behind every window, like the padding
-      kx[n] = (excl && excl[n]) ? 3.402823466e+38f : x; kidx[n] = n;
+      // a track the visual pass claimed sorts behind every window but in front of the padding (so that [0, N) holds
+      // exactly the N tracks)
+      kx[n] = (excl && excl[n]) ? 3.0e38f : x; kidx[n] = n;
       rmax = fmaxf(rmax, r);
     } else { kx[n] = 3.402823466e+38f; kidx[n] = -1; }
   }
