@@ -301,7 +301,7 @@ def main():
         for k_, v_ in t_dev.last_kernel_ms().items():
             dev_stage.setdefault(k_, []).append(v_)
         n_tracks_steps.append(n_before.astype(np.float64))   # the cost matrices of this step are built on the store BEFORE it
-        launches += 18 if visual else 9   # kernels per predict (see profiles/: launch list)
+        launches += 22 if visual else 9   # kernels per predict (profiles/r01_launches_cfg5_v2.csv: 22 in a visual step)
     ev1.record()
     if world > 1:
         dist.barrier()

@@ -677,7 +677,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.c_bf16 = tc.use_tc ? f_cbf16.p : nullptr; f.scene_max = f_scene_max.as<unsigned int>();
   // sparse entry lists + per-scene counters (pos_cnt | vis_cnt | scene_mode), zeroed every frame
   if ((rc = f_poslist.ensure(sizeof(sb::PosEntry) * (size_t)std::max<long long>(1, std::max(posl_total, hint_dets * 32)))) ||
-      (rc = f_counters.ensure(sizeof(int) * 5 * (size_t)n_scenes)))
+      (rc = f_counters.ensure(sizeof(int) * (5 * (size_t)n_scenes + 4))))
     return rc;
   if (P.is_visual && ((rc = f_pairs.ensure(sizeof(sb::VisPair) * (size_t)std::max<long long>(1, std::max(visl_total, hint_dets * 64)))) ||
                       (rc = f_visval.ensure(sizeof(float) * (size_t)std::max<long long>(1, std::max(visl_total, hint_dets * 64))))))
@@ -688,9 +688,10 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.scene_mode = f.pos_cnt + 2 * n_scenes;
   f.vis_mode = f.pos_cnt + 3 * n_scenes;
   f.refine_next = f.pos_cnt + 4 * n_scenes;
+  f.dense_cnt = f.pos_cnt + 5 * n_scenes;
   f.vis_pairs = f_pairs.as<sb::VisPair>();
   f.vis_val = f_visval.as<float>();
-  CU(cudaMemsetAsync(f_counters.p, 0, sizeof(int) * 5 * (size_t)n_scenes, stream));
+  CU(cudaMemsetAsync(f_counters.p, 0, sizeof(int) * (5 * (size_t)n_scenes + 4), stream));
   // outputs
   sb200_predict_out o{};
   if (out) o = *out;

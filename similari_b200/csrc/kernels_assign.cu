@@ -963,6 +963,7 @@ __global__ void scene_mode_kernel(Params p, Frame f, int n_scenes, int tc_used) 
   int mode = vis_side_mode(p, f, sc, s, tc_used);
   if (f.pos_cnt[s] > sc.pos_lcap || f.pos_cnt[s] > kVotePosCap) mode = 1;
   f.scene_mode[s] = mode;
+  if (mode != 0 && f.dense_cnt) atomicAdd(f.dense_cnt, 1);
 }
 // the visual half alone: decided right after the screen, so the refinement does not wait for the positional stage
 __global__ void vis_mode_kernel(Params p, Frame f, int n_scenes, int tc_used) {

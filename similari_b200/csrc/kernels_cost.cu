@@ -461,6 +461,7 @@ __device__ void vis_cost_tile(const Params& p, const TrackStore& ts, const Frame
 // Dense kernel over the scenes in dense mode.  The grid is a fixed number of CTAs that walk (scene, tile) pairs, so
 // when every scene took the screen + refine path (the common case) the launch costs a few microseconds.
 __global__ void __launch_bounds__(VT) vis_cost_kernel(Params p, TrackStore ts, Frame f, int n_scenes, int tiles_x, int tiles_y) {
+  if (f.dense_cnt && *f.dense_cnt == 0) return;   // the common case: every scene took the screen + refine path
   const long long per_scene = (long long)tiles_x * tiles_y;
   for (int scene = 0; scene < n_scenes; ++scene) {
     if (f.scene_mode[scene] == 0) continue;  // this scene's visual entries come from the screen + refine path

@@ -285,7 +285,7 @@ void launch_apply(const Params& p, const TrackStore& ts, const Frame& f, int n_s
 // host's epoch db) and the end-of-frame sweep (the scenes of the request, `scenes` != null, epoch = the scene's new epoch).
 // Only the small per-track arrays move (about 300 B per track).  Feature rows never do: an expired track's block of the
 // scene's feature arena goes to the free list and is handed to the next new track.
-constexpr int WT = 1024;   // threads of the sweep kernel
+constexpr int WT = 512;    // threads of the sweep kernel: two CTAs per SM, so 256 scenes are one wave
 constexpr int WR = 8;      // elements in flight per thread and round of compact_rows
 
 // Moves row j to row s_dst[j] (<= j; -1: dropped) for j in [first, n).  The flattened (row, column) elements are taken in

@@ -226,6 +226,7 @@ int sb200_visual_cost_matrix(int32_t visual_kind, float threshold, const float* 
     f.scene_mode = f.pos_cnt + 2;
     f.vis_mode = f.pos_cnt + 3;
     f.refine_next = f.pos_cnt + 4;
+    f.dense_cnt = f.pos_cnt + 5;
     f.pos_list = sc.alloc<sb::PosEntry>(1);
     if (!f.vis_pairs || !f.vis_val || !f.pos_cnt || !f.pos_list) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
   }

@@ -135,6 +135,7 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   // did not claim; a BestFit pre-pass publishes both sets and the culled scan skips everything else.
   unsigned char* decided;  // [total] candidate was decided by the visual pass
   unsigned char* excl;     // [slot * track_cap + n] track was claimed by the visual pass
+  int* dense_cnt;          // [1] scenes of the request in dense mode (null: unknown); lets the dense kernels leave at once
   int* refine_next;        // [n_scenes] next unclaimed survivor of the scene (the refinement's warps claim 32 at a time)
   // outputs (device), any may be null
   unsigned long long* o_ids;
