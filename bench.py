@@ -102,6 +102,32 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_near_gpu(local):
+    """Pins this process to the CPUs of the GPU's NUMA node before the pinned host buffers are allocated (first touch
+    puts them on that node), so the H2D copies of the e2e arm do not cross the socket interconnect.  Returns a short
+    description and the previous affinity (restored before the CPU baseline, which wants every core)."""
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return "numa node unknown", None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus:
+            return f"numa node {node}: no usable cpu", None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node} of GPU {bdf} ({len(cpus)} cpus)", old
+    except Exception as e:   # no sysfs / restricted container: run unpinned
+        return f"unpinned ({type(e).__name__})", None
+
+
 def make_frames(name, n_frames, scene_base, n_scenes_override=0):
     import dataclasses
 
@@ -191,6 +217,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+
+    affinity_note, old_affinity = ("disabled", None) if os.environ.get("SB200_BENCH_NUMA") == "0" else bind_near_gpu(local)
 
     import similari_b200.engine as eng
     from similari_b200._lib import default_options, pinned_empty
@@ -377,6 +405,7 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": config_dict(name, cfg),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(np.mean(h2d)),
                     "d2h_bytes_per_step": int(np.mean(d2h)), "ms_per_step": e2e_total_ms / K,
+                    "host_affinity": affinity_note,
                     "pipeline": "sb200_prefetch_inputs: the pinned-host -> device copy of frame i+1 is issued at the "
                                 "start of step i and overlaps its kernels; each timed step contains one full input "
                                 "copy and one result read-back"},
@@ -385,6 +414,8 @@ def main():
             "stages_ms": {k_: float(np.mean(v_)) for k_, v_ in dev_stage.items()},
             "roofline": roof,
         }
+        if old_affinity is not None:
+            os.sched_setaffinity(0, old_affinity)   # the CPU baseline uses every core
         if not args.no_cpu_baseline and world == 1:
             import oracle as orc
 

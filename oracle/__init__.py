@@ -339,6 +339,14 @@ def visual_voting(positional_threshold, max_allowed_feature_distance, min_votes,
     return {int(of[i]): [(int(ot[i]), int(ty[i]))] for i in range(n)}
 
 
+def own_area_shares(boxes):
+    """exclusively_owned_areas_normalized_shares of one scene's boxes (src/utils/clipping/bbox_own_areas.rs:8-46)."""
+    b = _f32(boxes).reshape(-1, 6)
+    out = np.zeros(len(b), dtype=np.float32)
+    lib().orc_own_area_shares(_p(b, C.c_float), len(b), _p(out, C.c_float))
+    return out
+
+
 def nms(boxes, scores, nms_threshold, score_threshold=None):
     b = _f32(boxes).reshape(-1, 6)
     s = _f32(scores) if scores is not None else None

@@ -13,6 +13,7 @@
 #include "similari_oracle.h"
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -169,6 +170,123 @@ bool iou(const Box& l, const Box& r, float* out) {
   double res = inter / uni;
   *out = (float)res;
   return true;
+}
+
+// ---------------------------------------------------------------- exclusively owned areas
+// exclusively_owned_areas + exclusively_owned_areas_normalized_shares, src/utils/clipping/bbox_own_areas.rs:8-46:
+//   share_i = min(1, area(box_i \ U_{j: !too_far(i, j)} box_j) / (box_i.area() + EPS)).
+// The reference takes the difference with geo::BooleanOps (geo = "0.27", Cargo.toml:35; not under /root/reference).  Its
+// published algorithm is a general polygon clipper; for convex quadrilaterals the same area is the Green's-theorem
+// integral over the boundary of the difference region: box_i's edges where no other box covers them, plus -- reversed --
+// the other boxes' edges where they run inside box_i outside every remaining box.  A segment meets a convex box in one
+// parameter interval, so each edge needs an interval union only.  Coincident outlines (exact zeros): a segment on an
+// edge line of another box is inside it iff both run the same way (between two covering boxes: only the lower index
+// covers), and never counts as inside box_i itself.  Pinned by the reference's own test (bbox_own_areas.rs:50-79:
+// 75 / 50 / 75) and cross-checked against inclusion-exclusion and Monte-Carlo in tests/test_own_area_cpu.py;
+// parity with geo's floating-point pipeline beyond that is unpinned (expected agreement ~1e-12 relative).
+namespace own {
+bool inside_interval(const P2& p, const P2& d, const P2 q[4], double s, bool on_edge_same_dir_inside, double* t0, double* t1) {
+  double lo = 0.0, hi = 1.0;
+  for (int a = 0; a < 4; ++a) {
+    const P2& A = q[a];
+    const P2& B = q[(a + 1) % 4];
+    const double ex = B.x - A.x, ey = B.y - A.y;
+    const double f0 = s * (ex * (p.y - A.y) - ey * (p.x - A.x));
+    const double f1 = s * (ex * d.y - ey * d.x);
+    if (f1 > 0.0) lo = std::max(lo, -f0 / f1);
+    else if (f1 < 0.0) hi = std::min(hi, -f0 / f1);
+    else {
+      if (f0 < 0.0) return false;
+      if (f0 == 0.0 && !(on_edge_same_dir_inside && (ex * d.x + ey * d.y) > 0.0)) return false;
+    }
+    if (!(lo < hi)) return false;
+  }
+  *t0 = lo; *t1 = hi;
+  return true;
+}
+// certain separation of two quadrilaterals on their edge directions (same margin as the product's pre-gate)
+bool apart(const P2 a[4], const P2 b[4]) {
+  double scale = 0.0;
+  for (int i = 0; i < 4; ++i) {
+    scale = std::max(scale, std::max(std::fabs(a[i].x), std::fabs(a[i].y)));
+    scale = std::max(scale, std::max(std::fabs(b[i].x), std::fabs(b[i].y)));
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    const P2* q = pass == 0 ? a : b;
+    for (int e = 0; e < 2; ++e) {
+      const double ux = q[e + 1].x - q[e].x, uy = q[e + 1].y - q[e].y;
+      double amin = 1e300, amax = -1e300, bmin = 1e300, bmax = -1e300;
+      for (int v = 0; v < 4; ++v) {
+        const double pa = a[v].x * ux + a[v].y * uy, pb = b[v].x * ux + b[v].y * uy;
+        amin = std::min(amin, pa); amax = std::max(amax, pa);
+        bmin = std::min(bmin, pb); bmax = std::max(bmax, pb);
+      }
+      const double tol = 1e-7 * (std::fabs(ux) + std::fabs(uy)) * (scale + 1.0);
+      if (bmin - amax > tol || amin - bmax > tol) return true;
+    }
+  }
+  return false;
+}
+}  // namespace own
+
+std::vector<float> own_area_shares(const std::vector<Box>& boxes) {
+  const int n = (int)boxes.size();
+  std::vector<float> out(n, 1.0f);
+  std::vector<std::array<P2, 4>> quad(n);
+  for (int i = 0; i < n; ++i) vertices(boxes[i], quad[i].data());
+  for (int i = 0; i < n; ++i) {
+    std::vector<const P2*> qs;   // qs[0] = box_i, then the boxes that can cover part of it
+    qs.push_back(quad[i].data());
+    for (int j = 0; j < n; ++j) {
+      if (j == i || too_far(boxes[i], boxes[j])) continue;          // bbox_own_areas.rs:10-15
+      if (own::apart(quad[i].data(), quad[j].data())) continue;      // disjoint: the difference removes nothing
+      qs.push_back(quad[j].data());
+    }
+    std::vector<P2> ring(quad[i].begin(), quad[i].end());
+    double signed_area = 0.0;
+    {
+      const P2 sh = ring[0];
+      for (int a = 0; a < 4; ++a) {
+        const P2 u{ring[a].x - sh.x, ring[a].y - sh.y}, v{ring[(a + 1) % 4].x - sh.x, ring[(a + 1) % 4].y - sh.y};
+        signed_area += u.x * v.y - u.y * v.x;
+      }
+    }
+    const double s = signed_area < 0.0 ? -1.0 : 1.0;
+    const int k = (int)qs.size() - 1;
+    double sum = 0.0;
+    for (int js = 0; js <= k; ++js) {
+      for (int e = 0; e < 4; ++e) {
+        const P2 p = qs[js][e];
+        const P2 d{qs[js][(e + 1) % 4].x - p.x, qs[js][(e + 1) % 4].y - p.y};
+        if (d.x == 0.0 && d.y == 0.0) continue;
+        double wa = 0.0, wb = 1.0;
+        if (js != 0 && !own::inside_interval(p, d, qs[0], s, false, &wa, &wb)) continue;
+        std::vector<std::pair<double, double>> iv;
+        for (int l = 1; l <= k; ++l) {
+          if (l == js) continue;
+          double t0, t1;
+          if (!own::inside_interval(p, d, qs[l], s, js == 0 || l < js, &t0, &t1)) continue;
+          t0 = std::max(t0, wa); t1 = std::min(t1, wb);
+          if (t0 < t1) iv.emplace_back(t0, t1);
+        }
+        std::stable_sort(iv.begin(), iv.end(), [](const std::pair<double, double>& x, const std::pair<double, double>& y) { return x.first < y.first; });
+        double covered = 0.0, ca = 0.0, cb = -1.0;
+        for (const auto& t : iv) {
+          if (cb < ca) { ca = t.first; cb = t.second; }
+          else if (t.first <= cb) cb = std::max(cb, t.second);
+          else { covered += cb - ca; ca = t.first; cb = t.second; }
+        }
+        if (cb >= ca) covered += cb - ca;
+        const double term = ((wb - wa) - covered) * (p.x * d.y - p.y * d.x);
+        sum += js == 0 ? term : -term;
+      }
+    }
+    double own_area = s * sum / 2.0;
+    if (!(own_area > 0.0)) own_area = 0.0;
+    const float e = (float)(own_area / (double)(area(boxes[i]) + EPS));   // bbox_own_areas.rs:42-45
+    out[i] = e >= 1.0f ? 1.0f : e;
+  }
+  return out;
 }
 
 // ---------------------------------------------------------------- Kalman (nalgebra-order f32 arithmetic)
@@ -828,14 +946,22 @@ struct orc_tracker {
     std::vector<Track>& cands = w.cands;
     cands.reserve(m);
     const bool use_own = visual && (o.visual_minimal_own_area_percentage_collect + o.visual_minimal_own_area_percentage_use > 0.0f);
+    // visual_sort/simple_api.rs:110-127: the shares are computed from the scene's observation boxes unless the caller
+    // supplied them
+    std::vector<float> own_local;
+    if (use_own && own_area == nullptr) {
+      std::vector<Box> obs_boxes(m);
+      for (int i = 0; i < m; ++i) obs_boxes[i] = load_box(boxes + (base + i) * 6);
+      own_local = own_area_shares(obs_boxes);
+    }
     for (int i = 0; i < m; ++i) {
       Box det = load_box(boxes + (base + i) * 6);
       bool hf = visual && features != nullptr && (has_feature == nullptr || has_feature[base + i]);
       float q = quality ? quality[base + i] : 1.0f;
-      bool ho = use_own && own_area != nullptr;
+      bool ho = use_own;
       Track c = make_candidate(scene, epoch, det, custom_ids ? custom_ids[base + i] : NONE_ID,
                                features ? features + (base + i) * (size_t)o.feature_dim : nullptr, hf, q, ho,
-                               ho ? own_area[base + i] : 0.0f);
+                               ho ? (own_area != nullptr ? own_area[base + i] : own_local[i]) : 0.0f);
       c.id = UINT64_MAX - (uint64_t)i;  // stand-in for rng.gen(): unique, never collides with real ids
       cands.push_back(std::move(c));
     }
@@ -1070,6 +1196,14 @@ int orc_visual_voting(float positional_threshold, float max_allowed_feature_dist
 }
 
 // nms, src/utils/nms.rs:32-72
+int orc_own_area_shares(const float* boxes, int n, float* out) {
+  std::vector<Box> b(n);
+  for (int i = 0; i < n; ++i) b[i] = load_box(boxes + (size_t)i * 6);
+  std::vector<float> r = own_area_shares(b);
+  for (int i = 0; i < n; ++i) out[i] = r[i];
+  return 0;
+}
+
 int orc_nms(const float* boxes, const float* scores, int n, float nms_threshold, float score_threshold,
             int has_score_threshold, int32_t* out_idx) {
   struct Cand { int src; float rank; int index; };

@@ -113,6 +113,9 @@ int orc_visual_voting(float positional_threshold, float max_allowed_feature_dist
                       const uint64_t* from, const uint64_t* to, const float* attr, const float* feat,
                       uint64_t* out_from, uint64_t* out_to, int32_t* out_type);
 
+/* ---- exclusively owned area shares: src/utils/clipping/bbox_own_areas.rs:8-46 (one scene's boxes) ---- */
+int orc_own_area_shares(const float* boxes, int n, float* out);
+
 /* ---- NMS: src/utils/nms.rs:32-72; scores NaN == None; returns kept count, out_idx = input indices in rank order ---- */
 int orc_nms(const float* boxes, const float* scores, int n, float nms_threshold, float score_threshold,
             int has_score_threshold, int32_t* out_idx);

@@ -2,6 +2,7 @@
 // compare it bit-for-bit with the oracle before any GPU time is spent.  TEST INFRASTRUCTURE: the product never
 // loads this library and has no CPU execution path.
 #include "../../similari_b200/csrc/sb_math.cuh"
+#include "../../similari_b200/csrc/sb_own_area.cuh"
 extern "C" {
 void shim_vertices(const float* b, double* out8) { sb::box_vertices(b[0], b[1], b[2], b[3], b[4], out8); }
 double shim_clip_area(const double* s8, const double* c8) { return sb::clip_area(s8, c8); }
@@ -27,6 +28,9 @@ float shim_maha(float pw, const float* st, const float* b) {
   return sb::maha_distance(st, l5, b[0], b[1], sb::angle_or0(b[2]), b[3], b[4]);
 }
 long long shim_weight(float v) { return sb::weight_i64(v); }
+void shim_own_area_shares(const float* boxes, int n, float* out) {
+  for (int i = 0; i < n; ++i) out[i] = sb::own_area_share_seq(boxes, n, i);
+}
 double shim_overlap_bound(const double* a8, const double* b8) { return sb::rect_overlap_bound(a8, b8); }
 int shim_iou_bound_fails(const float* l, const float* r, float conf, float thr) {
   return sb::iou_bound_fails(l[4], l[3], r[4], r[3], conf, thr) ? 1 : 0;
