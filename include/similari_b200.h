@@ -203,6 +203,12 @@ int sb200_kalman_initiate(float pos_weight, float vel_weight, const float* boxes
 int sb200_kalman_predict(float pos_weight, float vel_weight, const float* in30, int32_t n, float* out30, int32_t device);
 int sb200_kalman_update(float pos_weight, float vel_weight, const float* in30, const float* boxes, int32_t n,
                         float* out30, int32_t device);
+/* exclusively_owned_areas + exclusively_owned_areas_normalized_shares (src/utils/clipping/bbox_own_areas.rs:8-46) for the
+ * boxes of ONE scene: out[i] = share of box i that no other box covers, in [0, 1].  The visual trackers call the same
+ * kernel themselves when an own-area threshold is set and the request carries no `own_area` column
+ * (src/trackers/visual_sort/simple_api.rs:110-127).  SB200_ERR_CAPACITY if more than 32 boxes overlap one box. */
+int sb200_own_area_shares(const float* boxes, int32_t n, float* out, int32_t device);
+
 /* nms (src/utils/nms.rs:32-72): scores NULL or NaN entries == None; out_idx = kept input indices in rank order;
  * returns kept count or negative status. */
 int64_t sb200_nms(const float* boxes, const float* scores, int32_t n, float nms_threshold, float score_threshold,

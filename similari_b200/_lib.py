@@ -80,7 +80,7 @@ EXPORTS = [
     "sb200_current_epoch", "sb200_active_tracks", "sb200_scene_track_counts", "sb200_scene_live_counts", "sb200_set_auto_waste", "sb200_clear_wasted", "sb200_wasted",
     "sb200_idle_tracks", "sb200_scene_tracks", "sb200_last_costs", "sb200_last_stage_ms", "sb200_last_kernel_ms", "sb200_sort_cost_matrix",
     "sb200_visual_cost_matrix", "sb200_sort_voting", "sb200_visual_voting", "sb200_kalman_initiate",
-    "sb200_kalman_predict", "sb200_kalman_update", "sb200_nms", "sb200_host_alloc", "sb200_host_free",
+    "sb200_kalman_predict", "sb200_kalman_update", "sb200_nms", "sb200_own_area_shares", "sb200_host_alloc", "sb200_host_free",
 ]
 
 
@@ -126,6 +126,7 @@ def lib():
         "sb200_kalman_predict": (C.c_int, [f32, f32, vp, i32, vp, i32]),
         "sb200_kalman_update": (C.c_int, [f32, f32, vp, vp, i32, vp, i32]),
         "sb200_nms": (i64, [vp, vp, i32, f32, f32, i32, vp, i32]),
+        "sb200_own_area_shares": (C.c_int, [vp, i32, vp, i32]),
         "sb200_host_alloc": (vp, [C.c_size_t]),
         "sb200_host_free": (None, [vp]),
     }

@@ -200,7 +200,7 @@ struct sb200_tracker {
   } stg[2];
   int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_frameout, f_decided, f_excl, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
+      f_status, f_featdst, f_frameout, f_decided, f_excl, f_own, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
   HBuf h_tiles;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
@@ -212,7 +212,7 @@ struct sb200_tracker {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
                    &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_colb, &f_colvalid, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
-                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl,
+                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl, &f_own,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
                    &f_featdst, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
@@ -775,6 +775,13 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       if (c == 0) CU(cudaMemsetAsync(f_decided.p, 0, (size_t)std::max(total, 1), stream));
     }
     if (timed) CU(cudaEventRecord(ev[0], stream));
+    if (P.is_visual && P.use_own_area && fc.in_own == nullptr && total > 0) {
+      // visual_sort/simple_api.rs:110-127: with an own-area threshold and no shares supplied by the caller, the shares come
+      // from the scene's observation boxes (exclusively_owned_areas_normalized_shares)
+      if ((rc = f_own.ensure(T * 4))) return rc;
+      sb::launch_own_area(fc, s1 - s0, cm, fc.in_boxes, f_own.as<float>(), stream);
+      fc.in_own = f_own.as<float>();
+    }
     sb::launch_prep(P, fc, s1 - s0, cm, stream);
     if (timed) CU(cudaEventRecord(ev[1], stream));
     auto fill_tiles = [&]() -> int {
@@ -858,6 +865,9 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   if (trace) fprintf(stderr, "[sb200] predict: setup %.3f ms, launched at %.3f ms, synced at %.3f ms (total dets %d)\n", ms_setup, ms_launch, since(t_begin), total);
   long long new_total = 0;
   for (int s = 0; s < n_scenes; ++s) {
+    if (h_status[s] & 2)
+      return fail(SB200_ERR_CAPACITY, "more than %d boxes overlap one detection of scene %llu (own-area shares)", 32,
+                  (unsigned long long)sd[s].scene_id);
     if (h_status[s]) return fail(SB200_ERR_INTERNAL, "track store overflow in scene %llu", (unsigned long long)sd[s].scene_id);
     const int live = h_fo[3 * s], expired = h_fo[3 * s + 2];
     n_tracks[sd[s].slot] = live;

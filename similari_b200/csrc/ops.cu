@@ -326,6 +326,33 @@ int sb200_visual_voting(float positional_threshold, int32_t min_votes, const flo
   return run_voting(true, positional_threshold, min_votes, pos_mn, vis_mnk, m, n, k, winner, voting_type, device);
 }
 
+int sb200_own_area_shares(const float* boxes, int32_t n, float* out, int32_t device) {
+  if (n < 0 || (n > 0 && (!boxes || !out))) return ops_fail(SB200_ERR_INVALID, "bad arguments");
+  Scratch sc;
+  int rc = begin(sc, device);
+  if (rc) return rc;
+  if (n == 0) return 0;
+  sb::Frame f;
+  memset(&f, 0, sizeof(f));
+  f.total = n;
+  sb::SceneDesc sd;
+  memset(&sd, 0, sizeof(sd));
+  sd.m = n;
+  f.scenes = sc.upload(&sd, 1);
+  f.status = sc.alloc<int>(1, true);
+  float* d_boxes = sc.upload(boxes, (size_t)n * 6);
+  float* d_out = sc.alloc<float>(n);
+  if (!f.scenes || !f.status || !d_boxes || !d_out) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
+  sb::launch_own_area(f, 1, n, d_boxes, d_out, sc.st);
+  int status = 0;
+  cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, sc.st);
+  cudaMemcpyAsync(&status, f.status, sizeof(int), cudaMemcpyDeviceToHost, sc.st);
+  rc = finish(sc);
+  if (rc) return rc;
+  if (status & 2) return ops_fail(SB200_ERR_CAPACITY, "more than 32 boxes overlap one box (own-area shares)");
+  return 0;
+}
+
 static int kalman_op(int op, float pw, float vw, const float* in30, const float* boxes, int n, float* out30, int device) {
   if (n < 0 || (n > 0 && !out30) || (op != 0 && n > 0 && !in30) || (op != 1 && n > 0 && !boxes)) return ops_fail(SB200_ERR_INVALID, "bad arguments");
   Scratch sc;

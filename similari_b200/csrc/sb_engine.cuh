@@ -159,6 +159,9 @@ struct VisRowMeta { float rowk; int ok, pad0, pad1; };   // row constant of the 
 
 // ---- kernel launchers (each in its own .cu) ----
 void launch_prep(const Params& p, const Frame& f, int n_scenes, int max_m, cudaStream_t st);
+// own-area shares of every detection among the detections of its scene (raw request boxes [total][6]) -> d_out[total];
+// sets bit 1 of Frame::status[scene] when more than kOwnMaxNb boxes overlap one detection
+void launch_own_area(const Frame& f, int n_scenes, int max_m, const float* d_boxes, float* d_out, cudaStream_t st);
 // dst (device) <- src (device alias of mapped pinned host memory), bytes a multiple of 4; a kernel instead of a DMA
 void launch_pull(void* dst, const void* src, size_t bytes, cudaStream_t st);
 void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,

@@ -226,6 +226,14 @@ def kalman_update(states30, boxes, pw=1 / 20, vw=1 / 160, device=0):
     return out
 
 
+def own_area_shares(boxes, device=0):
+    """exclusively_owned_areas_normalized_shares of ONE scene's boxes ([n][6]) on the GPU."""
+    b = _f32(boxes).reshape(-1, 6)
+    out = np.zeros(len(b), np.float32)
+    check(lib().sb200_own_area_shares(ptr(b), len(b), ptr(out), device))
+    return out
+
+
 def nms_indices(boxes, scores, nms_threshold, score_threshold=None, device=0):
     b = _f32(boxes).reshape(-1, 6)
     s = _f32(scores) if scores is not None else None
