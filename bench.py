@@ -384,6 +384,10 @@ def main():
             roof = {"kernel": "vis_screen_kernel (tcgen05 BF16 screen of the visual cost matrix)", "bound": "tensor",
                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                     "traffic": traffic, "peak_source": peak_src, "algorithmic_flops_per_launch": float(np.mean(fl)),
+                    # the kernel runs ~0.25 ms of a ~1.15 ms step at full clocks, so the burst peak is the denominator;
+                    # against the sustained figure of MEASURED_PEAKS.json the fraction would be:
+                    "frac_of_sustained_peak": (achieved / float(peaks["bf16_tflops_sustained"])
+                                               if peaks.get("bf16_tflops_sustained") else None),
                     "kernel_ms": kms,
                     "visual_stage_hbm": {"stage_ms": float(np.mean(dev_stage["visual_cost"])),
                                          "algorithmic_bytes": float(np.mean(by)),
