@@ -102,6 +102,28 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def usable_cores():
+    """Host threads the CPU legs may really use: min(cpu_count, scheduler affinity, cgroup CPU quota)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:   # cgroup v2: "max 100000" or "<quota> <period>"; cgroup v1: cpu.cfs_quota_us / cpu.cfs_period_us (-1 == none)
+        if os.path.exists("/sys/fs/cgroup/cpu.max"):
+            q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+            if q != "max":
+                n = min(n, max(1, int(float(q) / float(p))))
+        else:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and p > 0:
+                n = min(n, max(1, q // p))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def bind_near_gpu(local):
     """Pins this process to the CPUs of the GPU's NUMA node before the pinned host buffers are allocated (first touch
     puts them on that node), so the H2D copies of the e2e arm do not cross the socket interconnect.  Returns a short
@@ -176,7 +198,7 @@ def run_reference(args):
     import oracle as orc
 
     orc.build()
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     sample_scenes = args.cpu_sample_scenes or max(cores, 8)
     warm = max(3, min(args.warmup, 4))
     steps = max(1, min(args.steps, 2))
@@ -424,7 +446,7 @@ def main():
             import oracle as orc
 
             orc.build()
-            cores = os.cpu_count() or 1
+            cores = usable_cores()
             sample = args.cpu_sample_scenes or min(cfg.n_scenes, max(cores, 8))
             ccfg, cframes = make_frames(name, 5, 0, sample)
             cu, cs = cpu_port_run(name, cframes, 4, 1, cores)

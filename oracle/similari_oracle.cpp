@@ -17,6 +17,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -489,8 +490,13 @@ inline float reduce_add8(const float l[8]) {
   float d0 = q0 + q2, d1 = q1 + q3;
   return d0 + d1;
 }
-// euclidean, src/distance.rs:9-19
-float euclidean_p(const float* a, const float* b, int blocks) {
+// The reference computes these with 8-lane SIMD vectors (ultraviolet / wide f32x8, src/distance.rs:9-47).  The scalar
+// loops below restate the arithmetic lane by lane; on x86-64 hosts with AVX2 the same operations are issued as 8-lane
+// vector instructions (sub / mul per lane, the reduce_add tree lo+hi -> pairs -> single, blocks accumulated one after the
+// other), which is bit-identical (every operation is the same IEEE f32 operation on the same operands; no FMA) and lets
+// the timed CPU baseline run at the speed a SIMD build of the reference would.  ORACLE_NO_SIMD=1 forces the scalar loops;
+// tests/test_oracle_simd.py checks both paths bit for bit.
+float euclidean_scalar(const float* a, const float* b, int blocks) {
   float acc = 0.0f;
   for (int i = 0; i < blocks; ++i) {
     float blk[8];
@@ -502,8 +508,7 @@ float euclidean_p(const float* a, const float* b, int blocks) {
   }
   return std::sqrt(acc);
 }
-// cosine, src/distance.rs:26-47
-float cosine_p(const float* a, const float* b, int blocks) {
+float cosine_scalar(const float* a, const float* b, int blocks) {
   float divided = 0.0f;
   for (int i = 0; i < blocks; ++i) {
     float blk[8];
@@ -522,6 +527,58 @@ float cosine_p(const float* a, const float* b, int blocks) {
     f2 = f2 + reduce_add8(blk);
   }
   return divided / std::sqrt(f1 * f2);
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#define ORC_HAVE_AVX2_PATH 1
+}  // namespace (intrinsics header must be included at file scope)
+#include <immintrin.h>
+namespace {
+// wide::f32x8::reduce_add on a vector register: (lo + hi) -> q0..q3; (q0 + q2, q1 + q3); d0 + d1
+__attribute__((target("avx2"))) inline float reduce_add8_v(__m256 t) {
+  const __m128 q = _mm_add_ps(_mm256_castps256_ps128(t), _mm256_extractf128_ps(t, 1));
+  const __m128 d = _mm_add_ps(q, _mm_movehl_ps(q, q));
+  return _mm_cvtss_f32(_mm_add_ss(d, _mm_shuffle_ps(d, d, 0x55)));
+}
+__attribute__((target("avx2"))) float euclidean_avx2(const float* a, const float* b, int blocks) {
+  float acc = 0.0f;
+  for (int i = 0; i < blocks; ++i) {
+    const __m256 t = _mm256_sub_ps(_mm256_loadu_ps(a + i * 8), _mm256_loadu_ps(b + i * 8));
+    acc += reduce_add8_v(_mm256_mul_ps(t, t));
+  }
+  return std::sqrt(acc);
+}
+__attribute__((target("avx2"))) float cosine_avx2(const float* a, const float* b, int blocks) {
+  float divided = 0.0f, f1 = 0.0f, f2 = 0.0f;
+  for (int i = 0; i < blocks; ++i) {
+    const __m256 va = _mm256_loadu_ps(a + i * 8), vb = _mm256_loadu_ps(b + i * 8);
+    divided += reduce_add8_v(_mm256_mul_ps(va, vb));
+    f1 = f1 + reduce_add8_v(_mm256_mul_ps(va, va));
+    f2 = f2 + reduce_add8_v(_mm256_mul_ps(vb, vb));
+  }
+  return divided / std::sqrt(f1 * f2);
+}
+inline bool use_avx2() {
+  static const bool ok = __builtin_cpu_supports("avx2") && std::getenv("ORACLE_NO_SIMD") == nullptr;
+  return ok;
+}
+#else
+inline bool use_avx2() { return false; }
+#endif
+
+// euclidean, src/distance.rs:9-19
+float euclidean_p(const float* a, const float* b, int blocks) {
+#ifdef ORC_HAVE_AVX2_PATH
+  if (use_avx2()) return euclidean_avx2(a, b, blocks);
+#endif
+  return euclidean_scalar(a, b, blocks);
+}
+// cosine, src/distance.rs:26-47
+float cosine_p(const float* a, const float* b, int blocks) {
+#ifdef ORC_HAVE_AVX2_PATH
+  if (use_avx2()) return cosine_avx2(a, b, blocks);
+#endif
+  return cosine_scalar(a, b, blocks);
 }
 
 // ---------------------------------------------------------------- voting
@@ -1196,6 +1253,13 @@ int orc_visual_voting(float positional_threshold, float max_allowed_feature_dist
 }
 
 // nms, src/utils/nms.rs:32-72
+// test hooks: the scalar and (when compiled and supported) the AVX2 restatement of the feature distances
+float orc_euclidean_scalar(const float* a, const float* b, int blocks) { return euclidean_scalar(a, b, blocks); }
+float orc_cosine_scalar(const float* a, const float* b, int blocks) { return cosine_scalar(a, b, blocks); }
+int orc_simd_active(void) { return use_avx2() ? 1 : 0; }
+float orc_euclidean_blocks(const float* a, const float* b, int blocks) { return euclidean_p(a, b, blocks); }
+float orc_cosine_blocks(const float* a, const float* b, int blocks) { return cosine_p(a, b, blocks); }
+
 int orc_own_area_shares(const float* boxes, int n, float* out) {
   std::vector<Box> b(n);
   for (int i = 0; i < n; ++i) b[i] = load_box(boxes + (size_t)i * 6);

@@ -113,6 +113,13 @@ int orc_visual_voting(float positional_threshold, float max_allowed_feature_dist
                       const uint64_t* from, const uint64_t* to, const float* attr, const float* feat,
                       uint64_t* out_from, uint64_t* out_to, int32_t* out_type);
 
+/* ---- test hooks for the two restatements of the feature distances (scalar lanes / AVX2 vectors), blocks of 8 floats ---- */
+float orc_euclidean_scalar(const float* a, const float* b, int blocks);
+float orc_cosine_scalar(const float* a, const float* b, int blocks);
+float orc_euclidean_blocks(const float* a, const float* b, int blocks);
+float orc_cosine_blocks(const float* a, const float* b, int blocks);
+int orc_simd_active(void);
+
 /* ---- exclusively owned area shares: src/utils/clipping/bbox_own_areas.rs:8-46 (one scene's boxes) ---- */
 int orc_own_area_shares(const float* boxes, int n, float* out);
 
