@@ -828,31 +828,50 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Tra
     int parity = 0;
     int root = 0;
     while (root < nrows) {
-      // ---- fast path (warp 0): roots whose tightest column is free are matched without a block-wide search
-      if (wid == 0) {
-        int r = root;
-        if (thr > 0) {
-          for (; r < nrows; ++r) {
+      // ---- fast path: roots whose tightest column is free are matched without a block-wide search.  The labels do not
+      // change on this path (delta = 0), so the tightest column of EVERY remaining root can be computed at once (one
+      // thread per row over its CSR entries); the sequential walk "commit while ok and the column is still free" then
+      // stops at the first root that is not ok, whose column was taken before this round, or whose column a lower
+      // remaining root also wants -- found with an atomicMin of the row index per column.  Everything below that root is
+      // committed in parallel: exactly the state the one-by-one walk reaches (tools/km_root_stats.py: in cfg2 / cfg4
+      // scenes every root ends here, so one round replaces a 500-step serial loop of a single warp).
+      {
+        int* cand = s.alt;        // [ny] scratch between searches: tightest column of row r, or -1
+        int* cfirst = s.slackx;   // [ny] lowest remaining row that wants column y
+        for (int y = tid; y < ny; y += VT_THREADS) cfirst[y] = 0x7fffffff;
+        if (tid == 0) s_misc[2] = nrows;
+        __syncthreads();
+        for (int r = root + tid; r < nrows; r += VT_THREADS) {
+          int besty = -1;
+          if (thr > 0) {
             const long long lxr = s.lx[r];
             // candidates for the minimum slack: own diagonal column and the row's valid entries
             MinPair best; best.v = lxr + s.ly[r] - thr; best.y = r;
-            if (lane != 0) { best.v = 9223372036854775807LL; best.y = 0x7fffffff; }
             if (r < n_seen_rows) {
               const int m = s.row_cand[r];
-              for (int q = s.row_ptr[m] + lane; q < s.row_ptr[m + 1]; q += 32) {
+              for (int q = s.row_ptr[m]; q < s.row_ptr[m + 1]; ++q) {
                 const int y = nrows + s.col_rank[s.csr_n[q]];
                 MinPair c; c.v = lxr + s.ly[y] - weight_i64(s.csr_v[q]); c.y = y;
                 best = min_pair(best, c);
               }
             }
-            best = warp_min(best);
             // every other column has weight 0 and slack >= lx[r] > 0, so a zero here is the global minimum
-            if (best.v != 0 || s.yx[best.y] >= 0 || lxr <= 0) break;
-            if (lane == 0) { s.xy[r] = best.y; s.yx[best.y] = r; }
-            __syncwarp();
+            if (best.v == 0 && lxr > 0) besty = best.y;
           }
+          cand[r] = besty;
+          if (besty >= 0) atomicMin(&cfirst[besty], r);
         }
-        if (lane == 0) s_misc[2] = r;
+        __syncthreads();
+        for (int r = root + tid; r < nrows; r += VT_THREADS) {
+          const int y = cand[r];
+          if (y < 0 || cfirst[y] != r || s.yx[y] >= 0) atomicMin(&s_misc[2], r);
+        }
+        __syncthreads();
+        const int first_fail = s_misc[2];
+        for (int r = root + tid; r < first_fail; r += VT_THREADS) {
+          const int y = cand[r];
+          s.xy[r] = y; s.yx[y] = r;
+        }
       }
       __syncthreads();
       root = s_misc[2];
