@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SB200_VERSION 1
+#define SB200_VERSION 2
 
 typedef enum {
   SB200_OK = 0,
@@ -140,9 +140,27 @@ int sb200_predict_batch(sb200_tracker* t, int32_t n_scenes, const uint64_t* scen
 int sb200_prefetch_inputs(sb200_tracker* t, int32_t total, const float* boxes, const float* features,
                           const uint8_t* has_feature, const float* quality, const int64_t* custom_ids,
                           const float* own_area);
+/* The asynchronous form of the same call -- what BatchSort::predict is in the reference, where the request is queued
+ * and the per-scene results arrive later on PredictionBatchResult's channel (src/trackers/sort/batch_api.rs:222-290,
+ * src/trackers/batch.rs:24-38).  The frame is enqueued on the tracker's stream and the call returns; up to four frames
+ * are in flight (a fifth call waits for the oldest).  The host buffers (inputs, and the `out` columns, which should be
+ * pinned: sb200_host_alloc) must stay valid and are only defined after sb200_sync() -- or after a later call has
+ * reported sb200_frames_in_flight() low enough.  An error inside an asynchronous frame is returned by the next
+ * predict / sync / query call on the tracker. */
+int sb200_predict_batch_async(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids, const int32_t* det_offsets,
+                              const float* boxes, const float* features, const uint8_t* has_feature, const float* quality,
+                              const int64_t* custom_ids, const float* own_area, const sb200_predict_out* out);
+/* Waits for every frame in flight (PredictionBatchResult::get until batch_size results arrived) and hands their
+ * bookkeeping to the host side of the tracker; returns the first error an asynchronous frame raised, if any. */
+int sb200_sync(sb200_tracker* t);
+/* Frames enqueued and not yet completed (PredictionBatchResult::ready is `== 0`); never blocks. */
+int sb200_frames_in_flight(sb200_tracker* t);
 /* Same call with boxes / features / has_feature / quality / custom_ids / own_area and every non-NULL `out` column
- * being DEVICE pointers (inputs already resident in HBM).  scene_ids and det_offsets stay host pointers.
- * The call is asynchronous on the tracker's stream except for one 4-byte-per-scene status read-back. */
+ * being DEVICE pointers (inputs already resident in HBM).  scene_ids and det_offsets stay host pointers (they are
+ * consumed before the call returns).  Stream-ordered like sb200_predict_batch_async: nothing in the call waits for
+ * the device -- the per-frame tables that depend on the previous frame's outcome (tracks per scene, matrix offsets, the
+ * tile list of the tensor-core kernel, the id counter) are built by a kernel -- so consecutive frames queue back to back
+ * and a caller can order its own work after the results with an event on the tracker's stream. */
 int sb200_predict_batch_device(sb200_tracker* t, int32_t n_scenes, const uint64_t* scene_ids,
                                const int32_t* det_offsets, const float* boxes, const float* features,
                                const uint8_t* has_feature, const float* quality, const int64_t* custom_ids,
@@ -177,7 +195,15 @@ int64_t sb200_scene_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uin
  * (src/trackers/visual_sort/voting.rs:45-100) can still consult -- so the other entries read None; with the environment
  * variable SB200_FULL_COSTS=1 every pair is evaluated as the reference does. */
 int64_t sb200_last_costs(sb200_tracker* t, uint64_t scene_id, int64_t cap, float* out, int32_t* m, int32_t* n);
-/* Per-stage device times (ms) of the last predict call: prep, positional cost, visual cost, voting, apply. */
+/* Cumulative work of all completed frames (waits for the frames in flight): counters3 = { sum over frames and scenes of
+ * M x N (pair-associations, N = tracks the device store held when the frame ran), sum of M x (feature rows scanned by the
+ * visual cost kernel), frames }, ms8 = { summed per-stage device times: prep, positional cost, visual cost, voting, apply;
+ * summed times of the dominant visual-cost kernel and of the refinement; frames in which those two ran }.  Either may
+ * be NULL.  bench.py reads it before and after its timed region. */
+int sb200_work_counters(sb200_tracker* t, uint64_t* counters3, double* ms8);
+/* Kernels this library has launched since it was loaded (every launch site counts itself). */
+uint64_t sb200_launch_count(void);
+/* Per-stage device times (ms) of the last completed predict call: prep, positional cost, visual cost, voting, apply. */
 int sb200_last_stage_ms(sb200_tracker* t, float* out5);
 /* Device times (ms) of the dominant visual-cost kernels of the last predict call: [0] tensor-core screen kernel,
  * [1] scene-mode + exact refinement kernels; 0 when the tensor-core path was not used. */
@@ -206,7 +232,8 @@ int sb200_kalman_update(float pos_weight, float vel_weight, const float* in30, c
 /* exclusively_owned_areas + exclusively_owned_areas_normalized_shares (src/utils/clipping/bbox_own_areas.rs:8-46) for the
  * boxes of ONE scene: out[i] = share of box i that no other box covers, in [0, 1].  The visual trackers call the same
  * kernel themselves when an own-area threshold is set and the request carries no `own_area` column
- * (src/trackers/visual_sort/simple_api.rs:110-127).  SB200_ERR_CAPACITY if more than 32 boxes overlap one box. */
+ * (src/trackers/visual_sort/simple_api.rs:110-127).  A box that more than 32 others overlap takes a second,
+ * CTA-per-box pass; SB200_ERR_CAPACITY only beyond 2800 overlapping boxes on one box. */
 int sb200_own_area_shares(const float* boxes, int32_t n, float* out, int32_t device);
 
 /* nms (src/utils/nms.rs:32-72): scores NULL or NaN entries == None; out_idx = kept input indices in rank order;

@@ -81,6 +81,7 @@ EXPORTS = [
     "sb200_idle_tracks", "sb200_scene_tracks", "sb200_last_costs", "sb200_last_stage_ms", "sb200_last_kernel_ms", "sb200_sort_cost_matrix",
     "sb200_visual_cost_matrix", "sb200_sort_voting", "sb200_visual_voting", "sb200_kalman_initiate",
     "sb200_kalman_predict", "sb200_kalman_update", "sb200_nms", "sb200_own_area_shares", "sb200_host_alloc", "sb200_host_free",
+    "sb200_predict_batch_async", "sb200_sync", "sb200_frames_in_flight", "sb200_work_counters", "sb200_launch_count",
 ]
 
 
@@ -104,6 +105,11 @@ def lib():
         "sb200_tracker_set_stream": (C.c_int, [vp, vp]),
         "sb200_predict_batch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PredictOut)]),
         "sb200_prefetch_inputs": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
+        "sb200_predict_batch_async": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PredictOut)]),
+        "sb200_sync": (C.c_int, [vp]),
+        "sb200_frames_in_flight": (C.c_int, [vp]),
+        "sb200_work_counters": (C.c_int, [vp, vp, vp]),
+        "sb200_launch_count": (u64, []),
         "sb200_predict_batch_device": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PredictOut)]),
         "sb200_skip_epochs": (C.c_int, [vp, u64, i32]),
         "sb200_current_epoch": (i64, [vp, u64]),

@@ -994,11 +994,13 @@ __global__ void vis_mode_kernel(Params p, Frame f, int n_scenes, int tc_used) {
 void launch_scene_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st) {
   if (n_scenes == 0) return;
   scene_mode_kernel<<<(n_scenes + 127) / 128, 128, 0, st>>>(p, f, n_scenes, tc_used ? 1 : 0);
+  note_launch();
 }
 
 void launch_vis_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st) {
   if (n_scenes == 0 || !f.vis_mode) return;
   vis_mode_kernel<<<(n_scenes + 127) / 128, 128, 0, st>>>(p, f, n_scenes, tc_used ? 1 : 0);
+  note_launch();
 }
 
 void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_only, cudaStream_t st) {
@@ -1009,6 +1011,7 @@ void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_o
     dim3 grid(32, n_scenes);
     vis_max_kernel<<<grid, 256, 0, st>>>(p, f, f.scene_max);
   }
+  note_launch();
 }
 
 size_t voting_smem_need(int max_m, int max_n) {
@@ -1027,11 +1030,13 @@ int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_s
     if ((e = cudaFuncSetAttribute(voting_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d)) != cudaSuccess) return (int)e;
     voting_sparse_kernel<true, false><<<n_scenes, VT_THREADS, smem_s, st>>>(p, ts, f);
     voting_kernel<true><<<n_scenes, VT_THREADS, smem_d, st>>>(p, f);
+    note_launch(2);
   } else {
     if ((e = cudaFuncSetAttribute(voting_sparse_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)) != cudaSuccess) return (int)e;
     if ((e = cudaFuncSetAttribute(voting_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d)) != cudaSuccess) return (int)e;
     voting_sparse_kernel<false, false><<<n_scenes, VT_THREADS, smem_s, st>>>(p, ts, f);
     voting_kernel<false><<<n_scenes, VT_THREADS, smem_d, st>>>(p, f);
+    note_launch(2);
   }
   return 0;
 }
@@ -1044,6 +1049,7 @@ int launch_vote_masks(const Params& p, const TrackStore& ts, const Frame& f, int
   cudaError_t e = cudaFuncSetAttribute(voting_sparse_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
   if (e != cudaSuccess) return (int)e;
   voting_sparse_kernel<true, true><<<n_scenes, VT_THREADS, smem_s, st>>>(p, ts, f);
+  note_launch();
   return 0;
 }
 

@@ -22,6 +22,7 @@ __global__ void prep_kernel(Params p, Frame f) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= f.total) return;
   i += f.det0;
+  if (f.decided) f.decided[i] = 0;   // lazy positional stage: nobody is decided before the BestFit pre-pass
   const float* b = f.in_boxes + (size_t)i * 6;
   float xc = b[0], yc = b[1], ang = b[2], asp = b[3], h = b[4], conf = b[5];
   if (ang == 0.0f) ang = nanf("");
@@ -98,9 +99,11 @@ void launch_prep(const Params& p, const Frame& f, int n_scenes, int max_m, cudaS
   (void)n_scenes; (void)max_m;
   if (f.total == 0) return;
   prep_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f);
+  note_launch();
   if (p.is_visual && f.in_feat) {  // squared norms (+ BF16 operand rows when f.c_bf16 is set for this frame)
     long long threads = (long long)f.total * 32;
     cand_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, f, reinterpret_cast<__nv_bfloat16*>(f.c_bf16));
+    note_launch();
   }
 }
 
@@ -219,6 +222,7 @@ __global__ void pos_fill_none_kernel(Frame f, long long total4, long long total)
   float4 q4 = make_float4(qnan, qnan, qnan, qnan);
   // chunk range [off, off + total): scalar head up to 16-byte alignment, vector body, scalar tail
   float* base = f.pos + f.pos_fill_off;
+  if (f.dyn) total = f.dyn->pos_total;   // stream-ordered predict: only the device knows the packed size
   const long long head = min(total, (long long)((4 - (f.pos_fill_off & 3)) & 3));
   float4* o4 = reinterpret_cast<float4*>(base + head);
   const long long n4 = (total - head) / 4;
@@ -401,8 +405,8 @@ void launch_pos_fill(const Params& p, const Frame& f, int n_scenes, int max_m, i
   (void)p;
   if (n_scenes == 0 || max_m == 0 || max_n == 0 || pos_use_dense(max_n)) return;   // the dense kernel writes every element
   // pos matrices are packed back to back: total elements = last offset + last size (the host passes it via f.pos_total)
-  const long long total = f.pos_total;
-  if (total > 0) pos_fill_none_kernel<<<1184, 256, 0, st>>>(f, total / 4, total);
+  const long long total = f.pos_total;   // exact (operators) or an upper bound (trackers: the kernel reads f.dyn)
+  if (total > 0) { pos_fill_none_kernel<<<1184, 256, 0, st>>>(f, total / 4, total); note_launch(); }
 }
 
 static void pos_scan_impl(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
@@ -415,6 +419,7 @@ static void pos_scan_impl(const Params& p, const TrackStore& ts, const Frame& f,
     dim3 block(TN, TY);
     if (p.positional_kind == 0) pos_cost_kernel<0><<<grid, block, 0, st>>>(p, ts, f);
     else pos_cost_kernel<1><<<grid, block, 0, st>>>(p, ts, f);
+    note_launch();
     return;
   }
   int Np = 1;
@@ -430,6 +435,7 @@ static void pos_scan_impl(const Params& p, const TrackStore& ts, const Frame& f,
     cudaFuncSetAttribute(pos_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     pos_scan_kernel<1><<<grid, PS_THREADS, smem, st>>>(p, ts, f, lazy_pass);
   }
+  note_launch();
 }
 
 void launch_pos_scan(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
@@ -635,6 +641,7 @@ int launch_vis_cost_b(const Params& p, const TrackStore& ts, const Frame& f, int
     const long long want = (long long)tx * ty * (use_tc ? 1 : n_scenes);
     const int grid = (int)std::min<long long>(want, 148 * 8);
     vis_cost_kernel<<<grid, VT, 0, st>>>(p, ts, f, n_scenes, tx, ty);
+    note_launch();
     launch_scene_max(p, f, n_scenes, /*init_only=*/false, st);
   }
   return 0;

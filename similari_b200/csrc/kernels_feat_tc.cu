@@ -188,9 +188,15 @@ constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)
 // cta_group::2: one MMA spans the CTA pair, M = 256 (128 accumulator rows in each CTA's TMEM), N = 256
 constexpr uint32_t kIdescBf16Pair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
-// BF16 operand rounding bound on a dot product: each operand carries relative error <= 2^-9, so
-// |dot~ - dot| <= (2^-8 + 2^-18) * sum|a_i b_i| <= ~2^-8 * ||a|| ||b||; 1.5x head-room covers the fp32 accumulation.
-constexpr float kScreenRelErr = 1.5f / 256.0f;
+// BF16 operand rounding bound on a dot product.  BF16 keeps 8 significant bits; round-to-nearest leaves a relative error
+// of at most u = 2^-8 per operand (a value just above a power of two sits half a 2^-7 spacing from its neighbours).
+// Two rounded operands: |a~ b~ - a b| <= (2u + u^2) |a b|, hence by Cauchy-Schwarz
+//   |dot~ - dot| <= (2^-7 + 2^-16) * sum|a_i b_i| <= (2^-7 + 2^-16) * ||a|| ||b||.
+// The fp32 accumulation in TMEM adds at most D * 2^-24 relative (truncation; D <= 4096: 2^-12).  Together
+// 2^-7 + 2^-16 + 2^-12 = 2.066 * 2^-8 <= kScreenRelErr = 2.1 * 2^-8.  (Round 1 used 1.5 * 2^-8: fine for the rounding
+// errors of real feature vectors, which average out, but below the adversarial worst case -- the screen must never drop
+// a pair the exact metric keeps.)
+constexpr float kScreenRelErr = 2.1f / 256.0f;
 
 // ------------------------------------------------------------------------------------------------ screen kernel
 // CL == 2: clusters of two CTAs work on two candidate tiles (m0, m0 + 128) of the same track-row tile; each CTA loads
@@ -202,8 +208,11 @@ constexpr float kScreenRelErr = 1.5f / 256.0f;
 template <int CL, bool COSINE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p,
-                  TrackStore ts, Frame f, const TcTile* tiles, int n_tiles, const VisColMeta* colmeta,
-                  const VisColGeo* colgeo, const VisRowMeta* rowmeta, const float* colb, const unsigned int* colvalid) {
+                  TrackStore ts, Frame f, const TcTile* tiles, int n_tiles_host, const int* n_tiles_dev,
+                  const VisColMeta* colmeta, const VisColGeo* colgeo, const VisRowMeta* rowmeta, const float* colb,
+                  const unsigned int* colvalid) {
+  // trackers: the tile list is built on the device (frame_setup_kernel) and so is its length
+  const int n_tiles = n_tiles_dev ? *n_tiles_dev : n_tiles_host;
   extern __shared__ unsigned char smem_raw_[];
   // offset arithmetic on the __shared__ array (not on an integer) keeps the accesses in the shared address space
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw_ + ((1024u - (smem_u32(smem_raw_) & 1023u)) & 1023u));
@@ -250,7 +259,9 @@ vis_screen_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      TcTile tl_n = tiles[cta_first < n_tiles ? cta_first : 0];
+      TcTile tl_n;
+      tl_n.scene = 0; tl_n.m0 = 0; tl_n.c0 = 0; tl_n.pad = 0;
+      if (cta_first < n_tiles) tl_n = tiles[cta_first];
       SceneDesc sc_n = f.scenes[tl_n.scene];
       for (int t = cta_first; t < n_tiles; t += cta_step, ++it) {
         const TcTile tl = tl_n;
@@ -583,6 +594,7 @@ void launch_vis_densify(const Params& p, const Frame& f, int n_scenes, cudaStrea
   dim3 grid(64, n_scenes);
   vis_fill_none_kernel<<<grid, 256, 0, st>>>(p, f);
   vis_scatter_kernel<<<grid, 256, 0, st>>>(p, f);
+  note_launch(2);
 }
 
 // ------------------------------------------------------------------------------------------------ bf16 operand copies
@@ -599,6 +611,7 @@ void launch_to_bf16(const float* src, int src_pitch, int d, int d8, long long ro
   if (rows == 0) return;
   long long n = rows * d8;
   to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, src_pitch, d, d8, rows, (__nv_bfloat16*)dst);
+  note_launch();
 }
 
 // ------------------------------------------------------------------------------------------------ host launcher
@@ -718,6 +731,7 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
       if (tail) vis_refine_kernel<false, true><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
       else vis_refine_kernel<false, false><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
     }
+    note_launch();
     if (tc.ev_refine1) cudaEventRecord(tc.ev_refine1, st);
     return 0;
   }
@@ -737,8 +751,10 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
   if (max_rows > 0) {
     dim3 grid((max_rows + 255) / 256, n_scenes);
     vis_meta_kernel<<<grid, 256, 0, st>>>(p, ts, f, n_scenes, max_rows, tc.colmeta, tc.colgeo, tc.colb, tc.colvalid);
+    note_launch();
   }
   vis_rowmeta_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f, tc.rowmeta);
+  note_launch();
   if (tc.ev_screen0) cudaEventRecord(tc.ev_screen0, st);
   {
     const int ncta = cluster ? 2 * std::min(tc.n_tiles, tc.num_sms / 2) : std::min(tc.n_tiles, tc.num_sms);
@@ -755,15 +771,17 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
     cfg.numAttrs = 1;
     const TcTile* d_tiles = tc.d_tiles;
     int n_tiles = tc.n_tiles;
+    const int* d_n_tiles = tc.d_n_tiles;
     const VisColMeta* cmeta = tc.colmeta;
     const VisColGeo* cgeo = tc.colgeo;
     const VisRowMeta* rmeta = tc.rowmeta;
     const float* cb = tc.colb;
     const unsigned int* cv = tc.colvalid;
     void* args[] = {(void*)&mA, (void*)&mB, (void*)&p, (void*)&ts, (void*)&f, (void*)&d_tiles, (void*)&n_tiles,
-                    (void*)&cmeta, (void*)&cgeo, (void*)&rmeta, (void*)&cb, (void*)&cv};
+                    (void*)&d_n_tiles, (void*)&cmeta, (void*)&cgeo, (void*)&rmeta, (void*)&cb, (void*)&cv};
     e = cudaLaunchKernelExC(&cfg, fn, args);
     if (e != cudaSuccess) return (int)e;
+    note_launch();
   }
   if (tc.ev_screen1) cudaEventRecord(tc.ev_screen1, st);
   return 0;

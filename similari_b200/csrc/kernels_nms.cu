@@ -151,6 +151,7 @@ int launch_nms(const float* d_boxes, const float* d_scores, int n, float nms_thr
   size_t smem = 8 * (size_t)words;
   if (smem > 48 * 1024) cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   nms_sweep_kernel<<<1, 32, smem, st>>>(nvalid, mask, words, order, d_out_idx, d_out_count);
+  note_launch(5);
   e = cudaStreamSynchronize(st);
   cudaFree(rank); cudaFree(sx); cudaFree(sy); cudaFree(sr); cudaFree(sa); cudaFree(valid); cudaFree(order);
   cudaFree(nvalid); cudaFree(vert); cudaFree(mask);

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
     const unsigned char flags = p.is_visual ? f.c_flags[g] : 0;
     const float quality = (p.is_visual && f.in_quality) ? f.in_quality[g] : 1.0f;
     unsigned long long tid64;
+    if (f.id_counter) id_base = *f.id_counter;   // stream-ordered predict: the counter lives on the device
     if (p.is_batch) tid64 = id_base + (unsigned long long)g + 1ull;  // one id per candidate (batch_api.rs:102-106)
     else tid64 = id_base + (unsigned long long)(s_newbefore + rank) + 1ull;
     size_t idx;
@@ -271,9 +272,11 @@ void launch_apply(const Params& p, const TrackStore& ts, const Frame& f, int n_s
   (void)max_m;
   if (n_scenes == 0) return;
   apply_kernel<<<n_scenes, AT, 0, st>>>(p, ts, f, n_scenes, id_base, d_n_tracks);
+  note_launch();
   if (p.is_visual && f.in_feat && f.total > 0) {
     long long threads = (long long)f.total * 32;
     feat_store_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, ts, f);
+    note_launch();
   }
 }
 
@@ -318,10 +321,19 @@ __device__ __forceinline__ void compact_rows(T* arr, size_t base, int width, con
 
 __global__ void __launch_bounds__(WT) waste_kernel(Params p, TrackStore ts, const unsigned int* cur_epoch,
                                                    const unsigned long long* scene_ids, int* n_tracks, WastedBuf wb,
-                                                   const SceneDesc* scenes, int* frame_out) {
+                                                   const SceneDesc* scenes, int* frame_out, unsigned long long* id_counter,
+                                                   long long id_add, const int* new_count, int n_scenes) {
   extern __shared__ int s_dst[];   // [n] destination row of every track (-1: expired)
   __shared__ int s_warp[WT / 32];
   __shared__ int s_wbase, s_wcount, s_first;
+  if (id_counter && blockIdx.x == 0 && threadIdx.x == 0) {
+    // ids consumed by this frame: one per detection (batch trackers) or one per new track (sort/simple_api.rs:99-102,170).
+    // Every apply_kernel CTA has read the old value: that kernel completed before this one started.
+    unsigned long long add = 0;
+    if (id_add >= 0) add = (unsigned long long)id_add;
+    else for (int s2 = 0; s2 < n_scenes; ++s2) add += (unsigned long long)new_count[s2];
+    *id_counter += add;
+  }
   const int slot = scenes ? scenes[blockIdx.x].slot : (int)blockIdx.x;
   const int n = n_tracks[slot];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -437,10 +449,13 @@ __global__ void __launch_bounds__(WT) waste_kernel(Params p, TrackStore ts, cons
 
 static void launch_waste_kernel(const Params& p, const TrackStore& ts, int n_ctas, const unsigned int* d_cur_epoch,
                                 const unsigned long long* d_scene_ids, int* d_n_tracks, const WastedBuf& wb,
-                                const SceneDesc* scenes, int* frame_out, cudaStream_t st) {
+                                const SceneDesc* scenes, int* frame_out, unsigned long long* id_counter, long long id_add,
+                                const int* new_count, cudaStream_t st) {
   const size_t smem = (size_t)std::max(1, ts.track_cap) * sizeof(int);   // s_dst for the largest possible scene
   if (smem > 48 * 1024) cudaFuncSetAttribute(waste_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  waste_kernel<<<n_ctas, WT, smem, st>>>(p, ts, d_cur_epoch, d_scene_ids, d_n_tracks, wb, scenes, frame_out);
+  waste_kernel<<<n_ctas, WT, smem, st>>>(p, ts, d_cur_epoch, d_scene_ids, d_n_tracks, wb, scenes, frame_out, id_counter,
+                                         id_add, new_count, n_ctas);
+  note_launch();
 }
 
 void launch_waste(const Params& p, const TrackStore& ts, int n_slots, const unsigned int* d_cur_epoch,
@@ -448,13 +463,14 @@ void launch_waste(const Params& p, const TrackStore& ts, int n_slots, const unsi
                   cudaStream_t st) {
   (void)max_n;
   if (n_slots == 0) return;
-  launch_waste_kernel(p, ts, n_slots, d_cur_epoch, d_scene_ids, d_n_tracks, wb, nullptr, nullptr, st);
+  launch_waste_kernel(p, ts, n_slots, d_cur_epoch, d_scene_ids, d_n_tracks, wb, nullptr, nullptr, nullptr, 0, nullptr, st);
 }
 
 void launch_frame_sweep(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int* d_n_tracks,
                         const WastedBuf& wb, cudaStream_t st) {
   if (n_scenes == 0) return;
-  launch_waste_kernel(p, ts, n_scenes, nullptr, nullptr, d_n_tracks, wb, f.scenes, f.frame_out, st);
+  launch_waste_kernel(p, ts, n_scenes, nullptr, nullptr, d_n_tracks, wb, f.scenes, f.frame_out, f.id_counter, f.id_add,
+                      f.new_count, st);
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -478,6 +494,7 @@ void launch_kalman_ops(int op, float pw, float vw, const float* in30, const floa
                        cudaStream_t st) {
   if (n == 0) return;
   kalman_ops_kernel<<<(n + 127) / 128, 128, 0, st>>>(op, pw, vw, in30, boxes, n, out30);
+  note_launch();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -494,6 +511,116 @@ void launch_pull(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   const size_t threads = n4 > n1 ? n4 : n1;
   pull_kernel<<<(unsigned int)((threads + 255) / 256), 256, 0, st>>>(reinterpret_cast<unsigned int*>(dst),
                                                                     reinterpret_cast<const unsigned int*>(src), n4, n1);
+  note_launch();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// frame_setup_kernel: the per-frame tables, built where the track counts live.  The host writes what it knows about the
+// request (SceneReq, mapped pinned memory: read over PCIe by this kernel, no copy-engine transfer) and upper bounds for
+// every buffer; the number of tracks each scene holds WHEN THIS FRAME RUNS (n_tracks, arena_top: left there by the previous
+// frame's apply / sweep kernels) is joined in here: matrix offsets, column offsets, the tile list of the tensor-core
+// kernel and the frame scalars.  One CTA: the tables are a few KB and three prefix sums.
+constexpr int FS_T = 1024;
+
+__global__ void __launch_bounds__(FS_T) frame_setup_kernel(Params p, TrackStore ts, Frame f, const SceneReq* req, int n_scenes,
+                                                           const int* n_tracks, int mstep, TcTile* tiles, FrameDyn* dyn,
+                                                           int* zero, int n_zero) {
+  __shared__ long long s_w[4][FS_T / 32];
+  __shared__ long long s_carry[4];
+  __shared__ unsigned long long s_red[3][FS_T / 32];
+  __shared__ int s_maxn, s_maxrows;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < n_zero; i += FS_T) zero[i] = 0;
+  if (tid < 4) s_carry[tid] = 0;
+  if (tid == 0) { s_maxn = 0; s_maxrows = 0; }
+  __syncthreads();
+  const int K = p.max_obs;
+  unsigned long long u_mn = 0, u_rows = 0, live = 0;
+  for (int base = 0; base < n_scenes; base += FS_T) {
+    const int s = base + tid;
+    SceneReq r;
+    r.slot = 0; r.m = 0; r.det_base = 0; r.epoch = 0; r.scene_id = 0; r.pos_lbase = r.pos_lcap = r.vis_lbase = r.vis_lcap = 0;
+    int n = 0, nb = 0, rows = 0;
+    long long v[4] = {0, 0, 0, 0};
+    if (s < n_scenes) {
+      r = req[s];
+      n = n_tracks[r.slot];
+      nb = (p.is_visual && ts.arena_top) ? ts.arena_top[r.slot] : 0;
+      rows = nb * K;
+      v[0] = (long long)r.m * n;
+      v[1] = p.is_visual ? (long long)r.m * n * K : 0;
+      v[2] = ((long long)rows + 127) / 128 * 128;   // 16-byte aligned bulk copies of 256-column slabs
+      v[3] = mstep > 0 ? (long long)((r.m + mstep - 1) / mstep) * ((rows + 255) / 256) : 0;
+      u_mn += (unsigned long long)v[0];
+      u_rows += (unsigned long long)r.m * (unsigned long long)rows;
+      live += (unsigned long long)n;
+      atomicMax(&s_maxn, n);
+      atomicMax(&s_maxrows, rows);
+    }
+    long long x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      x[q] = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, x[q], o);
+        if (lane >= o) x[q] += t;
+      }
+      if (lane == 31) s_w[q][wid] = x[q];
+    }
+    __syncthreads();
+    long long ex[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      long long woff = 0;
+      for (int w = 0; w < wid; ++w) woff += s_w[q][w];
+      ex[q] = s_carry[q] + woff + x[q] - v[q];
+    }
+    __syncthreads();
+    if (tid == FS_T - 1) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s_carry[q] = ex[q] + v[q];
+    }
+    if (s < n_scenes) {
+      SceneDesc d;
+      d.slot = r.slot; d.m = r.m; d.n = n; d.det_base = r.det_base;
+      d.pos_off = ex[0]; d.vis_off = ex[1];
+      d.epoch = r.epoch; d.col_off = (int)ex[2]; d.scene_id = r.scene_id;
+      d.pos_lbase = r.pos_lbase; d.pos_lcap = r.pos_lcap; d.vis_lbase = r.vis_lbase; d.vis_lcap = r.vis_lcap;
+      d.nb = nb; d.pad0 = 0;
+      f.scenes[s] = d;
+      if (mstep > 0 && tiles) {
+        int k = (int)ex[3];
+        for (int m0 = 0; m0 < r.m; m0 += mstep)
+          for (int c0 = 0; c0 < rows; c0 += 256) { TcTile t; t.scene = s; t.m0 = m0; t.c0 = c0; t.pad = 0; tiles[k++] = t; }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    u_mn += __shfl_xor_sync(0xffffffffu, u_mn, o);
+    u_rows += __shfl_xor_sync(0xffffffffu, u_rows, o);
+    live += __shfl_xor_sync(0xffffffffu, live, o);
+  }
+  if (lane == 0) { s_red[0][wid] = u_mn; s_red[1][wid] = u_rows; s_red[2][wid] = live; }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long a = 0, b = 0, c = 0;
+    for (int w = 0; w < FS_T / 32; ++w) { a += s_red[0][w]; b += s_red[1][w]; c += s_red[2][w]; }
+    FrameDyn d;
+    d.n_tiles = (int)s_carry[3]; d.total_cols = (int)s_carry[2]; d.max_rows = s_maxrows; d.max_n = s_maxn;
+    d.pos_total = s_carry[0]; d.vis_total = s_carry[1];
+    d.units_mn = a; d.units_rows = b; d.live_total = (long long)c; d.pad0 = 0;
+    *dyn = d;
+  }
+}
+
+void launch_frame_setup(const Params& p, const TrackStore& ts, const Frame& f, const SceneReq* req, int n_scenes,
+                        const int* d_n_tracks, int mstep, TcTile* tiles, FrameDyn* dyn, int* zero, int n_zero,
+                        cudaStream_t st) {
+  frame_setup_kernel<<<1, FS_T, 0, st>>>(p, ts, f, req, n_scenes, d_n_tracks, mstep, tiles, dyn, zero, n_zero);
+  note_launch();
 }
 
 }  // namespace sb

@@ -342,14 +342,16 @@ int sb200_own_area_shares(const float* boxes, int32_t n, float* out, int32_t dev
   f.status = sc.alloc<int>(1, true);
   float* d_boxes = sc.upload(boxes, (size_t)n * 6);
   float* d_out = sc.alloc<float>(n);
-  if (!f.scenes || !f.status || !d_boxes || !d_out) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
-  sb::launch_own_area(f, 1, n, d_boxes, d_out, sc.st);
+  int* d_ovf_cnt = sc.alloc<int>(1);
+  int2* d_ovf = sc.alloc<int2>(n);
+  if (!f.scenes || !f.status || !d_boxes || !d_out || !d_ovf_cnt || !d_ovf) return ops_fail(SB200_ERR_CUDA, "cudaMalloc failed");
+  sb::launch_own_area(f, 1, n, d_boxes, d_out, d_ovf_cnt, d_ovf, sc.st);
   int status = 0;
   cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, sc.st);
   cudaMemcpyAsync(&status, f.status, sizeof(int), cudaMemcpyDeviceToHost, sc.st);
   rc = finish(sc);
   if (rc) return rc;
-  if (status & 2) return ops_fail(SB200_ERR_CAPACITY, "more than 32 boxes overlap one box (own-area shares)");
+  if (status & 2) return ops_fail(SB200_ERR_CAPACITY, "more than 2800 boxes overlap one box (own-area shares)");
   return 0;
 }
 

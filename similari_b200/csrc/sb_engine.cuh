@@ -50,6 +50,28 @@ struct SceneDesc {  // one per scene of the current request
   int pad0;
 };
 
+// Host-written half of a scene descriptor.  The host knows the request (slot, detections, epoch, list slices) but -- with
+// several frames in flight -- not how many tracks the scene's store holds when this frame runs; frame_setup_kernel joins
+// the two on the device (n, nb, matrix / column / tile offsets) so that predict never waits for the previous frame.
+struct SceneReq {
+  int slot, m, det_base;
+  unsigned int epoch;
+  unsigned long long scene_id;
+  int pos_lbase, pos_lcap, vis_lbase, vis_lcap;
+};
+struct FrameDyn {   // per-frame scalars only the device knows (written by frame_setup_kernel, read by later kernels)
+  int n_tiles;            // tiles of the tensor-core visual cost kernel
+  int total_cols;         // padded physical feature rows of all scenes
+  int max_rows;           // max over the scenes of nb * K
+  int max_n;              // max over the scenes of n
+  long long pos_total;    // elements of the packed positional matrices
+  long long vis_total;    // elements of the packed visual matrices
+  unsigned long long units_mn;     // sum over the scenes of m * n   (pair-associations of this frame)
+  unsigned long long units_rows;   // sum over the scenes of m * nb * K (dot products the visual cost kernel evaluates)
+  long long live_total;   // sum over the scenes of n
+  long long pad0;
+};
+
 struct VisPair { int g, row, scene, outcol; };  // screen survivor: detection, feature row, scene, logical column
 struct PosEntry { unsigned short m, n; float v; };  // one valid (candidate, track, cost) positional entry
 constexpr int kVotePosCap = 3072;   // sparse entries per scene the voting kernel keeps in shared memory
@@ -122,6 +144,9 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   int* status;             // [n_scenes] per-scene status flags (capacity overflow etc.)
   int* feat_dst;           // [total] destination feature row (block*K + phys) or -1
   int* frame_out;          // [n_scenes][3] written by the end-of-frame sweep: live tracks, arena blocks, newly expired
+  const FrameDyn* dyn;     // device-built frame scalars (null in the stateless operators: host values are used)
+  unsigned long long* id_counter;   // device copy of the tracker's id counter (null: the id_base argument is used)
+  long long id_add;        // ids this frame consumes when known up front (batch trackers: one per detection), else -1
   // sparse views of the (mostly None) cost matrices, consumed by the voting stage
   PosEntry* pos_list;      // valid positional entries, per-scene slices
   int* pos_cnt;            // [n_scenes]
@@ -159,11 +184,22 @@ struct VisRowMeta { float rowk; int ok, pad0, pad1; };   // row constant of the 
 
 // ---- kernel launchers (each in its own .cu) ----
 void launch_prep(const Params& p, const Frame& f, int n_scenes, int max_m, cudaStream_t st);
-// own-area shares of every detection among the detections of its scene (raw request boxes [total][6]) -> d_out[total];
-// sets bit 1 of Frame::status[scene] when more than kOwnMaxNb boxes overlap one detection
-void launch_own_area(const Frame& f, int n_scenes, int max_m, const float* d_boxes, float* d_out, cudaStream_t st);
+// own-area shares of every detection among the detections of its scene (raw request boxes [total][6]) -> d_out[total].
+// d_ovf_cnt / d_ovf ([total] (scene, detection) pairs): detections that more than kOwnMaxNb boxes overlap, handled by a
+// second, CTA-per-detection pass; bit 1 of Frame::status[scene] is only set beyond kOwnBigNb overlapping boxes.
+void launch_own_area(const Frame& f, int n_scenes, int max_m, const float* d_boxes, float* d_out, int* d_ovf_cnt,
+                     int2* d_ovf, cudaStream_t st);
 // dst (device) <- src (device alias of mapped pinned host memory), bytes a multiple of 4; a kernel instead of a DMA
 void launch_pull(void* dst, const void* src, size_t bytes, cudaStream_t st);
+// Per-frame tables built on the device: scene descriptors (request half from `req`, a device alias of mapped pinned host
+// memory; store half from d_n_tracks / ts.arena_top), the tile list of the tensor-core visual cost kernel (mstep = 128 or
+// 256 candidate rows per tile, 0: none) and the frame scalars; also zeroes the `n_zero` ints at `zero` (list counters, status).
+void launch_frame_setup(const Params& p, const TrackStore& ts, const Frame& f, const SceneReq* req, int n_scenes,
+                        const int* d_n_tracks, int mstep, TcTile* tiles, FrameDyn* dyn, int* zero, int n_zero,
+                        cudaStream_t st);
+// kernels launched by this library since it was loaded (every launch site counts itself)
+void note_launch(int n = 1);
+unsigned long long launch_count();
 void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                      cudaStream_t st);
 // visual cost: fp32 SIMT kernel in the reference's summation order (use_tc == false) or the tcgen05 3xTF32 kernel
@@ -172,7 +208,8 @@ struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense ex
   bool cluster2;   // tiles describe candidate-tile PAIRS processed by 2-CTA clusters (multicast B loads, or pair MMAs)
   bool pair;       // with cluster2: cta_group::2 MMAs (256 x 256 x 16 across the CTA pair)
   const TcTile* d_tiles;
-  int n_tiles;
+  int n_tiles;            // tiles (stateless operators) or an upper bound of them (trackers: the count is d_n_tiles[0])
+  const int* d_n_tiles;   // device-side tile count (null: n_tiles is exact)
   long long a_rows, b_rows;
   int num_sms;
   cudaEvent_t ev_screen0, ev_screen1, ev_refine1;  // optional per-kernel timing (null: not timed)

@@ -25,7 +25,8 @@
 
 namespace sb {
 
-constexpr int kOwnMaxNb = 32;   // boxes overlapping one box that are kept on chip (more: SB200_ERR_CAPACITY)
+constexpr int kOwnMaxNb = 32;     // boxes overlapping one box the warp-per-detection kernel keeps on chip
+constexpr int kOwnBigNb = 2800;   // ... and the CTA-per-detection second pass (more: SB200_ERR_CAPACITY); 64 B each
 
 // signed shoelace area of a quadrilateral (x0,y0,...,x3,y3), coordinates shifted by the first vertex like geo
 SB_HD double quad_area_signed(const double* q) {
@@ -99,6 +100,57 @@ SB_HD double own_edge_term(const double* quads, int k, int js, int e, double s) 
     else { covered += cur_b - cur_a; cur_a = ia[qn]; cur_b = ib[qn]; }
   }
   if (cur_b >= cur_a) covered += cur_b - cur_a;
+  const double term = ((wb - wa) - covered) * (px * dy - py * dx);
+  return js == 0 ? term : -term;
+}
+
+// The same term without per-thread interval storage, for a box that more than kOwnMaxNb boxes overlap (second pass of
+// own_area_kernel).  The union of the covering intervals inside the window [wa, wb] is walked run by run: a run starts at
+// the smallest interval start beyond the previous run and grows while some interval starts inside it and ends beyond it.
+// The runs -- and therefore the partial sums -- are exactly those of the sorted merge above; cost O(k) per step.
+SB_HD double own_edge_term_big(const double* quads, int k, int js, int e, double s) {
+  const double* q = quads + js * 8;
+  const int e2 = (e + 1) & 3;
+  const double px = q[2 * e], py = q[2 * e + 1];
+  const double dx = q[2 * e2] - px, dy = q[2 * e2 + 1] - py;
+  if (dx == 0.0 && dy == 0.0) return 0.0;
+  double wa = 0.0, wb = 1.0;
+  if (js != 0 && !seg_inside_quad(px, py, dx, dy, quads, s, false, &wa, &wb)) return 0.0;
+  double covered = 0.0;
+  double done = -1.0;      // everything up to `done` is accounted for
+  bool first = true;
+  for (;;) {
+    // next run: the smallest clipped start that is >= wa and lies beyond `done` (first run: any start)
+    double ra = 0.0, rb = -1.0;
+    bool found = false;
+    for (int l = 1; l <= k; ++l) {
+      if (l == js) continue;
+      double t0, t1;
+      if (!seg_inside_quad(px, py, dx, dy, quads + l * 8, s, js == 0 || l < js, &t0, &t1)) continue;
+      if (t0 < wa) t0 = wa;
+      if (t1 > wb) t1 = wb;
+      if (!(t0 < t1)) continue;
+      if (!first && !(t0 > done)) continue;            // starts inside what is already merged
+      if (!found || t0 < ra || (t0 == ra && t1 > rb)) { ra = t0; rb = t1; found = true; }
+    }
+    if (!found) break;
+    // grow the run
+    for (bool grown = true; grown;) {
+      grown = false;
+      for (int l = 1; l <= k; ++l) {
+        if (l == js) continue;
+        double t0, t1;
+        if (!seg_inside_quad(px, py, dx, dy, quads + l * 8, s, js == 0 || l < js, &t0, &t1)) continue;
+        if (t0 < wa) t0 = wa;
+        if (t1 > wb) t1 = wb;
+        if (!(t0 < t1)) continue;
+        if (t0 <= rb && t0 >= ra && t1 > rb) { rb = t1; grown = true; }
+      }
+    }
+    covered += rb - ra;
+    done = rb;
+    first = false;
+  }
   const double term = ((wb - wa) - covered) * (px * dy - py * dx);
   return js == 0 ? term : -term;
 }

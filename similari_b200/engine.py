@@ -45,8 +45,9 @@ class Tracker:
 
     def predict_batch(self, scene_ids, det_offsets, boxes, features=None, has_feature=None, quality=None,
                       custom_ids=None, own_area=None, want=("ids", "epochs", "lengths", "voting_types", "predicted",
-                                                            "observed"), out=None):
-        """Host-pointer call (sb200_predict_batch).  Returns a dict of numpy arrays (the SortTrack columns)."""
+                                                            "observed"), out=None, wait=True):
+        """Host-pointer call (sb200_predict_batch).  Returns a dict of numpy arrays (the SortTrack columns).
+        wait=False: sb200_predict_batch_async -- the arrays (pass pinned ones in `out`) are defined after sync()."""
         scene_ids = np.ascontiguousarray(scene_ids, dtype=np.uint64)
         det_offsets = np.ascontiguousarray(det_offsets, dtype=np.int32)
         total = int(det_offsets[-1]) if len(det_offsets) else 0
@@ -74,10 +75,28 @@ class Tracker:
                 out["observed"] = np.zeros((total, 6), dtype=np.float32)
         po = PredictOut(ptr(out.get("ids")), ptr(out.get("epochs")), ptr(out.get("lengths")),
                         ptr(out.get("voting_types")), ptr(out.get("predicted")), ptr(out.get("observed")))
-        check(self._L.sb200_predict_batch(self._h, len(scene_ids), ptr(scene_ids), ptr(det_offsets), ptr(boxes),
-                                          ptr(features), ptr(has_feature), ptr(quality), ptr(custom_ids),
-                                          ptr(own_area), C.byref(po)))
+        fn = self._L.sb200_predict_batch if wait else self._L.sb200_predict_batch_async
+        check(fn(self._h, len(scene_ids), ptr(scene_ids), ptr(det_offsets), ptr(boxes), ptr(features), ptr(has_feature),
+                 ptr(quality), ptr(custom_ids), ptr(own_area), C.byref(po)))
+        if not wait:   # the caller's arrays must outlive the frame
+            self._keep = getattr(self, "_keep", [])[-16:] + [(boxes, features, has_feature, quality, custom_ids, own_area, out)]
         return out
+
+    def sync(self):
+        """sb200_sync: waits for every frame in flight; raises the first error an asynchronous frame produced."""
+        check(self._L.sb200_sync(self._h))
+
+    def frames_in_flight(self):
+        return int(check(self._L.sb200_frames_in_flight(self._h)))
+
+    def work_counters(self):
+        """Cumulative work of the completed frames (waits for the frames in flight)."""
+        c = np.zeros(3, np.uint64)
+        ms = np.zeros(8, np.float64)
+        check(self._L.sb200_work_counters(self._h, ptr(c), ptr(ms)))
+        return {"pair_associations": int(c[0]), "visual_dot_products": int(c[1]), "frames": int(c[2]),
+                "stage_ms": dict(zip(("prep", "positional_cost", "visual_cost", "voting", "apply"), map(float, ms[:5]))),
+                "vis_screen_ms": float(ms[5]), "vis_refine_ms": float(ms[6]), "tc_frames": int(ms[7])}
 
     def prefetch_inputs(self, boxes, features=None, has_feature=None, quality=None, custom_ids=None, own_area=None):
         """sb200_prefetch_inputs: start the H2D copy of a future request.  The arrays must be the very objects later
@@ -93,7 +112,8 @@ class Tracker:
     def predict_batch_device(self, scene_ids, det_offsets, d_boxes, d_features=0, d_has_feature=0, d_quality=0,
                              d_custom_ids=0, d_own_area=0, d_ids=0, d_epochs=0, d_lengths=0, d_voting_types=0,
                              d_predicted=0, d_observed=0):
-        """Device-pointer call (sb200_predict_batch_device); d_* are raw device addresses (0 == NULL)."""
+        """Device-pointer call (sb200_predict_batch_device); d_* are raw device addresses (0 == NULL).  Stream-ordered:
+        returns as soon as the frame is enqueued."""
         scene_ids = np.ascontiguousarray(scene_ids, dtype=np.uint64)
         det_offsets = np.ascontiguousarray(det_offsets, dtype=np.int32)
         vp = lambda a: C.c_void_p(a) if a else None  # noqa: E731
@@ -169,6 +189,11 @@ class Tracker:
         out = np.zeros(2, np.float32)
         check(self._L.sb200_last_kernel_ms(self._h, ptr(out)))
         return {"vis_screen": float(out[0]), "vis_refine": float(out[1])}
+
+
+def launch_count():
+    """Kernels launched by libsimilari_b200.so since it was loaded."""
+    return int(lib().sb200_launch_count())
 
 
 # ------------------------------------------------------------------------------------------------ stateless operators
