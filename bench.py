@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--scenes", type=int, default=0, help="override the scene count (debug)")
     ap.add_argument("--cpu-sample-scenes", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--visual-threshold", default=None,
+                    help="override the visual metric's threshold: a float, or 'max' = the reference's default Euclidean(f32::MAX)")
+    ap.add_argument("--feat-noise", type=float, default=None, help="override the workload's feature noise (sensitivity sweeps)")
     return ap.parse_args()
 
 
@@ -68,7 +71,11 @@ def config_dict(name, cfg, extra=None):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock and throttle reasons while the timed region runs.  Sampled in-process through NVML (a query costs
+    microseconds and holds no driver lock the compute path needs); falls back to forking nvidia-smi at 2 Hz when the
+    NVML binding is missing.  Round 1 forked nvidia-smi at 10 Hz from every rank, which slowed the host-bound loop down."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -76,30 +83,65 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
+        self.source = "nvml"
         self._halt = threading.Event()
+        self._h = None
+        try:
+            import pynvml
 
-    def run(self):
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps ordinals: resolve through the PCI bus id of the torch device
+            import torch
+
+            prop = torch.cuda.get_device_properties(index)
+            bdf = "%08x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        nv = self._nv
+        self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        for bit, nm in self.REASONS.items():
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for nm, v in zip(names, out[2:]):
+            if "Active" in v and "Not" not in v:
+                self.reasons.add(nm)
+
+    def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if "Active" in v and "Not" not in v:
-                        self.reasons.add(nm)
+                if self._h is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(0.02 if self._h is not None else 0.5)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=5)
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "source": self.source}
 
 
 def usable_cores():
@@ -150,7 +192,7 @@ def bind_near_gpu(local):
         return f"unpinned ({type(e).__name__})", None
 
 
-def make_frames(name, n_frames, scene_base, n_scenes_override=0):
+def make_frames(name, n_frames, scene_base, n_scenes_override=0, feat_noise=None):
     import dataclasses
 
     from similari_b200.workload import CONFIGS, Workload
@@ -158,17 +200,27 @@ def make_frames(name, n_frames, scene_base, n_scenes_override=0):
     cfg = CONFIGS[name]
     if n_scenes_override:
         cfg = dataclasses.replace(cfg, n_scenes=n_scenes_override)
+    if feat_noise is not None:
+        cfg = dataclasses.replace(cfg, feat_noise=feat_noise)
     cfg = dataclasses.replace(cfg, seed=cfg.seed + 7919 * scene_base)
     wl = Workload(cfg, scene_base=scene_base)
     return cfg, [wl.next_frame() for _ in range(n_frames)]
 
 
-def cpu_port_run(name, frames, warm, steps, threads):
+def option_overrides(args):
+    """Tracker option overrides of the command line (same for the GPU arm and the CPU arms)."""
+    over = {}
+    if args.visual_threshold is not None:
+        over["visual_threshold"] = 3.402823466e38 if args.visual_threshold == "max" else float(args.visual_threshold)
+    return over
+
+
+def cpu_port_run(name, frames, warm, steps, threads, over=None):
     """Times the oracle tracker (reference algorithm, reference execution order, `threads` host threads)."""
     import oracle as orc
     from similari_b200.workload import tracker_options_for
 
-    opts = tracker_options_for(name, orc.make_options)
+    opts = tracker_options_for(name, orc.make_options, **(over or {}))
     t = orc.Tracker(opts, threads=threads)
     units, secs = 0, 0.0
 
@@ -192,6 +244,9 @@ def cpu_port_run(name, frames, warm, steps, threads):
 
 
 def run_reference(args):
+    """The reference arm: the reference's algorithm (the C++ oracle port -- no Rust toolchain in this image) on the host
+    cores, SAME config, SAME step count as the GPU arm by default (all scenes; the oracle does a 256-scene cfg5 frame in
+    ~2 s on 16 threads); --cpu-sample-scenes bounds it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -199,27 +254,41 @@ def run_reference(args):
 
     orc.build()
     cores = usable_cores()
-    sample_scenes = args.cpu_sample_scenes or max(cores, 8)
-    warm = max(3, min(args.warmup, 4))
-    steps = max(1, min(args.steps, 2))
     from similari_b200.workload import CONFIGS
 
-    sample_scenes = min(sample_scenes, CONFIGS[args.config].n_scenes)
-    cfg, frames = make_frames(args.config, warm + steps, 0, sample_scenes)
-    units, secs = cpu_port_run(args.config, frames, warm, steps, cores)
+    full = CONFIGS[args.config].n_scenes
+    sample_scenes = min(args.cpu_sample_scenes or full, full)
+    warm = max(3, args.warmup)
+    steps = max(1, args.steps)
+    cfg, frames = make_frames(args.config, warm + steps, 0, sample_scenes, feat_noise=args.feat_noise)
+    units, secs = cpu_port_run(args.config, frames, warm, steps, cores, option_overrides(args))
     value = units / secs
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args.config, cfg, {"note": "bounded sample of the full workload: same per-scene shape"}),
+        "config": config_dict(args.config, cfg, {"note": "the whole workload" if sample_scenes == full else
+                                                 "bounded sample of the full workload: same per-scene shape"}),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample_scenes} of {CONFIGS[args.config].n_scenes} scenes, {steps} timed frame(s) "
+                         "sample": f"{sample_scenes} of {full} scenes, {steps} timed frame(s) "
                                    f"after {warm} warm-up frames, {cores} threads (scene-parallel)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def newest_traffic():
+    """DRAM bytes per launch of the dominant kernel from the newest ncu --set full capture under profiles/."""
+    import glob
+
+    best = None
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_dominant_kernel_traffic*.json"))):
+        try:
+            best = (fn, json.load(open(fn)))
+        except Exception:
+            pass
+    return best
 
 
 def main():
@@ -250,19 +319,30 @@ def main():
     W, K = max(args.warmup, 3), args.steps
     base_cfg = CONFIGS[name]
     n_sc = args.scenes or base_cfg.n_scenes
+    over = option_overrides(args)
     # one extra frame: the e2e loop prefetches frame i+1 while frame i computes, so K timed steps issue K copies
-    cfg, frames = make_frames(name, W + K + 1, scene_base=rank * n_sc, n_scenes_override=args.scenes)
+    cfg, frames = make_frames(name, W + K + 1, scene_base=rank * n_sc, n_scenes_override=args.scenes,
+                              feat_noise=args.feat_noise)
     D = cfg.feature_dim
     visual = D > 0
 
     def new_tracker():
         t = eng.Tracker(tracker_options_for(name, default_options, device=local, max_scenes_hint=cfg.n_scenes,
                                             max_tracks_per_scene_hint=3 * cfg.n_objects,
-                                            max_dets_per_scene_hint=cfg.n_objects))
+                                            max_dets_per_scene_hint=cfg.n_objects, **over))
         t.set_stream(torch.cuda.current_stream().cuda_stream)
         return t
 
+    def timed_region_begin():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     # ---------------------------------------------------------------- e2e: host pointers (pinned), H2D + D2H timed
+    # The call a user of the reference makes: BatchVisualSort.predict(batch) -> per-detection SortTrack records.
+    # sb200_predict_batch_async is that call (asynchronous like the reference's, results behind sb200_sync); each timed
+    # step copies its whole request host -> device and its whole result (ids, epochs, lengths, voting types, predicted
+    # and observed boxes = the SortTrack columns) device -> host.
     t_e2e = new_tracker()
     pinned = []
     for f in frames:
@@ -274,45 +354,41 @@ def main():
             ft[...] = f["features"]
         pinned.append((b, ft))
     max_total = cfg.n_scenes * cfg.n_objects   # same on every rank (all_gather needs equal shapes)
-    out_host = {"ids": pinned_empty((max_total,), np.uint64), "epochs": pinned_empty((max_total,), np.uint32),
-                "lengths": pinned_empty((max_total,), np.uint32), "voting_types": pinned_empty((max_total,), np.uint8)}
-    units_per_step, h2d, d2h = [], [], []
-    stage_acc = {}
+    RING = 5                                    # result buffers: one more than the frames the library keeps in flight
+    out_ring = [{"ids": pinned_empty((max_total,), np.uint64), "epochs": pinned_empty((max_total,), np.uint32),
+                 "lengths": pinned_empty((max_total,), np.uint32), "voting_types": pinned_empty((max_total,), np.uint8),
+                 "predicted": pinned_empty((max_total, 6), np.float32),
+                 "observed": pinned_empty((max_total, 6), np.float32)} for _ in range(RING)]
+    h2d, d2h = [], []
     sampler = None
-    # Whole-span timing: one event before the first timed step (after a device-wide sync, so nothing is in flight) and
-    # one after a device-wide sync behind the last one.  Software pipeline: each step starts the H2D copy of the NEXT
-    # frame and then runs this frame (whose copy was started one step earlier); the K timed steps therefore issue
-    # exactly K input copies, all of which complete inside the span, and K result read-backs.
     t_e2e.prefetch_inputs(pinned[0][0], features=pinned[0][1])
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i, f in enumerate(frames[: W + K]):
         total = len(f["boxes"])
-        out = {k: v[:total] for k, v in out_host.items()}
+        out = {k: v[:total] for k, v in out_ring[i % RING].items()}
         if i == W:
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
+            t_e2e.sync()
+            timed_region_begin()
             sampler = ClockSampler(local)
             sampler.start()
             ev0.record()
-        tw0 = time.perf_counter()
         t_e2e.prefetch_inputs(pinned[i + 1][0], features=pinned[i + 1][1])
-        t_e2e.predict_batch(f["scene_ids"], f["det_offsets"], pinned[i][0], features=pinned[i][1], out=out)
-        if os.environ.get("SB200_TRACE"):
-            print(f"[bench] e2e frame {i}: wall {1e3 * (time.perf_counter() - tw0):.3f} ms", file=sys.stderr)
+        t_e2e.predict_batch(f["scene_ids"], f["det_offsets"], pinned[i][0], features=pinned[i][1], out=out, wait=False)
         if i >= W:
             h2d.append(total * 24 + (total * D * 4 if visual else 0))
-            d2h.append(total * (8 + 4 + 4 + 1))
-            for k_, v_ in t_e2e.last_stage_ms().items():
-                stage_acc.setdefault(k_, []).append(v_)
+            d2h.append(total * (8 + 4 + 4 + 1 + 24 + 24))
+    t_e2e.sync()
     torch.cuda.synchronize()   # the prefetch issued by the last timed step has landed too
     ev1.record()
     ev1.synchronize()
     e2e_total_ms = float(ev0.elapsed_time(ev1))
-    ids_e2e_last = out_host["ids"][: len(frames[W + K - 1]["boxes"])].copy()
+    ids_e2e_last = out_ring[(W + K - 1) % RING]["ids"][: len(frames[W + K - 1]["boxes"])].copy()
     t_e2e.close()
 
     # ---------------------------------------------------------------- value: inputs resident in HBM
+    # One sb200_predict_batch_device call per step, stream-ordered: nothing in the loop waits for the device, nothing is
+    # queried per step.  Work (pair-associations, dot products) and kernel times come from the library's cumulative
+    # counters, read before and after the timed region.
     t_dev = new_tracker()
     dboxes = [torch.from_numpy(np.ascontiguousarray(f["boxes"])).to(dev) for f in frames[: W + K]]
     dfeats = [torch.from_numpy(f["features"]).to(dev) if visual else None for f in frames[: W + K]]
@@ -320,11 +396,16 @@ def main():
     d_ep = torch.zeros(max_total, dtype=torch.int32, device=dev)
     d_len = torch.zeros(max_total, dtype=torch.int32, device=dev)
     d_vt = torch.zeros(max_total, dtype=torch.uint8, device=dev)
-    gather_buf = torch.zeros(max_total * world, dtype=torch.int64, device=dev) if world > 1 else None
+    main_stream = torch.cuda.current_stream()
+    gather = None
+    if world > 1:
+        # NCCL gather of the assigned track ids (the one exchange of the path), one step behind on a side stream: step i
+        # snapshots its ids (1 MB device copy) and the side stream gathers them while step i+1 computes
+        gather = {"stream": torch.cuda.Stream(device=dev),
+                  "snap": [torch.zeros(max_total, dtype=torch.int64, device=dev) for _ in range(2)],
+                  "buf": [torch.zeros(max_total * world, dtype=torch.int64, device=dev) for _ in range(2)],
+                  "ready": [torch.cuda.Event() for _ in range(2)], "done": [None, None]}
     torch.cuda.synchronize()
-    dev_stage = {}
-    n_tracks_steps = []
-    launches = 0
 
     def step_dev(i):
         f = frames[i]
@@ -332,37 +413,58 @@ def main():
                                    dfeats[i].data_ptr() if visual else 0, d_ids=d_ids.data_ptr(),
                                    d_epochs=d_ep.data_ptr(), d_lengths=d_len.data_ptr(),
                                    d_voting_types=d_vt.data_ptr())
-        if world > 1:  # gather the assigned track ids of every shard (north_star: NCCL only to gather track ids)
-            dist.all_gather_into_tensor(gather_buf, d_ids)
+        if gather is not None:
+            b = i & 1
+            if gather["done"][b] is not None:
+                main_stream.wait_event(gather["done"][b])   # the gather that read this snapshot two steps ago
+            gather["snap"][b].copy_(d_ids, non_blocking=True)
+            gather["ready"][b].record(main_stream)
+            with torch.cuda.stream(gather["stream"]):
+                gather["stream"].wait_event(gather["ready"][b])
+                dist.all_gather_into_tensor(gather["buf"][b], gather["snap"][b])
+                ev = torch.cuda.Event()
+                ev.record(gather["stream"])
+                gather["done"][b] = ev
 
     for i in range(W):
         step_dev(i)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    c0 = t_dev.work_counters()          # waits for the warm-up frames
+    timed_region_begin()
+    l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler_dev = ClockSampler(local)
+    sampler_dev.start()
     ev0.record()
     for i in range(W, W + K):
-        n_before = t_dev.scene_live_counts(frames[i]["scene_ids"])[0].astype(np.int64)   # host-side mirror, no GPU work
-        units_per_step.append(int((np.diff(frames[i]["det_offsets"]).astype(np.int64) * n_before).sum()))
         step_dev(i)
-        for k_, v_ in t_dev.last_stage_ms().items():
-            dev_stage.setdefault(k_, []).append(v_)
-        for k_, v_ in t_dev.last_kernel_ms().items():
-            dev_stage.setdefault(k_, []).append(v_)
-        n_tracks_steps.append(n_before.astype(np.float64))   # the cost matrices of this step are built on the store BEFORE it
-        launches += 22 if visual else 9   # kernels per predict (profiles/r01_launches_cfg5_v2.csv: 22 in a visual step)
+    if gather is not None:
+        for e in gather["done"]:
+            if e is not None:
+                main_stream.wait_event(e)   # the last gathers are part of the timed work
     ev1.record()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     dev_ms = ev0.elapsed_time(ev1)
+    clocks_dev = sampler_dev.stop()
     clocks = sampler.stop() if sampler else None
+    launches = eng.launch_count() - l0
+    c1 = t_dev.work_counters()
     ids_dev_last = d_ids[: len(frames[W + K - 1]["boxes"])].cpu().numpy().astype(np.uint64)
     assert np.array_equal(ids_dev_last, ids_e2e_last), "device-pointer and host-pointer paths disagree"
+    if gather is not None:   # every rank holds every shard's ids of the last step
+        gl = gather["buf"][(W + K - 1) & 1].view(world, max_total)[rank][: len(ids_dev_last)].cpu().numpy().astype(np.uint64)
+        assert np.array_equal(gl, ids_dev_last), "gathered ids differ from the local shard"
     t_dev.close()
 
-    units = float(sum(units_per_step))
+    units = float(c1["pair_associations"] - c0["pair_associations"])
+    dots = float(c1["visual_dot_products"] - c0["visual_dot_products"])
+    assert c1["frames"] - c0["frames"] == K
+    stage_ms = {k_: (c1["stage_ms"][k_] - c0["stage_ms"][k_]) / K for k_ in c1["stage_ms"]}
+    tc_frames = c1["tc_frames"] - c0["tc_frames"]
+    if tc_frames:
+        stage_ms["vis_screen"] = (c1["vis_screen_ms"] - c0["vis_screen_ms"]) / tc_frames
+        stage_ms["vis_refine"] = (c1["vis_refine_ms"] - c0["vis_refine_ms"]) / tc_frames
     # max over ranks of the timed region, sum over ranks of the units
     if world > 1:
         tm = torch.tensor([dev_ms, e2e_total_ms], dtype=torch.float64, device=dev)
@@ -377,7 +479,7 @@ def main():
     if rank == 0:
         value = units_all / (dev_ms * 1e-3)
         e2e_value = units_all / (e2e_total_ms * 1e-3)
-        # roofline of the dominant cost-matrix kernel: the tensor-core screen of the visual cost (bound: tensor pipe),
+        # roofline of the dominant cost-matrix kernel: the tensor-core kernel of the visual cost (bound: tensor pipe),
         # timed with CUDA events on the tracker's stream inside the timed region; positional-only configs report the
         # positional stage against HBM.  The HBM-side view of the whole visual stage is kept as `visual_stage_hbm`.
         peaks = {}
@@ -387,59 +489,69 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         tf_peak = float(peaks.get("bf16_tflops", 1590.0))
-        peak_src = "measured (MEASURED_PEAKS.json, burst)" if peaks else "fallback"
+        peak_src = "measured (MEASURED_PEAKS.json, burst)" if peaks else "fallback (B200_PROFILING.md)"
         Kobs = 3 if visual else 1
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")))["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        if visual:
-            fl, by = [], []
-            for i in range(W, W + K):
-                m_l = np.diff(frames[i]["det_offsets"]).astype(np.float64)
-                n_l = n_tracks_steps[i - W]
-                fl.append(float((2.0 * m_l * n_l * Kobs * D).sum()))
-                by.append(float(((m_l + n_l * Kobs) * D * 4 + m_l * n_l * Kobs * 4).sum()))
-            kms = float(np.mean(dev_stage["vis_screen"]))
-            achieved = float(np.mean(fl)) / (kms * 1e-3) / 1e12
-            roof = {"kernel": "vis_screen_kernel (tcgen05 BF16 screen of the visual cost matrix)", "bound": "tensor",
+        tr = newest_traffic()
+        if visual and tc_frames:
+            fl = 2.0 * dots * D / K                       # algorithmic FLOP per launch: 2 * M * (feature rows) * D
+            m_tot = float(np.mean([len(frames[i]["boxes"]) for i in range(W, W + K)]))
+            kms = stage_ms["vis_screen"]
+            achieved = fl / (kms * 1e-3) / 1e12
+            floor_bytes = None
+            traffic = None
+            if tr:
+                traffic = tr[1].get("dram_bytes_per_launch")
+                floor_bytes = tr[1].get("operand_floor_bytes")
+            roof = {"kernel": "tensor-core visual cost kernel (tcgen05 BF16, kernels_feat_tc.cu)", "bound": "tensor",
                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                    "traffic": traffic, "peak_source": peak_src, "algorithmic_flops_per_launch": float(np.mean(fl)),
-                    # the kernel runs ~0.25 ms of a ~1.15 ms step at full clocks, so the burst peak is the denominator;
-                    # against the sustained figure of MEASURED_PEAKS.json the fraction would be:
+                    "traffic": traffic, "traffic_source": os.path.basename(tr[0]) if tr else None,
+                    "traffic_over_operand_floor": (traffic / floor_bytes) if traffic and floor_bytes else None,
+                    "peak_source": peak_src, "algorithmic_flops_per_launch": fl,
+                    # the kernel runs a fraction of a millisecond inside a ~1 ms step at full clocks, so the burst peak is
+                    # the denominator; against the sustained figure of MEASURED_PEAKS.json the fraction would be:
                     "frac_of_sustained_peak": (achieved / float(peaks["bf16_tflops_sustained"])
                                                if peaks.get("bf16_tflops_sustained") else None),
-                    "kernel_ms": kms,
-                    "visual_stage_hbm": {"stage_ms": float(np.mean(dev_stage["visual_cost"])),
-                                         "algorithmic_bytes": float(np.mean(by)),
-                                         "achieved_gbs": float(np.mean(by)) / (float(np.mean(dev_stage["visual_cost"])) * 1e-3) / 1e9,
-                                         "peak_gbs": hbm_peak}}
+                    "kernel_ms": kms, "candidate_rows_per_launch": m_tot,
+                    "visual_stage": {"stage_ms": stage_ms["visual_cost"], "refine_ms": stage_ms.get("vis_refine"),
+                                     "frac_of_peak_whole_stage": fl / (stage_ms["visual_cost"] * 1e-3) / 1e12 / tf_peak}}
+        elif visual:
+            # exact SIMT kernel (small frames / SB200_VIS_KERNEL=simt): FP32 pipe, no tensor cores
+            fl = 3.0 * dots * D / K
+            kms = stage_ms["visual_cost"]
+            roof = {"kernel": "vis_cost_kernel (exact f32 SIMT)", "bound": "fp32", "achieved": fl / (kms * 1e-3) / 1e12,
+                    "peak": 75.0, "unit": "TFLOP/s", "frac": fl / (kms * 1e-3) / 1e12 / 75.0, "traffic": None,
+                    "peak_source": "nominal FP32 (no measured figure)", "kernel_ms": kms}
         else:
-            f_last = frames[W + K - 1]
-            m_l = np.diff(f_last["det_offsets"]).astype(np.float64)
-            n_l = float(cfg.n_objects)
-            alg_bytes = float(((m_l + n_l) * 24 + m_l * n_l * 4).sum())
-            kms = float(np.mean(dev_stage["positional_cost"]))
+            m_l = np.concatenate([np.diff(frames[i]["det_offsets"]) for i in range(W, W + K)]).astype(np.float64)
+            n_mean = units / max(1.0, float(m_l.sum()))       # mean tracks per scene over the timed steps
+            alg_bytes = float(((m_l + n_mean) * 24).sum() / K + units * 4 / K)
+            kms = stage_ms["positional_cost"]
             achieved = alg_bytes / (kms * 1e-3) / 1e9
-            roof = {"kernel": "positional_cost stage", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            roof = {"kernel": "positional_cost stage (pos_fill_none + pos_scan)", "bound": "hbm", "achieved": achieved,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kms}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config_dict(name, cfg),
+            "dtype": "f32", "data": "synthetic",
+            "config": config_dict(name, cfg, {"option_overrides": {k_: (float(v_) if isinstance(v_, float) else v_) for k_, v_ in over.items()},
+                                              "feat_noise": cfg.feat_noise} if (over or args.feat_noise is not None) else None),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(np.mean(h2d)),
                     "d2h_bytes_per_step": int(np.mean(d2h)), "ms_per_step": e2e_total_ms / K,
                     "host_affinity": affinity_note,
-                    "pipeline": "sb200_prefetch_inputs: the pinned-host -> device copy of frame i+1 is issued at the "
-                                "start of step i and overlaps its kernels; each timed step contains one full input "
-                                "copy and one result read-back"},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "stages_ms": {k_: float(np.mean(v_)) for k_, v_ in dev_stage.items()},
+                    "pipeline": "sb200_predict_batch_async + sb200_prefetch_inputs: the pinned-host -> device copy of "
+                                "frame i+1 is issued at the start of step i and overlaps its kernels; each timed step "
+                                "contains one full input copy and one full SortTrack read-back (65 B per detection)"},
+            "gpu_launches": int(launches),
+            "gpu_launches_per_step": float(launches) / K,
+            "clocks": clocks_dev if clocks_dev and clocks_dev.get("samples") else clocks,
+            "clocks_e2e": clocks,
+            "stages_ms": stage_ms,
+            "host_sync": "none inside the timed region (stream-ordered predict, per-frame tables built on the device)",
             "roofline": roof,
         }
+        if world > 1:
+            line["id_gather"] = "NCCL all_gather of the assigned ids, one step behind on a side stream (included in the timed span)"
         if old_affinity is not None:
             os.sched_setaffinity(0, old_affinity)   # the CPU baseline uses every core
         if not args.no_cpu_baseline and world == 1:
@@ -447,11 +559,11 @@ def main():
 
             orc.build()
             cores = usable_cores()
-            sample = args.cpu_sample_scenes or min(cfg.n_scenes, max(cores, 8))
-            ccfg, cframes = make_frames(name, 5, 0, sample)
-            cu, cs = cpu_port_run(name, cframes, 4, 1, cores)
+            sample = args.cpu_sample_scenes or min(cfg.n_scenes, max(cores, 64))
+            ccfg, cframes = make_frames(name, 6, 0, sample, feat_noise=args.feat_noise)
+            cu, cs = cpu_port_run(name, cframes, 4, 2, cores, over)
             line["cpu_baseline"] = {"value": cu / cs, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{sample} of {cfg.n_scenes} scenes x 1 timed frame after 4 warm-up frames, "
+                                    "sample": f"{sample} of {cfg.n_scenes} scenes x 2 timed frames after 4 warm-up frames, "
                                               f"{cores} threads (scene-parallel), {cs:.1f} s"}
         print(json.dumps(line))
     if world > 1:

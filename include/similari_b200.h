@@ -119,6 +119,11 @@ void sb200_tracker_destroy(sb200_tracker* t);
  * bracket the work with its own CUDA events. */
 int sb200_tracker_set_stream(sb200_tracker* t, void* cuda_stream);
 
+/* VisualSortObservation::feature is an Option (src/trackers/visual_sort.rs:42-55): a tracker may see frames without any
+ * feature before it learns the feature length.  Until a request has carried feature rows the dimension given at creation
+ * is provisional and can be changed here; afterwards a different value is SB200_ERR_INVALID. */
+int sb200_set_feature_dim(sb200_tracker* t, int32_t feature_dim);
+
 /* ---- the hot path ----
  * One call == Sort::predict_with_scene (n_scenes = 1, src/trackers/sort/simple_api.rs:110-196) or
  * BatchSort::predict / BatchVisualSort::predict over a PredictionBatchRequest (src/trackers/sort/batch_api.rs:222-290,

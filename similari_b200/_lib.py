@@ -82,6 +82,7 @@ EXPORTS = [
     "sb200_visual_cost_matrix", "sb200_sort_voting", "sb200_visual_voting", "sb200_kalman_initiate",
     "sb200_kalman_predict", "sb200_kalman_update", "sb200_nms", "sb200_own_area_shares", "sb200_host_alloc", "sb200_host_free",
     "sb200_predict_batch_async", "sb200_sync", "sb200_frames_in_flight", "sb200_work_counters", "sb200_launch_count",
+    "sb200_set_feature_dim",
 ]
 
 
@@ -107,6 +108,7 @@ def lib():
         "sb200_prefetch_inputs": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
         "sb200_predict_batch_async": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PredictOut)]),
         "sb200_sync": (C.c_int, [vp]),
+        "sb200_set_feature_dim": (C.c_int, [vp, i32]),
         "sb200_frames_in_flight": (C.c_int, [vp]),
         "sb200_work_counters": (C.c_int, [vp, vp, vp]),
         "sb200_launch_count": (u64, []),

@@ -427,24 +427,39 @@ class VisualSortPredictionBatchRequest:
 
 
 class _VisualBase(_TrackerBase):
+    _dim_provisional = False
+
     def _ensure(self, kind, observations):
+        dim = next((len(o.feature) for o in observations if o.feature is not None), 0)
         if self._t is None:
-            dim = next((len(o.feature) for o in observations if o.feature is not None), 0)
             if dim == 0:
-                dim = 8  # no feature seen yet: any dimension works until the first feature arrives
+                dim = 8  # no feature seen yet (feature is an Option in the reference): provisional until one arrives
                 self._dim_provisional = True
             self._t = engine.Tracker(self._opts._build(kind, dim))
             self._dim = dim
+        elif self._dim_provisional and dim > 0:
+            # first featured observation: the tracker keeps its tracks, ids, epochs and Kalman state, only the (still
+            # empty) feature arena is re-created for the real feature length
+            self._t.set_feature_dim(dim)
+            self._dim = dim
+            self._dim_provisional = False
 
     def _flatten(self, observations):
         n = len(observations)
         boxes = np.array([o.bounding_box._row() for o in observations], dtype=np.float32).reshape(-1, 6)
-        feats = np.zeros((n, self._dim), dtype=np.float32)
         has = np.zeros(n, dtype=np.uint8)
-        for i, o in enumerate(observations):
-            if o.feature is not None:
-                assert len(o.feature) == self._dim, "all features of a tracker must have the same dimension"
-                feats[i], has[i] = o.feature, 1
+        if all(o.feature is None for o in observations):
+            feats = None    # a frame without features: the request carries no feature column at all
+            has = None
+        else:
+            if self._dim_provisional:
+                self._dim_provisional = False
+            feats = np.zeros((n, self._dim), dtype=np.float32)
+            for i, o in enumerate(observations):
+                if o.feature is not None:
+                    if len(o.feature) != self._dim:
+                        raise ValueError("all features of a tracker must have the same dimension")
+                    feats[i], has[i] = o.feature, 1
         q = np.array([1.0 if o.feature_quality is None else o.feature_quality for o in observations], dtype=np.float32)
         custom = np.array([NONE_ID if o.custom_object_id is None else o.custom_object_id for o in observations], dtype=np.int64)
         return boxes, feats, has, q, custom

@@ -235,6 +235,7 @@ struct sb200_tracker {
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
   HBuf h_small;
+  bool seen_features = false;   // a request has carried feature rows (the feature dimension is fixed from then on)
   int last_n_scenes = 0;   // scenes of the last frame (sb200_last_costs reads its scene table back from the device)
 
   ~sb200_tracker() {
@@ -883,6 +884,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   // ======================================================================== nothing below can fail for capacity reasons:
   // the request is committed (epochs, ring slot, bounds of the frames in flight)
   for (int s = 0; s < n_scenes; ++s) epoch[last_req_slots[s]] += 1;
+  if (features != nullptr && total > 0) seen_features = true;
   q.active = true;
   q.n_scenes = n_scenes;
   q.total = total;
@@ -1089,6 +1091,31 @@ int sb200_predict_batch_async(sb200_tracker* t, int32_t n_scenes, const uint64_t
                               const int64_t* custom_ids, const float* own_area, const sb200_predict_out* out) {
   if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
   return t->predict(n_scenes, scene_ids, det_offsets, boxes, features, has_feature, quality, custom_ids, own_area, out, false, false);
+}
+
+int sb200_set_feature_dim(sb200_tracker* t, int32_t feature_dim) {
+  if (!t || feature_dim <= 0) return fail(SB200_ERR_INVALID, "bad arguments");
+  if (!t->P.is_visual) return fail(SB200_ERR_INVALID, "not a visual tracker");
+  if (feature_dim == t->P.feature_dim) return 0;
+  if (t->seen_features) return fail(SB200_ERR_INVALID, "features of dimension %d are already stored", t->P.feature_dim);
+  CU(cudaSetDevice(t->device));
+  int rc = t->drain();
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(t->stream));
+  // no track holds a feature yet (obs_hasf == 0 everywhere): the feature arena is simply re-created for the new row size
+  t->P.feature_dim = feature_dim;
+  t->P.d8 = (feature_dim + 7) / 8 * 8;
+  t->opts.feature_dim = feature_dim;
+  t->b_feat.release(); t->b_feat_bf16.release(); t->f_cbf16.release();
+  t->ts.feat = nullptr; t->ts.feat_bf16 = nullptr;
+  const size_t rows = (size_t)t->scene_cap * t->track_cap * t->P.max_obs;
+  if (rows > 0) {
+    if ((rc = t->b_feat.ensure(rows * t->P.d8 * 4)) || (rc = t->b_feat_bf16.ensure(rows * t->P.d8 * 2))) return rc;
+    t->ts.feat = t->b_feat.as<float>();
+    t->ts.feat_bf16 = t->b_feat_bf16.p;
+  }
+  for (auto& g : t->stg) g.feat.release();
+  return 0;
 }
 
 int sb200_sync(sb200_tracker* t) {

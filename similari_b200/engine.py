@@ -82,6 +82,10 @@ class Tracker:
             self._keep = getattr(self, "_keep", [])[-16:] + [(boxes, features, has_feature, quality, custom_ids, own_area, out)]
         return out
 
+    def set_feature_dim(self, dim):
+        """sb200_set_feature_dim: fixes the feature length of a visual tracker that has not stored a feature yet."""
+        check(self._L.sb200_set_feature_dim(self._h, int(dim)))
+
     def sync(self):
         """sb200_sync: waits for every frame in flight; raises the first error an asynchronous frame produced."""
         check(self._L.sb200_sync(self._h))

@@ -64,3 +64,38 @@ def test_visual_sort_api_and_nms():
     bbox2 = (BoundingBox(10.3, 11.1, 2.9, 3.9).as_xyaah(), 0.9)
     res = nms([bbox2, bbox1], nms_threshold=0.7, score_threshold=0.0)  # src/utils/nms/nms_py.rs:23-39
     assert len(res) == 1 and abs(float(res[0].xc) - 11.5) < 1e-5
+
+
+def test_visual_sort_first_frames_without_features():
+    """VisualSortObservation.feature is an Option (src/trackers/visual_sort.rs:42-55): a tracker may be fed feature-less
+    frames before the first ReID vector arrives.  The track created by those frames must survive the switch to the real
+    feature length (round 1 pinned a provisional length of 8 and failed on the first 128-d feature)."""
+    from similari_b200.api import (BoundingBox, PositionalMetricType, VisualSort, VisualSortMetricType,
+                                   VisualSortObservation, VisualSortObservationSet, VisualSortOptions, VotingType)
+
+    o = VisualSortOptions()
+    o.max_idle_epochs(3)
+    o.visual_metric(VisualSortMetricType.euclidean(1.0))
+    o.positional_metric(PositionalMetricType.maha())
+    o.visual_minimal_track_length(2)
+    o.visual_max_observations(3)
+    o.visual_min_votes(2)
+    t = VisualSort(1, o)
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal(128).astype(np.float32)
+    v /= np.linalg.norm(v)
+
+    def step(feat, box):
+        s = VisualSortObservationSet()
+        s.add(VisualSortObservation(None if feat is None else list(map(float, feat)), 0.9, BoundingBox(*box).as_xyaah(), None))
+        return t.predict_with_scene(3, s)[0]
+
+    a = step(None, (1.0, 1.0, 3.0, 5.0))
+    b = step(None, (1.05, 1.05, 3.0, 5.0))
+    c = step(v, (1.1, 1.1, 3.02, 5.0))                       # first feature: 128-d
+    d = step(v + 0.01, (1.15, 1.15, 3.02, 5.0))
+    e = step(v - 0.01, (1.2, 1.2, 3.0, 5.0))
+    assert a.id == b.id == c.id == d.id == e.id and e.length == 5
+    assert c.voting_type == VotingType.Positional and e.voting_type == VotingType.Visual
+    with pytest.raises(Exception):
+        step(np.ones(64, np.float32), (1.2, 1.2, 3.0, 5.0))  # a second feature length is an error, as in the reference

@@ -18,13 +18,22 @@ def eng():
     return e
 
 
-def _run(eng, oracle, name, n_scenes, frames, threads=16, **cfg_over):
+def _threads():
+    import os
+
+    try:
+        return max(4, min(64, len(os.sched_getaffinity(0))))
+    except Exception:
+        return 16
+
+
+def _run(eng, oracle, name, n_scenes, frames, threads=None, opts_over=None, **cfg_over):
     from similari_b200._lib import default_options
     from similari_b200.workload import CONFIGS, Workload, tracker_options_for
 
     cfg = dataclasses.replace(CONFIGS[name], n_scenes=n_scenes, **cfg_over)
-    g = eng.Tracker(tracker_options_for(name, default_options))
-    o = oracle.Tracker(tracker_options_for(name, oracle.make_options), threads=threads)
+    g = eng.Tracker(tracker_options_for(name, default_options, **(opts_over or {})))
+    o = oracle.Tracker(tracker_options_for(name, oracle.make_options, **(opts_over or {})), threads=threads or _threads())
     wl = Workload(cfg)
     for fr in range(frames):
         f = wl.next_frame()
@@ -75,6 +84,91 @@ def test_cfg4_batchsort_maha_oriented_512x512_matches_oracle(eng, oracle):
 
 def test_cfg5_batchvisualsort_512x512x512_matches_oracle(eng, oracle):
     _run(eng, oracle, "cfg5", 8, 5)
+
+
+def test_cfg4_full_128_scenes_matches_oracle(eng, oracle):
+    """BASELINE cfg4 at its full size -- 128 scenes x 512 x 512, oriented boxes, Mahalanobis -- against the oracle, frame
+    by frame (the request the bench times: its own list-base / offset arithmetic included)."""
+    _run(eng, oracle, "cfg4", 128, 5)
+
+
+def test_cfg5_full_256_scenes_matches_oracle(eng, oracle):
+    """BASELINE cfg5 at its full size -- 256 scenes x 512 x 512 x 512-d -- against the oracle for five frames: every id,
+    epoch, length and voting type of ~124 k detections per frame.  This is the exact batch bench.py times (tile list,
+    column offsets and list bases of 256 scenes)."""
+    g, o = _run(eng, oracle, "cfg5", 256, 5)
+    assert g.active_tracks() == o.active_tracks()
+
+
+def test_cfg5_scene_with_degenerate_features_overflows_its_list_mid_batch(eng, oracle):
+    """List overflow at BASELINE size: in one scene of the batch every feature is (almost) the same vector, so every
+    (candidate, observation) pair passes the threshold -- ~512 x 1500 survivors against a list of 16 k -- and that scene
+    alone falls back to the dense exact kernels on the device while the others stay on the sparse path.  Assignments must
+    be the oracle's for every scene."""
+    from similari_b200._lib import default_options
+    from similari_b200.workload import CONFIGS, Workload, tracker_options_for
+
+    cfg = dataclasses.replace(CONFIGS["cfg5"], n_scenes=6)
+    g = eng.Tracker(tracker_options_for("cfg5", default_options))
+    o = oracle.Tracker(tracker_options_for("cfg5", oracle.make_options), threads=_threads())
+    wl = Workload(cfg)
+    rng = np.random.default_rng(77)
+    common = rng.standard_normal(512).astype(np.float32)
+    common /= np.linalg.norm(common)
+    for fr in range(5):
+        f = wl.next_frame()
+        offs = f["det_offsets"]
+        feats = f["features"].copy()
+        # scene 2: one shared vector plus a little noise (distances ~0.05 << 0.7)
+        n2 = offs[3] - offs[2]
+        v = common[None, :] + 0.002 * rng.standard_normal((n2, 512)).astype(np.float32)
+        feats[offs[2]:offs[3]] = v / np.linalg.norm(v, axis=1, keepdims=True)
+        rg = g.predict_batch(f["scene_ids"], offs, f["boxes"], features=feats)
+        ro = o.predict_batch(f["scene_ids"], offs, f["boxes"], features=feats)
+        for key in ("ids", "epochs", "lengths", "voting_types"):
+            assert np.array_equal(rg[key], ro[key]), (fr, key, int((rg[key] != ro[key]).sum()))
+
+
+@pytest.mark.parametrize("gate", ["quality", "area", "has_feature", "own_area"])
+def test_visual_gates_on_the_tensor_core_path_at_baseline_size(eng, oracle, gate, monkeypatch):
+    """The gates of VisualMetric::metric (src/trackers/visual_sort/metric.rs:227-249, 280-290) -- candidate quality,
+    minimal box area, feature present, own-area share -- at 512 x 512 x 512-d with the tcgen05 path forced: candidates the
+    gate rejects must not vote visually (row mask of the screen), tracks below the minimal feature count must not be
+    scored (column mask), and rejected features must not be collected."""
+    from similari_b200._lib import default_options
+    from similari_b200.workload import CONFIGS, Workload, tracker_options_for
+
+    monkeypatch.setenv("SB200_VIS_KERNEL", "tc")
+    over = {}
+    if gate == "quality":
+        over = dict(visual_minimal_quality_use=0.5, visual_minimal_quality_collect=0.7)
+    elif gate == "area":
+        over = dict(visual_minimal_area=5000.0)
+    elif gate == "own_area":
+        over = dict(visual_minimal_own_area_percentage_use=0.6, visual_minimal_own_area_percentage_collect=0.8)
+    over["visual_minimal_track_length"] = 2
+    cfg = dataclasses.replace(CONFIGS["cfg5"], n_scenes=3, canvas=(2600.0, 1500.0) if gate == "own_area" else (3840.0, 2160.0))
+    g = eng.Tracker(tracker_options_for("cfg5", default_options, **over))
+    o = oracle.Tracker(tracker_options_for("cfg5", oracle.make_options, **over), threads=_threads())
+    wl = Workload(cfg)
+    rng = np.random.default_rng(9)
+    vis_votes = 0
+    for fr in range(6):
+        f = wl.next_frame()
+        total = len(f["boxes"])
+        quality = rng.uniform(0.2, 1.0, total).astype(np.float32) if gate == "quality" else None
+        hasf = (rng.random(total) > 0.3).astype(np.uint8) if gate == "has_feature" else None
+        kw = dict(features=f["features"], quality=quality, has_feature=hasf)
+        rg = g.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], **kw)
+        ro = o.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], **kw)
+        for key in ("ids", "epochs", "lengths", "voting_types"):
+            assert np.array_equal(rg[key], ro[key]), (gate, fr, key, int((rg[key] != ro[key]).sum()))
+        vis_votes += int((ro["voting_types"] == 0).sum())
+        for sid in f["scene_ids"]:
+            assert np.array_equal(g.scene_tracks(int(sid))["feat_counts"], o.scene_tracks(int(sid))["feat_counts"]), (gate, fr)
+    assert vis_votes > 100     # the visual path did decide candidates; the gate did not switch it off altogether
+    n_pos = int((ro["voting_types"] == 1).sum())
+    assert n_pos > 20          # and the gate did send candidates to the positional stage
 
 
 def test_cfg5_full_size_properties(eng):

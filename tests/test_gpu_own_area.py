@@ -58,11 +58,43 @@ def test_operator_coincident_outlines_and_reference_case(eng, oracle):
     assert np.all(np.abs(got - np.array([0.75, 0.5, 0.75], np.float32)) < 1e-5)
 
 
-def test_operator_capacity_is_reported(eng):
-    from similari_b200._lib import Sb200Error
+def test_operator_crowds_take_the_second_pass(eng, oracle):
+    """More than 32 boxes overlapping one box (the warp kernel's on-chip list) go through the CTA-per-box second pass; the
+    reference has no limit (src/utils/clipping/bbox_own_areas.rs:8-46)."""
+    got = eng.own_area_shares([ltwh(0, 0, 10, 10)] * 40)         # 39 coincident boxes overlap each box
+    np.testing.assert_allclose(got, oracle.own_area_shares([ltwh(0, 0, 10, 10)] * 40), rtol=0, atol=1e-6)
+    r = np.random.default_rng(5)
+    for oriented in (False, True):
+        for n, span in ((60, 120.0), (150, 260.0), (400, 500.0)):   # dense crowds: 40..150 boxes overlap each box
+            b = random_boxes(r, n, oriented, span)
+            got, ref = eng.own_area_shares(b), oracle.own_area_shares(b)
+            np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6)
 
-    with pytest.raises(Sb200Error, match="overlap"):
-        eng.own_area_shares([ltwh(0, 0, 10, 10)] * 40)          # 39 boxes overlap each box: above the on-chip list
+
+def test_visual_tracker_in_a_crowd_never_errors(eng, oracle):
+    """The tracker path of the same: a crowded scene (every detection overlapped by > 32 others) inside a batch; predict
+    succeeds and matches the oracle (round 1 returned SB200_ERR_CAPACITY after the store had been advanced)."""
+    from similari_b200._lib import default_options
+
+    r = np.random.default_rng(8)
+    kw = dict(kind=3, positional_kind=1, iou_threshold=0.3, max_idle_epochs=3, visual_kind=0, visual_threshold=0.7,
+              feature_dim=32, visual_max_observations=3, visual_min_votes=1, visual_minimal_track_length=1,
+              visual_minimal_own_area_percentage_use=0.05, visual_minimal_own_area_percentage_collect=0.1)
+    g, o = eng.Tracker(default_options(**kw)), oracle.Tracker(oracle.make_options(**kw))
+    n_obj = 80
+    base = [random_boxes(r, n_obj, False, 150.0), random_boxes(r, n_obj, True, 1500.0)]   # scene 0 is the crowd
+    cent = r.standard_normal((2, n_obj, 32)).astype(np.float32)
+    offs = np.arange(3, dtype=np.int32) * n_obj
+    for fr in range(4):
+        boxes = np.concatenate(base).copy()
+        boxes[:, :2] += r.normal(0, 1.0, (len(boxes), 2)).astype(np.float32)
+        feats = (cent + 0.01 * r.standard_normal(cent.shape).astype(np.float32)).reshape(-1, 32)
+        rg = g.predict_batch(np.arange(2), offs, boxes, features=feats)
+        ro = o.predict_batch(np.arange(2), offs, boxes, features=feats)
+        for key in ("ids", "epochs", "lengths", "voting_types"):
+            assert np.array_equal(rg[key], ro[key]), (fr, key)
+        for s in range(2):
+            assert np.array_equal(g.scene_tracks(s)["feat_counts"], o.scene_tracks(s)["feat_counts"]), (fr, s)
 
 
 def test_visual_tracker_derives_shares_like_the_oracle(eng, oracle):

@@ -136,19 +136,93 @@ def test_screen_kernel_cta_organisations_match_oracle(eng, oracle, mode, vis, mo
                     visual_min_votes=2, visual_minimal_track_length=1, min_confidence=0.1))
 
 
-@pytest.mark.parametrize("kind,chunks", [(1, 3), (3, 2), (2, 4), (0, 5)])
-def test_chunked_requests_match_oracle(eng, oracle, kind, chunks, monkeypatch):
-    """The host-pointer path splits a request into scene chunks (H2D of chunk c+1 overlaps the kernels of chunk c);
-    ids of non-batch trackers need the cross-chunk prefix.  Forced here on small requests."""
-    monkeypatch.setenv("SB200_CHUNKS", str(chunks))
+@pytest.mark.parametrize("kind,device_io", [(1, False), (3, False), (2, False), (0, False), (3, True), (1, True)])
+def test_frames_in_flight_match_oracle(eng, oracle, kind, device_io):
+    """Stream-ordered predict: frames are enqueued back to back (sb200_predict_batch_async / _device) without waiting for
+    the device -- the per-frame tables (tracks per scene, offsets, tile list, id counter) are built by a kernel -- and the
+    results, read after sb200_sync, are those of the frame-by-frame oracle.  Seven scenes, 11 frames: the ring of four
+    frames in flight wraps, new tracks appear and expire while later frames are already queued."""
+    import torch
+
+    from similari_b200._lib import default_options, pinned_empty
+    from similari_b200.workload import Workload
+
     visual = kind >= 2
-    cfg = small("cfg5" if visual else "cfg2", n_scenes=7, n_objects=40, oriented=False, canvas=(700.0, 500.0),
-                feature_dim=64 if visual else 0)
-    kw = dict(kind=kind, positional_kind=1, iou_threshold=0.3, max_idle_epochs=3)
+    cfg = small("cfg5" if visual else "cfg2", n_scenes=7 if kind in (1, 3) else 1, n_objects=60, oriented=False,
+                canvas=(800.0, 600.0), feature_dim=64 if visual else 0, drop_frac=0.15, fresh_frac=0.15)
+    kw = dict(kind=kind, positional_kind=1, iou_threshold=0.3, max_idle_epochs=2)
     if visual:
         kw.update(visual_kind=0, visual_threshold=0.7, feature_dim=64, visual_max_observations=3, visual_min_votes=2,
                   visual_minimal_track_length=1, min_confidence=0.1)
-    run_frames(eng, oracle, cfg, 6, kw)
+    g, o = both(eng, oracle, **kw)
+    wl = Workload(cfg)
+    frames = [wl.next_frame() for _ in range(11)]
+    ref = [o.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"]) for f in frames]
+    outs = []
+    keep = []
+    for f in frames:
+        total = len(f["boxes"])
+        if device_io:
+            dev = torch.device("cuda", 0)
+            db = torch.from_numpy(np.ascontiguousarray(f["boxes"])).to(dev)
+            df = torch.from_numpy(np.ascontiguousarray(f["features"])).to(dev) if visual else None
+            d = {"ids": torch.zeros(total, dtype=torch.int64, device=dev), "epochs": torch.zeros(total, dtype=torch.int32, device=dev),
+                 "lengths": torch.zeros(total, dtype=torch.int32, device=dev), "voting_types": torch.zeros(total, dtype=torch.uint8, device=dev)}
+            keep.append((db, df))
+            torch.cuda.synchronize()
+            g.predict_batch_device(f["scene_ids"], f["det_offsets"], db.data_ptr(), df.data_ptr() if visual else 0,
+                                   d_ids=d["ids"].data_ptr(), d_epochs=d["epochs"].data_ptr(),
+                                   d_lengths=d["lengths"].data_ptr(), d_voting_types=d["voting_types"].data_ptr())
+            outs.append(d)
+        else:
+            out = {"ids": pinned_empty((total,), np.uint64), "epochs": pinned_empty((total,), np.uint32),
+                   "lengths": pinned_empty((total,), np.uint32), "voting_types": pinned_empty((total,), np.uint8)}
+            g.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"], out=out, wait=False)
+            outs.append(out)
+    assert g.frames_in_flight() <= 4
+    g.sync()
+    assert g.frames_in_flight() == 0
+    for fr, (r, ro) in enumerate(zip(outs, ref)):
+        for key in ("ids", "epochs", "lengths", "voting_types"):
+            got = r[key].cpu().numpy() if device_io else r[key]
+            assert np.array_equal(got.astype(np.uint64), ro[key].astype(np.uint64)), (fr, key)
+    assert g.active_tracks() == o.active_tracks()
+    wc = g.work_counters()
+    assert wc["frames"] == len(frames) and wc["pair_associations"] > 0
+
+
+def test_ragged_batches_empty_and_single_detection_scenes(eng, oracle, monkeypatch):
+    """A batch in which one scene is empty, one has a single detection and the others are full -- on the tensor-core path
+    (the tile list skips the empty scene, the one-row scene is a 1 x N tile) and on the exact path."""
+    from similari_b200.workload import Workload
+
+    for vis_kernel in ("tc", "simt"):
+        monkeypatch.setenv("SB200_VIS_KERNEL", vis_kernel)
+        cfg = small("cfg5", n_scenes=5, n_objects=140, oriented=False, canvas=(1400.0, 900.0), feature_dim=128)
+        kw = dict(kind=3, positional_kind=1, iou_threshold=0.3, max_idle_epochs=3, visual_kind=0, visual_threshold=0.7,
+                  feature_dim=128, visual_max_observations=3, visual_min_votes=2, visual_minimal_track_length=1,
+                  min_confidence=0.1)
+        g, o = both(eng, oracle, **kw)
+        wl = Workload(cfg)
+        for fr in range(7):
+            f = wl.next_frame()
+            offs = f["det_offsets"].astype(np.int64)
+            # scene (fr % 5) loses all its detections, scene ((fr + 2) % 5) keeps one
+            keep = []
+            for s in range(5):
+                idx = np.arange(offs[s], offs[s + 1])
+                if fr >= 2 and s == fr % 5:
+                    idx = idx[:0]
+                elif fr >= 2 and s == (fr + 2) % 5:
+                    idx = idx[:1]
+                keep.append(idx)
+            new_offs = np.concatenate([[0], np.cumsum([len(k) for k in keep])]).astype(np.int32)
+            sel = np.concatenate(keep)
+            rg = g.predict_batch(f["scene_ids"], new_offs, f["boxes"][sel], features=f["features"][sel])
+            ro = o.predict_batch(f["scene_ids"], new_offs, f["boxes"][sel], features=f["features"][sel])
+            for key in ("ids", "epochs", "lengths", "voting_types"):
+                assert np.array_equal(rg[key], ro[key]), (vis_kernel, fr, key)
+        assert g.active_tracks() == o.active_tracks()
 
 
 def test_expired_tracks_leave_the_device_store_but_not_the_api(eng, oracle):
