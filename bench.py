@@ -84,6 +84,9 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = None
         self.source = "nvml"
+        self.times = []          # perf_counter of every sample
+        self.call_ms = []        # host cost of every query
+        self.window = [None, None]
         self._halt = threading.Event()
         self._h = None
         try:
@@ -127,21 +130,38 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         while not self._halt.is_set():
+            t0 = time.perf_counter()
             try:
+                n0 = len(self.samples)
                 if self._h is not None:
                     self._sample_nvml()
                 else:
                     self._sample_smi()
+                if len(self.samples) > n0:
+                    self.times.append(t0)
+                    self.call_ms.append(1e3 * (time.perf_counter() - t0))
             except Exception:
                 pass
-            self._halt.wait(0.02 if self._h is not None else 0.5)
+            self._halt.wait(0.005 if self._h is not None else 0.5)
+
+    def mark_begin(self):
+        self.window[0] = time.perf_counter()
+
+    def mark_end(self):
+        self.window[1] = time.perf_counter()
 
     def stop(self):
+        """Median SM clock over the samples taken under load: the warm-up steps (same kernels, same clocks) and the
+        timed region; `samples_in_timed_region` says how many fell between the two marks."""
         self._halt.set()
         self.join(timeout=5)
         med = float(np.median(self.samples)) if self.samples else None
+        inside = 0
+        if self.window[0] is not None and self.window[1] is not None:
+            inside = sum(1 for t in self.times if self.window[0] <= t <= self.window[1])
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples),
-                "source": self.source}
+                "samples_in_timed_region": inside, "source": self.source,
+                "query_ms_max": max(self.call_ms) if self.call_ms else None}
 
 
 def usable_cores():
@@ -360,7 +380,8 @@ def main():
                  "predicted": pinned_empty((max_total, 6), np.float32),
                  "observed": pinned_empty((max_total, 6), np.float32)} for _ in range(RING)]
     h2d, d2h = [], []
-    sampler = None
+    sampler = ClockSampler(local)   # runs through the warm-up steps and the timed region (both under load)
+    sampler.start()
     t_e2e.prefetch_inputs(pinned[0][0], features=pinned[0][1])
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i, f in enumerate(frames[: W + K]):
@@ -369,8 +390,7 @@ def main():
         if i == W:
             t_e2e.sync()
             timed_region_begin()
-            sampler = ClockSampler(local)
-            sampler.start()
+            sampler.mark_begin()
             ev0.record()
         t_e2e.prefetch_inputs(pinned[i + 1][0], features=pinned[i + 1][1])
         t_e2e.predict_batch(f["scene_ids"], f["det_offsets"], pinned[i][0], features=pinned[i][1], out=out, wait=False)
@@ -381,6 +401,7 @@ def main():
     torch.cuda.synchronize()   # the prefetch issued by the last timed step has landed too
     ev1.record()
     ev1.synchronize()
+    sampler.mark_end()
     e2e_total_ms = float(ev0.elapsed_time(ev1))
     ids_e2e_last = out_ring[(W + K - 1) % RING]["ids"][: len(frames[W + K - 1]["boxes"])].copy()
     t_e2e.close()
@@ -426,14 +447,15 @@ def main():
                 ev.record(gather["stream"])
                 gather["done"][b] = ev
 
+    sampler_dev = ClockSampler(local)
+    sampler_dev.start()
     for i in range(W):
         step_dev(i)
     c0 = t_dev.work_counters()          # waits for the warm-up frames
     timed_region_begin()
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler_dev = ClockSampler(local)
-    sampler_dev.start()
+    sampler_dev.mark_begin()
     ev0.record()
     for i in range(W, W + K):
         step_dev(i)
@@ -445,6 +467,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    sampler_dev.mark_end()
     dev_ms = ev0.elapsed_time(ev1)
     clocks_dev = sampler_dev.stop()
     clocks = sampler.stop() if sampler else None
