@@ -200,12 +200,12 @@ int64_t sb200_scene_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uin
  * (src/trackers/visual_sort/voting.rs:45-100) can still consult -- so the other entries read None; with the environment
  * variable SB200_FULL_COSTS=1 every pair is evaluated as the reference does. */
 int64_t sb200_last_costs(sb200_tracker* t, uint64_t scene_id, int64_t cap, float* out, int32_t* m, int32_t* n);
-/* Cumulative work of all completed frames (waits for the frames in flight): counters3 = { sum over frames and scenes of
+/* Cumulative work of all completed frames (waits for the frames in flight): counters4 = { sum over frames and scenes of
  * M x N (pair-associations, N = tracks the device store held when the frame ran), sum of M x (feature rows scanned by the
- * visual cost kernel), frames }, ms8 = { summed per-stage device times: prep, positional cost, visual cost, voting, apply;
+ * visual cost kernel), frames, scenes the exact SIMT fallback kernels had to take }, ms8 = { summed per-stage device times: prep, positional cost, visual cost, voting, apply;
  * summed times of the dominant visual-cost kernel and of the refinement; frames in which those two ran }.  Either may
  * be NULL.  bench.py reads it before and after its timed region. */
-int sb200_work_counters(sb200_tracker* t, uint64_t* counters3, double* ms8);
+int sb200_work_counters(sb200_tracker* t, uint64_t* counters4, double* ms8);
 /* Kernels this library has launched since it was loaded (every launch site counts itself). */
 uint64_t sb200_launch_count(void);
 /* Per-stage device times (ms) of the last completed predict call: prep, positional cost, visual cost, voting, apply. */

@@ -231,10 +231,13 @@ struct sb200_tracker {
   } stg[2];
   int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_frameout, f_decided, f_excl, f_own, f_ownovf, f_dyn, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
+      f_status, f_featdst, f_frameout, f_decided, f_excl, f_own, f_ownovf, f_dyn, f_ws, f_tmeta, f_rowinfo, f_slabc, f_slabm, f_slabmask,
+      f_dscene, f_maxc, f_maxcval, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
   HBuf h_small;
+  bool adapt_dense = false;     // a nominally selective threshold whose survivor lists overflow: treat it as non-selective
+  unsigned long long acc_dense_scenes = 0;   // scenes the exact SIMT fallback had to take (over all absorbed frames)
   bool seen_features = false;   // a request has carried feature rows (the feature dimension is fixed from then on)
   int last_n_scenes = 0;   // scenes of the last frame (sb200_last_costs reads its scene table back from the device)
 
@@ -242,7 +245,7 @@ struct sb200_tracker {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
                    &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_colb, &f_colvalid, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
-                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl, &f_own, &f_ownovf, &f_dyn, &b_idc,
+                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl, &f_own, &f_ownovf, &f_dyn, &b_idc, &f_ws, &f_tmeta, &f_rowinfo, &f_slabc, &f_slabm, &f_slabmask, &f_dscene, &f_maxc, &f_maxcval,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
                    &f_featdst, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
@@ -484,6 +487,7 @@ struct sb200_tracker {
     return b.ensure(need);
   }
   static size_t dyn_offset(int n_scenes) { return ((size_t)n_scenes * 16 + 15) / 16 * 16; }
+  static constexpr int kDenseVoteCap = 8192;   // visual entries per scene of the voting kernel on the dense path (power of two)
 };
 
 // Reads back what the oldest frame in flight left for the host: per scene {live tracks, arena blocks, newly expired} and
@@ -520,6 +524,14 @@ int sb200_tracker::absorb_oldest(bool block) {
     acc_units_mn += dyn->units_mn;
     acc_units_rows += dyn->units_rows;
     acc_frames += 1;
+    {
+      const int dense_scenes = *reinterpret_cast<const int*>(reinterpret_cast<const char*>(dyn) + sizeof(sb::FrameDyn));
+      acc_dense_scenes += (unsigned long long)dense_scenes;
+      // most scenes of a screened frame overflowed their survivor lists: the threshold cuts (almost) nothing, so the
+      // following frames take the dense tensor-core path; and back, if that path's precondition keeps failing
+      if (q.mode == 1 && n >= 1 && dense_scenes * 4 > n) adapt_dense = true;
+      if (q.mode == 2 && n >= 1 && dense_scenes * 4 > n) adapt_dense = false;
+    }
     for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&stage_ms[i], q.ev[i], q.ev[i + 1]);
     if (q.pos_forked) {
       // lazy frame: the culled scan sits inside the visual span (after the BestFit pre-pass): report it on its own
@@ -601,7 +613,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       max_m0 = std::max(max_m0, m);
       max_n0 = std::max(max_n0, nub);
     }
-    if (sb::voting_smem_need(max_m0, max_n0) > sb::kVotingSmemLimit) {
+    const int cap0 = P.is_visual ? kDenseVoteCap : 0;
+    if (sb::voting_smem_need(max_m0, max_n0, cap0) > sb::kVotingSmemLimit) {
       if (pend_count > 0) {   // the bound counts every detection in flight as a new track: get the exact counts first
         if ((rc = drain())) return rc;
         max_n0 = 0;
@@ -610,7 +623,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
           if (it != slot_of.end()) max_n0 = std::max(max_n0, n_tracks[it->second]);
         }
       }
-      if (sb::voting_smem_need(max_m0, max_n0) > sb::kVotingSmemLimit)
+      if (sb::voting_smem_need(max_m0, max_n0, cap0) > sb::kVotingSmemLimit)
         return fail(SB200_ERR_CAPACITY, "scene too large for the on-chip assignment solver (m=%d, n=%d)", max_m0, max_n0);
     }
   }
@@ -686,8 +699,28 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     for (auto& e : q.ev_pos) CU(cudaEventCreate(&e));
   }
   if ((rc = q.h_req.ensure(sizeof(sb::SceneReq) * (size_t)n_scenes)) ||
-      (rc = q.h_out.ensure(dyn_offset(n_scenes) + sizeof(sb::FrameDyn))))
+      (rc = q.h_out.ensure(dyn_offset(n_scenes) + sizeof(sb::FrameDyn) + 16)))
     return rc;
+  // visual cost path of this frame: tensor-core screen + exact refinement for large frames with a selective threshold, the
+  // dense tensor-core weight sums for thresholds that cut nothing, the exact SIMT kernel otherwise (small frames, and as the
+  // device-side fallback of single scenes)
+  bool want_tc = false, want_dense = false;
+  if (P.is_visual && features != nullptr && total > 0) {
+    const bool selective = P.visual_kind == SB200_VIS_EUCLIDEAN ? (P.visual_threshold < 1e18f) : (P.visual_threshold > -1.0f);
+    const bool big = P.d8 >= 64 && work * P.d8 >= (1ll << 28);
+    const bool dense_ok = P.n_constraints == 0;
+    want_tc = selective && big;
+    want_dense = big && dense_ok && (!selective || adapt_dense);
+    if (want_dense) want_tc = false;
+    if (const char* e = getenv("SB200_VIS_KERNEL")) {
+      if (!strcmp(e, "simt")) { want_tc = false; want_dense = false; }
+      else if (!strcmp(e, "tc")) { want_tc = work > 0; want_dense = false; }
+      else if (!strcmp(e, "dense")) { want_dense = work > 0 && dense_ok; want_tc = work > 0 && !want_dense; }
+    }
+  }
+  const int vote_cap = want_dense ? kDenseVoteCap : sb::kVoteVisCap;
+  sb::Params Pf = P;
+  Pf.vote_vis_cap = vote_cap;
   sb::SceneReq* hreq = q.h_req.as<sb::SceneReq>();
   for (int s = 0; s < n_scenes; ++s) {
     sb::SceneReq& r = hreq[s];
@@ -700,7 +733,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     r.pos_lcap = (int)std::min<long long>((long long)r.m * 32, (long long)sb::kVotePosCap * 2);
     posl_total += r.pos_lcap;
     r.vis_lbase = (int)visl_total;
-    r.vis_lcap = P.is_visual ? (int)std::min<long long>((long long)r.m * 64, (long long)sb::kVoteVisCap * 4) : 0;
+    r.vis_lcap = P.is_visual ? (int)std::min<long long>((long long)r.m * 64, (long long)vote_cap * 4) : 0;
     visl_total += r.vis_lcap;
   }
   // ---- frame buffers (sized once from the capacity hints when given, so steady-state frames never reallocate)
@@ -725,49 +758,83 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
         (rc = ens(f_vis, std::max<size_t>(4, (size_t)vis_total * 4))) || (rc = ens(f_scene_max, 4 * (size_t)n_scenes)))
       return rc;
   }
-  // visual cost kernel selection: tensor-core screen + exact refinement for large frames with a selective threshold,
-  // the dense exact SIMT kernel otherwise (and as the device-side fallback when the survivor list overflows)
   sb::TcArgs tc;
   memset(&tc, 0, sizeof(tc));
   tc.num_sms = num_sms;
-  int mstep = 0;
-  if (P.is_visual && features != nullptr && total > 0) {
-    const bool selective = P.visual_kind == SB200_VIS_EUCLIDEAN ? (P.visual_threshold < 1e18f) : (P.visual_threshold > -1.0f);
-    tc.use_tc = selective && P.d8 >= 64 && work * P.d8 >= (1ll << 28);
-    if (const char* e = getenv("SB200_VIS_KERNEL")) {
-      if (!strcmp(e, "simt")) tc.use_tc = false;
-      else if (!strcmp(e, "tc")) tc.use_tc = work > 0;
+  int mstep = 0, cstep = 256;
+  const long long visl_alloc = std::max(visl_total, hint_dets * 64);
+  if (want_tc || want_dense) {
+    tc.use_tc = true;
+    tc.dense = want_dense;
+    {
+      // SB200_SCREEN = single | multicast | pair (default): CTA organisation of the screen kernel (the dense kernel: pairs)
+      const char* e = getenv("SB200_SCREEN");
+      tc.cluster2 = want_dense || (!(e && !strcmp(e, "single")) && getenv("SB200_SCREEN_SINGLE") == nullptr);
+      tc.pair = want_dense || (tc.cluster2 && !(e && !strcmp(e, "multicast")));
     }
-    if (tc.use_tc) {
-      {
-        // SB200_SCREEN = single | multicast | pair (default): CTA organisation of the screen kernel
-        const char* e = getenv("SB200_SCREEN");
-        tc.cluster2 = !(e && !strcmp(e, "single")) && getenv("SB200_SCREEN_SINGLE") == nullptr;
-        tc.pair = tc.cluster2 && !(e && !strcmp(e, "multicast"));
-      }
-      mstep = tc.cluster2 ? 256 : 128;   // a cluster covers two 128-row candidate tiles
-      long long tiles_ub = 0;
-      for (int s = 0; s < n_scenes; ++s)
-        tiles_ub += (long long)((m_of[s] + mstep - 1) / mstep) * (((long long)nb_ub[s] * K + 255) / 256);
-      tc.n_tiles = (int)tiles_ub;   // upper bound: the list and its length are built on the device
-      if ((rc = ens(f_cbf16, T * P.d8 * 2)) || (rc = ens(f_tiles, sizeof(sb::TcTile) * (size_t)std::max<long long>(1, tiles_ub))) ||
-          (rc = ens(f_colmeta, sizeof(sb::VisColMeta) * (size_t)(std::max(col_total, hint_cols) + 256))) ||
+    mstep = tc.cluster2 ? 256 : 128;   // a cluster covers two 128-row candidate tiles
+    if (want_dense) cstep = (256 / K) * K;   // column tiles end at block boundaries: a track's observations stay together
+    long long tiles_ub = 0, slabs_ub = 0, ws_ub = 0, blk_ub = 0;
+    for (int s = 0; s < n_scenes; ++s) {
+      const long long ct = ((long long)nb_ub[s] * K + cstep - 1) / cstep;
+      tiles_ub += (long long)((m_of[s] + mstep - 1) / mstep) * ct;
+      slabs_ub += ct;
+      ws_ub += (long long)nb_ub[s] * ((m_of[s] + 127) / 128 * 128);
+      blk_ub += nb_ub[s];
+    }
+    tc.n_tiles = (int)tiles_ub;   // upper bound: the list and its length are built on the device
+    if ((rc = ens(f_cbf16, T * P.d8 * 2)) || (rc = ens(f_tiles, sizeof(sb::TcTile) * (size_t)std::max<long long>(1, tiles_ub))) ||
+        (rc = ens(f_rowmeta, sizeof(sb::VisRowMeta) * (T + 256))))
+      return rc;
+    tc.rowmeta = f_rowmeta.as<sb::VisRowMeta>();
+    tc.max_rows = max_nb * K;
+    tc.d_tiles = f_tiles.as<sb::TcTile>();
+    tc.d_n_tiles = &f_dyn.as<sb::FrameDyn>()->n_tiles;
+    tc.a_rows = total;
+    tc.b_rows = (long long)scene_cap * track_cap * K;
+    if (!want_dense) {
+      if ((rc = ens(f_colmeta, sizeof(sb::VisColMeta) * (size_t)(std::max(col_total, hint_cols) + 256))) ||
           (rc = ens(f_colb, 4 * (size_t)(std::max(col_total, hint_cols) + 256))) ||
           (rc = ens(f_colvalid, (size_t)(std::max(col_total, hint_cols) + 256) / 8 + 16)) ||
-          (rc = ens(f_colgeo, sizeof(sb::VisColGeo) * (size_t)std::max<long long>(1, P.n_constraints > 0 ? std::max(col_total, hint_cols) : 1))) ||
-          (rc = ens(f_rowmeta, sizeof(sb::VisRowMeta) * (T + 256))))
+          (rc = ens(f_colgeo, sizeof(sb::VisColGeo) * (size_t)std::max<long long>(1, P.n_constraints > 0 ? std::max(col_total, hint_cols) : 1))))
         return rc;
       tc.colmeta = f_colmeta.as<sb::VisColMeta>();
       tc.colgeo = f_colgeo.as<sb::VisColGeo>();
       tc.colb = f_colb.as<float>();
       tc.colvalid = f_colvalid.as<unsigned int>();
-      tc.rowmeta = f_rowmeta.as<sb::VisRowMeta>();
       tc.total_cols = (int)col_total;
-      tc.max_rows = max_nb * K;
-      tc.d_tiles = f_tiles.as<sb::TcTile>();
-      tc.d_n_tiles = &f_dyn.as<sb::FrameDyn>()->n_tiles;
-      tc.a_rows = total;
-      tc.b_rows = (long long)scene_cap * track_cap * K;
+    } else {
+      // sized from the hints like the other frame buffers, so steady-state frames never reallocate
+      const long long hs = std::max(opts.max_scenes_hint, n_scenes), ht = std::max(opts.max_tracks_per_scene_hint, 0);
+      const long long hd = std::max(opts.max_dets_per_scene_hint, 0);
+      ws_ub = std::max(ws_ub, hs * ht * ((hd + 127) / 128 * 128));
+      blk_ub = std::max(blk_ub, hs * ht);
+      slabs_ub = std::max(slabs_ub, hs * ((ht * K + cstep - 1) / cstep + 1));
+      if ((rc = ens(f_ws, 8 * (size_t)std::max<long long>(1, ws_ub))) || (rc = ens(f_tmeta, sizeof(sb::DenseTrackMeta) * (size_t)std::max<long long>(1, blk_ub))) ||
+          (rc = ens(f_rowinfo, 8 * (size_t)std::max<long long>(1, blk_ub * K))) || (rc = ens(f_slabc, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))) ||
+          (rc = ens(f_slabm, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))) || (rc = ens(f_slabmask, 2 * 32 * (size_t)std::max<long long>(1, slabs_ub))) ||
+          (rc = ens(f_dscene, 4 * 6 * (size_t)n_scenes + 64)) || (rc = ens(f_maxc, sizeof(sb::VisPair) * (size_t)std::max<long long>(1, visl_alloc))) ||
+          (rc = ens(f_maxcval, 4 * (size_t)std::max<long long>(1, visl_alloc))))
+        return rc;
+      tc.cstep = cstep;
+      tc.max_blocks = max_nb;
+      tc.n_slabs_ub = (int)slabs_ub;
+      tc.ws = f_ws.as<float2>();
+      tc.tmeta = f_tmeta.as<sb::DenseTrackMeta>();
+      tc.rowinfo = f_rowinfo.as<int2>();
+      tc.slab_colc = f_slabc.as<float>();
+      tc.slab_cmax = f_slabm.as<float>();
+      tc.slab_vmask = f_slabmask.as<unsigned int>();
+      tc.slab_bmask = tc.slab_vmask + (size_t)slabs_ub * 8;
+      // per-scene scalars: maxc_cnt | maxc_next | dense_bad | zeros (ints, zeroed together), then l0 | cmax (floats)
+      tc.maxc_cnt = f_dscene.as<int>();
+      tc.maxc_next = tc.maxc_cnt + n_scenes;
+      tc.dense_bad = tc.maxc_cnt + 2 * n_scenes;
+      tc.zeros = tc.maxc_cnt + 3 * n_scenes;
+      tc.scene_l0 = reinterpret_cast<float*>(tc.maxc_cnt + 4 * n_scenes);
+      tc.scene_cmax = tc.scene_l0 + n_scenes;
+      tc.maxc = f_maxc.as<sb::VisPair>();
+      tc.maxc_val = f_maxcval.as<float>();
     }
   }
   sb::Frame f;
@@ -777,6 +844,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.dyn = f_dyn.as<sb::FrameDyn>();
   f.id_counter = b_idc.as<unsigned long long>();
   f.id_add = P.is_batch ? (long long)total : -1;
+  f.dense_bad = tc.dense ? tc.dense_bad : nullptr;
   bool prefetched = false;
   Staging* sin = nullptr;
   // inputs
@@ -834,8 +902,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   if ((rc = ens(f_poslist, sizeof(sb::PosEntry) * (size_t)std::max<long long>(1, std::max(posl_total, hint_dets * 32)))) ||
       (rc = ens(f_counters, sizeof(int) * n_counters)))
     return rc;
-  if (P.is_visual && ((rc = ens(f_pairs, sizeof(sb::VisPair) * (size_t)std::max<long long>(1, std::max(visl_total, hint_dets * 64)))) ||
-                      (rc = ens(f_visval, sizeof(float) * (size_t)std::max<long long>(1, std::max(visl_total, hint_dets * 64))))))
+  if (P.is_visual && ((rc = ens(f_pairs, sizeof(sb::VisPair) * (size_t)std::max<long long>(1, visl_alloc))) ||
+                      (rc = ens(f_visval, sizeof(float) * (size_t)std::max<long long>(1, visl_alloc)))))
     return rc;
   f.pos_list = f_poslist.as<sb::PosEntry>();
   f.pos_cnt = f_counters.as<int>();
@@ -893,7 +961,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   q.live_ub = live_ub;
   q.tc_timed = false;
   q.pos_forked = false;
-  q.mode = tc.use_tc ? 1 : 0;
+  q.mode = tc.dense ? 2 : (tc.use_tc ? 1 : 0);
   for (int s = 0; s < n_scenes; ++s) pending_add[last_req_slots[s]] += m_of[s];
   inflight_live_ub += live_ub;
   pend_count += 1;
@@ -924,7 +992,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   }
   // scene descriptors, tile list, frame scalars; list counters and status words zeroed
   sb::launch_frame_setup(P, ts, f, reinterpret_cast<const sb::SceneReq*>(q.h_req.dp), n_scenes, b_ntracks.as<int>(), mstep,
-                         f_tiles.as<sb::TcTile>(), f_dyn.as<sb::FrameDyn>(), f_counters.as<int>(), (int)n_counters, stream);
+                         cstep, tc.dense, f_tiles.as<sb::TcTile>(), f_dyn.as<sb::FrameDyn>(), f_counters.as<int>(), (int)n_counters, stream);
   CU(cudaEventRecord(q.ev[0], stream));
   if (derive_own) {
     // visual_sort/simple_api.rs:110-127: with an own-area threshold and no shares supplied by the caller, the shares come
@@ -933,42 +1001,42 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
                         reinterpret_cast<int2*>(f_ownovf.as<char>() + 16), stream);
     f.in_own = f_own.as<float>();
   }
-  sb::launch_prep(P, f, n_scenes, max_m, stream);
+  sb::launch_prep(Pf, f, n_scenes, max_m, stream);
   CU(cudaEventRecord(q.ev[1], stream));
   sb::TcArgs tcc = tc;
   if (tc.use_tc && tc.n_tiles > 0) { tcc.ev_screen0 = q.ev_k[0]; tcc.ev_screen1 = q.ev_k[1]; tcc.ev_refine1 = q.ev_k[2]; q.tc_timed = true; }
   if (!fork) {
-    sb::launch_pos_cost(P, ts, f, n_scenes, max_m, max_n, stream);
+    sb::launch_pos_cost(Pf, ts, f, n_scenes, max_m, max_n, stream);
     CU(cudaEventRecord(q.ev[2], stream));
-    int vr0 = sb::launch_vis_cost(P, ts, f, n_scenes, max_m, max_n, tcc, stream);
+    int vr0 = sb::launch_vis_cost(Pf, ts, f, n_scenes, max_m, max_n, tcc, stream);
     if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
   } else {
     CU(cudaEventRecord(ev_fork[0], stream));                  // scene table built, counters zeroed
     CU(cudaStreamWaitEvent(pos_stream, ev_fork[0], 0));
-    sb::launch_pos_fill(P, f, n_scenes, max_m, max_n, pos_stream);
+    sb::launch_pos_fill(Pf, f, n_scenes, max_m, max_n, pos_stream);
     CU(cudaEventRecord(ev_join, pos_stream));
     CU(cudaEventRecord(q.ev[2], stream));
     {
-      int vr0 = sb::launch_vis_cost_a(P, ts, f, n_scenes, max_m, max_n, tcc, stream);   // metadata, screen, vis_mode, refinement
+      int vr0 = sb::launch_vis_cost_a(Pf, ts, f, n_scenes, max_m, max_n, tcc, stream);   // metadata, screen, vis_mode, refinement
       if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
-      vr0 = sb::launch_vote_masks(P, ts, f, n_scenes, max_m, max_n, stream);            // who is still open positionally
+      vr0 = sb::launch_vote_masks(Pf, ts, f, n_scenes, max_m, max_n, stream);            // who is still open positionally
       if (vr0 != 0) return fail(SB200_ERR_CUDA, "voting launch failed: %s", cudaGetErrorString((cudaError_t)vr0));
     }
     CU(cudaStreamWaitEvent(stream, ev_join, 0));                // the None fill has landed
     CU(cudaEventRecord(q.ev_pos[0], stream));
-    sb::launch_pos_scan_lazy(P, ts, f, n_scenes, max_m, max_n, /*pass=*/0, stream);
+    sb::launch_pos_scan_lazy(Pf, ts, f, n_scenes, max_m, max_n, /*pass=*/0, stream);
     CU(cudaEventRecord(q.ev_pos[1], stream));
-    int vr1 = sb::launch_vis_cost_b(P, ts, f, n_scenes, max_m, max_n, tcc, stream);     // final scene mode, dense fallbacks
+    int vr1 = sb::launch_vis_cost_b(Pf, ts, f, n_scenes, max_m, max_n, tcc, stream);     // final scene mode, dense fallbacks
     if (vr1 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr1);
-    sb::launch_pos_scan_lazy(P, ts, f, n_scenes, max_m, max_n, /*pass=*/1, stream);     // scenes that fell back to dense voting
+    sb::launch_pos_scan_lazy(Pf, ts, f, n_scenes, max_m, max_n, /*pass=*/1, stream);     // scenes that fell back to dense voting
     q.pos_forked = true;
   }
   CU(cudaEventRecord(q.ev[3], stream));
-  int vr = sb::launch_voting(P, ts, f, n_scenes, max_m, max_n, stream);
+  int vr = sb::launch_voting(Pf, ts, f, n_scenes, max_m, max_n, stream);
   if (vr != 0) return fail(SB200_ERR_CUDA, "voting launch failed: %s", cudaGetErrorString((cudaError_t)vr));
   CU(cudaEventRecord(q.ev[4], stream));
-  sb::launch_apply(P, ts, f, n_scenes, max_m, 0ull, b_ntracks.as<int>(), stream);
-  sb::launch_frame_sweep(P, ts, f, n_scenes, b_ntracks.as<int>(), wb, stream);
+  sb::launch_apply(Pf, ts, f, n_scenes, max_m, 0ull, b_ntracks.as<int>(), stream);
+  sb::launch_frame_sweep(Pf, ts, f, n_scenes, b_ntracks.as<int>(), wb, stream);
   CU(cudaEventRecord(q.ev[5], stream));
   CU(cudaGetLastError());
 
@@ -986,6 +1054,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     CU(cudaMemcpyAsync(ho, f.frame_out, 12 * (size_t)n_scenes, cudaMemcpyDeviceToHost, stream));
     CU(cudaMemcpyAsync(ho + 12 * (size_t)n_scenes, f.status, 4 * (size_t)n_scenes, cudaMemcpyDeviceToHost, stream));
     CU(cudaMemcpyAsync(ho + dyn_offset(n_scenes), f_dyn.p, sizeof(sb::FrameDyn), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(ho + dyn_offset(n_scenes) + sizeof(sb::FrameDyn), f.dense_cnt, 4, cudaMemcpyDeviceToHost, stream));
   }
   CU(cudaEventRecord(q.done, stream));
   rollback.armed = false;
@@ -1131,12 +1200,12 @@ int sb200_frames_in_flight(sb200_tracker* t) {
   return t->pend_count;
 }
 
-int sb200_work_counters(sb200_tracker* t, uint64_t* out3, double* ms7 /* [8] */) {
+int sb200_work_counters(sb200_tracker* t, uint64_t* out3 /* [4] */, double* ms7 /* [8] */) {
   if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
   CU(cudaSetDevice(t->device));
   int rc = t->drain();
   if (rc) return rc;
-  if (out3) { out3[0] = t->acc_units_mn; out3[1] = t->acc_units_rows; out3[2] = t->acc_frames; }
+  if (out3) { out3[0] = t->acc_units_mn; out3[1] = t->acc_units_rows; out3[2] = t->acc_frames; out3[3] = t->acc_dense_scenes; }
   if (ms7) {
     for (int i = 0; i < 5; ++i) ms7[i] = t->acc_stage_ms[i];
     ms7[5] = t->acc_kernel_ms[0]; ms7[6] = t->acc_kernel_ms[1]; ms7[7] = (double)t->acc_tc_frames;

@@ -443,16 +443,18 @@ struct SparseSmem {
   int* bstart; int* bcur;   // per-candidate buckets of the valid visual entries (bucket path of BestFit)
 };
 
-__host__ __device__ inline size_t sparse_smem_bytes(int M, int N) {
+__host__ __device__ inline int vote_cap(const Params& p) { return p.vote_vis_cap > 0 ? p.vote_vis_cap : kVoteVisCap; }
+
+__host__ __device__ inline size_t sparse_smem_bytes(int M, int N, int viscap) {
   size_t ny = (size_t)M + N;
   size_t km = ny * 8 * 2 + (size_t)M * 8 * 2 + ny * 4 * 3 + (size_t)M * 4 * 4 + (size_t)N * 4 * 3 + (size_t)(M + 1) * 4 +
               (size_t)(N + 1) * 4 + (size_t)kVotePosCap * 12 + 64;
-  size_t bf = (size_t)kVoteVisCap * 12 + (size_t)M * 12 + (size_t)N * 12 + (size_t)(2 * M + 2) * 4 + 64;
+  size_t bf = (size_t)viscap * 12 + (size_t)M * 12 + (size_t)N * 12 + (size_t)(2 * M + 2) * 4 + 64;
   size_t persist = (size_t)M * 4 + (size_t)M * 2 + N + 64;  // fw, inS, seen_m, excl
   return (km > bf ? km : bf) + persist;
 }
 
-__device__ inline SparseSmem carve_sparse(unsigned char* base, int M, int N) {
+__device__ inline SparseSmem carve_sparse(unsigned char* base, int M, int N, int viscap) {
   SparseSmem s;
   size_t ny = (size_t)M + N;
   // persistent part first
@@ -489,11 +491,11 @@ __device__ inline SparseSmem carve_sparse(unsigned char* base, int M, int N) {
   s.csc_m = p2; p2 += kVotePosCap;
   // BestFit view of the same scratch
   unsigned long long* q8 = reinterpret_cast<unsigned long long*>(scratch);
-  s.vkey = q8; q8 += kVoteVisCap;
+  s.vkey = q8; q8 += viscap;
   s.rowW = q8; q8 += M;
   s.colW = q8; q8 += N;
   p4 = reinterpret_cast<int*>(q8);
-  s.vval = reinterpret_cast<float*>(p4); p4 += kVoteVisCap;
+  s.vval = reinterpret_cast<float*>(p4); p4 += viscap;
   s.rown = p4; p4 += M;
   s.colm = p4; p4 += N;
   s.bstart = p4; p4 += M + 1;
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Tra
     if (!MASK_ONLY && tid == 0) f.new_count[sidx] = 0;
     return;
   }
-  SparseSmem s = carve_sparse(smem_raw, M, N);
+  SparseSmem s = carve_sparse(smem_raw, M, N, vote_cap(p));
   for (int m = tid; m < M; m += VT_THREADS) {
     winner[m] = -1;
     cvt[m] = (unsigned char)1;
@@ -971,7 +973,8 @@ __device__ __forceinline__ int vis_side_mode(const Params& p, const Frame& f, co
   if (sc.m >= 65535 || sc.n >= 65535) return 1;
   if (p.is_visual) {
     if (!tc_used) return 1;
-    if (f.vis_cnt[s] > sc.vis_lcap || f.vis_cnt[s] > kVoteVisCap) return 1;
+    if (f.vis_cnt[s] > sc.vis_lcap || f.vis_cnt[s] > vote_cap(p)) return 1;
+    if (f.dense_bad && f.dense_bad[s]) return 1;   // dense tensor-core path: a precondition failed for this scene
   }
   return 0;
 }
@@ -1014,16 +1017,16 @@ void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_o
   note_launch();
 }
 
-size_t voting_smem_need(int max_m, int max_n) {
-  return std::max(vote_smem_bytes(max_m, max_n), sparse_smem_bytes(max_m, max_n));
+size_t voting_smem_need(int max_m, int max_n, int viscap) {
+  return std::max(vote_smem_bytes(max_m, max_n), sparse_smem_bytes(max_m, max_n, viscap > 0 ? viscap : kVoteVisCap));
 }
 
 int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                   cudaStream_t st) {
   if (n_scenes == 0) return 0;
   const size_t smem_d = vote_smem_bytes(max_m, max_n);
-  const size_t smem_s = sparse_smem_bytes(max_m, max_n);
-  if (smem_d > 200 * 1024 || smem_s > 200 * 1024) return -3;
+  const size_t smem_s = sparse_smem_bytes(max_m, max_n, vote_cap(p));
+  if (smem_d > kVotingSmemLimit || smem_s > kVotingSmemLimit) return -3;
   cudaError_t e;
   if (p.is_visual) {
     if ((e = cudaFuncSetAttribute(voting_sparse_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)) != cudaSuccess) return (int)e;
@@ -1044,8 +1047,8 @@ int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_s
 int launch_vote_masks(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                       cudaStream_t st) {
   if (n_scenes == 0 || !p.is_visual || !f.decided || !f.excl) return 0;
-  const size_t smem_s = sparse_smem_bytes(max_m, max_n);
-  if (smem_s > 200 * 1024) return -3;
+  const size_t smem_s = sparse_smem_bytes(max_m, max_n, vote_cap(p));
+  if (smem_s > kVotingSmemLimit) return -3;
   cudaError_t e = cudaFuncSetAttribute(voting_sparse_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s);
   if (e != cudaSuccess) return (int)e;
   voting_sparse_kernel<true, true><<<n_scenes, VT_THREADS, smem_s, st>>>(p, ts, f);

@@ -611,7 +611,11 @@ int launch_vis_cost_a(const Params& p, const TrackStore& ts, const Frame& f, int
   const bool any = max_m > 0 && max_n > 0 && f.in_feat != nullptr;
   const bool use_tc = tc.use_tc && any;
   launch_scene_max(p, f, n_scenes, /*init_only=*/true, st);
-  if (use_tc) {
+  if (use_tc && tc.dense) {
+    // thresholds that cut nothing: dense weight sums on the tensor cores, groups that can win go to the pair lists
+    int rc = launch_vis_dense(p, ts, f, n_scenes, max_m, tc, st);
+    if (rc != 0) return rc;
+  } else if (use_tc) {
     // tensor-core screen -> per-scene survivor lists
     // (the BF16 operand rows of the candidates were written by cand_norm_kernel in launch_prep)
     int rc = launch_vis_cost_tc(p, ts, f, n_scenes, max_n, tc, /*phase=*/0, st);

@@ -366,7 +366,7 @@ __device__ __forceinline__ float refine_block_sum(const float* __restrict__ a, c
 }
 
 template <bool COSINE, bool TAIL>
-__global__ void __launch_bounds__(RF_WARPS * 32) vis_refine_kernel(Params p, TrackStore ts, Frame f) {
+__global__ void __launch_bounds__(RF_WARPS * 32) vis_refine_kernel(Params p, TrackStore ts, Frame f, int* nan_flag) {
   __shared__ float s_bs[RF_WARPS][32][RF_PITCH];
   const int scene = blockIdx.y;
   if (f.vis_mode[scene] != 0) return;  // survivor list overflowed: this scene is computed densely
@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(RF_WARPS * 32) vis_refine_kernel(Params p, Tra
       }
       f.vis_val[sc.vis_lbase + i0 + lane] = v;
       if (!is_nan(v) && !(v <= vmax)) vmax = v;   // best.rs "max_dist": maximum over the entries that exist
+      if (nan_flag && is_nan(v)) nan_flag[scene] = 1;   // dense path: an entry the threshold cuts voids its precondition
     }
   }
   // one atomic per warp
@@ -580,23 +581,30 @@ __global__ void vis_rowmeta_kernel(Params p, Frame f, VisRowMeta* rowmeta) {
   rowmeta[g] = rm;
 }
 
+// exact refinement of the scene pair lists (f.vis_pairs / vis_cnt / refine_next / vis_val; scenes with vis_mode != 0 skipped)
+int launch_vis_refine(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int* nan_flag, cudaStream_t st) {
+  if (n_scenes == 0) return 0;
+  dim3 grid(16, n_scenes);   // 64 warps x 32 survivors per scene in flight; more survivors are claimed in further rounds
+  // the vector path needs 16-byte aligned input rows (a caller-owned device pointer on the device-io path)
+  const bool tail = p.feature_dim != p.d8 || (reinterpret_cast<uintptr_t>(f.in_feat) & 15) != 0;
+  if (p.visual_kind == 1) {
+    if (tail) vis_refine_kernel<true, true><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f, nan_flag);
+    else vis_refine_kernel<true, false><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f, nan_flag);
+  } else {
+    if (tail) vis_refine_kernel<false, true><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f, nan_flag);
+    else vis_refine_kernel<false, false><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f, nan_flag);
+  }
+  note_launch();
+  return 0;
+}
+
 int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
                        int phase, cudaStream_t st) {
   if (tc.n_tiles == 0) return 0;
   if (phase == 1) {
-    dim3 grid(16, n_scenes);   // 64 warps x 32 survivors per scene in flight; more survivors are claimed in further rounds
-    // the vector path needs 16-byte aligned input rows (a caller-owned device pointer on the device-io path)
-    const bool tail = p.feature_dim != p.d8 || (reinterpret_cast<uintptr_t>(f.in_feat) & 15) != 0;
-    if (p.visual_kind == 1) {
-      if (tail) vis_refine_kernel<true, true><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
-      else vis_refine_kernel<true, false><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
-    } else {
-      if (tail) vis_refine_kernel<false, true><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
-      else vis_refine_kernel<false, false><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f);
-    }
-    note_launch();
+    int rc = launch_vis_refine(p, ts, f, n_scenes, nullptr, st);
     if (tc.ev_refine1) cudaEventRecord(tc.ev_refine1, st);
-    return 0;
+    return rc;
   }
   const bool cluster = tc.cluster2;
   CUtensorMap mA, mB;

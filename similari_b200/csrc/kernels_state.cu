@@ -523,16 +523,18 @@ void launch_pull(void* dst, const void* src, size_t bytes, cudaStream_t st) {
 constexpr int FS_T = 1024;
 
 __global__ void __launch_bounds__(FS_T) frame_setup_kernel(Params p, TrackStore ts, Frame f, const SceneReq* req, int n_scenes,
-                                                           const int* n_tracks, int mstep, TcTile* tiles, FrameDyn* dyn,
-                                                           int* zero, int n_zero) {
-  __shared__ long long s_w[4][FS_T / 32];
-  __shared__ long long s_carry[4];
+                                                           const int* n_tracks, int mstep, int cstep, int dense_i,
+                                                           TcTile* tiles, FrameDyn* dyn, int* zero, int n_zero) {
+  constexpr int NQ = 6;   // scanned quantities: pos, vis, columns, tiles, weight sums, blocks
+  __shared__ long long s_w[NQ][FS_T / 32];
+  __shared__ long long s_carry[NQ];
   __shared__ unsigned long long s_red[3][FS_T / 32];
   __shared__ int s_maxn, s_maxrows;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i < n_zero; i += FS_T) zero[i] = 0;
-  if (tid < 4) s_carry[tid] = 0;
+  if (tid < NQ) s_carry[tid] = 0;
   if (tid == 0) { s_maxn = 0; s_maxrows = 0; }
+  const bool dense = dense_i != 0;
   __syncthreads();
   const int K = p.max_obs;
   unsigned long long u_mn = 0, u_rows = 0, live = 0;
@@ -541,7 +543,8 @@ __global__ void __launch_bounds__(FS_T) frame_setup_kernel(Params p, TrackStore 
     SceneReq r;
     r.slot = 0; r.m = 0; r.det_base = 0; r.epoch = 0; r.scene_id = 0; r.pos_lbase = r.pos_lcap = r.vis_lbase = r.vis_lcap = 0;
     int n = 0, nb = 0, rows = 0;
-    long long v[4] = {0, 0, 0, 0};
+    long long v[NQ] = {0, 0, 0, 0, 0, 0};
+    int ctiles = 0;
     if (s < n_scenes) {
       r = req[s];
       n = n_tracks[r.slot];
@@ -549,17 +552,21 @@ __global__ void __launch_bounds__(FS_T) frame_setup_kernel(Params p, TrackStore 
       rows = nb * K;
       v[0] = (long long)r.m * n;
       v[1] = p.is_visual ? (long long)r.m * n * K : 0;
-      v[2] = ((long long)rows + 127) / 128 * 128;   // 16-byte aligned bulk copies of 256-column slabs
-      v[3] = mstep > 0 ? (long long)((r.m + mstep - 1) / mstep) * ((rows + 255) / 256) : 0;
+      ctiles = (rows + cstep - 1) / cstep;          // column tiles of the scene
+      // screen: 128-padded columns (16-byte aligned bulk copies of 256-column slabs); dense: one 256-entry slab per tile
+      v[2] = dense ? (long long)ctiles * 256 : ((long long)rows + 127) / 128 * 128;
+      v[3] = mstep > 0 ? (long long)((r.m + mstep - 1) / mstep) * ctiles : 0;
+      v[4] = dense ? (long long)nb * ((r.m + 127) / 128 * 128) : 0;
+      v[5] = nb;
       u_mn += (unsigned long long)v[0];
       u_rows += (unsigned long long)r.m * (unsigned long long)rows;
       live += (unsigned long long)n;
       atomicMax(&s_maxn, n);
       atomicMax(&s_maxrows, rows);
     }
-    long long x[4];
+    long long x[NQ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       x[q] = v[q];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -569,9 +576,9 @@ __global__ void __launch_bounds__(FS_T) frame_setup_kernel(Params p, TrackStore 
       if (lane == 31) s_w[q][wid] = x[q];
     }
     __syncthreads();
-    long long ex[4];
+    long long ex[NQ];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       long long woff = 0;
       for (int w = 0; w < wid; ++w) woff += s_w[q][w];
       ex[q] = s_carry[q] + woff + x[q] - v[q];
@@ -579,7 +586,7 @@ __global__ void __launch_bounds__(FS_T) frame_setup_kernel(Params p, TrackStore 
     __syncthreads();
     if (tid == FS_T - 1) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) s_carry[q] = ex[q] + v[q];
+      for (int q = 0; q < NQ; ++q) s_carry[q] = ex[q] + v[q];
     }
     if (s < n_scenes) {
       SceneDesc d;
@@ -588,11 +595,12 @@ __global__ void __launch_bounds__(FS_T) frame_setup_kernel(Params p, TrackStore 
       d.epoch = r.epoch; d.col_off = (int)ex[2]; d.scene_id = r.scene_id;
       d.pos_lbase = r.pos_lbase; d.pos_lcap = r.pos_lcap; d.vis_lbase = r.vis_lbase; d.vis_lcap = r.vis_lcap;
       d.nb = nb; d.pad0 = 0;
+      d.ws_off = ex[4]; d.blk_off = (int)ex[5]; d.slab_off = dense ? (int)(ex[2] / 256) : 0;
       f.scenes[s] = d;
       if (mstep > 0 && tiles) {
         int k = (int)ex[3];
         for (int m0 = 0; m0 < r.m; m0 += mstep)
-          for (int c0 = 0; c0 < rows; c0 += 256) { TcTile t; t.scene = s; t.m0 = m0; t.c0 = c0; t.pad = 0; tiles[k++] = t; }
+          for (int j = 0; j < ctiles; ++j) { TcTile t; t.scene = s; t.m0 = m0; t.c0 = j * cstep; t.pad = j; tiles[k++] = t; }
       }
     }
     __syncthreads();
@@ -611,15 +619,17 @@ __global__ void __launch_bounds__(FS_T) frame_setup_kernel(Params p, TrackStore 
     FrameDyn d;
     d.n_tiles = (int)s_carry[3]; d.total_cols = (int)s_carry[2]; d.max_rows = s_maxrows; d.max_n = s_maxn;
     d.pos_total = s_carry[0]; d.vis_total = s_carry[1];
-    d.units_mn = a; d.units_rows = b; d.live_total = (long long)c; d.pad0 = 0;
+    d.units_mn = a; d.units_rows = b; d.live_total = (long long)c;
+    d.ws_total = s_carry[4]; d.blk_total = (int)s_carry[5]; d.dense_scenes = 0;
     *dyn = d;
   }
 }
 
 void launch_frame_setup(const Params& p, const TrackStore& ts, const Frame& f, const SceneReq* req, int n_scenes,
-                        const int* d_n_tracks, int mstep, TcTile* tiles, FrameDyn* dyn, int* zero, int n_zero,
-                        cudaStream_t st) {
-  frame_setup_kernel<<<1, FS_T, 0, st>>>(p, ts, f, req, n_scenes, d_n_tracks, mstep, tiles, dyn, zero, n_zero);
+                        const int* d_n_tracks, int mstep, int cstep, bool dense, TcTile* tiles, FrameDyn* dyn, int* zero,
+                        int n_zero, cudaStream_t st) {
+  frame_setup_kernel<<<1, FS_T, 0, st>>>(p, ts, f, req, n_scenes, d_n_tracks, mstep, cstep > 0 ? cstep : 256, dense ? 1 : 0, tiles,
+                                         dyn, zero, n_zero);
   note_launch();
 }
 

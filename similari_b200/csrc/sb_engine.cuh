@@ -30,6 +30,7 @@ struct Params {  // immutable per tracker, passed by value to kernels
   float constraint_max_dist[kMaxConstraints];
   float visual_threshold;
   int feature_dim, d8, max_obs, min_votes, min_track_length;
+  int vote_vis_cap;   // visual entries per scene the sparse voting kernel keeps in shared memory (0: kVoteVisCap)
   float min_area, min_quality_use, min_quality_collect, min_own_use, min_own_collect;
   bool is_visual, is_batch, use_own_area;
 };
@@ -48,6 +49,10 @@ struct SceneDesc {  // one per scene of the current request
   int vis_lbase, vis_lcap;  // this scene's slice of the visual survivor list
   int nb;             // feature blocks of this scene's arena in use (physical rows scanned by the screen = nb * K)
   int pad0;
+  // dense tensor-core visual cost (kernels_feat_dense.cu) only:
+  long long ws_off;   // first element of this scene's weight-sum matrix ws[block][candidate] (row pitch = m rounded up to 128)
+  int blk_off;        // first entry of this scene in the per-block metadata (prefix of nb)
+  int slab_off;       // first 256-column metadata slab of this scene (one slab per column tile)
 };
 
 // Host-written half of a scene descriptor.  The host knows the request (slot, detections, epoch, list slices) but -- with
@@ -61,7 +66,7 @@ struct SceneReq {
 };
 struct FrameDyn {   // per-frame scalars only the device knows (written by frame_setup_kernel, read by later kernels)
   int n_tiles;            // tiles of the tensor-core visual cost kernel
-  int total_cols;         // padded physical feature rows of all scenes
+  int total_cols;         // padded physical feature rows of all scenes (dense kernel: 256 x metadata slabs)
   int max_rows;           // max over the scenes of nb * K
   int max_n;              // max over the scenes of n
   long long pos_total;    // elements of the packed positional matrices
@@ -69,7 +74,9 @@ struct FrameDyn {   // per-frame scalars only the device knows (written by frame
   unsigned long long units_mn;     // sum over the scenes of m * n   (pair-associations of this frame)
   unsigned long long units_rows;   // sum over the scenes of m * nb * K (dot products the visual cost kernel evaluates)
   long long live_total;   // sum over the scenes of n
-  long long pad0;
+  long long ws_total;     // elements of the dense kernel's weight-sum matrices
+  int blk_total;          // arena blocks of all scenes
+  int dense_scenes;       // scenes the dense exact kernels had to take (written late in the frame by scene_mode_kernel)
 };
 
 struct VisPair { int g, row, scene, outcol; };  // screen survivor: detection, feature row, scene, logical column
@@ -162,6 +169,7 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   unsigned char* excl;     // [slot * track_cap + n] track was claimed by the visual pass
   int* dense_cnt;          // [1] scenes of the request in dense mode (null: unknown); lets the dense kernels leave at once
   int* refine_next;        // [n_scenes] next unclaimed survivor of the scene (the refinement's warps claim 32 at a time)
+  const int* dense_bad;    // [n_scenes] dense tensor-core path only: != 0 sends the scene to the exact SIMT kernels
   // outputs (device), any may be null
   unsigned long long* o_ids;
   unsigned int* o_epochs;
@@ -171,7 +179,7 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   float* o_obs;
 };
 
-struct TcTile { int scene, m0, c0, pad; };  // one 128 x 256 output tile of the tensor-core visual cost kernel
+struct TcTile { int scene, m0, c0, pad; };  // pad: column-tile index inside the scene (dense kernel: its metadata slab)  // one 128 x 256 output tile of the tensor-core visual cost kernel
 // per-frame metadata of one physical feature row (track n, physical slot p) of a scene, built once per frame
 struct VisColMeta {
   float colb;    // column constant of the screen test (copy of TcArgs::colb)
@@ -181,6 +189,7 @@ struct VisColMeta {
 };
 struct VisColGeo { float tx, ty, tr; unsigned int tep; };  // only read when spatio-temporal constraints exist
 struct VisRowMeta { float rowk; int ok, pad0, pad1; };   // row constant of the screen test, candidate may vote visually
+struct DenseTrackMeta { int n; int kt; float cmax; int pad; };   // arena block: owner (store index, -1: none), valid observations
 
 // ---- kernel launchers (each in its own .cu) ----
 void launch_prep(const Params& p, const Frame& f, int n_scenes, int max_m, cudaStream_t st);
@@ -194,9 +203,11 @@ void launch_pull(void* dst, const void* src, size_t bytes, cudaStream_t st);
 // Per-frame tables built on the device: scene descriptors (request half from `req`, a device alias of mapped pinned host
 // memory; store half from d_n_tracks / ts.arena_top), the tile list of the tensor-core visual cost kernel (mstep = 128 or
 // 256 candidate rows per tile, 0: none) and the frame scalars; also zeroes the `n_zero` ints at `zero` (list counters, status).
+// cstep: feature rows per column tile (256 for the screen; (256 / K) * K for the dense kernel, which also gets ws_off /
+// blk_off / slab_off and one metadata slab per column tile instead of 128-padded columns)
 void launch_frame_setup(const Params& p, const TrackStore& ts, const Frame& f, const SceneReq* req, int n_scenes,
-                        const int* d_n_tracks, int mstep, TcTile* tiles, FrameDyn* dyn, int* zero, int n_zero,
-                        cudaStream_t st);
+                        const int* d_n_tracks, int mstep, int cstep, bool dense, TcTile* tiles, FrameDyn* dyn, int* zero,
+                        int n_zero, cudaStream_t st);
 // kernels launched by this library since it was loaded (every launch site counts itself)
 void note_launch(int n = 1);
 unsigned long long launch_count();
@@ -220,9 +231,35 @@ struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense ex
   VisRowMeta* rowmeta;   // [total]
   int total_cols;
   int max_rows;          // max over the scenes of nb * K
+  // ---- dense weight-sum path (mode 2)
+  bool dense;            // run launch_vis_dense instead of the screen
+  int cstep;             // feature rows per column tile: (256 / K) * K, so that no track straddles two tiles
+  int max_blocks;        // upper bound of nb over the scenes
+  int n_slabs_ub;        // upper bound of the 256-column metadata slabs of the frame
+  float2* ws;            // weight sums {S~, per-observation error bound} per (block, candidate)
+  DenseTrackMeta* tmeta; // per arena block
+  int2* rowinfo;         // per physical feature row: {logical output column, feature row or -1}
+  float* slab_colc;      // [slab][256] column constant (|b|^2, or 1/|b| for cosine)
+  float* slab_cmax;      // [slab][256] maximum of |b|^2 over the observations of the column's track
+  unsigned int* slab_vmask;  // [slab][8] bit per column: observation takes part in the metric
+  unsigned int* slab_bmask;  // [slab][8] bit per column: last physical slot of its block (flush the weight sum)
+  float* scene_l0;       // [n_scenes] sampled lower bound of the scene's maximal distance (domain of the kernel's x)
+  float* scene_cmax;     // [n_scenes] max |b|^2 of the scene
+  VisPair* maxc;         // candidates for the maximal distance (same per-scene slices as the pair lists)
+  float* maxc_val;
+  int* maxc_cnt;         // [n_scenes]
+  int* maxc_next;        // [n_scenes]
+  int* dense_bad;        // [n_scenes] != 0: the dense result cannot be used for this scene (exact SIMT path takes it)
+  int* zeros;            // [n_scenes] all zero (vis_mode view for the max refinement)
 };
 int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                     const TcArgs& tc, cudaStream_t st);
+// Dense tensor-core visual cost for thresholds that cut nothing (the reference's default Euclidean(f32::MAX), the published
+// bench's Euclidean(10.0) on unit vectors): see kernels_feat_dense.cu.  Fills the same per-scene pair lists the screen fills
+// (whole (candidate, track) groups that can be a row or column maximum of BestFit's weight matrix), which the exact
+// refinement and the sparse voting kernel then consume unchanged.
+int launch_vis_dense(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, const TcArgs& tc,
+                     cudaStream_t st);
 // The same in two halves, so that the positional cost can run on a second stream next to the refinement:
 //   _a: metadata, tensor-core screen, vis_mode, exact refinement of the survivors (needs nothing from the positional stage)
 //   _b: final scene_mode (needs the positional list counters), dense exact kernel for the scenes in dense mode
@@ -253,8 +290,8 @@ void launch_scene_max(const Params& p, const Frame& f, int n_scenes, bool init_o
 void launch_scene_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st);
 void launch_vis_mode(const Params& p, const Frame& f, int n_scenes, bool tc_used, cudaStream_t st);
 // shared memory the voting kernels need for scenes of up to max_m x max_n (limit: kVotingSmemLimit)
-size_t voting_smem_need(int max_m, int max_n);
-constexpr size_t kVotingSmemLimit = 200 * 1024;
+size_t voting_smem_need(int max_m, int max_n, int viscap = 0);
+constexpr size_t kVotingSmemLimit = 220 * 1024;
 // returns cudaError from configuration (dynamic smem), 0 on success
 int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                   cudaStream_t st);

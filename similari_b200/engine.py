@@ -95,10 +95,10 @@ class Tracker:
 
     def work_counters(self):
         """Cumulative work of the completed frames (waits for the frames in flight)."""
-        c = np.zeros(3, np.uint64)
+        c = np.zeros(4, np.uint64)
         ms = np.zeros(8, np.float64)
         check(self._L.sb200_work_counters(self._h, ptr(c), ptr(ms)))
-        return {"pair_associations": int(c[0]), "visual_dot_products": int(c[1]), "frames": int(c[2]),
+        return {"pair_associations": int(c[0]), "visual_dot_products": int(c[1]), "frames": int(c[2]), "dense_fallback_scenes": int(c[3]),
                 "stage_ms": dict(zip(("prep", "positional_cost", "visual_cost", "voting", "apply"), map(float, ms[:5]))),
                 "vis_screen_ms": float(ms[5]), "vis_refine_ms": float(ms[6]), "tc_frames": int(ms[7])}
 

@@ -218,3 +218,19 @@ def test_nms_10k_oriented_boxes_matches_oracle(eng, oracle):
     ref = oracle.nms(boxes, scores, 0.8)
     got = eng.nms_indices(boxes, scores, 0.8)
     assert list(ref) == list(got) and 2000 <= len(got) < 10000
+
+
+def test_cfg5_default_visual_metric_dense_path_matches_oracle(eng, oracle):
+    """BASELINE cfg5 with the reference's DEFAULT visual metric, Euclidean(f32::MAX)
+    (src/trackers/visual_sort/metric/builder.rs:26-42): every distance is an entry, BestFit decides every candidate that
+    carries a feature.  32 scenes x 512 x 512 x 512-d on the dense tensor-core path against the oracle."""
+    g, o = _run(eng, oracle, "cfg5", 32, 5, opts_over=dict(visual_threshold=float(np.finfo(np.float32).max)))
+    wc = g.work_counters()
+    assert wc["tc_frames"] >= 3 and wc["dense_fallback_scenes"] == 0
+
+
+def test_cfg5_published_bench_metric_euclidean_10_matches_oracle(eng, oracle):
+    """The published VisualSORT bench's metric, Euclidean(10.0) on unit vectors (benches/simple_visual_sort_tracker.rs:111),
+    at cfg5's per-scene size: screen first (lists overflow), then the dense path."""
+    g, o = _run(eng, oracle, "cfg5", 8, 7, opts_over=dict(visual_threshold=10.0))
+    assert g.work_counters()["tc_frames"] >= 5

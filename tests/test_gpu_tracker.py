@@ -447,3 +447,65 @@ def test_full_size_properties_cfg2(eng):
             assert np.all(r["lengths"][~np.isin(r["ids"], prev_all)] == 1)
         prev_ids = r["ids"].copy()
         prev_all = r["ids"].copy() if fr == 0 else np.union1d(prev_all, r["ids"])
+
+
+F32MAX = float(np.finfo(np.float32).max)
+
+
+@pytest.mark.parametrize("kind", [2, 3])
+@pytest.mark.parametrize("vis,thr", [(0, F32MAX), (1, -1.0), (0, 10.0)])
+@pytest.mark.parametrize("kobs,min_votes", [(3, 2), (5, 1), (2, 2), (4, 3)])
+def test_dense_tensor_core_path_matches_oracle(eng, oracle, kind, vis, thr, kobs, min_votes, monkeypatch):
+    """Thresholds that cut nothing -- the reference's default Euclidean(f32::MAX), cosine(-1), the published bench's
+    Euclidean(10.0) on unit vectors -- on the dense tensor-core path (kernels_feat_dense.cu): tcgen05 weight sums with error
+    bounds, exact max_dist, selection of the groups that can be a BestFit row / column maximum, exact refinement, voting.
+    Every id / voting type must be the oracle's.  K = 2..5 observations exercise column tiles of 256, 255, 256 and 255
+    feature rows (tiles end at block boundaries), min_votes the block filter."""
+    monkeypatch.setenv("SB200_VIS_KERNEL", "dense")
+    cfg = small("cfg5", n_scenes=1 if kind == 2 else 3, n_objects=170, oriented=False, canvas=(1500.0, 1000.0),
+                feature_dim=128, drop_frac=0.1, fresh_frac=0.1)
+    g, o = run_frames(eng, oracle, cfg, 7,
+                      dict(kind=kind, positional_kind=1, iou_threshold=0.3, max_idle_epochs=3, visual_kind=vis,
+                           visual_threshold=thr, feature_dim=128, visual_max_observations=kobs,
+                           visual_min_votes=min_votes, visual_minimal_track_length=1, min_confidence=0.1),
+                      check_costs=False)
+    wc = g.work_counters()
+    assert wc["tc_frames"] >= 5 and wc["dense_fallback_scenes"] == 0    # the tensor-core path did the work, no scene fell back
+
+
+def test_dense_path_preconditions_fall_back_per_scene(eng, oracle, monkeypatch):
+    """The dense path forced onto a threshold that DOES cut (1.38 on unit vectors: about a third of the distances pass): the
+    exact max_dist exceeds the threshold, the scene is flagged on the device and the exact SIMT kernels take it -- slow, but
+    the assignments are still the oracle's."""
+    monkeypatch.setenv("SB200_VIS_KERNEL", "dense")
+    cfg = small("cfg5", n_scenes=2, n_objects=120, oriented=False, canvas=(1200.0, 800.0), feature_dim=64)
+    g, o = run_frames(eng, oracle, cfg, 5,
+                      dict(kind=3, positional_kind=1, iou_threshold=0.3, max_idle_epochs=3, visual_kind=0,
+                           visual_threshold=1.38, feature_dim=64, visual_max_observations=3, visual_min_votes=2,
+                           visual_minimal_track_length=1, min_confidence=0.1), check_costs=False)
+    assert g.work_counters()["dense_fallback_scenes"] > 0
+
+
+def test_threshold_that_cuts_nothing_switches_to_the_dense_path(eng, oracle):
+    """Euclidean(10.0) on unit vectors looks selective to the host (finite threshold), so the first frames take the screen,
+    whose survivor lists overflow in every scene (device-side exact fallback).  The tracker notices and moves to the dense
+    tensor-core path: after the switch no scene falls back any more, and every frame matches the oracle."""
+    from similari_b200._lib import default_options
+    from similari_b200.workload import Workload
+
+    cfg = small("cfg5", n_scenes=3, n_objects=420, oriented=False, canvas=(2600.0, 1600.0), feature_dim=256)
+    kw = dict(kind=3, positional_kind=1, iou_threshold=0.3, max_idle_epochs=3, visual_kind=0, visual_threshold=10.0,
+              feature_dim=256, visual_max_observations=3, visual_min_votes=2, visual_minimal_track_length=1,
+              min_confidence=0.1)
+    g, o = both(eng, oracle, **kw)
+    wl = Workload(cfg)
+    fallback = []
+    for fr in range(9):
+        f = wl.next_frame()
+        rg = g.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"])
+        ro = o.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"])
+        for key in ("ids", "epochs", "lengths", "voting_types"):
+            assert np.array_equal(rg[key], ro[key]), (fr, key)
+        fallback.append(g.work_counters()["dense_fallback_scenes"])
+    assert fallback[2] > 0                      # the screen's lists overflowed at first
+    assert fallback[-1] == fallback[3]          # ... and nothing fell back once the dense path had taken over
