@@ -238,6 +238,7 @@ struct sb200_tracker {
   HBuf h_small;
   bool adapt_dense = false;     // a nominally selective threshold whose survivor lists overflow: treat it as non-selective
   unsigned long long acc_dense_scenes = 0;   // scenes the exact SIMT fallback had to take (over all absorbed frames)
+  int last_dense_scenes = 0;
   bool seen_features = false;   // a request has carried feature rows (the feature dimension is fixed from then on)
   int last_n_scenes = 0;   // scenes of the last frame (sb200_last_costs reads its scene table back from the device)
 
@@ -527,6 +528,7 @@ int sb200_tracker::absorb_oldest(bool block) {
     {
       const int dense_scenes = *reinterpret_cast<const int*>(reinterpret_cast<const char*>(dyn) + sizeof(sb::FrameDyn));
       acc_dense_scenes += (unsigned long long)dense_scenes;
+      last_dense_scenes = dense_scenes;
       // most scenes of a screened frame overflowed their survivor lists: the threshold cuts (almost) nothing, so the
       // following frames take the dense tensor-core path; and back, if that path's precondition keeps failing
       if (q.mode == 1 && n >= 1 && dense_scenes * 4 > n) adapt_dense = true;
@@ -545,6 +547,10 @@ int sb200_tracker::absorb_oldest(bool block) {
     if (tc_timed) { cudaEventElapsedTime(&kernel_ms[0], q.ev_k[0], q.ev_k[1]); cudaEventElapsedTime(&kernel_ms[1], q.ev_k[1], q.ev_k[2]); }
     for (int i = 0; i < 5; ++i) acc_stage_ms[i] += stage_ms[i];
     if (tc_timed) { acc_kernel_ms[0] += kernel_ms[0]; acc_kernel_ms[1] += kernel_ms[1]; acc_tc_frames += 1; }
+    static const bool trace_abs = getenv("SB200_TRACE") != nullptr;
+    if (trace_abs)
+      fprintf(stderr, "[sb200] frame absorbed: mode %d, %d of %d scenes on the exact SIMT fallback; prep %.3f pos %.3f vis %.3f vote %.3f apply %.3f ms (main kernel %.3f, refine %.3f)\n",
+              q.mode, last_dense_scenes, n, stage_ms[0], stage_ms[1], stage_ms[2], stage_ms[3], stage_ms[4], kernel_ms[0], kernel_ms[1]);
     cudaGetLastError();   // an event that was never recorded in this frame leaves cudaErrorInvalidResourceHandle behind
   }
   for (int s = 0; s < n; ++s) pending_add[q.slots[s]] -= q.m[s];
@@ -845,6 +851,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.id_counter = b_idc.as<unsigned long long>();
   f.id_add = P.is_batch ? (long long)total : -1;
   f.dense_bad = tc.dense ? tc.dense_bad : nullptr;
+  // dense positional matrices for every scene only on request (SB200_FULL_COSTS / SB200_NO_FORK: parity of sb200_last_costs)
+  f.pos_dense_all = getenv("SB200_FULL_COSTS") != nullptr || getenv("SB200_NO_FORK") != nullptr;
   bool prefetched = false;
   Staging* sin = nullptr;
   // inputs
@@ -937,11 +945,6 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   const bool full_costs = getenv("SB200_FULL_COSTS") != nullptr || getenv("SB200_NO_FORK") != nullptr;
   const bool fork = P.is_visual && tc.use_tc && tc.n_tiles > 0 && !full_costs;
   if (fork) {
-    if (!pos_stream) {
-      CU(cudaStreamCreateWithFlags(&pos_stream, cudaStreamNonBlocking));
-      for (auto& e : ev_fork) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    }
     if ((rc = ens(f_decided, T)) || (rc = ens(f_excl, (size_t)scene_cap * track_cap + 16))) return rc;
     f.decided = f_decided.as<unsigned char>();
     f.excl = f_excl.as<unsigned char>();
@@ -1010,11 +1013,9 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     CU(cudaEventRecord(q.ev[2], stream));
     int vr0 = sb::launch_vis_cost(Pf, ts, f, n_scenes, max_m, max_n, tcc, stream);
     if (vr0 != 0) return fail(SB200_ERR_CUDA, "visual cost launch failed (%d)", vr0);
+    // scenes whose entry list overflowed vote on the dense matrix: it is filled and scanned for them alone, now
+    if (!f.pos_dense_all) sb::launch_pos_scan_lazy(Pf, ts, f, n_scenes, max_m, max_n, /*pass=*/1, stream);
   } else {
-    CU(cudaEventRecord(ev_fork[0], stream));                  // scene table built, counters zeroed
-    CU(cudaStreamWaitEvent(pos_stream, ev_fork[0], 0));
-    sb::launch_pos_fill(Pf, f, n_scenes, max_m, max_n, pos_stream);
-    CU(cudaEventRecord(ev_join, pos_stream));
     CU(cudaEventRecord(q.ev[2], stream));
     {
       int vr0 = sb::launch_vis_cost_a(Pf, ts, f, n_scenes, max_m, max_n, tcc, stream);   // metadata, screen, vis_mode, refinement
@@ -1022,7 +1023,6 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       vr0 = sb::launch_vote_masks(Pf, ts, f, n_scenes, max_m, max_n, stream);            // who is still open positionally
       if (vr0 != 0) return fail(SB200_ERR_CUDA, "voting launch failed: %s", cudaGetErrorString((cudaError_t)vr0));
     }
-    CU(cudaStreamWaitEvent(stream, ev_join, 0));                // the None fill has landed
     CU(cudaEventRecord(q.ev_pos[0], stream));
     sb::launch_pos_scan_lazy(Pf, ts, f, n_scenes, max_m, max_n, /*pass=*/0, stream);
     CU(cudaEventRecord(q.ev_pos[1], stream));
@@ -1439,13 +1439,38 @@ int64_t sb200_last_costs(sb200_tracker* t, uint64_t scene_id, int64_t cap, float
   std::vector<sb::SceneDesc> sd((size_t)t->last_n_scenes);
   CU(cudaMemcpyAsync(sd.data(), t->f_scenes.p, sizeof(sb::SceneDesc) * sd.size(), cudaMemcpyDeviceToHost, t->stream));
   CU(cudaStreamSynchronize(t->stream));
-  for (const sb::SceneDesc& d : sd) {
+  for (size_t si = 0; si < sd.size(); ++si) {
+    const sb::SceneDesc& d = sd[si];
     if (d.scene_id != scene_id) continue;
     *m = d.m; *n = d.n;
-    int64_t cnt = std::min<int64_t>(cap, (int64_t)d.m * d.n);
-    if (cnt > 0) {
+    const int64_t full = (int64_t)d.m * d.n;
+    const int64_t cnt = std::min<int64_t>(cap, full);
+    if (cnt <= 0) return 0;
+    // the dense matrix exists for scenes in dense voting mode and in SB200_FULL_COSTS runs; elsewhere the entry list is
+    // the matrix (None wherever no entry is listed)
+    int h[2] = {0, 0};   // pos_cnt, scene_mode
+    const int ns = t->last_n_scenes;
+    CU(cudaMemcpyAsync(&h[0], t->f_counters.as<int>() + si, 4, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaMemcpyAsync(&h[1], t->f_counters.as<int>() + 2 * (size_t)ns + si, 4, cudaMemcpyDeviceToHost, t->stream));
+    CU(cudaStreamSynchronize(t->stream));
+    const bool dense_exists = h[1] != 0 || getenv("SB200_FULL_COSTS") != nullptr || getenv("SB200_NO_FORK") != nullptr;
+    if (dense_exists) {
       CU(cudaMemcpyAsync(out, t->f_pos.as<float>() + d.pos_off, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, t->stream));
       CU(cudaStreamSynchronize(t->stream));
+      return cnt;
+    }
+    const int ne = std::min(h[0], d.pos_lcap);
+    std::vector<sb::PosEntry> ents((size_t)std::max(ne, 0));
+    if (ne > 0) {
+      CU(cudaMemcpyAsync(ents.data(), t->f_poslist.as<sb::PosEntry>() + d.pos_lbase, sizeof(sb::PosEntry) * (size_t)ne,
+                         cudaMemcpyDeviceToHost, t->stream));
+      CU(cudaStreamSynchronize(t->stream));
+    }
+    const float qnan = std::nanf("");
+    for (int64_t i = 0; i < cnt; ++i) out[i] = qnan;
+    for (const sb::PosEntry& e : ents) {
+      const int64_t idx = (int64_t)e.m * d.n + e.n;
+      if (idx < cnt) out[idx] = e.v;
     }
     return cnt;
   }

@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Tra
     // (best.rs:97).  Row maxima need no atomics (a thread owns its row), column maxima are order-preserving
     // atomicMax / atomicMin.  A pathological bucket (> kBucketMax entries of one candidate) takes the whole-list
     // bitonic sort instead.
-    constexpr int kBucketMax = 32;
+    constexpr int kBucketMax = 160;   // (the dense tensor-core path lists ~10 near-equal groups for an unmatched candidate)
     for (int m = tid; m <= M; m += VT_THREADS) s.bstart[m] = 0;
     for (int m = tid; m < M; m += VT_THREADS) { s.rowW[m] = 0ull; s.rown[m] = 0x7fffffff; }
     for (int n = tid; n < N; n += VT_THREADS) { s.colW[n] = 0ull; s.colm[n] = 0x7fffffff; }

@@ -239,7 +239,7 @@ constexpr int PS_QCAP = 4096;
 // exact metric of one gated (candidate, track) pair; valid results go to the dense matrix and the sparse list
 template <int POS>
 __device__ __forceinline__ void pos_eval_pair(const Params& p, const TrackStore& ts, const Frame& f, const SceneDesc& sc,
-                                              int sidx, size_t tbase, int m, int n, float* out) {
+                                              int sidx, size_t tbase, int m, int n, float* out, bool dense, bool list) {
   const int g = sc.det_base + m;
   const float* cb = f.c_box + (size_t)g * 6;
   const float cconf = f.c_conf[g];
@@ -274,11 +274,13 @@ __device__ __forceinline__ void pos_eval_pair(const Params& p, const TrackStore&
     }
   }
   if (!is_nan(v)) {
-    out[(size_t)m * sc.n + n] = v;
-    const int slot = atomicAdd(&f.pos_cnt[sidx], 1);
-    if (slot < sc.pos_lcap) {
-      PosEntry e; e.m = (unsigned short)m; e.n = (unsigned short)n; e.v = v;
-      f.pos_list[sc.pos_lbase + slot] = e;
+    if (dense) out[(size_t)m * sc.n + n] = v;
+    if (list) {
+      const int slot = atomicAdd(&f.pos_cnt[sidx], 1);
+      if (slot < sc.pos_lcap) {
+        PosEntry e; e.m = (unsigned short)m; e.n = (unsigned short)n; e.v = v;
+        f.pos_list[sc.pos_lbase + slot] = e;
+      }
     }
   }
 }
@@ -296,8 +298,12 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
   const SceneDesc sc = f.scenes[sidx];
   const int N = sc.n, M = sc.m;
   if (N == 0 || M == 0 || N > PS_MAXN) return;   // N > PS_MAXN: the dense kernel handles this scene
-  if (lazy_pass == 1 && !(f.scene_mode[sidx] != 0 && f.vis_mode[sidx] == 0)) return;
+  // pass 1: the scenes that ended in dense voting mode get their dense matrix now -- None fill and a full scan (their first
+  // scan, if any, was a lazy one and wrote the entry list only)
+  if (lazy_pass == 1 && f.scene_mode[sidx] == 0) return;
   const bool lazy = lazy_pass == 0 && f.vis_mode[sidx] == 0;
+  const bool wdense = f.pos_dense_all || lazy_pass == 1;
+  const bool wlist = lazy_pass != 1;
   const unsigned char* excl = lazy ? f.excl + (size_t)sc.slot * ts.track_cap : nullptr;
   // gridDim.y CTAs share a scene (few scenes, many SMs): each sorts the tracks for itself and takes a slice of candidates
   const int mchunk = (M + (int)gridDim.y - 1) / (int)gridDim.y;
@@ -356,6 +362,11 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
   }
   __syncthreads();
   float* out = f.pos + sc.pos_off;
+  if (lazy_pass == 1 && !f.pos_dense_all) {   // this CTA's candidate rows of the dense matrix: None everywhere first
+    const float qnan = nanf("");
+    for (long long i = (long long)m_begin * N + tid; i < (long long)m_end * N; i += PS_THREADS) out[i] = qnan;
+    __syncthreads();
+  }
   const bool bad = s_bad != 0;
   int2* queue = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(sep + N) + 7) & ~(uintptr_t)7);   // [PS_QCAP] gated pairs
   for (int m0 = m_begin; m0 < m_end; m0 += PS_THREADS) {
@@ -385,7 +396,7 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
         if (!compat_ok(p, sc.epoch, sep[i], cx, cy, cr, tx, ty, tr) || too_far(cx, cy, cr, tx, ty, tr)) continue;
         const int slot = atomicAdd(&s_qn, 1);
         if (slot < PS_QCAP) queue[slot] = make_int2(m, i);
-        else pos_eval_pair<POS>(p, ts, f, sc, sidx, tbase, m, kidx[i], out);   // queue full: evaluate in place
+        else pos_eval_pair<POS>(p, ts, f, sc, sidx, tbase, m, kidx[i], out, wdense, wlist);   // queue full: evaluate in place
       }
     }
     __syncthreads();
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
     const int qn = min(s_qn, PS_QCAP);
     for (int e = tid; e < qn; e += PS_THREADS) {
       const int2 q = queue[e];
-      pos_eval_pair<POS>(p, ts, f, sc, sidx, tbase, q.x, kidx[q.y], out);
+      pos_eval_pair<POS>(p, ts, f, sc, sidx, tbase, q.x, kidx[q.y], out, wdense, wlist);
     }
     __syncthreads();
   }
@@ -403,6 +414,7 @@ static bool pos_use_dense(int max_n) { return max_n > PS_MAXN || getenv("SB200_P
 
 void launch_pos_fill(const Params& p, const Frame& f, int n_scenes, int max_m, int max_n, cudaStream_t st) {
   (void)p;
+  if (!f.pos_dense_all) return;   // trackers: only the scenes that need the dense matrix fill it (pos_scan pass 1)
   if (n_scenes == 0 || max_m == 0 || max_n == 0 || pos_use_dense(max_n)) return;   // the dense kernel writes every element
   // pos matrices are packed back to back: total elements = last offset + last size (the host passes it via f.pos_total)
   const long long total = f.pos_total;   // exact (operators) or an upper bound (trackers: the kernel reads f.dyn)

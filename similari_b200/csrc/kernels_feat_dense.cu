@@ -207,7 +207,7 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       float2* wsp = dd.ws + h.ws_base + m;
       const float* gcolc = S.colc[ms];
       const float* gcmax = S.cmax[ms];
-      float s_acc = 0.0f, xmin = finf;
+      float s_acc = 0.0f, dmin = finf;
       mbar_wait(&S.tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       uint32_t acc[2][32];
@@ -222,45 +222,65 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (ch + 1 < TC_BN / 32) tc_ld32_issue(taddr + (ch + 1) * 32, acc[par ^ 1]);
           const unsigned int vm = S.vmask[ms][ch], bm = S.bmask[ms][ch];
           if ((vm | bm) != 0u) {   // warp-uniform, like every test on vm / bm below: column properties
+            // phase 1, straight-line: the 32 accumulators of the chunk become distances in place (independent chains, so
+            // the loads, the MUFU and the arithmetic of different columns overlap); candidates for max_dist as a bit mask
+            unsigned int cmask = 0u;
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 4) {
+              const float4 c4 = *reinterpret_cast<const float4*>(gcolc + ch * 32 + jj);
+              const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float a = __uint_as_float(acc[par][jj + u]);
+                float dval, key;
+                if (COSINE) {
+                  dval = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(a, rowc), cc[u]));
+                  key = dval;
+                } else {
+                  float x = __fmaf_rn(-2.0f, a, __fadd_rn(rowc, cc[u]));
+                  x = fmaxf(x, 1e-30f);
+                  dval = __fmul_rn(x, rsqrtf(x));
+                  key = x;
+                }
+                cmask |= (key >= T ? 1u : 0u) << (jj + u);
+                acc[par][jj + u] = __float_as_uint(dval);
+              }
+            }
+            cmask &= vm;
+            if (cmask) {   // rare
+              while (cmask) {
+                const int jj = __ffs(cmask) - 1;
+                cmask &= cmask - 1;
+                const int slot = atomicAdd(&dd.maxc_cnt[h.scene], 1);
+                if (slot < h.vis_lcap) {
+                  VisPair vp;
+                  vp.g = g; vp.row = h.rowB + ch * 32 + jj; vp.scene = h.scene; vp.outcol = -1;
+                  dd.maxc[h.vis_lbase + slot] = vp;
+                }
+              }
+            }
+            // phase 2: per-block sums and minima (two short chains), one store per (candidate, block)
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
               if (vm & (1u << jj)) {
-                const float a = __uint_as_float(acc[par][jj]);
-                const float cc = gcolc[ch * 32 + jj];
-                float dval, key;
-                if (COSINE) {
-                  const float c = __fmul_rn(__fmul_rn(a, rowc), cc);
-                  dval = __fsub_rn(1.0f, c);
-                  key = dval;
-                } else {
-                  float x = __fmaf_rn(-2.0f, a, __fadd_rn(rowc, cc));
-                  x = fmaxf(x, 1e-30f);
-                  dval = __fmul_rn(x, rsqrtf(x));
-                  xmin = fminf(xmin, x);
-                  key = x;
-                }
+                const float dval = __uint_as_float(acc[par][jj]);
                 s_acc = __fadd_rn(s_acc, dval);
-                if (key >= T) {
-                  const int slot = atomicAdd(&dd.maxc_cnt[h.scene], 1);
-                  if (slot < h.vis_lcap) {
-                    VisPair vp;
-                    vp.g = g; vp.row = h.rowB + ch * 32 + jj; vp.scene = h.scene; vp.outcol = -1;
-                    dd.maxc[h.vis_lbase + slot] = vp;
-                  }
-                }
+                dmin = fminf(dmin, dval);
               }
               if (bm & (1u << jj)) {   // last physical slot of a block: one {sum, bound} per (candidate, track)
                 float del;
                 if (COSINE) del = kDenseErrC;
                 else {
-                  const float e = kDenseErrE * (rowc + gcmax[ch * 32 + jj]);
-                  // |d - d~| <= e / (d + d~) <= 0.536 e / d~ once x >= 4 e; both d, d~ <= sqrt(5 e) otherwise
-                  del = xmin >= 4.0f * e ? 0.536f * e * rsqrtf(xmin) : sqrtf(5.0f * e);
-                  del = del * 1.0001f + 1e-6f * sqrtf(rowc + gcmax[ch * 32 + jj]);   // rsqrt approximation of d~ itself
+                  const float cmx = gcmax[ch * 32 + jj];
+                  const float e = kDenseErrE * (rowc + cmx);
+                  // |d - d~| <= e / (d + d~) <= 0.536 e / d~ once d~^2 >= 4 e; both d, d~ <= sqrt(5 e) otherwise
+                  const float dm = dmin * (1.0f - 1e-6f);
+                  del = dm * dm >= 4.0f * e ? 0.536f * e / dm : sqrtf(5.0f * e);
+                  del = del * 1.0001f + 1e-6f * sqrtf(rowc + cmx);   // rsqrt approximation of d~ itself
                 }
                 if (row_ok) *wsp = make_float2(s_acc, del);
                 wsp += h.mpad;
-                s_acc = 0.0f; xmin = finf;
+                s_acc = 0.0f; dmin = finf;
               }
             }
           }
@@ -357,7 +377,7 @@ __global__ void vis_dense_rowmeta_kernel(Params p, Frame f, VisRowMeta* rowmeta)
 // Sampled lower bound of the scene's maximal distance (in the weight-sum kernel's domain: squared distance, or 1 - cos):
 // up to 64 candidates x 64 valid feature rows, plain f32 dot products.  Any real element bounds the maximum from below, so
 // whatever the sample is, the candidates the weight-sum kernel keeps (x~ >= l0 - bound) contain the true maximum.
-constexpr int DSAMP = 64;
+constexpr int DSAMP = 32;
 __global__ void __launch_bounds__(256) vis_dense_sample_kernel(Params p, TrackStore ts, Frame f, const int2* rowinfo, float* scene_l0) {
   __shared__ int s_q[DSAMP], s_r[DSAMP];
   __shared__ int s_nq, s_nr;
@@ -365,7 +385,7 @@ __global__ void __launch_bounds__(256) vis_dense_sample_kernel(Params p, TrackSt
   const int s = blockIdx.x;
   const SceneDesc sc = f.scenes[s];
   const int K = p.max_obs;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) { s_nq = 0; s_nr = 0; }
   __syncthreads();
   const int rows = sc.nb * K;
@@ -378,31 +398,36 @@ __global__ void __launch_bounds__(256) vis_dense_sample_kernel(Params p, TrackSt
   } else if (tid < 2 * DSAMP) {
     const int i = tid - DSAMP;
     if (rows > 0) {
-      const int pr = (int)(((long long)i * rows) / DSAMP);
-      const bool dup = i > 0 && (int)(((long long)(i - 1) * rows) / DSAMP) == pr;
-      const int fr = rowinfo[(size_t)sc.blk_off * K + pr].y;
-      if (!dup && fr >= 0) s_r[atomicAdd(&s_nr, 1)] = fr;
+      // evenly spaced starting points; a free block or an unused slot moves on to the next valid row (at most 2 K steps)
+      int pr = (int)(((long long)i * rows) / DSAMP);
+      int fr = -1;
+      for (int step = 0; step < 2 * K && pr < rows; ++step, ++pr) {
+        fr = rowinfo[(size_t)sc.blk_off * K + pr].y;
+        if (fr >= 0) break;
+      }
+      if (fr >= 0) s_r[atomicAdd(&s_nr, 1)] = fr;   // duplicates are harmless: any real element is a lower bound
     }
   }
   __syncthreads();
   const int nq = s_nq, nr = s_nr;
   float best = 0.0f;
   const int D = p.feature_dim;
-  for (int pi = tid; pi < nq * nr; pi += 256) {
+  // one warp per sampled pair: the lanes stride over the features (coalesced), shuffle tree at the end
+  for (int pi = wid; pi < nq * nr; pi += 8) {
     const int g = s_q[pi / nr], fr = s_r[pi % nr];
     const float* a = f.in_feat + (size_t)g * D;
     const float* b = ts.feat + (size_t)fr * p.d8;
     float dot = 0.0f;
-    for (int d = 0; d < D; ++d) dot = __fmaf_rn(a[d], b[d], dot);
+    for (int d = lane; d < D; d += 32) dot = __fmaf_rn(a[d], b[d], dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
     const float na = f.c_norm2[g], nb2 = ts.fnorm2[fr];
     float v;
     if (p.visual_kind == 1) v = 1.0f - dot * rsqrtf(na) * rsqrtf(nb2) - 1e-4f;
     else v = (na + nb2 - 2.0f * dot) - 1e-4f * (na + nb2);
     best = fmaxf(best, v);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-  if ((tid & 31) == 0) s_w[tid >> 5] = best;
+  if (lane == 0) s_w[wid] = best;
   __syncthreads();
   if (tid == 0) {
     for (int w = 1; w < 8; ++w) best = fmaxf(best, s_w[w]);
@@ -427,8 +452,9 @@ __global__ void __launch_bounds__(SEL_T) vis_dense_select_kernel(Params p, Frame
   // preconditions of the dense result
   const unsigned int um = f.scene_max[s];
   const float maxd = __uint_as_float((um & 0x80000000u) ? (um & 0x7fffffffu) : ~um);
-  bool bad = maxc_cnt[s] > sc.vis_lcap || max_nan[s] != 0 || !(maxd >= 0.0f);
-  if (bad) { if (tid == 0) dense_bad[s] = 1; return; }
+  // reasons: 1 an entry the threshold cuts (set by the max refinement), 2 max-candidate list overflow, 4 no maximum found
+  const int reason = (max_nan[s] != 0 ? 1 : 0) | (maxc_cnt[s] > sc.vis_lcap ? 2 : 0) | (!(maxd >= 0.0f) ? 4 : 0);
+  if (reason) { if (tid == 0) dense_bad[s] = reason; return; }
   unsigned int* lcol = reinterpret_cast<unsigned int*>(sel_smem);          // [nb] order-preserving f32 encoding
   short* kt = reinterpret_cast<short*>(lcol + nb);                          // [nb] valid observations (0: block takes no part)
   const int need_votes = p.min_votes > 1 ? p.min_votes : 1;
@@ -450,44 +476,53 @@ __global__ void __launch_bounds__(SEL_T) vis_dense_select_kernel(Params p, Frame
       float lrow = fneg;
       if (pass == 1 && row_ok) lrow = f.vis_val[sc.vis_lbase + m];   // pass A parked the row bounds in the (still unused) value list
       const float2* wrow = w0 + m;
-      for (int b = 0; b < nb; ++b) {
-        const int k = kt[b];
-        if (k == 0) continue;   // block-uniform
-        const float fk = (float)k, a = fk * maxd;
-        if (pass == 0) {
-          float wlo = fneg;
-          if (row_ok) {
-            const float2 e = wrow[(size_t)b * mpad];
-            wlo = (a * (1.0f - 2e-6f) - 1e-7f) - (e.x * (1.0f + 2e-6f) + fk * e.y);
-          }
-          lrow = fmaxf(lrow, wlo);
-          unsigned int u = __float_as_uint(wlo);
-          u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-          u = __reduce_max_sync(0xffffffffu, u);   // one instruction: the warp's best lower bound for this column
-          if (lane == 0 && u > lcol[b]) atomicMax(&lcol[b], u);
-        } else if (row_ok) {
-          const float2 e = wrow[(size_t)b * mpad];
-          const float whi = (a * (1.0f + 2e-6f) + 1e-7f) - (e.x * (1.0f - 2e-6f) - fk * e.y);
-          const unsigned int u = lcol[b];
-          const float lc = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-          if (whi >= lrow || whi >= lc) {
-            // the group may hold a row or column maximum: all its valid observations go to the exact pass
-            const int g = sc.det_base + m;
-            int cnt = 0;
-            int2 ri[kMaxObs];
-            for (int ph = 0; ph < K; ++ph) {
-              ri[ph] = rowinfo[(size_t)sc.blk_off * K + (size_t)b * K + ph];
-              cnt += ri[ph].y >= 0;
-            }
-            int pos = atomicAdd(&f.vis_cnt[s], cnt);
-            for (int ph = 0; ph < K; ++ph) {
-              if (ri[ph].y < 0) continue;
-              if (pos < sc.vis_lcap) {
-                VisPair vp;
-                vp.g = g; vp.row = ri[ph].y; vp.scene = s; vp.outcol = ri[ph].x;
-                f.vis_pairs[sc.vis_lbase + pos] = vp;
+      constexpr int UB = 8;   // blocks per round: the loads of a round are issued together (memory-level parallelism)
+      for (int b0 = 0; b0 < nb; b0 += UB) {
+        int kk[UB];
+        float2 ee[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          kk[u] = b0 + u < nb ? (int)kt[b0 + u] : 0;
+          ee[u] = make_float2(0.0f, 0.0f);
+          if (row_ok && kk[u] != 0) ee[u] = __ldcs(wrow + (size_t)(b0 + u) * mpad);
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int k = kk[u], b = b0 + u;
+          if (k == 0) continue;   // block-uniform
+          const float fk = (float)k, a = fk * maxd;
+          const float2 e = ee[u];
+          if (pass == 0) {
+            float wlo = fneg;
+            if (row_ok) wlo = (a * (1.0f - 2e-6f) - 1e-7f) - (e.x * (1.0f + 2e-6f) + fk * e.y);
+            lrow = fmaxf(lrow, wlo);
+            unsigned int uu = __float_as_uint(wlo);
+            uu = (uu & 0x80000000u) ? ~uu : (uu | 0x80000000u);
+            uu = __reduce_max_sync(0xffffffffu, uu);   // one instruction: the warp's best lower bound for this column
+            if (lane == 0 && uu > lcol[b]) atomicMax(&lcol[b], uu);
+          } else if (row_ok) {
+            const float whi = (a * (1.0f + 2e-6f) + 1e-7f) - (e.x * (1.0f - 2e-6f) - fk * e.y);
+            const unsigned int uu = lcol[b];
+            const float lc = __uint_as_float((uu & 0x80000000u) ? (uu & 0x7fffffffu) : ~uu);
+            if (whi >= lrow || whi >= lc) {
+              // the group may hold a row or column maximum: all its valid observations go to the exact pass
+              const int g = sc.det_base + m;
+              int cnt = 0;
+              int2 ri[kMaxObs];
+              for (int ph = 0; ph < K; ++ph) {
+                ri[ph] = rowinfo[(size_t)sc.blk_off * K + (size_t)b * K + ph];
+                cnt += ri[ph].y >= 0;
               }
-              ++pos;
+              int pos = atomicAdd(&f.vis_cnt[s], cnt);
+              for (int ph = 0; ph < K; ++ph) {
+                if (ri[ph].y < 0) continue;
+                if (pos < sc.vis_lcap) {
+                  VisPair vp;
+                  vp.g = g; vp.row = ri[ph].y; vp.scene = s; vp.outcol = ri[ph].x;
+                  f.vis_pairs[sc.vis_lbase + pos] = vp;
+                }
+                ++pos;
+              }
             }
           }
         }

@@ -121,6 +121,7 @@ int sb200_sort_cost_matrix(int32_t positional_kind, float iou_threshold, float m
   f.c_vert = sc.alloc<double>((size_t)m * 8);
   f.pos = sc.alloc<float>((size_t)m * n);
   f.pos_total = (long long)m * n;
+  f.pos_dense_all = true;               // the operator returns the dense matrix
   f.pos_cnt = sc.alloc<int>(4, true);   // sparse list disabled here (capacity 0): only the dense matrix is returned
   f.pos_list = sc.alloc<sb::PosEntry>(1);
   sb::SceneDesc d;

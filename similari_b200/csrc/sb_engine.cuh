@@ -144,6 +144,10 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   int* winner;             // [total] track index within the scene or -1
   unsigned char* c_vt;     // voting type of the decision
   float* pos;              // packed positional cost matrices
+  // The dense positional matrices are only materialised where somebody reads them: the stateless operators and
+  // SB200_FULL_COSTS runs (pos_dense_all), and the scenes that fall back to the dense voting kernel (filled and scanned
+  // again after scene_mode is known).  Everywhere else the per-scene entry list IS the cost matrix.
+  bool pos_dense_all;
   long long pos_total;     // elements in `pos` this frame
   float* vis;              // packed visual matrices
   SceneDesc* scenes;       // [n_scenes]
