@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--visual-threshold", default=None,
                     help="override the visual metric's threshold: a float, or 'max' = the reference's default Euclidean(f32::MAX)")
     ap.add_argument("--feat-noise", type=float, default=None, help="override the workload's feature noise (sensitivity sweeps)")
+    ap.add_argument("--no-scatter", action="store_true", help="N > 1: skip the ingest-rank scatter arm (sb200_shard_*)")
     return ap.parse_args()
 
 
@@ -311,6 +312,132 @@ def newest_traffic():
     return best
 
 
+def run_scatter_arm(eng, torch, dist, new_tracker, frames, dboxes, dfeats, W, K, D, visual, max_total, rank, world, local,
+                    ids_ref_last):
+    """N > 1: the request enters on ONE rank.  Rank 0 holds the detections of all shards; every step it scatters them to the
+    ranks that own the scenes (sb200_shard_scatter: ncclSend/ncclRecv grouped, on a side stream, one frame ahead of the
+    kernels) and gathers the assigned track records back (sb200_shard_gather) -- the exchange step of the sharded path
+    inside the library.  Same frames as the local-ingest arm, so every rank's ids must equal that arm's."""
+    dev = torch.device("cuda", local)
+    uid = [eng.Comm.unique_id() if rank == 0 else None, eng.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    c_sc = eng.Comm(rank, world, uid[0], local)     # scatter traffic (side stream)
+    c_ga = eng.Comm(rank, world, uid[1], local)     # gather traffic (compute stream)
+    # untimed set-up: rank 0 collects the timed frames of every shard (what an ingest node would have received)
+    totals = torch.zeros(world, K, dtype=torch.int64, device=dev)
+    mine_tot = torch.tensor([len(frames[W + j]["boxes"]) for j in range(K)], dtype=torch.int64, device=dev)
+    tl = [torch.zeros(K, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(tl, mine_tot)
+    totals = torch.stack(tl).cpu().numpy()          # [world][K]
+    all_boxes, all_feats, ranges = [], [], []
+    for j in range(K):
+        pad_b = torch.zeros(max_total, 6, dtype=torch.float32, device=dev)
+        pad_b[: len(frames[W + j]["boxes"])] = dboxes[W + j]
+        gb = [torch.empty_like(pad_b) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad_b, gb, dst=0)
+        gf = None
+        if visual:
+            pad_f = torch.zeros(max_total, D, dtype=torch.float32, device=dev)
+            pad_f[: len(frames[W + j]["boxes"])] = dfeats[W + j]
+            gf = [torch.empty_like(pad_f) for _ in range(world)] if rank == 0 else None
+            dist.gather(pad_f, gf, dst=0)
+            del pad_f
+        rng = np.concatenate([[0], np.cumsum(totals[:, j])]).astype(np.int32)
+        ranges.append(rng)
+        if rank == 0:
+            all_boxes.append(torch.cat([gb[r][: totals[r, j]] for r in range(world)]).contiguous())
+            all_feats.append(torch.cat([gf[r][: totals[r, j]] for r in range(world)]).contiguous() if visual else None)
+        del gb, gf
+    torch.cuda.synchronize()
+    t = new_tracker()
+    d_out = {"ids": torch.zeros(max_total, dtype=torch.int64, device=dev), "epochs": torch.zeros(max_total, dtype=torch.int32, device=dev),
+             "lengths": torch.zeros(max_total, dtype=torch.int32, device=dev), "voting_types": torch.zeros(max_total, dtype=torch.uint8, device=dev)}
+    all_out = None
+    if rank == 0:
+        n_all = int(max(r[-1] for r in ranges))
+        all_out = {"ids": torch.zeros(n_all, dtype=torch.int64, device=dev), "epochs": torch.zeros(n_all, dtype=torch.int32, device=dev),
+                   "lengths": torch.zeros(n_all, dtype=torch.int32, device=dev), "voting_types": torch.zeros(n_all, dtype=torch.uint8, device=dev)}
+    rb = [torch.zeros(max_total, 6, dtype=torch.float32, device=dev) for _ in range(2)]
+    rf = [torch.zeros(max_total, D, dtype=torch.float32, device=dev) if visual else None for _ in range(2)]
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=dev)
+    landed = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [None, None]
+
+    def addr(d):
+        return {k: v.data_ptr() for k, v in d.items()} if d is not None else None
+
+    def scatter(j):
+        b = j & 1
+        with torch.cuda.stream(side):
+            if consumed[b] is not None:
+                side.wait_event(consumed[b])
+            c_sc.scatter(0, ranges[j], D, all_boxes[j].data_ptr() if rank == 0 else 0,
+                         all_feats[j].data_ptr() if (rank == 0 and visual) else 0, rb[b].data_ptr(),
+                         rf[b].data_ptr() if visual else 0, side.cuda_stream)
+            landed[b].record(side)
+
+    for i in range(W):   # warm-up on the local copies (identical data)
+        f = frames[i]
+        t.predict_batch_device(f["scene_ids"], f["det_offsets"], dboxes[i].data_ptr(), dfeats[i].data_ptr() if visual else 0,
+                               d_ids=d_out["ids"].data_ptr(), d_epochs=d_out["epochs"].data_ptr(),
+                               d_lengths=d_out["lengths"].data_ptr(), d_voting_types=d_out["voting_types"].data_ptr())
+    t.sync()
+    # scatter alone (K back-to-back scatters, nothing else running): what the exchange costs
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(side)
+    for j in range(K):
+        scatter(j)
+    e1.record(side)
+    dist.barrier()
+    torch.cuda.synchronize()
+    scatter_only_ms = e0.elapsed_time(e1) / K
+    consumed[0] = consumed[1] = None
+    # timed: scatter of frame j+1 overlaps the kernels of frame j
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    scatter(0)
+    for j in range(K):
+        b = j & 1
+        if j + 1 < K:
+            scatter(j + 1)
+        f = frames[W + j]
+        main.wait_event(landed[b])
+        t.predict_batch_device(f["scene_ids"], f["det_offsets"], rb[b].data_ptr(), rf[b].data_ptr() if visual else 0,
+                               d_ids=d_out["ids"].data_ptr(), d_epochs=d_out["epochs"].data_ptr(),
+                               d_lengths=d_out["lengths"].data_ptr(), d_voting_types=d_out["voting_types"].data_ptr())
+        ev = torch.cuda.Event()
+        ev.record(main)
+        consumed[b] = ev
+        c_ga.gather(0, ranges[j], addr(d_out), addr(all_out), main.cuda_stream)
+    ev1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    t.sync()
+    n_last = len(frames[W + K - 1]["boxes"])
+    ok = bool(np.array_equal(d_out["ids"][:n_last].cpu().numpy().astype(np.uint64), ids_ref_last))
+    if rank == 0:
+        r0 = ranges[K - 1]
+        ok = ok and bool(np.array_equal(all_out["ids"][r0[0]:r0[1]].cpu().numpy().astype(np.uint64), ids_ref_last))
+    t.close()
+    c_sc.close()
+    c_ga.close()
+    tm = torch.tensor([ms, scatter_only_ms, 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    bytes_root = float(np.mean([(r[-1] - r[1]) * (24 + (D * 4 if visual else 0)) for r in ranges]))
+    return {"ms_per_step": float(tm[0]) / K, "scatter_only_ms_per_step": float(tm[1]),
+            "bytes_sent_by_the_ingest_rank_per_step": bytes_root, "ids_identical_to_local_ingest": float(tm[2]) == 0.0,
+            "ingest_rank_egress_gbs": bytes_root / (float(tm[1]) * 1e-3) / 1e9 if float(tm[1]) > 0 else None,
+            "how": "rank 0 holds every shard's detections; per step sb200_shard_scatter (ncclSend/Recv in one group, side "
+                   "stream, one frame ahead) + sb200_predict_batch_device + sb200_shard_gather of ids / epochs / lengths / "
+                   "voting types to rank 0"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -479,6 +606,13 @@ def main():
         gl = gather["buf"][(W + K - 1) & 1].view(world, max_total)[rank][: len(ids_dev_last)].cpu().numpy().astype(np.uint64)
         assert np.array_equal(gl, ids_dev_last), "gathered ids differ from the local shard"
     t_dev.close()
+    scatter_info = None
+    if world > 1 and not args.no_scatter:
+        try:
+            scatter_info = run_scatter_arm(eng, torch, dist, new_tracker, frames, dboxes, dfeats, W, K, D, visual, max_total,
+                                           rank, world, local, ids_dev_last)
+        except Exception as e:   # the headline line must survive a failure of this arm
+            scatter_info = {"error": f"{type(e).__name__}: {e}"}
 
     units = float(c1["pair_associations"] - c0["pair_associations"])
     dots = float(c1["visual_dot_products"] - c0["visual_dot_products"])
@@ -575,6 +709,10 @@ def main():
         }
         if world > 1:
             line["id_gather"] = "NCCL all_gather of the assigned ids, one step behind on a side stream (included in the timed span)"
+            if scatter_info is not None:
+                if "ms_per_step" in scatter_info:
+                    scatter_info["value"] = units_all / (scatter_info["ms_per_step"] * K * 1e-3)
+                line["scatter_ingest"] = scatter_info
         if old_affinity is not None:
             os.sched_setaffinity(0, old_affinity)   # the CPU baseline uses every core
         if not args.no_cpu_baseline and world == 1:

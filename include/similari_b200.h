@@ -147,8 +147,8 @@ int sb200_prefetch_inputs(sb200_tracker* t, int32_t total, const float* boxes, c
                           const float* own_area);
 /* The asynchronous form of the same call -- what BatchSort::predict is in the reference, where the request is queued
  * and the per-scene results arrive later on PredictionBatchResult's channel (src/trackers/sort/batch_api.rs:222-290,
- * src/trackers/batch.rs:24-38).  The frame is enqueued on the tracker's stream and the call returns; up to four frames
- * are in flight (a fifth call waits for the oldest).  The host buffers (inputs, and the `out` columns, which should be
+ * src/trackers/batch.rs:24-38).  The frame is enqueued on the tracker's stream and the call returns; up to three frames
+ * are in flight (a fourth call waits for the oldest).  The host buffers (inputs, and the `out` columns, which should be
  * pinned: sb200_host_alloc) must stay valid and are only defined after sb200_sync() -- or after a later call has
  * reported sb200_frames_in_flight() low enough.  An error inside an asynchronous frame is returned by the next
  * predict / sync / query call on the tracker. */
@@ -245,6 +245,30 @@ int sb200_own_area_shares(const float* boxes, int32_t n, float* out, int32_t dev
  * returns kept count or negative status. */
 int64_t sb200_nms(const float* boxes, const float* scores, int32_t n, float nms_threshold, float score_threshold,
                   int32_t has_score_threshold, int32_t* out_idx, int32_t device);
+
+/* ---- multi-GPU: the one exchange step of the scene-sharded path (csrc/comm.cu) ----
+ * Scenes are independent and track state is sticky per GPU (rank = scene shard), so N GPUs run N independent trackers; the
+ * only data that crosses GPUs is the request on its way from an ingest rank to the owners of its scenes and the assigned
+ * track records on their way back -- the counterpart of the reference's voting-shard fan-out and result channel
+ * (src/trackers/sort/batch_api.rs:197-207,222-290).  One process per GPU.  NCCL (send/recv over NVLink) is loaded at run
+ * time; rank 0 creates the 128-byte unique id and the caller ships it to the other ranks on its own control channel.
+ * All data pointers are DEVICE pointers; calls are asynchronous on `cuda_stream`, so the scatter of frame i+1 can overlap
+ * the kernels of frame i on another stream.  det_range[world + 1]: rank r owns detections [det_range[r], det_range[r+1])
+ * of the root's request (its scenes' detections are contiguous).  Non-root ranks pass NULL for the `all_*` arguments. */
+typedef struct sb200_comm sb200_comm;
+int sb200_comm_unique_id(void* out128);
+int sb200_comm_create(int32_t rank, int32_t world, const void* id128, int32_t device, sb200_comm** out);
+void sb200_comm_destroy(sb200_comm* c);
+/* root -> owners: boxes [6 f32], features [feature_dim f32], has_feature, quality, custom ids; a column is skipped on every
+ * rank when its `my_*` pointer is NULL (all ranks must agree). */
+int sb200_shard_scatter(sb200_comm* c, int32_t root, const int32_t* det_range, int32_t feature_dim, const float* all_boxes,
+                        const float* all_features, const uint8_t* all_has_feature, const float* all_quality,
+                        const int64_t* all_custom_ids, float* my_boxes, float* my_features, uint8_t* my_has_feature,
+                        float* my_quality, int64_t* my_custom_ids, void* cuda_stream);
+/* owners -> root: the SortTrack columns (`mine`: this rank's results as written by sb200_predict_batch_device; `all`: the
+ * root's buffers for the whole request; a column is skipped when `mine` has it NULL). */
+int sb200_shard_gather(sb200_comm* c, int32_t root, const int32_t* det_range, const sb200_predict_out* mine,
+                       const sb200_predict_out* all, void* cuda_stream);
 
 /* Pinned host memory for callers that want the predict H2D/D2H copies to run at full PCIe speed. */
 void* sb200_host_alloc(size_t bytes);

@@ -10,8 +10,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsimilari_b200.so")
-SOURCES = ["engine.cu", "ops.cu", "kernels_cost.cu", "kernels_feat_tc.cu", "kernels_feat_dense.cu", "kernels_assign.cu", "kernels_state.cu", "kernels_nms.cu", "kernels_own.cu"]
-HEADERS = ["sb_engine.cuh", "sb_math.cuh", "sb_own_area.cuh", "sb_tc.cuh", os.path.join("..", "..", "include", "similari_b200.h")]
+SOURCES = ["engine.cu", "ops.cu", "kernels_cost.cu", "kernels_feat_tc.cu", "kernels_feat_dense.cu", "kernels_assign.cu", "kernels_state.cu", "kernels_nms.cu", "kernels_own.cu", "comm.cu"]
+HEADERS = ["sb_engine.cuh", "sb_math.cuh", "sb_own_area.cuh", "sb_tc.cuh", "sb_sincos.cuh", "sb_sincos_table.inc", os.path.join("..", "..", "include", "similari_b200.h")]
 
 # --fmad=false: the reference (Rust) never contracts a*b+c; parity of the i64 weights depends on it.
 NVCC_FLAGS = [
@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))
-    cmd = [nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -82,7 +82,8 @@ EXPORTS = [
     "sb200_visual_cost_matrix", "sb200_sort_voting", "sb200_visual_voting", "sb200_kalman_initiate",
     "sb200_kalman_predict", "sb200_kalman_update", "sb200_nms", "sb200_own_area_shares", "sb200_host_alloc", "sb200_host_free",
     "sb200_predict_batch_async", "sb200_sync", "sb200_frames_in_flight", "sb200_work_counters", "sb200_launch_count",
-    "sb200_set_feature_dim",
+    "sb200_set_feature_dim", "sb200_comm_unique_id", "sb200_comm_create", "sb200_comm_destroy", "sb200_shard_scatter",
+    "sb200_shard_gather",
 ]
 
 
@@ -109,6 +110,11 @@ def lib():
         "sb200_predict_batch_async": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PredictOut)]),
         "sb200_sync": (C.c_int, [vp]),
         "sb200_set_feature_dim": (C.c_int, [vp, i32]),
+        "sb200_comm_unique_id": (C.c_int, [vp]),
+        "sb200_comm_create": (C.c_int, [i32, i32, vp, i32, C.POINTER(vp)]),
+        "sb200_comm_destroy": (None, [vp]),
+        "sb200_shard_scatter": (C.c_int, [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "sb200_shard_gather": (C.c_int, [vp, i32, vp, C.POINTER(PredictOut), C.POINTER(PredictOut), vp]),
         "sb200_frames_in_flight": (C.c_int, [vp]),
         "sb200_work_counters": (C.c_int, [vp, vp, vp]),
         "sb200_launch_count": (u64, []),

@@ -168,7 +168,7 @@ struct sb200_tracker {
   // ---- frames in flight.  predict() is stream-ordered: it enqueues a frame and returns; what only the device knows when
   // the call is made (tracks per scene, ids consumed, expired tracks) is joined in by frame_setup_kernel and read back
   // into the host mirrors when the frame is absorbed -- lazily, by a later call, or by sb200_sync().
-  static constexpr int kDepth = 4;
+  static constexpr int kDepth = 3;
   struct Pending {
     bool active = false;
     int n_scenes = 0, total = 0;
@@ -675,14 +675,18 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   };
   bounds();
   {
-    int hint_t = std::max(need_tracks, opts.max_tracks_per_scene_hint);
+    // Capacity has to hold the UPPER BOUNDS: with frames in flight every queued detection counts as a possible new track.
+    // So the store is sized for the pipeline once -- the caller's hint (or what this frame needs) plus the detections of
+    // kDepth frames -- and later frames neither wait for the device nor reallocate.
+    const int pipe_room = kDepth * std::max(max_m, opts.max_dets_per_scene_hint);
     int hint_s = std::max((int)scene_of_slot.size(), opts.max_scenes_hint);
-    if (hint_s > scene_cap || hint_t > track_cap) {
-      // the store has to grow: meet the device first (exact counts may show that it does not have to)
+    if (hint_s > scene_cap || need_tracks > track_cap) {
+      // the store has to grow: meet the device first (the exact counts are the ones to grow from)
       if ((rc = drain())) return rc;
       bounds();
-      hint_t = std::max(need_tracks, opts.max_tracks_per_scene_hint);
-      if ((rc = ensure_store(hint_s, hint_t))) return rc;
+      const int want_t = std::max(need_tracks, opts.max_tracks_per_scene_hint) + pipe_room;
+      if (hint_s > scene_cap || need_tracks > track_cap)
+        if ((rc = ensure_store(hint_s, std::max(want_t, track_cap)))) return rc;
     }
     // room for every live track of the frames in flight and of this one in the wasted buffer: the end-of-frame sweep
     // appends without a host check
@@ -745,11 +749,11 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   // ---- frame buffers (sized once from the capacity hints when given, so steady-state frames never reallocate)
   const long long hint_dets = (long long)std::max(opts.max_scenes_hint, n_scenes) * opts.max_dets_per_scene_hint;
   const size_t T = (size_t)std::max<long long>(std::max(total, 1), hint_dets);
-  const long long hint_cols = (long long)std::max(opts.max_scenes_hint, n_scenes) *
-                              (((long long)std::max(opts.max_tracks_per_scene_hint, 0) * K + 127) / 128 * 128);
+  const int hint_tracks = opts.max_tracks_per_scene_hint > 0 ? track_cap : 0;   // the store's rows per scene: hint + pipeline room
+  const long long hint_cols = (long long)std::max(opts.max_scenes_hint, n_scenes) * (((long long)hint_tracks * K + 127) / 128 * 128);
   const long long pos_ub = pos_total;
   {
-    const long long hint_pos = hint_dets * std::max(opts.max_tracks_per_scene_hint, 0);
+    const long long hint_pos = hint_dets * hint_tracks;
     pos_total = std::max(pos_total, hint_pos);
     if (P.is_visual) vis_total = std::max(vis_total, hint_pos * K);
   }
@@ -811,7 +815,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       tc.total_cols = (int)col_total;
     } else {
       // sized from the hints like the other frame buffers, so steady-state frames never reallocate
-      const long long hs = std::max(opts.max_scenes_hint, n_scenes), ht = std::max(opts.max_tracks_per_scene_hint, 0);
+      const long long hs = std::max(opts.max_scenes_hint, n_scenes), ht = hint_tracks;
       const long long hd = std::max(opts.max_dets_per_scene_hint, 0);
       ws_ub = std::max(ws_ub, hs * ht * ((hd + 127) / 128 * 128));
       blk_ub = std::max(blk_ub, hs * ht);
@@ -819,7 +823,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       if ((rc = ens(f_ws, 8 * (size_t)std::max<long long>(1, ws_ub))) || (rc = ens(f_tmeta, sizeof(sb::DenseTrackMeta) * (size_t)std::max<long long>(1, blk_ub))) ||
           (rc = ens(f_rowinfo, 8 * (size_t)std::max<long long>(1, blk_ub * K))) || (rc = ens(f_slabc, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))) ||
           (rc = ens(f_slabm, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))) || (rc = ens(f_slabmask, 2 * 32 * (size_t)std::max<long long>(1, slabs_ub))) ||
-          (rc = ens(f_dscene, 4 * 6 * (size_t)n_scenes + 64)) || (rc = ens(f_maxc, sizeof(sb::VisPair) * (size_t)std::max<long long>(1, visl_alloc))) ||
+          (rc = ens(f_dscene, 4 * 6 * (size_t)n_scenes + 128)) || (rc = ens(f_maxc, sizeof(sb::VisPair) * (size_t)std::max<long long>(1, visl_alloc))) ||
           (rc = ens(f_maxcval, 4 * (size_t)std::max<long long>(1, visl_alloc))))
         return rc;
       tc.cstep = cstep;
@@ -839,6 +843,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       tc.zeros = tc.maxc_cnt + 3 * n_scenes;
       tc.scene_l0 = reinterpret_cast<float*>(tc.maxc_cnt + 4 * n_scenes);
       tc.scene_cmax = tc.scene_l0 + n_scenes;
+      tc.dbg_counts = reinterpret_cast<int*>(tc.scene_cmax + n_scenes) + 4;
       tc.maxc = f_maxc.as<sb::VisPair>();
       tc.maxc_val = f_maxcval.as<float>();
     }
@@ -1056,6 +1061,19 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     CU(cudaMemcpyAsync(ho + dyn_offset(n_scenes), f_dyn.p, sizeof(sb::FrameDyn), cudaMemcpyDeviceToHost, stream));
     CU(cudaMemcpyAsync(ho + dyn_offset(n_scenes) + sizeof(sb::FrameDyn), f.dense_cnt, 4, cudaMemcpyDeviceToHost, stream));
   }
+  if (trace && tc.dense && tc.n_tiles > 0) {
+    int hc[8] = {0};
+    int vc = 0;
+    CU(cudaMemcpyAsync(hc, tc.dbg_counts, sizeof(hc), cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    std::vector<int> vcnt((size_t)n_scenes);
+    CU(cudaMemcpy(vcnt.data(), f.vis_cnt, 4 * (size_t)n_scenes, cudaMemcpyDeviceToHost));
+    long long tot = 0; int mx = 0;
+    for (int v : vcnt) { tot += v; mx = std::max(mx, v); }
+    (void)vc;
+    fprintf(stderr, "[sb200] dense frame: fallback reasons threshold %d, max-list overflow %d, no maximum %d; max candidates %d; pairs to refine %lld (largest scene %d)\n",
+            hc[0], hc[1], hc[2], hc[3], tot, mx);
+  }
   CU(cudaEventRecord(q.done, stream));
   rollback.armed = false;
   if (sin) { CU(cudaEventRecord(sin->ev_read, stream)); sin->read_pending = true; }
@@ -1127,7 +1145,9 @@ int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out) {
     if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)); }
   }
   if (opts->max_scenes_hint > 0 || opts->max_tracks_per_scene_hint > 0) {
-    rc = t->ensure_store(std::max(1, opts->max_scenes_hint), std::max(64, opts->max_tracks_per_scene_hint));
+    // + room for the tracks the frames in flight may add (see predict())
+    rc = t->ensure_store(std::max(1, opts->max_scenes_hint),
+                         std::max(64, opts->max_tracks_per_scene_hint + sb200_tracker::kDepth * std::max(0, opts->max_dets_per_scene_hint)));
     if (rc) { delete t; return rc; }
   }
   *out = t;

@@ -31,6 +31,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "sb_engine.cuh"
@@ -79,6 +80,7 @@ struct DenseDev {   // device pointers of the path (TcArgs subset, passed by val
   const float* scene_l0; const float* scene_cmax;
   VisPair* maxc; int* maxc_cnt;
   const VisRowMeta* rowmeta;
+  int dbg;   // SB200_DENSE_DBG (timing experiments only, results are wrong): 1 no ws stores, 2 no max candidates, 4 no phase 2
 };
 
 // ------------------------------------------------------------------------------------------------ weight-sum kernel
@@ -247,6 +249,7 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
               }
             }
             cmask &= vm;
+            if (dd.dbg & 2) cmask = 0u;
             if (cmask) {   // rare
               while (cmask) {
                 const int jj = __ffs(cmask) - 1;
@@ -260,6 +263,7 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
               }
             }
             // phase 2: per-block sums and minima (two short chains), one store per (candidate, block)
+            if (!(dd.dbg & 4))
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
               if (vm & (1u << jj)) {
@@ -278,7 +282,7 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                   del = dm * dm >= 4.0f * e ? 0.536f * e / dm : sqrtf(5.0f * e);
                   del = del * 1.0001f + 1e-6f * sqrtf(rowc + cmx);   // rsqrt approximation of d~ itself
                 }
-                if (row_ok) *wsp = make_float2(s_acc, del);
+                if (row_ok && !(dd.dbg & 1)) *wsp = make_float2(s_acc, del);
                 wsp += h.mpad;
                 s_acc = 0.0f; dmin = finf;
               }
@@ -441,7 +445,7 @@ __global__ void __launch_bounds__(256) vis_dense_sample_kernel(Params p, TrackSt
 constexpr int SEL_T = 512;
 __global__ void __launch_bounds__(SEL_T) vis_dense_select_kernel(Params p, Frame f, const float2* ws, const DenseTrackMeta* tmeta,
                                                                  const int2* rowinfo, const int* maxc_cnt, const int* max_nan,
-                                                                 int* dense_bad) {
+                                                                 int* dense_bad, int* dbg_counts) {
   extern __shared__ unsigned char sel_smem[];
   const int s = blockIdx.x;
   const SceneDesc sc = f.scenes[s];
@@ -454,6 +458,12 @@ __global__ void __launch_bounds__(SEL_T) vis_dense_select_kernel(Params p, Frame
   const float maxd = __uint_as_float((um & 0x80000000u) ? (um & 0x7fffffffu) : ~um);
   // reasons: 1 an entry the threshold cuts (set by the max refinement), 2 max-candidate list overflow, 4 no maximum found
   const int reason = (max_nan[s] != 0 ? 1 : 0) | (maxc_cnt[s] > sc.vis_lcap ? 2 : 0) | (!(maxd >= 0.0f) ? 4 : 0);
+  if (tid == 0) {   // diagnostics of the frame (SB200_TRACE): fallback reasons, list lengths
+    if (reason & 1) atomicAdd(&dbg_counts[0], 1);
+    if (reason & 2) atomicAdd(&dbg_counts[1], 1);
+    if (reason & 4) atomicAdd(&dbg_counts[2], 1);
+    atomicAdd(&dbg_counts[3], maxc_cnt[s]);
+  }
   if (reason) { if (tid == 0) dense_bad[s] = reason; return; }
   unsigned int* lcol = reinterpret_cast<unsigned int*>(sel_smem);          // [nb] order-preserving f32 encoding
   short* kt = reinterpret_cast<short*>(lcol + nb);                          // [nb] valid observations (0: block takes no part)
@@ -565,6 +575,7 @@ int launch_vis_dense(const Params& p, const TrackStore& ts, const Frame& f, int 
                      cudaStream_t st) {
   if (n_scenes == 0) return 0;
   cudaMemsetAsync(tc.maxc_cnt, 0, (size_t)n_scenes * 4 * 4, st);   // maxc_cnt | maxc_next | dense_bad | zeros (contiguous)
+  cudaMemsetAsync(tc.dbg_counts, 0, 8 * 4, st);
   if (tc.n_tiles == 0 || max_m == 0) return 0;
   CUtensorMap mA, mB;
   if (make_map_d(&mA, f.c_bf16, tc.a_rows, p.d8, TC_BM) || make_map_d(&mB, ts.feat_bf16, tc.b_rows, p.d8, TC_BN / 2)) return -1;
@@ -604,6 +615,8 @@ int launch_vis_dense(const Params& p, const TrackStore& ts, const Frame& f, int 
     dd.ws = tc.ws; dd.slab_colc = tc.slab_colc; dd.slab_cmax = tc.slab_cmax; dd.slab_vmask = tc.slab_vmask;
     dd.slab_bmask = tc.slab_bmask; dd.scene_l0 = tc.scene_l0; dd.scene_cmax = tc.scene_cmax; dd.maxc = tc.maxc;
     dd.maxc_cnt = tc.maxc_cnt; dd.rowmeta = tc.rowmeta;
+    static const int dbg = getenv("SB200_DENSE_DBG") ? atoi(getenv("SB200_DENSE_DBG")) : 0;
+    dd.dbg = dbg;
     const TcTile* d_tiles = tc.d_tiles;
     const int* d_n_tiles = tc.d_n_tiles;
     void* args[] = {(void*)&mA, (void*)&mB, (void*)&p, (void*)&ts, (void*)&f, (void*)&d_tiles, (void*)&d_n_tiles, (void*)&dd};
@@ -623,7 +636,8 @@ int launch_vis_dense(const Params& p, const TrackStore& ts, const Frame& f, int 
   {
     const size_t smem = (size_t)std::max(1, tc.max_blocks) * 6 + 64;
     if (smem > 48 * 1024) cudaFuncSetAttribute(vis_dense_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vis_dense_select_kernel<<<n_scenes, SEL_T, smem, st>>>(p, f, tc.ws, tc.tmeta, tc.rowinfo, tc.maxc_cnt, tc.dense_bad, tc.dense_bad);
+    vis_dense_select_kernel<<<n_scenes, SEL_T, smem, st>>>(p, f, tc.ws, tc.tmeta, tc.rowinfo, tc.maxc_cnt, tc.dense_bad, tc.dense_bad,
+                                                           tc.dbg_counts);
     note_launch();
   }
   return 0;

@@ -343,11 +343,9 @@ constexpr int RF_WARPS = 4;
 constexpr int RF_SEG = 64;             // blocks per segment
 constexpr int RF_PITCH = RF_SEG + 1;   // +1: lane p reads row p, rows must start in different banks
 
-template <bool COSINE, bool TAIL>
-__device__ __forceinline__ float refine_block_sum(const float* __restrict__ a, const float* __restrict__ b, int blk, int D) {
-  const float4 b0 = *reinterpret_cast<const float4*>(b + blk * 8);
-  const float4 b1 = *reinterpret_cast<const float4*>(b + blk * 8 + 4);
-  float av[8];
+// a-side of a block sum: the candidate's 8 features of block `blk` (zero padded past D on the TAIL path)
+template <bool TAIL>
+__device__ __forceinline__ void refine_load_a(const float* __restrict__ a, int blk, int D, float* av) {
   if (!TAIL) {
     const float4 a0 = *reinterpret_cast<const float4*>(a + blk * 8);
     const float4 a1 = *reinterpret_cast<const float4*>(a + blk * 8 + 4);
@@ -356,6 +354,11 @@ __device__ __forceinline__ float refine_block_sum(const float* __restrict__ a, c
 #pragma unroll
     for (int l = 0; l < 8; ++l) av[l] = blk * 8 + l < D ? a[blk * 8 + l] : 0.0f;   // the input row has D, not d8, floats
   }
+}
+template <bool COSINE>
+__device__ __forceinline__ float refine_block_sum(const float* av, const float* __restrict__ b, int blk) {
+  const float4 b0 = *reinterpret_cast<const float4*>(b + blk * 8);
+  const float4 b1 = *reinterpret_cast<const float4*>(b + blk * 8 + 4);
   const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
   float t[8];
 #pragma unroll
@@ -391,16 +394,27 @@ __global__ void __launch_bounds__(RF_WARPS * 32) vis_refine_kernel(Params p, Tra
     float acc = 0.0f;
     for (int seg0 = 0; seg0 < nblk; seg0 += RF_SEG) {
       const int segn = min(RF_SEG, nblk - seg0);
+      // A candidate's survivors sit next to each other in the list (the observations of its track are adjacent columns
+      // of one screen tile; the dense path emits whole groups): its row is loaded once and reused while the candidate
+      // stays the same -- a third of the L2 -> SM traffic of this kernel.
+      int g_prev = -1;
+      float av[RF_SEG / 32][8];
 #pragma unroll 4
       for (int pp = 0; pp < npair; ++pp) {
         const int g = __shfl_sync(0xffffffffu, mine.g, pp);
         const int row = __shfl_sync(0xffffffffu, mine.row, pp);
-        const float* a = f.in_feat + (size_t)g * D;
         const float* b = ts.feat + (size_t)row * p.d8;
+        if (g != g_prev) {   // warp-uniform
+          const float* a = f.in_feat + (size_t)g * D;
+#pragma unroll
+          for (int h = 0; h < RF_SEG / 32; ++h)
+            if (h * 32 + lane < segn) refine_load_a<TAIL>(a, seg0 + h * 32 + lane, D, av[h]);
+          g_prev = g;
+        }
 #pragma unroll
         for (int h = 0; h < RF_SEG / 32; ++h) {
           const int j = h * 32 + lane;
-          if (j < segn) bs[pp][j] = refine_block_sum<COSINE, TAIL>(a, b, seg0 + j, D);
+          if (j < segn) bs[pp][j] = refine_block_sum<COSINE>(av[h], b, seg0 + j);
         }
       }
       __syncwarp();
@@ -728,8 +742,10 @@ int launch_vis_refine(const Params& p, const TrackStore& ts, const Frame& f, int
   dim3 grid(16, n_scenes);   // 64 warps x 32 survivors per scene in flight; more survivors are claimed in further rounds
   // the vector path needs 16-byte aligned input rows (a caller-owned device pointer on the device-io path)
   const bool tail = p.feature_dim != p.d8 || (reinterpret_cast<uintptr_t>(f.in_feat) & 15) != 0;
-  static const bool reg_staged = getenv("SB200_REFINE") != nullptr && !strcmp(getenv("SB200_REFINE"), "regs");
-  if (!tail && !reg_staged) {
+  // SB200_REFINE=async: the cp.async variant (measured slower on B200: 0.39 vs 0.25 ms at cfg5 -- one CTA of six warps per
+  // SM cannot keep the block-sum arithmetic fed; kept for experiments)
+  static const bool async_copy = getenv("SB200_REFINE") != nullptr && !strcmp(getenv("SB200_REFINE"), "async");
+  if (!tail && async_copy) {
     // asynchronous-copy kernel: 3 x 8 KB stages + the parked block sums per warp
     const size_t smem = (size_t)RA_WARPS * (RA_STAGES * RA_STAGE_FLOATS + 32 * RF_PITCH) * sizeof(float);
     const void* fn = p.visual_kind == 1 ? (const void*)vis_refine_async_kernel<true> : (const void*)vis_refine_async_kernel<false>;

@@ -255,6 +255,7 @@ struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense ex
   int* maxc_next;        // [n_scenes]
   int* dense_bad;        // [n_scenes] != 0: the dense result cannot be used for this scene (exact SIMT path takes it)
   int* zeros;            // [n_scenes] all zero (vis_mode view for the max refinement)
+  int* dbg_counts;       // [8] per-frame diagnostics: scenes per fallback reason (1, 2, 4), max candidates
 };
 int launch_vis_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                     const TcArgs& tc, cudaStream_t st);

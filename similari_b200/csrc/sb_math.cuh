@@ -25,6 +25,8 @@
 #endif
 #define SB_HD __host__ __device__ __forceinline__
 
+#include "sb_sincos.cuh"
+
 namespace sb {
 
 constexpr float kEps = 0.00001f;            // EPS, src/lib.rs:80
@@ -71,8 +73,9 @@ SB_HD void box_vertices(float xc, float yc, float angle, float aspect_f, float h
   double a = (double)angle_or0(angle);
   double height = (double)height_f;
   double aspect = (double)aspect_f;
-  double c = cos(a);
-  double s = sin(a);
+  // correctly rounded, identical on host and device: the reference's vertices bit for bit (sb_sincos.cuh)
+  double c, s;
+  sc::sincos_cr(a, &s, &c);
   double half_width = height * aspect / 2.0;
   double half_height = height / 2.0;
   double r1x = -half_width * c - half_height * s;

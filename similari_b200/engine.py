@@ -195,6 +195,45 @@ class Tracker:
         return {"vis_screen": float(out[0]), "vis_refine": float(out[1])}
 
 
+class Comm:
+    """NCCL communicator of the scene-sharded path (sb200_comm_*): scatter a request from an ingest rank to the ranks that
+    own its scenes, gather the assigned track records back.  All pointers are raw device addresses."""
+
+    def __init__(self, rank, world, unique_id: bytes, device):
+        self._L = lib()
+        h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, 128)
+        check(self._L.sb200_comm_create(rank, world, buf, device, C.byref(h)))
+        self._h, self.rank, self.world = h, rank, world
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().sb200_comm_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sb200_comm_destroy(self._h)
+            self._h = None
+
+    def scatter(self, root, det_range, feature_dim, all_boxes, all_features, my_boxes, my_features, stream):
+        det_range = np.ascontiguousarray(det_range, dtype=np.int32)
+        vp = lambda a: C.c_void_p(a) if a else None  # noqa: E731
+        check(self._L.sb200_shard_scatter(self._h, root, ptr(det_range), feature_dim, vp(all_boxes), vp(all_features), None,
+                                          None, None, vp(my_boxes), vp(my_features), None, None, None, C.c_void_p(stream)))
+
+    def gather(self, root, det_range, mine: dict, all_: dict, stream):
+        """mine / all_: {"ids": addr, "epochs": addr, "lengths": addr, "voting_types": addr} (device addresses)."""
+        det_range = np.ascontiguousarray(det_range, dtype=np.int32)
+        vp = lambda a: C.c_void_p(a) if a else None  # noqa: E731
+        keys = ("ids", "epochs", "lengths", "voting_types", "predicted", "observed")
+        pm = PredictOut(*[vp(mine.get(k, 0)) for k in keys])
+        pa = PredictOut(*[vp((all_ or {}).get(k, 0)) for k in keys])
+        check(self._L.sb200_shard_gather(self._h, root, ptr(det_range), C.byref(pm), C.byref(pa) if all_ else None,
+                                         C.c_void_p(stream)))
+
+
 def launch_count():
     """Kernels launched by libsimilari_b200.so since it was loaded."""
     return int(lib().sb200_launch_count())

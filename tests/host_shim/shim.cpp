@@ -1,6 +1,7 @@
 // Host build of the product's per-pair arithmetic (similari_b200/csrc/sb_math.cuh) so that the CPU test-suite can
 // compare it bit-for-bit with the oracle before any GPU time is spent.  TEST INFRASTRUCTURE: the product never
 // loads this library and has no CPU execution path.
+#include <string.h>
 #include "../../similari_b200/csrc/sb_math.cuh"
 #include "../../similari_b200/csrc/sb_own_area.cuh"
 extern "C" {
@@ -35,4 +36,11 @@ double shim_overlap_bound(const double* a8, const double* b8) { return sb::rect_
 int shim_iou_bound_fails(const float* l, const float* r, float conf, float thr) {
   return sb::iou_bound_fails(l[4], l[3], r[4], r[3], conf, thr) ? 1 : 0;
 }
+}
+// sincos_cr (sb_sincos.cuh) and the C library's sin / cos over an array of f32 angles
+extern "C" void shim_sincos(const float* angles, long long n, double* s, double* c) {
+  for (long long i = 0; i < n; ++i) sb::sc::sincos_cr((double)angles[i], &s[i], &c[i]);
+}
+extern "C" void shim_libm_sincos(const float* angles, long long n, double* s, double* c) {
+  for (long long i = 0; i < n; ++i) { s[i] = sin((double)angles[i]); c[i] = cos((double)angles[i]); }
 }
