@@ -69,7 +69,7 @@ typedef struct {
   float iou_threshold;            /* PositionalMetricType::IoU(t) */
   float min_confidence;           /* min_confidence / positional_min_confidence */
   int32_t max_idle_epochs;
-  int32_t history_length;         /* bbox_history / kept_history_length (only the last boxes are kept on device) */
+  int32_t history_length;         /* bbox_history / kept_history_length: boxes of history per track (device cap 64; 0 = that cap) */
   float kalman_position_weight;
   float kalman_velocity_weight;
   int32_t n_constraints;          /* SpatioTemporalConstraints: (epoch_delta, max_distance) pairs */
@@ -188,6 +188,12 @@ int sb200_clear_wasted(sb200_tracker* t);
 /* wasted(): drains up to `cap` wasted tracks; returns the count (>= 0) or a negative status. */
 int64_t sb200_wasted(sb200_tracker* t, int64_t cap, uint64_t* ids, uint64_t* scene_ids, uint32_t* epochs,
                      uint32_t* lengths, float* predicted_boxes, float* observed_boxes);
+/* wasted() with the box history of WastedSortTrack (src/trackers/sort.rs:316-341: predicted_boxes / observed_boxes, the last
+ * history_length boxes of the track, oldest first, kept by SortAttributes::update_history, sort.rs:157-171).
+ * predicted_history / observed_history: [cap][history_cap][6], history_counts[cap] = boxes filled for each track. */
+int64_t sb200_wasted_history(sb200_tracker* t, int64_t cap, uint64_t* ids, uint64_t* scene_ids, uint32_t* epochs,
+                             uint32_t* lengths, float* predicted_boxes, float* observed_boxes, int32_t history_cap,
+                             float* predicted_history, float* observed_history, int32_t* history_counts);
 /* idle_tracks_with_scene() (src/trackers/sort/simple_api.rs:198-215) */
 int64_t sb200_idle_tracks(sb200_tracker* t, uint64_t scene_id, int64_t cap, uint64_t* ids, uint32_t* epochs,
                           uint32_t* lengths, float* predicted_boxes, float* observed_boxes);

@@ -83,7 +83,7 @@ EXPORTS = [
     "sb200_kalman_predict", "sb200_kalman_update", "sb200_nms", "sb200_own_area_shares", "sb200_host_alloc", "sb200_host_free",
     "sb200_predict_batch_async", "sb200_sync", "sb200_frames_in_flight", "sb200_work_counters", "sb200_launch_count",
     "sb200_set_feature_dim", "sb200_comm_unique_id", "sb200_comm_create", "sb200_comm_destroy", "sb200_shard_scatter",
-    "sb200_shard_gather",
+    "sb200_shard_gather", "sb200_wasted_history",
 ]
 
 
@@ -127,6 +127,7 @@ def lib():
         "sb200_set_auto_waste": (C.c_int, [vp, i32]),
         "sb200_clear_wasted": (C.c_int, [vp]),
         "sb200_wasted": (i64, [vp, i64, vp, vp, vp, vp, vp, vp]),
+        "sb200_wasted_history": (i64, [vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
         "sb200_idle_tracks": (i64, [vp, u64, i64, vp, vp, vp, vp, vp]),
         "sb200_scene_tracks": (i64, [vp, u64, i64, vp, vp, vp, vp]),
         "sb200_last_costs": (i64, [vp, u64, i64, vp, C.POINTER(i32), C.POINTER(i32)]),

@@ -168,14 +168,15 @@ class SortTrack:
 
 
 class WastedSortTrack:
-    """src/trackers/sort.rs:316-341 `PyWastedSortTrack` (only the last boxes are kept on the device)."""
+    """src/trackers/sort.rs:316-341 `PyWastedSortTrack`: predicted_boxes / observed_boxes hold the last bbox_history boxes."""
 
     __slots__ = ("id", "epoch", "predicted_bbox", "observed_bbox", "scene_id", "length", "predicted_boxes", "observed_boxes")
 
-    def __init__(self, id, epoch, predicted_bbox, observed_bbox, scene_id, length):
+    def __init__(self, id, epoch, predicted_bbox, observed_bbox, scene_id, length, predicted_boxes=None, observed_boxes=None):
         self.id, self.epoch, self.scene_id, self.length = int(id), int(epoch), int(scene_id), int(length)
         self.predicted_bbox, self.observed_bbox = predicted_bbox, observed_bbox
-        self.predicted_boxes, self.observed_boxes = [predicted_bbox], [observed_bbox]
+        self.predicted_boxes = predicted_boxes if predicted_boxes is not None else [predicted_bbox]
+        self.observed_boxes = observed_boxes if observed_boxes is not None else [observed_bbox]
 
 
 WastedVisualSortTrack = WastedSortTrack
@@ -215,9 +216,11 @@ class _TrackerBase:
         return self._t.current_epoch(int(scene_id))
 
     def wasted(self):
-        w = self._t.wasted()
+        w = self._t.wasted_history()
         return [WastedSortTrack(w["ids"][i], w["epochs"][i], Universal2DBox._from_row(w["predicted"][i]),
-                                Universal2DBox._from_row(w["observed"][i]), w["scene_ids"][i], w["lengths"][i])
+                                Universal2DBox._from_row(w["observed"][i]), w["scene_ids"][i], w["lengths"][i],
+                                [Universal2DBox._from_row(r) for r in w["predicted_history"][i]],
+                                [Universal2DBox._from_row(r) for r in w["observed_history"][i]])
                 for i in range(len(w["ids"]))]
 
     def clear_wasted(self):

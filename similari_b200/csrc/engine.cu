@@ -211,12 +211,13 @@ struct sb200_tracker {
   int64_t wasted_count = 0;
   // device track store
   sb::TrackStore ts{};
-  DBuf b_id, b_epoch, b_length, b_custom, b_vt, b_pred, b_obs, b_radius, b_kst, b_vert, b_feat, b_feat_bf16, b_fnorm2, b_obs_phys,
+  DBuf b_id, b_epoch, b_length, b_custom, b_vt, b_pred, b_obs, b_radius, b_kst, b_vert, b_hpred, b_hobs, b_feat, b_feat_bf16, b_fnorm2, b_obs_phys,
       b_obs_hasf, b_obs_q, b_obs_n, b_feat_cnt, b_fblk, b_blk_owner, b_blk_free;
   DBuf b_ntracks, b_cur_epoch, b_scene_ids, b_nfree, b_atop;
   // wasted
   sb::WastedBuf wb{};
-  DBuf w_count, w_id, w_scene, w_epoch, w_length, w_pred, w_obs;
+  DBuf w_count, w_id, w_scene, w_epoch, w_length, w_pred, w_obs, w_hpred, w_hobs;
+  int hist_len = 1;   // boxes of history kept per track (1: only the last ones, the SortTrack columns)
   // frame buffers
   // two input staging sets: sb200_prefetch_inputs() fills one while the kernels of the previous frame read the other
   struct Staging {
@@ -231,7 +232,7 @@ struct sb200_tracker {
   } stg[2];
   int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_frameout, f_decided, f_excl, f_own, f_ownovf, f_dyn, f_ws, f_tmeta, f_rowinfo, f_slabc, f_slabm, f_slabmask,
+      f_status, f_featdst, f_frameout, f_decided, f_excl, f_prewin, f_own, f_ownovf, f_dyn, f_ws, f_tmeta, f_rowinfo, f_slabc, f_slabm, f_slabmask,
       f_dscene, f_maxc, f_maxcval, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
@@ -244,9 +245,9 @@ struct sb200_tracker {
 
   ~sb200_tracker() {
     cudaSetDevice(device);
-    DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_feat,
+    DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_hpred, &b_hobs, &w_hpred, &w_hobs, &b_feat,
                    &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_colb, &f_colvalid, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
-                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl, &f_own, &f_ownovf, &f_dyn, &b_idc, &f_ws, &f_tmeta, &f_rowinfo, &f_slabc, &f_slabm, &f_slabmask, &f_dscene, &f_maxc, &f_maxcval,
+                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl, &f_prewin, &f_own, &f_ownovf, &f_dyn, &b_idc, &f_ws, &f_tmeta, &f_rowinfo, &f_slabc, &f_slabm, &f_slabmask, &f_dscene, &f_maxc, &f_maxcval,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
                    &f_featdst, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
@@ -312,6 +313,11 @@ struct sb200_tracker {
     if ((rc = regrow(b_kst, &ts.kst, sb::kStateFloats, ns, nt))) return rc;
     if (P.positional_kind == SB200_POS_IOU)
       if ((rc = regrow(b_vert, &ts.vert, 8, ns, nt))) return rc;
+    if (hist_len > 1) {
+      if ((rc = regrow(b_hpred, &ts.hist_pred, 6 * hist_len, ns, nt))) return rc;
+      if ((rc = regrow(b_hobs, &ts.hist_obs, 6 * hist_len, ns, nt))) return rc;
+      ts.hist_len = hist_len;
+    }
     if (P.is_visual) {
       if ((rc = regrow(b_feat, &ts.feat, K * P.d8, ns, nt))) return rc;
       {
@@ -376,11 +382,13 @@ struct sb200_tracker {
     if (need <= wb.cap) return 0;
     int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(1024, (int64_t)wb.cap * 2));
     // wasted records are drained by sb200_wasted; growing preserves the pending ones
-    DBuf nid, nsc, nep, nle, npr, nob;
+    DBuf nid, nsc, nep, nle, npr, nob, nhp, nho;
     int rc;
     if ((rc = nid.ensure(8 * ncap)) || (rc = nsc.ensure(8 * ncap)) || (rc = nep.ensure(4 * ncap)) ||
         (rc = nle.ensure(4 * ncap)) || (rc = npr.ensure(24 * ncap)) || (rc = nob.ensure(24 * ncap)))
       return rc;
+    const size_t hrow = (size_t)24 * hist_len;
+    if (hist_len > 1 && ((rc = nhp.ensure(hrow * ncap)) || (rc = nho.ensure(hrow * ncap)))) return rc;
     if (wasted_count > 0) {
       CU(cudaMemcpyAsync(nid.p, w_id.p, 8 * wasted_count, cudaMemcpyDeviceToDevice, stream));
       CU(cudaMemcpyAsync(nsc.p, w_scene.p, 8 * wasted_count, cudaMemcpyDeviceToDevice, stream));
@@ -388,10 +396,17 @@ struct sb200_tracker {
       CU(cudaMemcpyAsync(nle.p, w_length.p, 4 * wasted_count, cudaMemcpyDeviceToDevice, stream));
       CU(cudaMemcpyAsync(npr.p, w_pred.p, 24 * wasted_count, cudaMemcpyDeviceToDevice, stream));
       CU(cudaMemcpyAsync(nob.p, w_obs.p, 24 * wasted_count, cudaMemcpyDeviceToDevice, stream));
+      if (hist_len > 1) {
+        CU(cudaMemcpyAsync(nhp.p, w_hpred.p, hrow * wasted_count, cudaMemcpyDeviceToDevice, stream));
+        CU(cudaMemcpyAsync(nho.p, w_hobs.p, hrow * wasted_count, cudaMemcpyDeviceToDevice, stream));
+      }
       CU(cudaStreamSynchronize(stream));
     }
     w_id.release(); w_scene.release(); w_epoch.release(); w_length.release(); w_pred.release(); w_obs.release();
-    w_id = nid; w_scene = nsc; w_epoch = nep; w_length = nle; w_pred = npr; w_obs = nob;
+    w_hpred.release(); w_hobs.release();
+    w_id = nid; w_scene = nsc; w_epoch = nep; w_length = nle; w_pred = npr; w_obs = nob; w_hpred = nhp; w_hobs = nho;
+    wb.hist_pred = w_hpred.as<float>();
+    wb.hist_obs = w_hobs.as<float>();
     if (!w_count.p) {
       if ((rc = w_count.ensure(sizeof(int)))) return rc;
       CU(cudaMemsetAsync(w_count.p, 0, sizeof(int), stream));
@@ -464,6 +479,11 @@ struct sb200_tracker {
       if ((rc = shift(wb.id, 8)) || (rc = shift(wb.scene, 8)) || (rc = shift(wb.epoch, 4)) || (rc = shift(wb.length, 4)) ||
           (rc = shift(wb.pred, 24)) || (rc = shift(wb.obs, 24)))
         return rc;
+      if (hist_len > 1) {
+        tmp.release();
+        if ((rc = tmp.ensure((size_t)rest * 24 * hist_len))) return rc;
+        if ((rc = shift(wb.hist_pred, (size_t)24 * hist_len)) || (rc = shift(wb.hist_obs, (size_t)24 * hist_len))) return rc;
+      }
       CU(cudaStreamSynchronize(st));
       tmp.release();
     }
@@ -527,7 +547,7 @@ int sb200_tracker::absorb_oldest(bool block) {
     acc_frames += 1;
     {
       const int dense_scenes = *reinterpret_cast<const int*>(reinterpret_cast<const char*>(dyn) + sizeof(sb::FrameDyn));
-      acc_dense_scenes += (unsigned long long)dense_scenes;
+      if (q.mode != 0) acc_dense_scenes += (unsigned long long)dense_scenes;   // mode 0 IS the exact kernel: not a fallback
       last_dense_scenes = dense_scenes;
       // most scenes of a screened frame overflowed their survivor lists: the threshold cuts (almost) nothing, so the
       // following frames take the dense tensor-core path; and back, if that path's precondition keeps failing
@@ -950,9 +970,10 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   const bool full_costs = getenv("SB200_FULL_COSTS") != nullptr || getenv("SB200_NO_FORK") != nullptr;
   const bool fork = P.is_visual && tc.use_tc && tc.n_tiles > 0 && !full_costs;
   if (fork) {
-    if ((rc = ens(f_decided, T)) || (rc = ens(f_excl, (size_t)scene_cap * track_cap + 16))) return rc;
+    if ((rc = ens(f_decided, T)) || (rc = ens(f_excl, (size_t)scene_cap * track_cap + 16)) || (rc = ens(f_prewin, T * 4))) return rc;
     f.decided = f_decided.as<unsigned char>();
     f.excl = f_excl.as<unsigned char>();
+    f.pre_winner = f_prewin.as<int>();
   }
   const bool derive_own = P.is_visual && P.use_own_area && f.in_own == nullptr && total > 0;
   if (derive_own && ((rc = ens(f_own, T * 4)) || (rc = ens(f_ownovf, 16 + T * sizeof(int2))))) return rc;
@@ -1132,6 +1153,8 @@ int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out) {
   t->opts = *opts;
   t->P = P;
   t->device = opts->device;
+  // history_length 0 means "unlimited" in the reference (sort.rs:166); the device keeps at most kMaxHist boxes per track
+  t->hist_len = opts->history_length <= 0 ? sb::kMaxHist : std::min<int>(opts->history_length, sb::kMaxHist);
   {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, opts->device) == cudaSuccess && sms > 0) t->num_sms = sms;
@@ -1365,6 +1388,55 @@ int64_t sb200_wasted(sb200_tracker* t, int64_t cap, uint64_t* ids, uint64_t* sce
   if (predicted_boxes) CU(cudaMemcpyAsync(predicted_boxes, t->wb.pred, 24 * n, cudaMemcpyDeviceToHost, st));
   if (observed_boxes) CU(cudaMemcpyAsync(observed_boxes, t->wb.obs, 24 * n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  if ((rc = t->drop_wasted_front(n))) return rc;   // drain
+  return n;
+}
+
+int64_t sb200_wasted_history(sb200_tracker* t, int64_t cap, uint64_t* ids, uint64_t* scene_ids, uint32_t* epochs, uint32_t* lengths,
+                             float* predicted_boxes, float* observed_boxes, int32_t history_cap, float* predicted_history,
+                             float* observed_history, int32_t* history_counts) {
+  if (!t || cap < 0 || history_cap < 0) return fail(SB200_ERR_INVALID, "bad arguments");
+  CU(cudaSetDevice(t->device));
+  { int rc_ = t->drain(); if (rc_) return rc_; }
+  int rc = t->run_waste();  // wasted() starts with auto_waste (tracker_api.rs:90-91)
+  if (rc) return rc;
+  const int64_t n = std::min<int64_t>(cap, t->wasted_count);
+  if (n == 0) return 0;
+  cudaStream_t st = t->stream;
+  std::vector<uint32_t> hlen((size_t)n);
+  if (ids) CU(cudaMemcpyAsync(ids, t->wb.id, 8 * n, cudaMemcpyDeviceToHost, st));
+  if (scene_ids) CU(cudaMemcpyAsync(scene_ids, t->wb.scene, 8 * n, cudaMemcpyDeviceToHost, st));
+  if (epochs) CU(cudaMemcpyAsync(epochs, t->wb.epoch, 4 * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hlen.data(), t->wb.length, 4 * n, cudaMemcpyDeviceToHost, st));
+  std::vector<float> lastp((size_t)n * 6), lasto((size_t)n * 6);
+  CU(cudaMemcpyAsync(lastp.data(), t->wb.pred, 24 * n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(lasto.data(), t->wb.obs, 24 * n, cudaMemcpyDeviceToHost, st));
+  const int H = t->hist_len;
+  std::vector<float> hp, ho;
+  if (H > 1 && history_cap > 0) {
+    hp.resize((size_t)n * H * 6); ho.resize((size_t)n * H * 6);
+    CU(cudaMemcpyAsync(hp.data(), t->wb.hist_pred, sizeof(float) * hp.size(), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ho.data(), t->wb.hist_obs, sizeof(float) * ho.size(), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  if (lengths) memcpy(lengths, hlen.data(), 4 * (size_t)n);
+  if (predicted_boxes) memcpy(predicted_boxes, lastp.data(), 24 * (size_t)n);
+  if (observed_boxes) memcpy(observed_boxes, lasto.data(), 24 * (size_t)n);
+  // rings -> chronological order (oldest first), at most history_cap boxes per track
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t len = hlen[(size_t)i];
+    int cnt = (int)std::min<uint32_t>(len, (uint32_t)H);
+    cnt = std::min(cnt, (int)history_cap);
+    if (history_counts) history_counts[i] = history_cap > 0 ? cnt : 0;
+    for (int c = 0; c < cnt; ++c) {
+      const uint32_t j = len - (uint32_t)cnt + (uint32_t)c;   // observation number
+      const float* sp; const float* so;
+      if (H > 1) { sp = &hp[((size_t)i * H + j % H) * 6]; so = &ho[((size_t)i * H + j % H) * 6]; }
+      else { sp = &lastp[(size_t)i * 6]; so = &lasto[(size_t)i * 6]; }
+      if (predicted_history) memcpy(predicted_history + ((size_t)i * history_cap + c) * 6, sp, 24);
+      if (observed_history) memcpy(observed_history + ((size_t)i * history_cap + c) * 6, so, 24);
+    }
+  }
   if ((rc = t->drop_wasted_front(n))) return rc;   // drain
   return n;
 }

@@ -564,7 +564,24 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Tra
   __syncthreads();
 
   // ------------------------------------------------------------------ BestFit on the valid visual entries
-  if (VISUAL && N > 0) {
+  // The full pass of a frame whose BestFit pre-pass already ran for this scene (lazy positional stage: f.decided / f.excl
+  // are set and the scene's visual list was complete) takes the decisions from there instead of computing them twice.
+  const bool have_prepass = VISUAL && !MASK_ONLY && f.decided != nullptr && f.excl != nullptr && f.vis_mode[sidx] == 0;
+  if (have_prepass) {
+    const unsigned char* dec = f.decided + sc.det_base;
+    const unsigned char* ex = f.excl + (size_t)sc.slot * ts.track_cap;
+    const int* pw = f.pre_winner + sc.det_base;
+    for (int m = tid; m < M; m += VT_THREADS) {
+      if (dec[m]) {
+        const int n1 = pw[m];
+        cvt[m] = (unsigned char)0;
+        if (n1 >= 0) { winner[m] = n1; s.fw[m] = n1; }
+        else s.fw[m] = kSelf;
+      }
+    }
+    for (int n = tid; n < N; n += VT_THREADS) s.excl[n] = ex[n];
+    __syncthreads();
+  } else if (VISUAL && N > 0) {
     const int K = p.max_obs;
     const float maxd = dec_f32(f.scene_max[sidx]);
     const int nraw = min(f.vis_cnt[sidx], sc.vis_lcap);
@@ -721,7 +738,8 @@ __global__ void __launch_bounds__(VT_THREADS) voting_sparse_kernel(Params p, Tra
     // pre-pass: publish who is still open for the positional stage (the full pass recomputes the same decisions)
     unsigned char* dec = f.decided + sc.det_base;
     unsigned char* ex = f.excl + (size_t)sc.slot * ts.track_cap;
-    for (int m = tid; m < M; m += VT_THREADS) dec[m] = s.fw[m] != kNone;
+    int* pw = f.pre_winner + sc.det_base;
+    for (int m = tid; m < M; m += VT_THREADS) { dec[m] = s.fw[m] != kNone; pw[m] = s.fw[m] >= 0 ? s.fw[m] : -1; }
     for (int n = tid; n < N; n += VT_THREADS) ex[n] = s.excl[n];
     return;
   }

@@ -86,7 +86,40 @@ struct DenseDev {   // device pointers of the path (TcArgs subset, passed by val
 // ------------------------------------------------------------------------------------------------ weight-sum kernel
 // CTA pairs (cta_group::2): one 256 x 256 x 16 MMA per instruction issued by the leader, each CTA stages its own 128
 // candidate rows and half of the B tile; accumulator rows 0-127 / 128-255 in the two CTAs' TMEM; double-buffered accumulators.
+// approximate MUFU operations (2 ulp), one instruction each: only upper bounds and the approximate distances use them
+__device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// Rare path of the weight-sum epilogue, one copy of code: some element of a 32-column chunk may be the scene's maximal
+// distance.  The whole warp re-reads the chunk from TMEM (the accumulator buffer is still owned by this warp's group) and
+// every lane appends its own candidates (feature row = row0 + column) for the exact pass.
 template <bool COSINE>
+__device__ __noinline__ void dense_max_candidates(uint32_t taddr_chunk, float rowc, const float* colc32, unsigned int vm, float T,
+                                                  int g, int row0, int scene, int lbase, int lcap, VisPair* maxc, int* maxc_cnt) {
+  uint32_t av[32];
+  tc_ld32(taddr_chunk, av);
+#pragma unroll
+  for (int jj = 0; jj < 32; ++jj) {
+    if (!((vm >> jj) & 1u)) continue;
+    const float a = __uint_as_float(av[jj]);
+    float key;
+    if (COSINE) key = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(a, rowc), colc32[jj]));
+    else key = fmaxf(__fmaf_rn(-2.0f, a, __fadd_rn(rowc, colc32[jj])), 1e-30f);
+    if (key >= T) {
+      const int slot = atomicAdd(&maxc_cnt[scene], 1);
+      if (slot < lcap) {
+        VisPair vp;
+        vp.g = g; vp.row = row0 + jj; vp.scene = scene; vp.outcol = -1;
+        maxc[lbase + slot] = vp;
+      }
+    }
+  }
+}
+
+// KT > 0: the number of observations per track is a compile-time constant, so the positions where a block of the
+// accumulator ends (every KT-th column: tiles start at block boundaries) are too and the epilogue is straight-line code.
+// KT == 0: any K, block ends come from the bmask slab (uniform branches).
+template <bool COSINE, int KT>
 __global__ void __launch_bounds__(DS_THREADS, 1)
 vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, Params p, TrackStore ts,
                 Frame f, const TcTile* tiles, const int* n_tiles_dev, DenseDev dd) {
@@ -215,76 +248,102 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       uint32_t acc[2][32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BN);
       tc_ld32_issue(taddr, acc[0]);
-#pragma unroll 1
-      for (int ch2 = 0; ch2 < TC_BN / 32; ch2 += 2) {
+      // one flush per block: {sum of the block's distances, per-observation error bound}
+      auto flush = [&](float cmx) {
+        float del;
+        if (COSINE) del = kDenseErrC;
+        else {
+          const float rc = rowc + cmx;
+          const float e = kDenseErrE * rc;
+          // |d - d~| <= e / (d + d~) <= 0.536 e / d~ once d~^2 >= 4 e; both d, d~ <= sqrt(5 e) otherwise.  Only an upper
+          // bound is needed: approximate reciprocal / rsqrt (2 ulp) under a 1.0001 safety factor, and 1e-6 (rc + 1) >=
+          // 1e-6 sqrt(rc) for the rsqrt approximation of d~ itself.
+          const float dm = dmin * (1.0f - 1e-6f);
+          const float e5 = 5.0f * e;
+          del = dm * dm >= 4.0f * e ? 0.536f * e * rcp_approx(dm) : e5 * rsqrt_approx(e5);
+          del = __fmaf_rn(del, 1.0001f, 1e-6f * (rc + 1.0f));
+        }
+        if (row_ok && !(dd.dbg & 1)) *wsp = make_float2(s_acc, del);
+        wsp += h.mpad;
+        s_acc = 0.0f; dmin = finf;
+      };
+      // distances of one 32-column chunk in place; returns the largest key (squared distance, or 1 - cos) of the chunk
+      auto distances = [&](uint32_t* av, int ch) -> float {
+        float kmax = -finf;
 #pragma unroll
-        for (int par = 0; par < 2; ++par) {
-          const int ch = ch2 + par;
-          tc_ld_wait32(acc[par]);
-          if (ch + 1 < TC_BN / 32) tc_ld32_issue(taddr + (ch + 1) * 32, acc[par ^ 1]);
-          const unsigned int vm = S.vmask[ms][ch], bm = S.bmask[ms][ch];
-          if ((vm | bm) != 0u) {   // warp-uniform, like every test on vm / bm below: column properties
-            // phase 1, straight-line: the 32 accumulators of the chunk become distances in place (independent chains, so
-            // the loads, the MUFU and the arithmetic of different columns overlap); candidates for max_dist as a bit mask
-            unsigned int cmask = 0u;
+        for (int jj = 0; jj < 32; jj += 4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(gcolc + ch * 32 + jj);
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
-            for (int jj = 0; jj < 32; jj += 4) {
-              const float4 c4 = *reinterpret_cast<const float4*>(gcolc + ch * 32 + jj);
-              const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float a = __uint_as_float(acc[par][jj + u]);
-                float dval, key;
-                if (COSINE) {
-                  dval = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(a, rowc), cc[u]));
-                  key = dval;
-                } else {
-                  float x = __fmaf_rn(-2.0f, a, __fadd_rn(rowc, cc[u]));
-                  x = fmaxf(x, 1e-30f);
-                  dval = __fmul_rn(x, rsqrtf(x));
-                  key = x;
-                }
-                cmask |= (key >= T ? 1u : 0u) << (jj + u);
-                acc[par][jj + u] = __float_as_uint(dval);
-              }
+          for (int u = 0; u < 4; ++u) {
+            const float a = __uint_as_float(av[jj + u]);
+            float dval, key;
+            if (COSINE) {
+              dval = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(a, rowc), cc[u]));
+              key = dval;
+            } else {
+              float x = __fmaf_rn(-2.0f, a, __fadd_rn(rowc, cc[u]));
+              x = fmaxf(x, 1e-30f);
+              dval = __fmul_rn(x, rsqrt_approx(x));
+              key = x;
             }
-            cmask &= vm;
-            if (dd.dbg & 2) cmask = 0u;
-            if (cmask) {   // rare
-              while (cmask) {
-                const int jj = __ffs(cmask) - 1;
-                cmask &= cmask - 1;
-                const int slot = atomicAdd(&dd.maxc_cnt[h.scene], 1);
-                if (slot < h.vis_lcap) {
-                  VisPair vp;
-                  vp.g = g; vp.row = h.rowB + ch * 32 + jj; vp.scene = h.scene; vp.outcol = -1;
-                  dd.maxc[h.vis_lbase + slot] = vp;
-                }
-              }
-            }
-            // phase 2: per-block sums and minima (two short chains), one store per (candidate, block)
-            if (!(dd.dbg & 4))
+            kmax = fmaxf(kmax, key);
+            av[jj + u] = __float_as_uint(dval);
+          }
+        }
+        return kmax;
+      };
+      // rare: some element of the chunk may be the scene's maximal distance -> candidates for the exact pass (warp-wide call)
+      auto candidates = [&](int ch, unsigned int vm) {
+        dense_max_candidates<COSINE>(taddr + ch * 32, rowc, gcolc + ch * 32, vm, T, g, h.rowB + ch * 32, h.scene, h.vis_lbase,
+                                     h.vis_lcap, dd.maxc, dd.maxc_cnt);
+      };
+      if (KT > 0) {
+        constexpr int KC = KT > 0 ? KT : 1;
+        constexpr int CSTEP = (TC_BN / KC) * KC;   // columns of the tile that belong to whole blocks
+#pragma unroll
+        for (int ch = 0; ch < TC_BN / 32; ++ch) {
+          uint32_t* av = acc[ch & 1];
+          tc_ld_wait32(av);
+          if (ch + 1 < TC_BN / 32) tc_ld32_issue(taddr + (ch + 1) * 32, acc[(ch + 1) & 1]);
+          const unsigned int vm = S.vmask[ms][ch];
+          const float kmax = distances(av, ch);
+          if (__any_sync(0xffffffffu, kmax >= T) && !(dd.dbg & 2)) candidates(ch, vm);
+          if (!(dd.dbg & 4)) {
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
-              if (vm & (1u << jj)) {
-                const float dval = __uint_as_float(acc[par][jj]);
-                s_acc = __fadd_rn(s_acc, dval);
-                dmin = fminf(dmin, dval);
+              const int col = ch * 32 + jj;
+              if (col < CSTEP) {   // compile time
+                const bool valid = (vm >> jj) & 1u;
+                const float dval = __uint_as_float(av[jj]);
+                s_acc = __fadd_rn(s_acc, valid ? dval : 0.0f);
+                dmin = fminf(dmin, valid ? dval : finf);
+                if (col % KC == KC - 1) flush(gcmax[col]);   // compile time: last physical slot of a block
               }
-              if (bm & (1u << jj)) {   // last physical slot of a block: one {sum, bound} per (candidate, track)
-                float del;
-                if (COSINE) del = kDenseErrC;
-                else {
-                  const float cmx = gcmax[ch * 32 + jj];
-                  const float e = kDenseErrE * (rowc + cmx);
-                  // |d - d~| <= e / (d + d~) <= 0.536 e / d~ once d~^2 >= 4 e; both d, d~ <= sqrt(5 e) otherwise
-                  const float dm = dmin * (1.0f - 1e-6f);
-                  del = dm * dm >= 4.0f * e ? 0.536f * e / dm : sqrtf(5.0f * e);
-                  del = del * 1.0001f + 1e-6f * sqrtf(rowc + cmx);   // rsqrt approximation of d~ itself
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int ch2 = 0; ch2 < TC_BN / 32; ch2 += 2) {
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            const int ch = ch2 + par;
+            tc_ld_wait32(acc[par]);
+            if (ch + 1 < TC_BN / 32) tc_ld32_issue(taddr + (ch + 1) * 32, acc[par ^ 1]);
+            const unsigned int vm = S.vmask[ms][ch], bm = S.bmask[ms][ch];
+            if ((vm | bm) != 0u) {   // warp-uniform, like every test on vm / bm below: column properties
+              const float kmax = distances(acc[par], ch);
+              if (__any_sync(0xffffffffu, kmax >= T) && !(dd.dbg & 2)) candidates(ch, vm);
+              if (!(dd.dbg & 4)) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) {
+                  const bool valid = (vm >> jj) & 1u;
+                  const float dval = __uint_as_float(acc[par][jj]);
+                  s_acc = __fadd_rn(s_acc, valid ? dval : 0.0f);
+                  dmin = fminf(dmin, valid ? dval : finf);
+                  if (bm & (1u << jj)) flush(gcmax[ch * 32 + jj]);
                 }
-                if (row_ok && !(dd.dbg & 1)) *wsp = make_float2(s_acc, del);
-                wsp += h.mpad;
-                s_acc = 0.0f; dmin = finf;
               }
             }
           }
@@ -596,7 +655,18 @@ int launch_vis_dense(const Params& p, const TrackStore& ts, const Frame& f, int 
   if (tc.ev_screen0) cudaEventRecord(tc.ev_screen0, st);
   {
     const size_t smem = sizeof(DsSmem) + 1024;
-    const void* fn = cosine ? (const void*)vis_wsum_kernel<true> : (const void*)vis_wsum_kernel<false>;
+    const void* fn = nullptr;
+#define SB_WSUM(KT) (cosine ? (const void*)vis_wsum_kernel<true, KT> : (const void*)vis_wsum_kernel<false, KT>)
+    switch (p.max_obs) {   // the reference's default is 5 observations per track, its published bench uses 3
+      case 1: fn = SB_WSUM(1); break;
+      case 2: fn = SB_WSUM(2); break;
+      case 3: fn = SB_WSUM(3); break;
+      case 4: fn = SB_WSUM(4); break;
+      case 5: fn = SB_WSUM(5); break;
+      default: fn = SB_WSUM(0); break;
+    }
+    if (getenv("SB200_DENSE_GENERIC")) fn = SB_WSUM(0);   // the any-K epilogue (tests)
+#undef SB_WSUM
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int ncta = 2 * std::min(tc.n_tiles, tc.num_sms / 2);

@@ -15,7 +15,7 @@
 
 namespace sb {
 
-constexpr int AT = 256;
+constexpr int AT = 512;
 
 __device__ __forceinline__ void write_box(float* dst, const Box& b) {
   dst[0] = b.xc; dst[1] = b.yc; dst[2] = b.angle; dst[3] = b.aspect; dst[4] = b.height; dst[5] = b.conf;
@@ -201,6 +201,14 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
     ts.radius[idx] = box_radius(pred.aspect, pred.height);
     if (p.positional_kind == 1) box_vertices(pred.xc, pred.yc, pred.angle, pred.aspect, pred.height, ts.vert + idx * 8);
     if (f.feat_dst) f.feat_dst[g] = fdst;
+    if (ts.hist_len > 1) {   // update_history: observation number o_len - 1 goes to ring slot (o_len - 1) % hist_len
+      const size_t hslot = (idx * ts.hist_len + (size_t)((o_len - 1u) % (unsigned int)ts.hist_len)) * 6;
+      write_box(ts.hist_pred + hslot, pred);
+      if (isnew) {
+        const float* rb2 = f.in_boxes + (size_t)g * 6;
+        write_box(ts.hist_obs + hslot, Box{rb2[0], rb2[1], rb2[2], rb2[3], rb2[4], rb2[5]});
+      } else write_box(ts.hist_obs + hslot, cb);
+    }
     // SortTrack (src/trackers/sort.rs:286-311)
     if (f.o_ids) f.o_ids[g] = o_id;
     if (f.o_epochs) f.o_epochs[g] = sc.epoch;
@@ -396,6 +404,13 @@ __global__ void __launch_bounds__(WT) waste_kernel(Params p, TrackStore ts, cons
       wb.id[o] = ts.id[base + j]; wb.scene[o] = scene_id; wb.epoch[o] = ts.epoch[base + j];
       wb.length[o] = ts.length[base + j];
       for (int c = 0; c < 6; ++c) { wb.pred[(size_t)o * 6 + c] = ts.pred[(base + j) * 6 + c]; wb.obs[(size_t)o * 6 + c] = ts.obs[(base + j) * 6 + c]; }
+      if (ts.hist_len > 1) {
+        const int hw = ts.hist_len * 6;
+        for (int c = 0; c < hw; ++c) {
+          wb.hist_pred[(size_t)o * hw + c] = ts.hist_pred[(base + j) * hw + c];
+          wb.hist_obs[(size_t)o * hw + c] = ts.hist_obs[(base + j) * hw + c];
+        }
+      }
     }
     if (arena) {
       const int b = ts.fblk[base + j];
@@ -439,6 +454,10 @@ __global__ void __launch_bounds__(WT) waste_kernel(Params p, TrackStore ts, cons
   compact_rows(ts.obs, base, 6, s_dst, first, n);
   compact_rows(ts.kst, base, kStateFloats, s_dst, first, n);
   if (p.positional_kind == 1) compact_rows(ts.vert, base, 8, s_dst, first, n);
+  if (ts.hist_len > 1) {
+    compact_rows(ts.hist_pred, base, ts.hist_len * 6, s_dst, first, n);
+    compact_rows(ts.hist_obs, base, ts.hist_len * 6, s_dst, first, n);
+  }
   const int kept = n - wcount;
   if (arena) {   // owners follow the compaction
     for (int j = first + tid; j < kept; j += WT) ts.blk_owner[base + ts.fblk[base + j]] = j;

@@ -20,6 +20,7 @@ namespace sb {
 
 constexpr int kMaxConstraints = 8;
 constexpr int kMaxObs = 8;  // visual_max_observations supported on device (reference default 5)
+constexpr int kMaxHist = 64;  // box history kept per track on the device (history_length above it, or 0 = unlimited, is capped)
 
 struct Params {  // immutable per tracker, passed by value to kernels
   int kind, positional_kind, visual_kind;
@@ -96,6 +97,11 @@ struct TrackStore {
   float* radius;         // [idx]
   float* kst;            // [idx][30]
   double* vert;          // [idx][8] vertex cache (IoU mode)
+  // box history (SortAttributes::update_history, src/trackers/sort.rs:157-171): the last hist_len observed / predicted boxes
+  // of every track as a ring, observation number j (0-based) in slot j % hist_len; null unless history_length > 1
+  int hist_len;
+  float* hist_pred;      // [idx][hist_len][6]
+  float* hist_obs;       // [idx][hist_len][6]
   // visual
   float* feat;           // [idx][K][d8]
   void* feat_bf16;       // [idx][K][d8] bf16 copy of feat: B operand of the tensor-core screen
@@ -171,6 +177,7 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   // did not claim; a BestFit pre-pass publishes both sets and the culled scan skips everything else.
   unsigned char* decided;  // [total] candidate was decided by the visual pass
   unsigned char* excl;     // [slot * track_cap + n] track was claimed by the visual pass
+  int* pre_winner;         // [total] the pre-pass's decision: track index the candidate won, -1 = decided as a new track
   int* dense_cnt;          // [1] scenes of the request in dense mode (null: unknown); lets the dense kernels leave at once
   int* refine_next;        // [n_scenes] next unclaimed survivor of the scene (the refinement's warps claim 32 at a time)
   const int* dense_bad;    // [n_scenes] dense tensor-core path only: != 0 sends the scene to the exact SIMT kernels
@@ -312,6 +319,8 @@ struct WastedBuf {
   unsigned int* length;
   float* pred;
   float* obs;
+  float* hist_pred;   // [cap][hist_len][6] rings of the wasted tracks (null unless history_length > 1)
+  float* hist_obs;
 };
 void launch_waste(const Params& p, const TrackStore& ts, int n_slots, const unsigned int* d_cur_epoch,
                   const unsigned long long* d_scene_ids, int* d_n_tracks, const WastedBuf& wb, int max_n,

@@ -163,6 +163,21 @@ class Tracker:
         return {"ids": ids[:n], "scene_ids": sc[:n], "epochs": ep[:n], "lengths": ln[:n], "predicted": pr[:n],
                 "observed": ob[:n]}
 
+    def wasted_history(self, cap=1 << 14, history_cap=None):
+        """wasted() plus the box history of every wasted track (oldest first): predicted_history / observed_history are
+        lists of [count][6] arrays."""
+        H = int(history_cap if history_cap is not None else max(1, min(64, self.opts.history_length or 64)))
+        ids, sc = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64)
+        ep, ln = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        pr, ob = np.zeros((cap, 6), np.float32), np.zeros((cap, 6), np.float32)
+        hp, ho = np.zeros((cap, H, 6), np.float32), np.zeros((cap, H, 6), np.float32)
+        hc = np.zeros(cap, np.int32)
+        n = check(self._L.sb200_wasted_history(self._h, cap, ptr(ids), ptr(sc), ptr(ep), ptr(ln), ptr(pr), ptr(ob), H,
+                                               ptr(hp), ptr(ho), ptr(hc)))
+        return {"ids": ids[:n], "scene_ids": sc[:n], "epochs": ep[:n], "lengths": ln[:n], "predicted": pr[:n],
+                "observed": ob[:n], "predicted_history": [hp[i, : hc[i]].copy() for i in range(n)],
+                "observed_history": [ho[i, : hc[i]].copy() for i in range(n)]}
+
     def idle_tracks(self, scene_id=0, cap=1 << 16):
         ids = np.zeros(cap, np.uint64)
         ep, ln = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)

@@ -509,3 +509,42 @@ def test_threshold_that_cuts_nothing_switches_to_the_dense_path(eng, oracle):
         fallback.append(g.work_counters()["dense_fallback_scenes"])
     assert fallback[2] > 0                      # the screen's lists overflowed at first
     assert fallback[-1] == fallback[3]          # ... and nothing fell back once the dense path had taken over
+
+
+@pytest.mark.parametrize("kind,hist", [(1, 4), (0, 7), (3, 3)])
+def test_wasted_tracks_carry_their_box_history(eng, kind, hist):
+    """WastedSortTrack.predicted_boxes / observed_boxes (src/trackers/sort.rs:316-341): the last `history_length` boxes of
+    the track, oldest first, as SortAttributes::update_history keeps them (sort.rs:157-171).  The expected history of a
+    track is rebuilt from the per-frame SortTrack records the tracker itself returned."""
+    from similari_b200._lib import default_options
+    from similari_b200.workload import Workload
+
+    visual = kind >= 2
+    cfg = small("cfg5" if visual else "cfg2", n_scenes=3 if kind in (1, 3) else 1, n_objects=50, oriented=True,
+                canvas=(900.0, 600.0), feature_dim=32 if visual else 0, drop_frac=0.2, fresh_frac=0.15)
+    kw = dict(kind=kind, positional_kind=0, max_idle_epochs=1, history_length=hist)
+    if visual:
+        kw.update(visual_kind=0, visual_threshold=0.7, feature_dim=32, visual_max_observations=3, visual_min_votes=1,
+                  visual_minimal_track_length=1)
+    g = eng.Tracker(default_options(**kw))
+    wl = Workload(cfg)
+    seen = {}
+    n_checked = 0
+    for fr in range(14):
+        f = wl.next_frame()
+        r = g.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"])
+        for i, tid in enumerate(r["ids"]):
+            seen.setdefault(int(tid), []).append((r["predicted"][i].copy(), r["observed"][i].copy()))
+        if fr % 4 == 3:
+            w = g.wasted_history()
+            for i, tid in enumerate(w["ids"]):
+                exp = seen[int(tid)][-hist:]
+                assert int(w["lengths"][i]) == len(seen[int(tid)])
+                gp, go = w["predicted_history"][i], w["observed_history"][i]
+                assert len(gp) == len(exp) == len(go)
+                for (ep, eo), p_, o_ in zip(exp, gp, go):
+                    assert np.array_equal(np.nan_to_num(ep, nan=-7.0), np.nan_to_num(p_, nan=-7.0))
+                    assert np.array_equal(np.nan_to_num(eo, nan=-7.0), np.nan_to_num(o_, nan=-7.0))
+                assert np.array_equal(np.nan_to_num(w["predicted"][i], nan=-7.0), np.nan_to_num(gp[-1], nan=-7.0))
+                n_checked += 1
+    assert n_checked > 30
