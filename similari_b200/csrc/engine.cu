@@ -233,7 +233,7 @@ struct sb200_tracker {
   int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
       f_status, f_featdst, f_frameout, f_decided, f_excl, f_prewin, f_own, f_ownovf, f_dyn, f_ws, f_tmeta, f_rowinfo, f_slabc, f_slabm, f_slabmask,
-      f_dscene, f_maxc, f_maxcval, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
+      f_dscene, f_maxc, f_maxcval, f_drowb, f_dcolb, f_slabk, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
   HBuf h_small;
@@ -247,7 +247,7 @@ struct sb200_tracker {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_hpred, &b_hobs, &w_hpred, &w_hobs, &b_feat,
                    &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_colb, &f_colvalid, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
-                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl, &f_prewin, &f_own, &f_ownovf, &f_dyn, &b_idc, &f_ws, &f_tmeta, &f_rowinfo, &f_slabc, &f_slabm, &f_slabmask, &f_dscene, &f_maxc, &f_maxcval,
+                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl, &f_prewin, &f_own, &f_ownovf, &f_dyn, &b_idc, &f_ws, &f_tmeta, &f_rowinfo, &f_slabc, &f_slabm, &f_slabmask, &f_dscene, &f_maxc, &f_maxcval, &f_drowb, &f_dcolb, &f_slabk,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
                    &f_featdst, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
@@ -840,7 +840,10 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       ws_ub = std::max(ws_ub, hs * ht * ((hd + 127) / 128 * 128));
       blk_ub = std::max(blk_ub, hs * ht);
       slabs_ub = std::max(slabs_ub, hs * ((ht * K + cstep - 1) / cstep + 1));
-      if ((rc = ens(f_ws, 8 * (size_t)std::max<long long>(1, ws_ub))) || (rc = ens(f_tmeta, sizeof(sb::DenseTrackMeta) * (size_t)std::max<long long>(1, blk_ub))) ||
+      if ((rc = ens(f_drowb, 4 * 5 * T)) || (rc = ens(f_dcolb, 4 * (size_t)std::max<long long>(1, blk_ub))) ||
+          (rc = ens(f_slabk, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))))
+        return rc;
+      if ((rc = ens(f_ws, 4 * (size_t)std::max<long long>(1, ws_ub))) || (rc = ens(f_tmeta, sizeof(sb::DenseTrackMeta) * (size_t)std::max<long long>(1, blk_ub))) ||
           (rc = ens(f_rowinfo, 8 * (size_t)std::max<long long>(1, blk_ub * K))) || (rc = ens(f_slabc, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))) ||
           (rc = ens(f_slabm, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))) || (rc = ens(f_slabmask, 2 * 32 * (size_t)std::max<long long>(1, slabs_ub))) ||
           (rc = ens(f_dscene, 4 * 6 * (size_t)n_scenes + 128)) || (rc = ens(f_maxc, sizeof(sb::VisPair) * (size_t)std::max<long long>(1, visl_alloc))) ||
@@ -849,7 +852,11 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       tc.cstep = cstep;
       tc.max_blocks = max_nb;
       tc.n_slabs_ub = (int)slabs_ub;
-      tc.ws = f_ws.as<float2>();
+      tc.ws = f_ws.p;
+      tc.d_rowb = f_drowb.as<unsigned int>();
+      tc.d_colb = f_dcolb.as<unsigned int>();
+      tc.blk_ub = blk_ub;
+      tc.slab_ktf = f_slabk.as<float>();
       tc.tmeta = f_tmeta.as<sb::DenseTrackMeta>();
       tc.rowinfo = f_rowinfo.as<int2>();
       tc.slab_colc = f_slabc.as<float>();

@@ -27,6 +27,7 @@
 // on the host (they make the matrix sparse in a way only the per-pair gate knows).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -55,11 +56,14 @@ struct DsHdr {
   int vis_lbase, vis_lcap, mpad;
   long long ws_base; // ws element of (first block of the tile, candidate 0)
   float l0, scmax;
+  int blk0;          // global index (frame-wide) of the tile's first block
+  int pad;
 };
 struct DsSmem {
   unsigned char stage[DS_STAGES][DS_STAGE_BYTES];   // 1024-byte aligned operand stages first
   float colc[4][TC_BN];
   float cmax[4][TC_BN];
+  float ktf[4][TC_BN];   // valid observations of the column's block when the block can vote (>= min_votes), else 0
   VisRowMeta rowm[4][TC_BM];
   unsigned int vmask[4][TC_BN / 32];
   unsigned int bmask[4][TC_BN / 32];
@@ -73,8 +77,22 @@ struct DsSmem {
   unsigned int tmem_base;
 };
 
+constexpr int kDenseKClasses = 5;   // observation counts the fused row bounds distinguish (templated kernels: K <= 5)
+constexpr float kHalfRel = 4.9e-4f; // 2^-11 (+): relative rounding error of a sum stored as fp16
+
+__device__ __forceinline__ unsigned int enc_ord(float v) {   // order-preserving f32 -> u32 (0 is below every value)
+  const unsigned int u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ord(unsigned int u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
 struct DenseDev {   // device pointers of the path (TcArgs subset, passed by value)
-  float2* ws;
+  __half2* ws;           // {sum of the block's distances (rn), per-observation error bound (ru)} per (block, candidate)
+  unsigned int* rowb;    // [total][kDenseKClasses] best lower bound of -(S + k del) per candidate and observation count
+  unsigned int* colb;    // [blocks of the frame] the same per block (column of the weight matrix)
+  const float* slab_ktf;
   const float* slab_colc; const float* slab_cmax;
   const unsigned int* slab_vmask; const unsigned int* slab_bmask;
   const float* scene_l0; const float* scene_cmax;
@@ -172,9 +190,11 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           h.mpad = (sc.m + 127) / 128 * 128;
           h.ws_base = sc.ws_off + (long long)(tl.c0 / K) * h.mpad;
           h.l0 = dd.scene_l0[tl.scene]; h.scmax = dd.scene_cmax[tl.scene];
+          h.blk0 = sc.blk_off + tl.c0 / K; h.pad = 0;
           S.hdr[g] = h;
           const size_t slab = (size_t)sc.slab_off + tl.pad;
-          mbar_expect_tx(&S.meta_full[g], (uint32_t)(4 * TC_BN * 2 + sizeof(VisRowMeta) * TC_BM + (TC_BN / 8) * 2));
+          mbar_expect_tx(&S.meta_full[g], (uint32_t)(4 * TC_BN * 3 + sizeof(VisRowMeta) * TC_BM + (TC_BN / 8) * 2));
+          bulk_load(S.ktf[g], dd.slab_ktf + slab * TC_BN, 4 * TC_BN, &S.meta_full[g]);
           bulk_load(S.colc[g], dd.slab_colc + slab * TC_BN, 4 * TC_BN, &S.meta_full[g]);
           bulk_load(S.cmax[g], dd.slab_cmax + slab * TC_BN, 4 * TC_BN, &S.meta_full[g]);
           bulk_load(S.rowm[g], dd.rowmeta + rowA, (uint32_t)(sizeof(VisRowMeta) * TC_BM), &S.meta_full[g]);
@@ -239,17 +259,26 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       // an element can be the scene's maximal distance only above the sampled lower bound minus the error bound
       float T = COSINE ? h.l0 - kDenseErrC : h.l0 - kDenseErrE * (rowc + h.scmax);
       if (!row_ok) T = finf;
-      float2* wsp = dd.ws + h.ws_base + m;
+      __half2* wsp = dd.ws + h.ws_base + m;
       const float* gcolc = S.colc[ms];
       const float* gcmax = S.cmax[ms];
+      const float* gktf = S.ktf[ms];
       float s_acc = 0.0f, dmin = finf;
+      // fused "pass A" of the selection (templated kernels): best lower bound of the maxd-independent part of the weight,
+      // -(S + k del), per observation count for this row, per block over the rows (warp maximum + one atomic)
+      constexpr bool FUSED = KT > 0;
+      float lrow[kDenseKClasses];
+#pragma unroll
+      for (int kc = 0; kc < kDenseKClasses; ++kc) lrow[kc] = -finf;
+      int bidx = h.blk0;
       mbar_wait(&S.tmem_full[buf], (it >> 1) & 1);
       tc_fence_after();
       uint32_t acc[2][32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TC_BN);
       tc_ld32_issue(taddr, acc[0]);
       // one flush per block: {sum of the block's distances, per-observation error bound}
-      auto flush = [&](float cmx) {
+      auto flush = [&](int col) {
+        const float cmx = gcmax[col];
         float del;
         if (COSINE) del = kDenseErrC;
         else {
@@ -263,8 +292,18 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           del = dm * dm >= 4.0f * e ? 0.536f * e * rcp_approx(dm) : e5 * rsqrt_approx(e5);
           del = __fmaf_rn(del, 1.0001f, 1e-6f * (rc + 1.0f));
         }
-        if (row_ok && !(dd.dbg & 1)) *wsp = make_float2(s_acc, del);
+        if (row_ok && !(dd.dbg & 1)) *wsp = __halves2half2(__float2half_rn(s_acc), __float2half_ru(del));
         wsp += h.mpad;
+        if (FUSED) {
+          const float kf = gktf[col];   // block-uniform; 0: the block takes no part in the voting
+          float base = -finf;
+          if (row_ok && kf > 0.0f) base = -(s_acc * (1.0f + 2e-6f) + kf * del);
+#pragma unroll
+          for (int kc = 0; kc < (KT > 0 ? KT : 1); ++kc) lrow[kc] = fmaxf(lrow[kc], kf == (float)(kc + 1) ? base : -finf);
+          const unsigned int u = __reduce_max_sync(0xffffffffu, enc_ord(base));
+          if (lane == 0 && kf > 0.0f && u > 0x007fffffu) atomicMax(&dd.colb[bidx], u);   // 0x007fffff == enc(-inf)
+        }
+        ++bidx;
         s_acc = 0.0f; dmin = finf;
       };
       // distances of one 32-column chunk in place; returns the largest key (squared distance, or 1 - cos) of the chunk
@@ -318,7 +357,7 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const float dval = __uint_as_float(av[jj]);
                 s_acc = __fadd_rn(s_acc, valid ? dval : 0.0f);
                 dmin = fminf(dmin, valid ? dval : finf);
-                if (col % KC == KC - 1) flush(gcmax[col]);   // compile time: last physical slot of a block
+                if (col % KC == KC - 1) flush(col);   // compile time: last physical slot of a block
               }
             }
           }
@@ -342,7 +381,7 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                   const float dval = __uint_as_float(acc[par][jj]);
                   s_acc = __fadd_rn(s_acc, valid ? dval : 0.0f);
                   dmin = fminf(dmin, valid ? dval : finf);
-                  if (bm & (1u << jj)) flush(gcmax[ch * 32 + jj]);
+                  if (bm & (1u << jj)) flush(ch * 32 + jj);
                 }
               }
             }
@@ -354,6 +393,11 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       if (lane == 0) {
         mbar_arrive_cluster(leader_addr(&S.tmem_empty[buf]));
         mbar_arrive(&S.meta_empty[ms]);
+      }
+      if (FUSED && row_ok) {
+#pragma unroll
+        for (int kc = 0; kc < (KT > 0 ? KT : 1); ++kc)
+          if (lrow[kc] > -finf) atomicMax(&dd.rowb[(size_t)g * kDenseKClasses + kc], enc_ord(lrow[kc]));
       }
     }
   }
@@ -371,8 +415,8 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 // the tile-major slabs the weight-sum kernel bulk-copies (column constant, block maximum, validity / block-end masks) and
 // the block record of the selection kernel (owner, valid observations).  Same validity rule as vis_meta_kernel.
 __global__ void vis_dense_meta_kernel(Params p, TrackStore ts, Frame f, int max_blocks, int cstep, DenseTrackMeta* tmeta,
-                                      int2* rowinfo, float* slab_colc, float* slab_cmax, unsigned int* slab_vmask,
-                                      unsigned int* slab_bmask, float* scene_cmax) {
+                                      int2* rowinfo, float* slab_colc, float* slab_cmax, float* slab_ktf,
+                                      unsigned int* slab_vmask, unsigned int* slab_bmask, float* scene_cmax) {
   const int s = blockIdx.y;
   const SceneDesc sc = f.scenes[s];
   const int K = p.max_obs;
@@ -409,6 +453,8 @@ __global__ void vis_dense_meta_kernel(Params p, TrackStore ts, Frame f, int max_
       tm.cmax = cmax;
     }
     tmeta[sc.blk_off + b] = tm;
+    const int need_votes = p.min_votes > 1 ? p.min_votes : 1;
+    const float ktf = (tm.n >= 0 && tm.kt >= need_votes) ? (float)tm.kt : 0.0f;
     for (int ph = 0; ph < K; ++ph) {
       const int prow = b * K + ph;
       rowinfo[(size_t)sc.blk_off * K + prow] = make_int2(outcol[ph], frow_of[ph]);
@@ -416,6 +462,7 @@ __global__ void vis_dense_meta_kernel(Params p, TrackStore ts, Frame f, int max_
       const size_t slab = (size_t)sc.slab_off + j;
       slab_colc[slab * TC_BN + cc] = colc[ph];
       slab_cmax[slab * TC_BN + cc] = cmax;
+      slab_ktf[slab * TC_BN + cc] = ktf;
       if (frow_of[ph] >= 0) atomicOr(&slab_vmask[slab * (TC_BN / 32) + (cc >> 5)], 1u << (cc & 31));
       if (ph == K - 1) atomicOr(&slab_bmask[slab * (TC_BN / 32) + (cc >> 5)], 1u << (cc & 31));
     }
@@ -502,9 +549,10 @@ __global__ void __launch_bounds__(256) vis_dense_sample_kernel(Params p, TrackSt
 // One CTA per scene.  Pass A: best lower bound of every row (candidate) and column (block) of the weight matrix; pass B:
 // every group whose upper bound reaches one of the two is emitted to the scene's pair list with all its valid observations.
 constexpr int SEL_T = 512;
-__global__ void __launch_bounds__(SEL_T) vis_dense_select_kernel(Params p, Frame f, const float2* ws, const DenseTrackMeta* tmeta,
+__global__ void __launch_bounds__(SEL_T) vis_dense_select_kernel(Params p, Frame f, const __half2* ws, const DenseTrackMeta* tmeta,
                                                                  const int2* rowinfo, const int* maxc_cnt, const int* max_nan,
-                                                                 int* dense_bad, int* dbg_counts) {
+                                                                 int* dense_bad, int* dbg_counts, const unsigned int* rowb,
+                                                                 const unsigned int* colb, int fused) {
   extern __shared__ unsigned char sel_smem[];
   const int s = blockIdx.x;
   const SceneDesc sc = f.scenes[s];
@@ -529,22 +577,39 @@ __global__ void __launch_bounds__(SEL_T) vis_dense_select_kernel(Params p, Frame
   const int need_votes = p.min_votes > 1 ? p.min_votes : 1;
   for (int b = tid; b < nb; b += SEL_T) {
     const DenseTrackMeta tm = tmeta[sc.blk_off + b];
-    kt[b] = (short)((tm.n >= 0 && tm.kt >= need_votes) ? tm.kt : 0);
-    lcol[b] = 0x00800000u;   // encoding of -3.4e38-ish: below every real bound, decodes to a finite value
+    const int kb = (tm.n >= 0 && tm.kt >= need_votes) ? tm.kt : 0;
+    kt[b] = (short)kb;
+    unsigned int u = 0x00800000u;   // encoding of -3.4e38-ish: below every real bound, decodes to a finite value
+    if (fused && kb > 0) {
+      // the weight-sum kernel left max over the rows of -(S + k del); W_lo = k maxd (1 - 2e-6) - 1e-7 + that
+      const unsigned int cb = colb[sc.blk_off + b];
+      if (cb != 0u) u = enc_ord(((float)kb * maxd * (1.0f - 2e-6f) - 1e-7f) + dec_ord(cb));
+    }
+    lcol[b] = u;
   }
   __syncthreads();
   const int mpad = (M + 127) / 128 * 128;
-  const float2* w0 = ws + sc.ws_off;
+  const __half2* w0 = ws + sc.ws_off;
   const float fneg = -3.0e38f;
   // W = k maxd - S, slack = k del + 2e-6 (k maxd + S) + 1e-7 (f32 roundings of both sides):
   //   W_lo = k maxd (1 - 2e-6) - 1e-7 - (1 + 2e-6) S - k del,   W_hi = k maxd (1 + 2e-6) + 1e-7 - (1 - 2e-6) S + k del
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = fused ? 1 : 0; pass < 2; ++pass) {
     for (int m0 = 0; m0 < mpad; m0 += SEL_T) {
       const int m = m0 + tid;
       const bool row_ok = m < M && (f.c_flags[sc.det_base + m] & 2);
       float lrow = fneg;
-      if (pass == 1 && row_ok) lrow = f.vis_val[sc.vis_lbase + m];   // pass A parked the row bounds in the (still unused) value list
-      const float2* wrow = w0 + m;
+      if (pass == 1 && row_ok) {
+        if (!fused) lrow = f.vis_val[sc.vis_lbase + m];   // pass A parked the row bounds in the (still unused) value list
+        else {
+          const unsigned int* rb = rowb + (size_t)(sc.det_base + m) * kDenseKClasses;
+#pragma unroll
+          for (int kc = 0; kc < kDenseKClasses; ++kc) {
+            const unsigned int u = rb[kc];
+            if (u != 0u) lrow = fmaxf(lrow, ((float)(kc + 1) * maxd * (1.0f - 2e-6f) - 1e-7f) + dec_ord(u));
+          }
+        }
+      }
+      const __half2* wrow = w0 + m;
       constexpr int UB = 8;   // blocks per round: the loads of a round are issued together (memory-level parallelism)
       for (int b0 = 0; b0 < nb; b0 += UB) {
         int kk[UB];
@@ -553,7 +618,12 @@ __global__ void __launch_bounds__(SEL_T) vis_dense_select_kernel(Params p, Frame
         for (int u = 0; u < UB; ++u) {
           kk[u] = b0 + u < nb ? (int)kt[b0 + u] : 0;
           ee[u] = make_float2(0.0f, 0.0f);
-          if (row_ok && kk[u] != 0) ee[u] = __ldcs(wrow + (size_t)(b0 + u) * mpad);
+          if (row_ok && kk[u] != 0) {
+            const unsigned int raw = __ldcs(reinterpret_cast<const unsigned int*>(wrow + (size_t)(b0 + u) * mpad));
+            const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+            // the sum was rounded to fp16 (relative 2^-11): widen the bound by that much
+            ee[u] = make_float2(v.x, v.y + (v.x * kHalfRel) / (float)kk[u]);
+          }
         }
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
@@ -568,9 +638,10 @@ __global__ void __launch_bounds__(SEL_T) vis_dense_select_kernel(Params p, Frame
             unsigned int uu = __float_as_uint(wlo);
             uu = (uu & 0x80000000u) ? ~uu : (uu | 0x80000000u);
             uu = __reduce_max_sync(0xffffffffu, uu);   // one instruction: the warp's best lower bound for this column
-            if (lane == 0 && uu > lcol[b]) atomicMax(&lcol[b], uu);
+            if (lane == 0 && uu > lcol[b]) atomicMax(&lcol[b], uu);   // (pass A only runs for the any-K kernel)
           } else if (row_ok) {
-            const float whi = (a * (1.0f + 2e-6f) + 1e-7f) - (e.x * (1.0f - 2e-6f) - fk * e.y);
+            float whi = (a * (1.0f + 2e-6f) + 1e-7f) - (e.x * (1.0f - 2e-6f) - fk * e.y);
+            if (!(e.x < 6.0e4f)) whi = 3.0e38f;   // the fp16 sum overflowed (huge unnormalised features): never rule the group out
             const unsigned int uu = lcol[b];
             const float lc = __uint_as_float((uu & 0x80000000u) ? (uu & 0x7fffffffu) : ~uu);
             if (whi >= lrow || whi >= lc) {
@@ -643,10 +714,15 @@ int launch_vis_dense(const Params& p, const TrackStore& ts, const Frame& f, int 
   cudaMemsetAsync(tc.slab_vmask, 0, (size_t)tc.n_slabs_ub * (TC_BN / 32) * 4, st);
   cudaMemsetAsync(tc.slab_bmask, 0, (size_t)tc.n_slabs_ub * (TC_BN / 32) * 4, st);
   cudaMemsetAsync(tc.scene_cmax, 0, (size_t)n_scenes * 4, st);
+  const bool fused = p.max_obs <= kDenseKClasses && getenv("SB200_DENSE_GENERIC") == nullptr;
+  if (fused) {
+    cudaMemsetAsync(tc.d_rowb, 0, (size_t)f.total * kDenseKClasses * 4, st);
+    cudaMemsetAsync(tc.d_colb, 0, (size_t)tc.blk_ub * 4, st);
+  }
   if (tc.max_blocks > 0) {
     dim3 grid((tc.max_blocks + 127) / 128, n_scenes);
     vis_dense_meta_kernel<<<grid, 128, 0, st>>>(p, ts, f, tc.max_blocks, tc.cstep, tc.tmeta, tc.rowinfo, tc.slab_colc, tc.slab_cmax,
-                                                tc.slab_vmask, tc.slab_bmask, tc.scene_cmax);
+                                                tc.slab_ktf, tc.slab_vmask, tc.slab_bmask, tc.scene_cmax);
     note_launch();
   }
   vis_dense_rowmeta_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f, tc.rowmeta);
@@ -682,7 +758,8 @@ int launch_vis_dense(const Params& p, const TrackStore& ts, const Frame& f, int 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     DenseDev dd;
-    dd.ws = tc.ws; dd.slab_colc = tc.slab_colc; dd.slab_cmax = tc.slab_cmax; dd.slab_vmask = tc.slab_vmask;
+    dd.ws = reinterpret_cast<__half2*>(tc.ws); dd.rowb = tc.d_rowb; dd.colb = tc.d_colb; dd.slab_ktf = tc.slab_ktf;
+    dd.slab_colc = tc.slab_colc; dd.slab_cmax = tc.slab_cmax; dd.slab_vmask = tc.slab_vmask;
     dd.slab_bmask = tc.slab_bmask; dd.scene_l0 = tc.scene_l0; dd.scene_cmax = tc.scene_cmax; dd.maxc = tc.maxc;
     dd.maxc_cnt = tc.maxc_cnt; dd.rowmeta = tc.rowmeta;
     static const int dbg = getenv("SB200_DENSE_DBG") ? atoi(getenv("SB200_DENSE_DBG")) : 0;
@@ -706,8 +783,9 @@ int launch_vis_dense(const Params& p, const TrackStore& ts, const Frame& f, int 
   {
     const size_t smem = (size_t)std::max(1, tc.max_blocks) * 6 + 64;
     if (smem > 48 * 1024) cudaFuncSetAttribute(vis_dense_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vis_dense_select_kernel<<<n_scenes, SEL_T, smem, st>>>(p, f, tc.ws, tc.tmeta, tc.rowinfo, tc.maxc_cnt, tc.dense_bad, tc.dense_bad,
-                                                           tc.dbg_counts);
+    vis_dense_select_kernel<<<n_scenes, SEL_T, smem, st>>>(p, f, reinterpret_cast<const __half2*>(tc.ws), tc.tmeta, tc.rowinfo,
+                                                           tc.maxc_cnt, tc.dense_bad, tc.dense_bad, tc.dbg_counts, tc.d_rowb,
+                                                           tc.d_colb, fused ? 1 : 0);
     note_launch();
   }
   return 0;

@@ -247,7 +247,11 @@ struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense ex
   int cstep;             // feature rows per column tile: (256 / K) * K, so that no track straddles two tiles
   int max_blocks;        // upper bound of nb over the scenes
   int n_slabs_ub;        // upper bound of the 256-column metadata slabs of the frame
-  float2* ws;            // weight sums {S~, per-observation error bound} per (block, candidate)
+  void* ws;              // weight sums {S~, per-observation error bound} per (block, candidate), packed as half2
+  unsigned int* d_rowb;  // [total][5] fused row bounds (per candidate and observation count)
+  unsigned int* d_colb;  // [blk_ub] fused column bounds (per arena block of the frame)
+  long long blk_ub;      // upper bound of the arena blocks of the frame
+  float* slab_ktf;       // [slab][256] voting observations of the column's block (0: none)
   DenseTrackMeta* tmeta; // per arena block
   int2* rowinfo;         // per physical feature row: {logical output column, feature row or -1}
   float* slab_colc;      // [slab][256] column constant (|b|^2, or 1/|b| for cosine)
