@@ -57,7 +57,7 @@ struct DsHdr {
   long long ws_base; // ws element of (first block of the tile, candidate 0)
   float l0, scmax;
   int blk0;          // global index (frame-wide) of the tile's first block
-  int pad;
+  int nblk;          // blocks of the scene inside this tile (the last tile of a scene is partial)
 };
 struct DsSmem {
   unsigned char stage[DS_STAGES][DS_STAGE_BYTES];   // 1024-byte aligned operand stages first
@@ -190,7 +190,8 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           h.mpad = (sc.m + 127) / 128 * 128;
           h.ws_base = sc.ws_off + (long long)(tl.c0 / K) * h.mpad;
           h.l0 = dd.scene_l0[tl.scene]; h.scmax = dd.scene_cmax[tl.scene];
-          h.blk0 = sc.blk_off + tl.c0 / K; h.pad = 0;
+          h.blk0 = sc.blk_off + tl.c0 / K;
+          h.nblk = min(TC_BN / K, sc.nb - tl.c0 / K);
           S.hdr[g] = h;
           const size_t slab = (size_t)sc.slab_off + tl.pad;
           mbar_expect_tx(&S.meta_full[g], (uint32_t)(4 * TC_BN * 3 + sizeof(VisRowMeta) * TC_BM + (TC_BN / 8) * 2));
@@ -357,7 +358,9 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const float dval = __uint_as_float(av[jj]);
                 s_acc = __fadd_rn(s_acc, valid ? dval : 0.0f);
                 dmin = fminf(dmin, valid ? dval : finf);
-                if (col % KC == KC - 1) flush(col);   // compile time: last physical slot of a block
+                // compile-time position: last physical slot of a block; blocks past the scene's arena (partial last tile) are
+                // not the scene's: nothing is stored or bounded for them
+                if (col % KC == KC - 1 && col / KC < h.nblk) flush(col);
               }
             }
           }

@@ -22,7 +22,7 @@ def _threads():
     import os
 
     try:
-        return max(4, min(64, len(os.sched_getaffinity(0))))
+        return max(4, min(24, len(os.sched_getaffinity(0))))
     except Exception:
         return 16
 
