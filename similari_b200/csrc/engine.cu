@@ -809,8 +809,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       const long long ct = ((long long)nb_ub[s] * K + cstep - 1) / cstep;
       tiles_ub += (long long)((m_of[s] + mstep - 1) / mstep) * ct;
       slabs_ub += ct;
-      ws_ub += (long long)nb_ub[s] * ((m_of[s] + 127) / 128 * 128);
-      blk_ub += nb_ub[s];
+      ws_ub += ct * (cstep / K) * ((m_of[s] + 127) / 128 * 128);   // blocks padded to whole column tiles
+      blk_ub += ct * (cstep / K);
     }
     tc.n_tiles = (int)tiles_ub;   // upper bound: the list and its length are built on the device
     if ((rc = ens(f_cbf16, T * P.d8 * 2)) || (rc = ens(f_tiles, sizeof(sb::TcTile) * (size_t)std::max<long long>(1, tiles_ub))) ||
@@ -837,8 +837,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       // sized from the hints like the other frame buffers, so steady-state frames never reallocate
       const long long hs = std::max(opts.max_scenes_hint, n_scenes), ht = hint_tracks;
       const long long hd = std::max(opts.max_dets_per_scene_hint, 0);
-      ws_ub = std::max(ws_ub, hs * ht * ((hd + 127) / 128 * 128));
-      blk_ub = std::max(blk_ub, hs * ht);
+      ws_ub = std::max(ws_ub, hs * (ht + 256) * ((hd + 127) / 128 * 128));
+      blk_ub = std::max(blk_ub, hs * (ht + 256));
       slabs_ub = std::max(slabs_ub, hs * ((ht * K + cstep - 1) / cstep + 1));
       if ((rc = ens(f_drowb, 4 * 5 * T)) || (rc = ens(f_dcolb, 4 * (size_t)std::max<long long>(1, blk_ub))) ||
           (rc = ens(f_slabk, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))))

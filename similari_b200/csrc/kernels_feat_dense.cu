@@ -108,6 +108,17 @@ struct DenseDev {   // device pointers of the path (TcArgs subset, passed by val
 __device__ __forceinline__ float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
+// Rare path of the weight-sum epilogue (about one element in a thousand): the element may be the scene's maximal distance.
+__device__ __noinline__ void dense_append_candidate(VisPair* maxc, int* maxc_cnt, int scene, int lbase, int lcap, int g, int row) {
+  const int slot = atomicAdd(&maxc_cnt[scene], 1);
+  if (slot < lcap) {
+    VisPair vp;
+    vp.g = g; vp.row = row; vp.scene = scene; vp.outcol = -1;
+    maxc[lbase + slot] = vp;
+  }
+}
+
+// (superseded by the per-element test above; kept for the any-K kernel)
 // Rare path of the weight-sum epilogue, one copy of code: some element of a 32-column chunk may be the scene's maximal
 // distance.  The whole warp re-reads the chunk from TMEM (the accumulator buffer is still owned by this warp's group) and
 // every lane appends its own candidates (feature row = row0 + column) for the exact pass.
@@ -288,9 +299,12 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           // |d - d~| <= e / (d + d~) <= 0.536 e / d~ once d~^2 >= 4 e; both d, d~ <= sqrt(5 e) otherwise.  Only an upper
           // bound is needed: approximate reciprocal / rsqrt (2 ulp) under a 1.0001 safety factor, and 1e-6 (rc + 1) >=
           // 1e-6 sqrt(rc) for the rsqrt approximation of d~ itself.
+          // |d - d~| <= |d^2 - d~^2| / (d + d~) <= e / d~ always, <= 0.536 e / d~ once d~^2 >= 4 e (then d >= 0.866 d~),
+          // and <= sqrt(e) always.  Approximate reciprocal / rsqrt (2 ulp) under a 1.0001 safety factor; 1e-6 (rc + 1) >=
+          // 1e-6 sqrt(rc) covers the rsqrt approximation of d~ itself.
           const float dm = dmin * (1.0f - 1e-6f);
-          const float e5 = 5.0f * e;
-          del = dm * dm >= 4.0f * e ? 0.536f * e * rcp_approx(dm) : e5 * rsqrt_approx(e5);
+          const float q = e * rcp_approx(dm);
+          del = fminf(dm * dm >= 4.0f * e ? 0.536f * q : q, e * rsqrt_approx(e));
           del = __fmaf_rn(del, 1.0001f, 1e-6f * (rc + 1.0f));
         }
         if (row_ok && !(dd.dbg & 1)) *wsp = __halves2half2(__float2half_rn(s_acc), __float2half_ru(del));
@@ -307,9 +321,11 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         ++bidx;
         s_acc = 0.0f; dmin = finf;
       };
-      // distances of one 32-column chunk in place; returns the largest key (squared distance, or 1 - cos) of the chunk
-      auto distances = [&](uint32_t* av, int ch) -> float {
-        float kmax = -finf;
+      // distances of one 32-column chunk in place; an element that can be the scene's maximal distance (approximate distance
+      // above the bound Td, valid column) is appended to the candidate list on the spot
+      const float Td = COSINE ? T : (T > 0.0f ? T * rsqrt_approx(T) * (1.0f - 1e-6f) : -1.0f);   // sqrt(T), a hair low
+      auto distances = [&](uint32_t* av, int ch, unsigned int vm) {
+        unsigned int cmask = 0u;
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 4) {
           const float4 c4 = *reinterpret_cast<const float4*>(gcolc + ch * 32 + jj);
@@ -317,26 +333,24 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float a = __uint_as_float(av[jj + u]);
-            float dval, key;
-            if (COSINE) {
-              dval = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(a, rowc), cc[u]));
-              key = dval;
-            } else {
+            float dval;
+            if (COSINE) dval = __fsub_rn(1.0f, __fmul_rn(__fmul_rn(a, rowc), cc[u]));
+            else {
               float x = __fmaf_rn(-2.0f, a, __fadd_rn(rowc, cc[u]));
               x = fmaxf(x, 1e-30f);
               dval = __fmul_rn(x, rsqrt_approx(x));
-              key = x;
             }
-            kmax = fmaxf(kmax, key);
+            if (dval >= Td) cmask |= 1u << (jj + u);
             av[jj + u] = __float_as_uint(dval);
           }
         }
-        return kmax;
-      };
-      // rare: some element of the chunk may be the scene's maximal distance -> candidates for the exact pass (warp-wide call)
-      auto candidates = [&](int ch, unsigned int vm) {
-        dense_max_candidates<COSINE>(taddr + ch * 32, rowc, gcolc + ch * 32, vm, T, g, h.rowB + ch * 32, h.scene, h.vis_lbase,
-                                     h.vis_lcap, dd.maxc, dd.maxc_cnt);
+        cmask &= vm;
+        if (dd.dbg & 2) cmask = 0u;
+        while (cmask) {   // about one element in a thousand
+          const int jj = __ffs(cmask) - 1;
+          cmask &= cmask - 1;
+          dense_append_candidate(dd.maxc, dd.maxc_cnt, h.scene, h.vis_lbase, h.vis_lcap, g, h.rowB + ch * 32 + jj);
+        }
       };
       if (KT > 0) {
         constexpr int KC = KT > 0 ? KT : 1;
@@ -347,8 +361,7 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           tc_ld_wait32(av);
           if (ch + 1 < TC_BN / 32) tc_ld32_issue(taddr + (ch + 1) * 32, acc[(ch + 1) & 1]);
           const unsigned int vm = S.vmask[ms][ch];
-          const float kmax = distances(av, ch);
-          if (__any_sync(0xffffffffu, kmax >= T) && !(dd.dbg & 2)) candidates(ch, vm);
+          distances(av, ch, vm);
           if (!(dd.dbg & 4)) {
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) {
@@ -358,9 +371,9 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const float dval = __uint_as_float(av[jj]);
                 s_acc = __fadd_rn(s_acc, valid ? dval : 0.0f);
                 dmin = fminf(dmin, valid ? dval : finf);
-                // compile-time position: last physical slot of a block; blocks past the scene's arena (partial last tile) are
-                // not the scene's: nothing is stored or bounded for them
-                if (col % KC == KC - 1 && col / KC < h.nblk) flush(col);
+                // compile-time position: last physical slot of a block (the per-scene arrays are padded to whole tiles, so a
+                // block position past the scene's arena is stored too: kt = 0 there, nobody reads it)
+                if (col % KC == KC - 1) flush(col);
               }
             }
           }
@@ -375,8 +388,7 @@ vis_wsum_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (ch + 1 < TC_BN / 32) tc_ld32_issue(taddr + (ch + 1) * 32, acc[par ^ 1]);
             const unsigned int vm = S.vmask[ms][ch], bm = S.bmask[ms][ch];
             if ((vm | bm) != 0u) {   // warp-uniform, like every test on vm / bm below: column properties
-              const float kmax = distances(acc[par], ch);
-              if (__any_sync(0xffffffffu, kmax >= T) && !(dd.dbg & 2)) candidates(ch, vm);
+              distances(acc[par], ch, vm);
               if (!(dd.dbg & 4)) {
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) {

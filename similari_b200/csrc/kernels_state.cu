@@ -575,8 +575,11 @@ __global__ void __launch_bounds__(FS_T) frame_setup_kernel(Params p, TrackStore 
       // screen: 128-padded columns (16-byte aligned bulk copies of 256-column slabs); dense: one 256-entry slab per tile
       v[2] = dense ? (long long)ctiles * 256 : ((long long)rows + 127) / 128 * 128;
       v[3] = mstep > 0 ? (long long)((r.m + mstep - 1) / mstep) * ctiles : 0;
-      v[4] = dense ? (long long)nb * ((r.m + 127) / 128 * 128) : 0;
-      v[5] = nb;
+      // dense kernel: the weight-sum matrix and the per-block arrays are padded to whole column tiles, so its epilogue
+      // stores one record per block position of every tile without asking whether the block exists
+      const int nbpad = dense ? ctiles * (cstep / (K > 0 ? K : 1)) : nb;
+      v[4] = dense ? (long long)nbpad * ((r.m + 127) / 128 * 128) : 0;
+      v[5] = nbpad;
       u_mn += (unsigned long long)v[0];
       u_rows += (unsigned long long)r.m * (unsigned long long)rows;
       live += (unsigned long long)n;
