@@ -729,6 +729,8 @@ int launch_vis_dense(const Params& p, const TrackStore& ts, const Frame& f, int 
   cudaMemsetAsync(tc.slab_vmask, 0, (size_t)tc.n_slabs_ub * (TC_BN / 32) * 4, st);
   cudaMemsetAsync(tc.slab_bmask, 0, (size_t)tc.n_slabs_ub * (TC_BN / 32) * 4, st);
   cudaMemsetAsync(tc.scene_cmax, 0, (size_t)n_scenes * 4, st);
+  // block positions past a scene's arena (the last column tile is padded to whole blocks) must read "no voting observations"
+  cudaMemsetAsync(tc.slab_ktf, 0, (size_t)tc.n_slabs_ub * TC_BN * 4, st);
   const bool fused = p.max_obs <= kDenseKClasses && getenv("SB200_DENSE_GENERIC") == nullptr;
   if (fused) {
     cudaMemsetAsync(tc.d_rowb, 0, (size_t)f.total * kDenseKClasses * 4, st);

@@ -548,3 +548,41 @@ def test_wasted_tracks_carry_their_box_history(eng, kind, hist):
                 assert np.array_equal(np.nan_to_num(w["predicted"][i], nan=-7.0), np.nan_to_num(gp[-1], nan=-7.0))
                 n_checked += 1
     assert n_checked > 30
+
+
+@pytest.mark.parametrize("kind", [1, 3])
+def test_positional_list_overflow_takes_the_dense_voting_kernels(eng, oracle, kind, monkeypatch):
+    """A crowd: 260 boxes on a 500 x 400 canvas, Mahalanobis metric -- nearly every (candidate, track) pair passes the 2R
+    gate, ~60 k positional entries per scene against a list of 6 k.  That scene's entry list overflows, the device flags
+    it, fills and rescans its dense matrix and the dense Kuhn-Munkres kernel solves it, while the sparse scene next to it
+    stays on the lists.  Assignments must be the oracle's."""
+    from similari_b200.workload import Workload
+
+    visual = kind == 3
+    if visual:
+        monkeypatch.setenv("SB200_VIS_KERNEL", "tc")
+    crowd = small("cfg5" if visual else "cfg2", n_scenes=1, n_objects=260, oriented=False, canvas=(500.0, 400.0),
+                  feature_dim=64 if visual else 0, seed=11)
+    sparse = small("cfg5" if visual else "cfg2", n_scenes=1, n_objects=120, oriented=False, canvas=(2500.0, 1800.0),
+                   feature_dim=64 if visual else 0, seed=12)
+    kw = dict(kind=kind, positional_kind=0, max_idle_epochs=3)
+    if visual:
+        kw.update(visual_kind=0, visual_threshold=0.7, feature_dim=64, visual_max_observations=3, visual_min_votes=2,
+                  visual_minimal_track_length=1, min_confidence=0.1)
+    g, o = both(eng, oracle, **kw)
+    w1, w2 = Workload(crowd), Workload(sparse, scene_base=1)
+    for fr in range(5):
+        f1, f2 = w1.next_frame(), w2.next_frame()
+        if visual and fr >= 1:     # half of the crowd's detections carry no feature: they go to the positional stage
+            hasf = np.ones(len(f1["boxes"]) + len(f2["boxes"]), np.uint8)
+            hasf[: len(f1["boxes"]) : 2] = 0
+        else:
+            hasf = None
+        boxes = np.concatenate([f1["boxes"], f2["boxes"]])
+        feats = np.concatenate([f1["features"], f2["features"]]) if visual else None
+        offs = np.array([0, len(f1["boxes"]), len(boxes)], np.int32)
+        rg = g.predict_batch([0, 1], offs, boxes, features=feats, has_feature=hasf)
+        ro = o.predict_batch([0, 1], offs, boxes, features=feats, has_feature=hasf)
+        for key in ("ids", "epochs", "lengths", "voting_types"):
+            assert np.array_equal(rg[key], ro[key]), (fr, key, int((rg[key] != ro[key]).sum()))
+    assert g.active_tracks() == o.active_tracks()
