@@ -475,7 +475,7 @@ def main():
 
     def new_tracker():
         t = eng.Tracker(tracker_options_for(name, default_options, device=local, max_scenes_hint=cfg.n_scenes,
-                                            max_tracks_per_scene_hint=3 * cfg.n_objects,
+                                            max_tracks_per_scene_hint=4 * cfg.n_objects,
                                             max_dets_per_scene_hint=cfg.n_objects, **over))
         t.set_stream(torch.cuda.current_stream().cuda_stream)
         return t

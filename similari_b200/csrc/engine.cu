@@ -704,9 +704,11 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       // the store has to grow: meet the device first (the exact counts are the ones to grow from)
       if ((rc = drain())) return rc;
       bounds();
+      // grow generously (a regrow copies the whole feature arena: tens of milliseconds): what is needed now plus the
+      // pipeline's room, and at least half again as much as before
       const int want_t = std::max(need_tracks, opts.max_tracks_per_scene_hint) + pipe_room;
       if (hint_s > scene_cap || need_tracks > track_cap)
-        if ((rc = ensure_store(hint_s, std::max(want_t, track_cap)))) return rc;
+        if ((rc = ensure_store(hint_s, std::max(want_t, track_cap + track_cap / 2)))) return rc;
     }
     // room for every live track of the frames in flight and of this one in the wasted buffer: the end-of-frame sweep
     // appends without a host check

@@ -26,7 +26,7 @@ def main():
     cfg = CONFIGS[name]
     dev = torch.device("cuda", 0)
     t = eng.Tracker(tracker_options_for(name, default_options, max_scenes_hint=cfg.n_scenes,
-                                        max_tracks_per_scene_hint=3 * cfg.n_objects, max_dets_per_scene_hint=cfg.n_objects, **over))
+                                        max_tracks_per_scene_hint=4 * cfg.n_objects, max_dets_per_scene_hint=cfg.n_objects, **over))
     t.set_stream(torch.cuda.current_stream().cuda_stream)
     wl = Workload(cfg)
     rt = torch.cuda.cudart()
