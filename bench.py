@@ -319,6 +319,10 @@ def run_scatter_arm(eng, torch, dist, new_tracker, frames, dboxes, dfeats, W, K,
     kernels) and gathers the assigned track records back (sb200_shard_gather) -- the exchange step of the sharded path
     inside the library.  Same frames as the local-ingest arm, so every rank's ids must equal that arm's."""
     dev = torch.device("cuda", local)
+    # NCCL gives a send/recv pair two channels by default (~20 GB/s between two B200s); the scatter is one big
+    # point-to-point transfer per peer, so let it use more of the 18 NVLinks (read when the communicator is created)
+    os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
+    os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
     uid = [eng.Comm.unique_id() if rank == 0 else None, eng.Comm.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     c_sc = eng.Comm(rank, world, uid[0], local)     # scatter traffic (side stream)
