@@ -319,10 +319,6 @@ def run_scatter_arm(eng, torch, dist, new_tracker, frames, dboxes, dfeats, W, K,
     kernels) and gathers the assigned track records back (sb200_shard_gather) -- the exchange step of the sharded path
     inside the library.  Same frames as the local-ingest arm, so every rank's ids must equal that arm's."""
     dev = torch.device("cuda", local)
-    # NCCL gives a send/recv pair two channels by default (~20 GB/s between two B200s); the scatter is one big
-    # point-to-point transfer per peer, so let it use more of the 18 NVLinks (read when the communicator is created)
-    os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "16")
-    os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
     uid = [eng.Comm.unique_id() if rank == 0 else None, eng.Comm.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     c_sc = eng.Comm(rank, world, uid[0], local)     # scatter traffic (side stream)
@@ -623,6 +619,7 @@ def main():
     assert c1["frames"] - c0["frames"] == K
     stage_ms = {k_: (c1["stage_ms"][k_] - c0["stage_ms"][k_]) / K for k_ in c1["stage_ms"]}
     tc_frames = c1["tc_frames"] - c0["tc_frames"]
+    fallback_scenes = (c1["dense_fallback_scenes"] - c0["dense_fallback_scenes"]) / K
     if tc_frames:
         stage_ms["vis_screen"] = (c1["vis_screen_ms"] - c0["vis_screen_ms"]) / tc_frames
         stage_ms["vis_refine"] = (c1["vis_refine_ms"] - c0["vis_refine_ms"]) / tc_frames
@@ -708,6 +705,7 @@ def main():
             "clocks": clocks_dev if clocks_dev and clocks_dev.get("samples") else clocks,
             "clocks_e2e": clocks,
             "stages_ms": stage_ms,
+            "exact_fallback_scenes_per_step": fallback_scenes,
             "host_sync": "none inside the timed region (stream-ordered predict, per-frame tables built on the device)",
             "roofline": roof,
         }
