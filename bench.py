@@ -383,6 +383,12 @@ def run_scatter_arm(eng, torch, dist, new_tracker, frames, dboxes, dfeats, W, K,
                                d_ids=d_out["ids"].data_ptr(), d_epochs=d_out["epochs"].data_ptr(),
                                d_lengths=d_out["lengths"].data_ptr(), d_voting_types=d_out["voting_types"].data_ptr())
     t.sync()
+    # NCCL sets up its peer-to-peer channels on a communicator's first operation (tens of milliseconds): one untimed
+    # scatter and gather first
+    scatter(0)
+    main.wait_event(landed[0])
+    c_ga.gather(0, ranges[0], addr(d_out), addr(all_out), main.cuda_stream)
+    torch.cuda.synchronize()
     # scatter alone (K back-to-back scatters, nothing else running): what the exchange costs
     dist.barrier()
     torch.cuda.synchronize()
