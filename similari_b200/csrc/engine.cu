@@ -192,7 +192,8 @@ struct sb200_tracker {
   unsigned long long acc_tc_frames = 0;
   // side stream of the positional stage (visual trackers): the culled scan runs next to the refinement of the visual
   // survivors instead of in front of the screen
-  cudaStream_t pos_stream = nullptr;
+  cudaStream_t pos_stream = nullptr;   // side stream: frame tables beside the candidate preparation, sweep beside the feature store
+  bool side_off = false;
   cudaEvent_t ev_fork[2]{}, ev_join = nullptr;
   float stage_ms[5]{};
   // scene table
@@ -232,7 +233,7 @@ struct sb200_tracker {
   } stg[2];
   int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_frameout, f_decided, f_excl, f_prewin, f_own, f_ownovf, f_dyn, f_ws, f_tmeta, f_rowinfo, f_slabc, f_slabm, f_slabmask,
+      f_status, f_featdst, f_apprank, f_appmeta, f_frameout, f_decided, f_excl, f_prewin, f_own, f_ownovf, f_dyn, f_ws, f_tmeta, f_rowinfo, f_slabc, f_slabm, f_slabmask,
       f_dscene, f_maxc, f_maxcval, f_drowb, f_dcolb, f_slabk, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
@@ -250,7 +251,7 @@ struct sb200_tracker {
                    &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl, &f_prewin, &f_own, &f_ownovf, &f_dyn, &b_idc, &f_ws, &f_tmeta, &f_rowinfo, &f_slabc, &f_slabm, &f_slabmask, &f_dscene, &f_maxc, &f_maxcval, &f_drowb, &f_dcolb, &f_slabk,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
-                   &f_featdst, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
+                   &f_featdst, &f_apprank, &f_appmeta, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
     for (DBuf* b : all) b->release();
     if (stream) cudaStreamSynchronize(stream);
     h_small.release();
@@ -782,6 +783,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   if ((rc = ens(f_cbox, T * 24)) || (rc = ens(f_cradius, T * 4)) || (rc = ens(f_cconf, T * 4)) ||
       (rc = ens(f_winner, T * 4)) || (rc = ens(f_cvt, T)) || (rc = ens(f_scenes, sizeof(sb::SceneDesc) * n_scenes)) ||
       (rc = ens(f_newcount, 4 * (size_t)n_scenes)) || (rc = ens(f_dyn, sizeof(sb::FrameDyn))) ||
+      (rc = ens(f_apprank, T * 8)) || (rc = ens(f_appmeta, 16 * (size_t)n_scenes)) ||
       (rc = ens(f_pos, std::max<size_t>(4, (size_t)pos_total * 4))))
     return rc;
   if (P.positional_kind == SB200_POS_IOU && (rc = ens(f_cvert, T * 64))) return rc;
@@ -935,6 +937,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.scenes = f_scenes.as<sb::SceneDesc>(); f.new_count = f_newcount.as<int>();
   f.new_count_all = f.new_count;
   f.feat_dst = P.is_visual ? f_featdst.as<int>() : nullptr;
+  f.app_rank = f_apprank.as<int2>(); f.app_meta = f_appmeta.as<int4>();
   if ((rc = ens(f_frameout, sizeof(int) * 3 * (size_t)n_scenes))) return rc;
   f.frame_out = f_frameout.as<int>();
   f.c_bf16 = tc.use_tc ? f_cbf16.p : nullptr; f.scene_max = f_scene_max.as<unsigned int>();
@@ -1029,8 +1032,36 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     if (f.in_own) CU(cudaMemcpyAsync(sin->own.p, own_area, n * 4, cudaMemcpyHostToDevice, stream));
   }
   // scene descriptors, tile list, frame scalars; list counters and status words zeroed
+  if (!pos_stream && !side_off) {
+    static const bool off = [] { const char* e = getenv("SB200_SIDE_STREAM"); return e && e[0] == '0'; }();
+    side_off = off;
+    if (!side_off) {
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&pos_stream, cudaStreamNonBlocking, hi));
+      for (auto& e : ev_fork) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+  }
+  const bool side_ok = pos_stream != nullptr;
+  // The frame's tables come from one small CTA: with nothing else to wait for (no own-area derivation, which reads them) it
+  // runs beside the candidate preparation, on the side stream, and the main stream joins before the first kernel that reads them.
+  const bool side_setup = side_ok && !derive_own && total > 0;
+  cudaStream_t s_setup = stream;
+  if (side_setup) {
+    CU(cudaEventRecord(ev_fork[0], stream));
+    CU(cudaStreamWaitEvent(pos_stream, ev_fork[0], 0));
+    s_setup = pos_stream;
+  }
   sb::launch_frame_setup(P, ts, f, reinterpret_cast<const sb::SceneReq*>(q.h_req.dp), n_scenes, b_ntracks.as<int>(), mstep,
-                         cstep, tc.dense, f_tiles.as<sb::TcTile>(), f_dyn.as<sb::FrameDyn>(), f_counters.as<int>(), (int)n_counters, stream);
+                         cstep, tc.dense, f_tiles.as<sb::TcTile>(), f_dyn.as<sb::FrameDyn>(), f_counters.as<int>(), (int)n_counters, s_setup);
+  tc.max_init_done = 1;   // frame_setup resets scene_max
+  if (side_setup && Pf.is_visual && tc.use_tc && !tc.dense && tc.n_tiles > 0 && max_m > 0 && max_n > 0 && f.in_feat) {
+    // the screen's column metadata reads the tables and the store only: it follows the setup on the side stream
+    sb::launch_vis_colmeta(Pf, ts, f, n_scenes, max_n, tc, pos_stream);
+    tc.colmeta_done = 1;
+  }
+  if (side_setup) CU(cudaEventRecord(ev_join, pos_stream));
   CU(cudaEventRecord(q.ev[0], stream));
   if (derive_own) {
     // visual_sort/simple_api.rs:110-127: with an own-area threshold and no shares supplied by the caller, the shares come
@@ -1040,6 +1071,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     f.in_own = f_own.as<float>();
   }
   sb::launch_prep(Pf, f, n_scenes, max_m, stream);
+  if (side_setup) CU(cudaStreamWaitEvent(stream, ev_join, 0));
   CU(cudaEventRecord(q.ev[1], stream));
   sb::TcArgs tcc = tc;
   if (tc.use_tc && tc.n_tiles > 0) { tcc.ev_screen0 = q.ev_k[0]; tcc.ev_screen1 = q.ev_k[1]; tcc.ev_refine1 = q.ev_k[2]; q.tc_timed = true; }
@@ -1071,7 +1103,20 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   if (vr != 0) return fail(SB200_ERR_CUDA, "voting launch failed: %s", cudaGetErrorString((cudaError_t)vr));
   CU(cudaEventRecord(q.ev[4], stream));
   sb::launch_apply(Pf, ts, f, n_scenes, max_m, 0ull, b_ntracks.as<int>(), stream);
-  sb::launch_frame_sweep(Pf, ts, f, n_scenes, b_ntracks.as<int>(), wb, stream);
+  // The sweep (latency-bound, one CTA per scene) and the feature store (HBM-bound) touch disjoint arrays -- a track's feature
+  // block is not moved by the compaction -- so the sweep runs on the side stream beside the store; the frame ends at the join.
+  const bool side_sweep = side_ok && Pf.is_visual && f.in_feat && total > 0;
+  if (side_sweep) {
+    CU(cudaEventRecord(ev_fork[1], stream));
+    CU(cudaStreamWaitEvent(pos_stream, ev_fork[1], 0));
+    sb::launch_frame_sweep(Pf, ts, f, n_scenes, b_ntracks.as<int>(), wb, pos_stream);
+    CU(cudaEventRecord(ev_join, pos_stream));
+    sb::launch_feat_store(Pf, ts, f, stream);
+    CU(cudaStreamWaitEvent(stream, ev_join, 0));
+  } else {
+    sb::launch_feat_store(Pf, ts, f, stream);
+    sb::launch_frame_sweep(Pf, ts, f, n_scenes, b_ntracks.as<int>(), wb, stream);
+  }
   CU(cudaEventRecord(q.ev[5], stream));
   CU(cudaGetLastError());
 

@@ -622,7 +622,7 @@ int launch_vis_cost_a(const Params& p, const TrackStore& ts, const Frame& f, int
   if (n_scenes == 0 || !p.is_visual) return 0;
   const bool any = max_m > 0 && max_n > 0 && f.in_feat != nullptr;
   const bool use_tc = tc.use_tc && any;
-  launch_scene_max(p, f, n_scenes, /*init_only=*/true, st);
+  if (!tc.max_init_done) launch_scene_max(p, f, n_scenes, /*init_only=*/true, st);
   if (use_tc && tc.dense) {
     // thresholds that cut nothing: dense weight sums on the tensor cores, groups that can win go to the pair lists
     int rc = launch_vis_dense(p, ts, f, n_scenes, max_m, tc, st);

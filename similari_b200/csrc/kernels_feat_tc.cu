@@ -768,6 +768,15 @@ int launch_vis_refine(const Params& p, const TrackStore& ts, const Frame& f, int
   return 0;
 }
 
+void launch_vis_colmeta(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
+                        cudaStream_t st) {
+  const int max_rows = tc.max_rows > 0 ? tc.max_rows : max_n * p.max_obs;
+  if (tc.n_tiles == 0 || max_rows <= 0) return;
+  dim3 grid((max_rows + 255) / 256, n_scenes);
+  vis_meta_kernel<<<grid, 256, 0, st>>>(p, ts, f, n_scenes, max_rows, tc.colmeta, tc.colgeo, tc.colb, tc.colvalid);
+  note_launch();
+}
+
 int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
                        int phase, cudaStream_t st) {
   if (tc.n_tiles == 0) return 0;
@@ -788,12 +797,7 @@ int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, in
                              : (cosine ? (const void*)vis_screen_kernel<1, true> : (const void*)vis_screen_kernel<1, false>);
   e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const int max_rows = tc.max_rows > 0 ? tc.max_rows : max_n * p.max_obs;
-  if (max_rows > 0) {
-    dim3 grid((max_rows + 255) / 256, n_scenes);
-    vis_meta_kernel<<<grid, 256, 0, st>>>(p, ts, f, n_scenes, max_rows, tc.colmeta, tc.colgeo, tc.colb, tc.colvalid);
-    note_launch();
-  }
+  if (!tc.colmeta_done) launch_vis_colmeta(p, ts, f, n_scenes, max_n, tc, st);
   vis_rowmeta_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, f, tc.rowmeta);
   note_launch();
   if (tc.ev_screen0) cudaEventRecord(tc.ev_screen0, st);

@@ -21,15 +21,15 @@ __device__ __forceinline__ void write_box(float* dst, const Box& b) {
   dst[0] = b.xc; dst[1] = b.yc; dst[2] = b.angle; dst[3] = b.aspect; dst[4] = b.height; dst[5] = b.conf;
 }
 
-__global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Frame f, int n_scenes,
-                                                   unsigned long long id_base, int* n_tracks) {
+// Phase 1 of apply (one CTA per scene): rank of every new-track candidate among the scene's new candidates (candidate
+// order), the scene of every detection, and the scene's counters.  The per-detection work is phase 2, one thread each.
+__global__ void __launch_bounds__(AT) apply_rank_kernel(Params p, TrackStore ts, Frame f, int n_scenes, int* n_tracks) {
   __shared__ int s_warp[AT / 32];
   __shared__ int s_carry;
   __shared__ int s_newbefore;
   const int sidx = blockIdx.x;
   const SceneDesc sc = f.scenes[sidx];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int K = p.max_obs;
   // ids of non-batch trackers are consumed by new tracks only, in request order => prefix over earlier scenes
   if (!p.is_batch) {
     int c = 0;
@@ -44,19 +44,14 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
       s_newbefore = t;
     }
   }
-  if (tid == 0) s_carry = 0;
+  if (tid == 0) { s_carry = 0; if (p.is_batch) s_newbefore = 0; }
   __syncthreads();
-  // feature arena of this scene (visual trackers): new tracks take blocks from the free list first, then fresh ones
-  const size_t sbase = (size_t)sc.slot * ts.track_cap;
-  const int nfree0 = ts.fblk ? ts.n_free[sc.slot] : 0;
-  const int top0 = ts.fblk ? ts.arena_top[sc.slot] : 0;
   const int* winner = f.winner + sc.det_base;
   for (int base = 0; base < sc.m; base += AT) {
     const int m = base + tid;
     const bool active = m < sc.m;
     const int win = active ? winner[m] : 0;
     const int isnew = (active && win < 0) ? 1 : 0;
-    // block scan of new flags -> rank among new candidates (candidate order)
     int x = isnew;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -72,9 +67,39 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
     __syncthreads();
     if (tid == AT - 1) s_carry = carry + woff + x;
     __syncthreads();
-    if (!active) continue;
+    if (active) f.app_rank[sc.det_base + m] = make_int2(sidx, rank);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // feature arena of this scene (visual trackers): new tracks take blocks from the free list first, then fresh ones
+    const int nfree0 = ts.fblk ? ts.n_free[sc.slot] : 0;
+    const int top0 = ts.fblk ? ts.arena_top[sc.slot] : 0;
+    f.app_meta[sidx] = make_int4(s_newbefore, nfree0, top0, 0);
+    const int added = min(sc.n + s_carry, ts.track_cap) - sc.n;
+    n_tracks[sc.slot] = sc.n + added;
+    if (ts.fblk) {
+      ts.n_free[sc.slot] = nfree0 - min(nfree0, added);
+      ts.arena_top[sc.slot] = top0 + max(0, added - nfree0);
+    }
+  }
+}
 
-    const int g = sc.det_base + m;
+// Phase 2 of apply: one thread per detection creates its track or merges into the track it won.
+__global__ void __launch_bounds__(256) apply_kernel(Params p, TrackStore ts, Frame f, unsigned long long id_base) {
+  const int K = p.max_obs;
+  {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= f.total) return;
+    const int g = f.det0 + i;
+    const int2 sr = f.app_rank[g];
+    const int sidx = sr.x, rank = sr.y;
+    const SceneDesc& sc = f.scenes[sidx];
+    const int4 meta = f.app_meta[sidx];
+    const int s_newbefore = meta.x, nfree0 = meta.y, top0 = meta.z;
+    const size_t sbase = (size_t)sc.slot * ts.track_cap;
+    const int win = f.winner[g];
+    const int isnew = win < 0 ? 1 : 0;
+
     const float* cbp = f.c_box + (size_t)g * 6;
     const Box cb{cbp[0], cbp[1], cbp[2], cbp[3], cbp[4], cbp[5]};
     const long long custom = f.in_custom ? f.in_custom[g] : (-9223372036854775807LL - 1);
@@ -91,7 +116,7 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
     unsigned long long o_id = 0; unsigned int o_len = 0; signed char o_vt = -1;   // SortTrack columns of this detection
     if (isnew) {
       const int j = sc.n + rank;
-      if (j >= ts.track_cap) { atomicOr(&f.status[sidx], 1); continue; }
+      if (j >= ts.track_cap) { atomicOr(&f.status[sidx], 1); return; }
       idx = (size_t)sc.slot * ts.track_cap + j;
       const float* rb = f.in_boxes + (size_t)g * 6;
       const Box raw{rb[0], rb[1], rb[2], rb[3], rb[4], rb[5]};
@@ -131,8 +156,11 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
       size_t blk = idx;
       if (p.is_visual) {
         on = ts.obs_n[idx];
-        for (int k = 0; k < K; ++k) {
-          l_hasf[k] = ts.obs_hasf[idx * K + k]; l_phys[k] = ts.obs_phys[idx * K + k]; l_q[k] = ts.obs_q[idx * K + k];
+        for (int k = 0; k < K; ++k) {   // slots at and beyond obs_n were never written
+          const bool have = k < on;
+          l_hasf[k] = have ? ts.obs_hasf[idx * K + k] : (unsigned char)0;
+          l_phys[k] = have ? ts.obs_phys[idx * K + k] : (unsigned char)0;
+          l_q[k] = have ? ts.obs_q[idx * K + k] : 0.0f;
         }
         blk = feat_block(ts, sc.slot, idx);
       }
@@ -217,15 +245,6 @@ __global__ void __launch_bounds__(AT) apply_kernel(Params p, TrackStore ts, Fram
     if (f.o_pred) write_box(f.o_pred + (size_t)g * 6, pred);
     if (f.o_obs) write_box(f.o_obs + (size_t)g * 6, isnew ? Box{f.in_boxes[(size_t)g * 6], f.in_boxes[(size_t)g * 6 + 1], f.in_boxes[(size_t)g * 6 + 2], f.in_boxes[(size_t)g * 6 + 3], f.in_boxes[(size_t)g * 6 + 4], f.in_boxes[(size_t)g * 6 + 5]} : cb);
   }
-  __syncthreads();
-  if (tid == 0) {
-    const int added = min(sc.n + s_carry, ts.track_cap) - sc.n;
-    n_tracks[sc.slot] = sc.n + added;
-    if (ts.fblk) {
-      ts.n_free[sc.slot] = nfree0 - min(nfree0, added);
-      ts.arena_top[sc.slot] = top0 + max(0, added - nfree0);
-    }
-  }
 }
 
 // copies the features that VisualMetric::optimize keeps into the track's free physical slot (warp per detection)
@@ -279,13 +298,20 @@ void launch_apply(const Params& p, const TrackStore& ts, const Frame& f, int n_s
                   unsigned long long id_base, int* d_n_tracks, cudaStream_t st) {
   (void)max_m;
   if (n_scenes == 0) return;
-  apply_kernel<<<n_scenes, AT, 0, st>>>(p, ts, f, n_scenes, id_base, d_n_tracks);
+  apply_rank_kernel<<<n_scenes, AT, 0, st>>>(p, ts, f, n_scenes, d_n_tracks);
   note_launch();
-  if (p.is_visual && f.in_feat && f.total > 0) {
-    long long threads = (long long)f.total * 32;
-    feat_store_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, ts, f);
+  if (f.total > 0) {
+    apply_kernel<<<(f.total + 255) / 256, 256, 0, st>>>(p, ts, f, id_base);
     note_launch();
   }
+}
+
+bool launch_feat_store(const Params& p, const TrackStore& ts, const Frame& f, cudaStream_t st) {
+  if (!(p.is_visual && f.in_feat && f.total > 0)) return false;
+  long long threads = (long long)f.total * 32;
+  feat_store_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(p, ts, f);
+  note_launch();
+  return true;
 }
 
 // --------------------------------------------------------------------------------------------------------
@@ -551,6 +577,8 @@ __global__ void __launch_bounds__(FS_T) frame_setup_kernel(Params p, TrackStore 
   __shared__ int s_maxn, s_maxrows;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i < n_zero; i += FS_T) zero[i] = 0;
+  // per-scene maximum of the valid visual distances starts at -1.0 (order-preserving u32 code of kernels_assign.cu: ~bits)
+  if (f.scene_max) for (int i = tid; i < n_scenes; i += FS_T) f.scene_max[i] = ~__float_as_uint(-1.0f);
   if (tid < NQ) s_carry[tid] = 0;
   if (tid == 0) { s_maxn = 0; s_maxrows = 0; }
   const bool dense = dense_i != 0;

@@ -160,6 +160,8 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   int* new_count;          // [n_scenes] new tracks per scene (written by voting)
   int* status;             // [n_scenes] per-scene status flags (capacity overflow etc.)
   int* feat_dst;           // [total] destination feature row (block*K + phys) or -1
+  int2* app_rank;          // [total] apply phase 1: (scene of the detection, rank among the scene's new tracks)
+  int4* app_meta;          // [scenes] apply phase 1: (new tracks of earlier scenes, free blocks, arena top) before the frame
   int* frame_out;          // [n_scenes][3] written by the end-of-frame sweep: live tracks, arena blocks, newly expired
   const FrameDyn* dyn;     // device-built frame scalars (null in the stateless operators: host values are used)
   unsigned long long* id_counter;   // device copy of the tracker's id counter (null: the id_base argument is used)
@@ -225,7 +227,9 @@ unsigned long long launch_count();
 void launch_pos_cost(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                      cudaStream_t st);
 // visual cost: fp32 SIMT kernel in the reference's summation order (use_tc == false) or the tcgen05 3xTF32 kernel
-struct TcArgs {  // tensor-core screen resources (all null / 0 when the dense exact kernel is used)
+struct TcArgs {
+  int max_init_done;   // the frame's setup kernel already reset scene_max
+  int colmeta_done;    // the column metadata of the screen was launched by the caller (side stream)  // tensor-core screen resources (all null / 0 when the dense exact kernel is used)
   bool use_tc;
   bool cluster2;   // tiles describe candidate-tile PAIRS processed by 2-CTA clusters (multicast B loads, or pair MMAs)
   bool pair;       // with cluster2: cta_group::2 MMAs (256 x 256 x 16 across the CTA pair)
@@ -295,6 +299,9 @@ void launch_pos_scan_lazy(const Params& p, const TrackStore& ts, const Frame& f,
 int launch_vote_masks(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,
                       cudaStream_t st);
 // phase 0: metadata + tensor-core screen; phase 1: exact refinement of the survivors of the sparse scenes
+// screen metadata of the stored feature rows (needs the frame tables and the store, not the candidates)
+void launch_vis_colmeta(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
+                        cudaStream_t st);
 int launch_vis_cost_tc(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_n, const TcArgs& tc,
                        int phase, cudaStream_t st);
 // materialises the dense visual matrix of the sparse scenes (operators / debugging only)
@@ -313,6 +320,8 @@ int launch_voting(const Params& p, const TrackStore& ts, const Frame& f, int n_s
                   cudaStream_t st);
 void launch_apply(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m,
                   unsigned long long id_base, int* d_n_tracks, cudaStream_t st);
+// the kept features of the frame -> the tracks' feature blocks; false when the frame has none (no launch)
+bool launch_feat_store(const Params& p, const TrackStore& ts, const Frame& f, cudaStream_t st);
 // stable compaction of wasted tracks; appends them to the wasted buffers
 struct WastedBuf {
   int cap;
