@@ -589,9 +589,13 @@ def main():
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler_dev.mark_begin()
+    h0 = t_dev.host_counters()
+    th0 = time.perf_counter()
     ev0.record()
     for i in range(W, W + K):
         step_dev(i)
+    th1 = time.perf_counter()
+    h1 = t_dev.host_counters()
     if gather is not None:
         for e in gather["done"]:
             if e is not None:
@@ -713,6 +717,10 @@ def main():
             "stages_ms": stage_ms,
             "exact_fallback_scenes_per_step": fallback_scenes,
             "host_sync": "none inside the timed region (stream-ordered predict, per-frame tables built on the device)",
+            # what one frame costs the calling thread: library time not blocked on the device, and the whole Python loop
+            "host_ms_per_step": {"library_unblocked": (h1["ms_total"] - h1["ms_blocked"] - h0["ms_total"] + h0["ms_blocked"]) / K,
+                                 "library_blocked_on_device": (h1["ms_blocked"] - h0["ms_blocked"]) / K,
+                                 "python_loop_wall": 1e3 * (th1 - th0) / K},
             "roofline": roof,
         }
         if world > 1:

@@ -160,6 +160,12 @@ int sb200_predict_batch_async(sb200_tracker* t, int32_t n_scenes, const uint64_t
 int sb200_sync(sb200_tracker* t);
 /* Frames enqueued and not yet completed (PredictionBatchResult::ready is `== 0`); never blocks. */
 int sb200_frames_in_flight(sb200_tracker* t);
+
+/* Host-side cost of the predict entry points since the tracker was created: out3 = {calls, wall milliseconds spent inside
+ * them, milliseconds of that spent blocked on the device (ring of frames in flight full, wait == true, reallocation)}.
+ * (total - blocked) / calls is what one frame costs the calling thread; the stream-ordered design needs it below the
+ * frame's device time (no reference counterpart: the reference's predict is synchronous). */
+int sb200_host_counters(sb200_tracker* t, double* out3);
 /* Same call with boxes / features / has_feature / quality / custom_ids / own_area and every non-NULL `out` column
  * being DEVICE pointers (inputs already resident in HBM).  scene_ids and det_offsets stay host pointers (they are
  * consumed before the call returns).  Stream-ordered like sb200_predict_batch_async: nothing in the call waits for

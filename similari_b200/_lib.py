@@ -83,7 +83,7 @@ EXPORTS = [
     "sb200_kalman_predict", "sb200_kalman_update", "sb200_nms", "sb200_own_area_shares", "sb200_host_alloc", "sb200_host_free",
     "sb200_predict_batch_async", "sb200_sync", "sb200_frames_in_flight", "sb200_work_counters", "sb200_launch_count",
     "sb200_set_feature_dim", "sb200_comm_unique_id", "sb200_comm_create", "sb200_comm_destroy", "sb200_shard_scatter",
-    "sb200_shard_gather", "sb200_wasted_history",
+    "sb200_shard_gather", "sb200_wasted_history", "sb200_host_counters",
 ]
 
 
@@ -118,6 +118,7 @@ def lib():
         "sb200_frames_in_flight": (C.c_int, [vp]),
         "sb200_work_counters": (C.c_int, [vp, vp, vp]),
         "sb200_launch_count": (u64, []),
+        "sb200_host_counters": (C.c_int, [vp, vp]),
         "sb200_predict_batch_device": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PredictOut)]),
         "sb200_skip_epochs": (C.c_int, [vp, u64, i32]),
         "sb200_current_epoch": (i64, [vp, u64]),

@@ -188,6 +188,8 @@ struct sb200_tracker {
   std::string async_err;
   // cumulative work counters over the absorbed frames (bench.py reads them around its timed region)
   unsigned long long acc_units_mn = 0, acc_units_rows = 0, acc_frames = 0;
+  double host_ms_total = 0.0, host_ms_blocked = 0.0;   // wall time inside predict(), and the part of it spent waiting for the device
+  unsigned long long host_calls = 0;
   double acc_stage_ms[5]{}, acc_kernel_ms[2]{};
   unsigned long long acc_tc_frames = 0;
   // side stream of the positional stage (visual trackers): the culled scan runs next to the refinement of the visual
@@ -501,10 +503,12 @@ struct sb200_tracker {
               const float* own_area, const sb200_predict_out* out, bool device_io, bool wait);
   int absorb_oldest(bool block);
   int poll();
-  int drain();
-  int ens(DBuf& b, size_t need) {   // ensure() that never reallocates under a frame in flight
+  int drain(const char* why = nullptr);
+  int ens(DBuf& b, size_t need, const char* name = "") {   // ensure() that never reallocates under a frame in flight
     if (need <= b.bytes) return 0;
-    int rc = drain();
+    static const bool trace_ens = getenv("SB200_TRACE") != nullptr;
+    if (trace_ens) fprintf(stderr, "[sb200] %s grows: %zu -> %zu bytes\n", name, b.bytes, need);
+    int rc = drain("frame buffer grows");
     if (rc) return rc;
     return b.ensure(need);
   }
@@ -518,7 +522,14 @@ struct sb200_tracker {
 int sb200_tracker::absorb_oldest(bool block) {
   if (pend_count == 0) return 1;
   Pending& q = pend[pend_head];
-  cudaError_t e = block ? cudaEventSynchronize(q.done) : cudaEventQuery(q.done);
+  cudaError_t e;
+  if (block) {
+    const auto w0 = std::chrono::steady_clock::now();
+    e = cudaEventSynchronize(q.done);
+    host_ms_blocked += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+  } else {
+    e = cudaEventQuery(q.done);
+  }
   if (e == cudaErrorNotReady) { cudaGetLastError(); return 1; }
   const int n = q.n_scenes;
   if (e != cudaSuccess) {
@@ -587,7 +598,9 @@ int sb200_tracker::poll() {
   return 0;
 }
 
-int sb200_tracker::drain() {
+int sb200_tracker::drain(const char* why) {
+  static const bool trace_dr = getenv("SB200_TRACE") != nullptr;
+  if (trace_dr && why && pend_count > 0) fprintf(stderr, "[sb200] predict waits for %d frame(s) in flight: %s\n", pend_count, why);
   while (pend_count > 0) absorb_oldest(true);
   if (async_rc) {
     const int rc = async_rc;
@@ -597,6 +610,7 @@ int sb200_tracker::drain() {
   return 0;
 }
 
+#define ENS(b, ...) ens(b, __VA_ARGS__, #b)
 int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const int32_t* det_offsets, const float* boxes,
                            const float* features, const uint8_t* has_feature, const float* quality,
                            const int64_t* custom_ids, const float* own_area, const sb200_predict_out* out,
@@ -618,7 +632,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   // frames that have completed since the last call hand over their results; an error of an earlier asynchronous frame
   // is reported now
   poll();
-  if (async_rc) { if ((rc = drain())) return rc; }
+  if (async_rc) { if ((rc = drain("error of an earlier frame"))) return rc; }
   // same scene list as the previous request (the steady state of a batch tracker): validated slots are reused
   const bool same_req = (int)last_req_scenes.size() == n_scenes && n_scenes > 0 &&
                         memcmp(last_req_scenes.data(), scene_ids, sizeof(uint64_t) * (size_t)n_scenes) == 0;
@@ -643,7 +657,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     const int cap0 = P.is_visual ? kDenseVoteCap : 0;
     if (sb::voting_smem_need(max_m0, max_n0, cap0) > sb::kVotingSmemLimit) {
       if (pend_count > 0) {   // the bound counts every detection in flight as a new track: get the exact counts first
-        if ((rc = drain())) return rc;
+        if ((rc = drain("assignment solver bound"))) return rc;
         max_n0 = 0;
         for (int s = 0; s < n_scenes; ++s) {
           auto it = slot_of.find(scene_ids[s]);
@@ -656,7 +670,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   }
   // auto-waste tick (src/trackers/sort/simple_api.rs:115-120): a collection point of the reference, host and device meet
   if (auto_waste_counter == 0) {
-    if ((rc = drain())) return rc;
+    if ((rc = drain("auto-waste tick"))) return rc;
     if ((rc = run_waste())) return rc;
     auto_waste_counter = auto_waste_periodicity;
   } else auto_waste_counter -= 1;
@@ -667,7 +681,10 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     for (int s = 0; s < n_scenes; ++s) last_req_slots[s] = slot_for(scene_ids[s], true);
     last_req_scenes.assign(scene_ids, scene_ids + n_scenes);
   }
-  if (pend_count == kDepth) absorb_oldest(true);   // back-pressure: at most kDepth frames in flight
+  if (pend_count == kDepth) {
+    if (trace) fprintf(stderr, "[sb200] predict waits: ring of %d frames full\n", kDepth);
+    absorb_oldest(true);
+  }   // back-pressure: at most kDepth frames in flight
 
   // ---- upper bounds of everything the device will size exactly (tracks per scene with frames still in flight)
   const int K = P.max_obs;
@@ -703,7 +720,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     int hint_s = std::max((int)scene_of_slot.size(), opts.max_scenes_hint);
     if (hint_s > scene_cap || need_tracks > track_cap) {
       // the store has to grow: meet the device first (the exact counts are the ones to grow from)
-      if ((rc = drain())) return rc;
+      if ((rc = drain("track store bound"))) return rc;
       bounds();
       // grow generously (a regrow copies the whole feature arena: tens of milliseconds): what is needed now plus the
       // pipeline's room, and at least half again as much as before
@@ -714,9 +731,15 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     // room for every live track of the frames in flight and of this one in the wasted buffer: the end-of-frame sweep
     // appends without a host check
     if (wasted_count + inflight_live_ub + live_ub + 1 > wb.cap) {
-      if ((rc = drain())) return rc;
+      // the bound that failed is the pipeline's (frames in flight + this one): grow for twice that, or the next frame meets
+      // the same bound again -- after the wait the exact counts alone would fit and nothing would grow
+      const long long pipe_need = inflight_live_ub + live_ub;
+      if ((rc = drain("wasted buffer bound"))) return rc;
       bounds();
-      if ((rc = ensure_wasted(wasted_count + live_ub + 1))) return rc;
+      // a full ring: kDepth frames in flight plus this one, each bounded by the live tracks plus every detection queued before it
+      const long long dets = std::max<long long>(total, (long long)std::max(opts.max_scenes_hint, n_scenes) * opts.max_dets_per_scene_hint);
+      const long long ring_need = (long long)(kDepth + 1) * (live_ub + (long long)kDepth * dets);
+      if ((rc = ensure_wasted(wasted_count + std::max<long long>(ring_need, 2 * pipe_need) + 1))) return rc;
     }
     if (!b_idc.p) {
       if ((rc = b_idc.ensure(8))) return rc;
@@ -780,16 +803,16 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     pos_total = std::max(pos_total, hint_pos);
     if (P.is_visual) vis_total = std::max(vis_total, hint_pos * K);
   }
-  if ((rc = ens(f_cbox, T * 24)) || (rc = ens(f_cradius, T * 4)) || (rc = ens(f_cconf, T * 4)) ||
-      (rc = ens(f_winner, T * 4)) || (rc = ens(f_cvt, T)) || (rc = ens(f_scenes, sizeof(sb::SceneDesc) * n_scenes)) ||
-      (rc = ens(f_newcount, 4 * (size_t)n_scenes)) || (rc = ens(f_dyn, sizeof(sb::FrameDyn))) ||
-      (rc = ens(f_apprank, T * 8)) || (rc = ens(f_appmeta, 16 * (size_t)n_scenes)) ||
-      (rc = ens(f_pos, std::max<size_t>(4, (size_t)pos_total * 4))))
+  if ((rc = ENS(f_cbox, T * 24)) || (rc = ENS(f_cradius, T * 4)) || (rc = ENS(f_cconf, T * 4)) ||
+      (rc = ENS(f_winner, T * 4)) || (rc = ENS(f_cvt, T)) || (rc = ENS(f_scenes, sizeof(sb::SceneDesc) * n_scenes)) ||
+      (rc = ENS(f_newcount, 4 * (size_t)n_scenes)) || (rc = ENS(f_dyn, sizeof(sb::FrameDyn))) ||
+      (rc = ENS(f_apprank, T * 8)) || (rc = ENS(f_appmeta, 16 * (size_t)n_scenes)) ||
+      (rc = ENS(f_pos, std::max<size_t>(4, (size_t)pos_total * 4))))
     return rc;
-  if (P.positional_kind == SB200_POS_IOU && (rc = ens(f_cvert, T * 64))) return rc;
+  if (P.positional_kind == SB200_POS_IOU && (rc = ENS(f_cvert, T * 64))) return rc;
   if (P.is_visual) {
-    if ((rc = ens(f_cflags, T)) || (rc = ens(f_cnorm2, T * 4)) || (rc = ens(f_featdst, T * 4)) ||
-        (rc = ens(f_vis, std::max<size_t>(4, (size_t)vis_total * 4))) || (rc = ens(f_scene_max, 4 * (size_t)n_scenes)))
+    if ((rc = ENS(f_cflags, T)) || (rc = ENS(f_cnorm2, T * 4)) || (rc = ENS(f_featdst, T * 4)) ||
+        (rc = ENS(f_vis, std::max<size_t>(4, (size_t)vis_total * 4))) || (rc = ENS(f_scene_max, 4 * (size_t)n_scenes)))
       return rc;
   }
   sb::TcArgs tc;
@@ -817,8 +840,17 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       blk_ub += ct * (cstep / K);
     }
     tc.n_tiles = (int)tiles_ub;   // upper bound: the list and its length are built on the device
-    if ((rc = ens(f_cbf16, T * P.d8 * 2)) || (rc = ens(f_tiles, sizeof(sb::TcTile) * (size_t)std::max<long long>(1, tiles_ub))) ||
-        (rc = ens(f_rowmeta, sizeof(sb::VisRowMeta) * (T + 256))))
+    // the list is sized from the hints like the other frame buffers (the bound grows with the frames in flight: a list
+    // sized for this frame alone would be outgrown, and wait for the device, again and again)
+    long long tiles_alloc = tiles_ub;
+    {
+      const long long hs = std::max(opts.max_scenes_hint, n_scenes), hd = std::max(opts.max_dets_per_scene_hint, max_m);
+      const long long ht = std::max(hint_tracks, max_nb);
+      tiles_alloc = std::max(tiles_alloc, hs * ((hd + mstep - 1) / mstep) * ((ht * K + cstep - 1) / cstep + 1));
+      if (f_tiles.bytes > 0 && sizeof(sb::TcTile) * (size_t)tiles_alloc > f_tiles.bytes) tiles_alloc += tiles_alloc / 2;
+    }
+    if ((rc = ENS(f_cbf16, T * P.d8 * 2)) || (rc = ENS(f_tiles, sizeof(sb::TcTile) * (size_t)std::max<long long>(1, tiles_alloc))) ||
+        (rc = ENS(f_rowmeta, sizeof(sb::VisRowMeta) * (T + 256))))
       return rc;
     tc.rowmeta = f_rowmeta.as<sb::VisRowMeta>();
     tc.max_rows = max_nb * K;
@@ -827,10 +859,10 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     tc.a_rows = total;
     tc.b_rows = (long long)scene_cap * track_cap * K;
     if (!want_dense) {
-      if ((rc = ens(f_colmeta, sizeof(sb::VisColMeta) * (size_t)(std::max(col_total, hint_cols) + 256))) ||
-          (rc = ens(f_colb, 4 * (size_t)(std::max(col_total, hint_cols) + 256))) ||
-          (rc = ens(f_colvalid, (size_t)(std::max(col_total, hint_cols) + 256) / 8 + 16)) ||
-          (rc = ens(f_colgeo, sizeof(sb::VisColGeo) * (size_t)std::max<long long>(1, P.n_constraints > 0 ? std::max(col_total, hint_cols) : 1))))
+      if ((rc = ENS(f_colmeta, sizeof(sb::VisColMeta) * (size_t)(std::max(col_total, hint_cols) + 256))) ||
+          (rc = ENS(f_colb, 4 * (size_t)(std::max(col_total, hint_cols) + 256))) ||
+          (rc = ENS(f_colvalid, (size_t)(std::max(col_total, hint_cols) + 256) / 8 + 16)) ||
+          (rc = ENS(f_colgeo, sizeof(sb::VisColGeo) * (size_t)std::max<long long>(1, P.n_constraints > 0 ? std::max(col_total, hint_cols) : 1))))
         return rc;
       tc.colmeta = f_colmeta.as<sb::VisColMeta>();
       tc.colgeo = f_colgeo.as<sb::VisColGeo>();
@@ -844,14 +876,14 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       ws_ub = std::max(ws_ub, hs * (ht + 256) * ((hd + 127) / 128 * 128));
       blk_ub = std::max(blk_ub, hs * (ht + 256));
       slabs_ub = std::max(slabs_ub, hs * ((ht * K + cstep - 1) / cstep + 1));
-      if ((rc = ens(f_drowb, 4 * 5 * T)) || (rc = ens(f_dcolb, 4 * (size_t)std::max<long long>(1, blk_ub))) ||
-          (rc = ens(f_slabk, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))))
+      if ((rc = ENS(f_drowb, 4 * 5 * T)) || (rc = ENS(f_dcolb, 4 * (size_t)std::max<long long>(1, blk_ub))) ||
+          (rc = ENS(f_slabk, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))))
         return rc;
-      if ((rc = ens(f_ws, 4 * (size_t)std::max<long long>(1, ws_ub))) || (rc = ens(f_tmeta, sizeof(sb::DenseTrackMeta) * (size_t)std::max<long long>(1, blk_ub))) ||
-          (rc = ens(f_rowinfo, 8 * (size_t)std::max<long long>(1, blk_ub * K))) || (rc = ens(f_slabc, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))) ||
-          (rc = ens(f_slabm, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))) || (rc = ens(f_slabmask, 2 * 32 * (size_t)std::max<long long>(1, slabs_ub))) ||
-          (rc = ens(f_dscene, 4 * 6 * (size_t)n_scenes + 128)) || (rc = ens(f_maxc, sizeof(sb::VisPair) * (size_t)std::max<long long>(1, visl_alloc))) ||
-          (rc = ens(f_maxcval, 4 * (size_t)std::max<long long>(1, visl_alloc))))
+      if ((rc = ENS(f_ws, 4 * (size_t)std::max<long long>(1, ws_ub))) || (rc = ENS(f_tmeta, sizeof(sb::DenseTrackMeta) * (size_t)std::max<long long>(1, blk_ub))) ||
+          (rc = ENS(f_rowinfo, 8 * (size_t)std::max<long long>(1, blk_ub * K))) || (rc = ENS(f_slabc, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))) ||
+          (rc = ENS(f_slabm, 4 * 256 * (size_t)std::max<long long>(1, slabs_ub))) || (rc = ENS(f_slabmask, 2 * 32 * (size_t)std::max<long long>(1, slabs_ub))) ||
+          (rc = ENS(f_dscene, 4 * 6 * (size_t)n_scenes + 128)) || (rc = ENS(f_maxc, sizeof(sb::VisPair) * (size_t)std::max<long long>(1, visl_alloc))) ||
+          (rc = ENS(f_maxcval, 4 * (size_t)std::max<long long>(1, visl_alloc))))
         return rc;
       tc.cstep = cstep;
       tc.max_blocks = max_nb;
@@ -917,19 +949,19 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       // the filled set is smaller than this frame's sizing rule (hints changed?): re-copy instead of reallocating
       prefetched = false;
     }
-    if ((rc = ens(S.boxes, T * 24))) return rc;
+    if ((rc = ENS(S.boxes, T * 24))) return rc;
     f.in_boxes = S.boxes.as<float>();
     if (features && total > 0) {
-      if ((rc = ens(S.feat, T * (size_t)P.feature_dim * 4))) return rc;
+      if ((rc = ENS(S.feat, T * (size_t)P.feature_dim * 4))) return rc;
       f.in_feat = S.feat.as<float>();
       if (has_feature) {
-        if ((rc = ens(S.hasf, T))) return rc;
+        if ((rc = ENS(S.hasf, T))) return rc;
         f.in_hasf = S.hasf.as<unsigned char>();
       }
     }
-    if (quality && total > 0) { if ((rc = ens(S.quality, T * 4))) return rc; f.in_quality = S.quality.as<float>(); }
-    if (custom_ids && total > 0) { if ((rc = ens(S.custom, T * 8))) return rc; f.in_custom = S.custom.as<long long>(); }
-    if (own_area && total > 0) { if ((rc = ens(S.own, T * 4))) return rc; f.in_own = S.own.as<float>(); }
+    if (quality && total > 0) { if ((rc = ENS(S.quality, T * 4))) return rc; f.in_quality = S.quality.as<float>(); }
+    if (custom_ids && total > 0) { if ((rc = ENS(S.custom, T * 8))) return rc; f.in_custom = S.custom.as<long long>(); }
+    if (own_area && total > 0) { if ((rc = ENS(S.own, T * 4))) return rc; f.in_own = S.own.as<float>(); }
   }
   f.c_box = f_cbox.as<float>(); f.c_radius = f_cradius.as<float>(); f.c_conf = f_cconf.as<float>();
   f.c_vert = f_cvert.as<double>(); f.c_flags = f_cflags.as<unsigned char>(); f.c_norm2 = f_cnorm2.as<float>();
@@ -938,17 +970,17 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.new_count_all = f.new_count;
   f.feat_dst = P.is_visual ? f_featdst.as<int>() : nullptr;
   f.app_rank = f_apprank.as<int2>(); f.app_meta = f_appmeta.as<int4>();
-  if ((rc = ens(f_frameout, sizeof(int) * 3 * (size_t)n_scenes))) return rc;
+  if ((rc = ENS(f_frameout, sizeof(int) * 3 * (size_t)n_scenes))) return rc;
   f.frame_out = f_frameout.as<int>();
   f.c_bf16 = tc.use_tc ? f_cbf16.p : nullptr; f.scene_max = f_scene_max.as<unsigned int>();
   // sparse entry lists + per-scene counters (pos_cnt | vis_cnt | scene_mode | vis_mode | refine_next | dense_cnt | status),
   // zeroed every frame by frame_setup_kernel
   const size_t n_counters = 6 * (size_t)n_scenes + 4;
-  if ((rc = ens(f_poslist, sizeof(sb::PosEntry) * (size_t)std::max<long long>(1, std::max(posl_total, hint_dets * 32)))) ||
-      (rc = ens(f_counters, sizeof(int) * n_counters)))
+  if ((rc = ENS(f_poslist, sizeof(sb::PosEntry) * (size_t)std::max<long long>(1, std::max(posl_total, hint_dets * 32)))) ||
+      (rc = ENS(f_counters, sizeof(int) * n_counters)))
     return rc;
-  if (P.is_visual && ((rc = ens(f_pairs, sizeof(sb::VisPair) * (size_t)std::max<long long>(1, visl_alloc))) ||
-                      (rc = ens(f_visval, sizeof(float) * (size_t)std::max<long long>(1, visl_alloc)))))
+  if (P.is_visual && ((rc = ENS(f_pairs, sizeof(sb::VisPair) * (size_t)std::max<long long>(1, visl_alloc))) ||
+                      (rc = ENS(f_visval, sizeof(float) * (size_t)std::max<long long>(1, visl_alloc)))))
     return rc;
   f.pos_list = f_poslist.as<sb::PosEntry>();
   f.pos_cnt = f_counters.as<int>();
@@ -967,12 +999,12 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     f.o_ids = reinterpret_cast<unsigned long long*>(o.ids); f.o_epochs = o.epochs; f.o_lengths = o.lengths;
     f.o_vt = o.voting_types; f.o_pred = o.predicted_boxes; f.o_obs = o.observed_boxes;
   } else {
-    if (o.ids) { if ((rc = ens(o_ids, T * 8))) return rc; f.o_ids = o_ids.as<unsigned long long>(); }
-    if (o.epochs) { if ((rc = ens(o_epochs, T * 4))) return rc; f.o_epochs = o_epochs.as<unsigned int>(); }
-    if (o.lengths) { if ((rc = ens(o_lengths, T * 4))) return rc; f.o_lengths = o_lengths.as<unsigned int>(); }
-    if (o.voting_types) { if ((rc = ens(o_vt, T))) return rc; f.o_vt = o_vt.as<unsigned char>(); }
-    if (o.predicted_boxes) { if ((rc = ens(o_pred, T * 24))) return rc; f.o_pred = o_pred.as<float>(); }
-    if (o.observed_boxes) { if ((rc = ens(o_obs, T * 24))) return rc; f.o_obs = o_obs.as<float>(); }
+    if (o.ids) { if ((rc = ENS(o_ids, T * 8))) return rc; f.o_ids = o_ids.as<unsigned long long>(); }
+    if (o.epochs) { if ((rc = ENS(o_epochs, T * 4))) return rc; f.o_epochs = o_epochs.as<unsigned int>(); }
+    if (o.lengths) { if ((rc = ENS(o_lengths, T * 4))) return rc; f.o_lengths = o_lengths.as<unsigned int>(); }
+    if (o.voting_types) { if ((rc = ENS(o_vt, T))) return rc; f.o_vt = o_vt.as<unsigned char>(); }
+    if (o.predicted_boxes) { if ((rc = ENS(o_pred, T * 24))) return rc; f.o_pred = o_pred.as<float>(); }
+    if (o.observed_boxes) { if ((rc = ENS(o_obs, T * 24))) return rc; f.o_obs = o_obs.as<float>(); }
   }
   // Visual trackers on the tensor-core path evaluate the positional metric lazily: VisualVoting only consults it for
   // candidates the visual BestFit pass left undecided, against tracks that pass did not claim, so the order is
@@ -982,13 +1014,13 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   const bool full_costs = getenv("SB200_FULL_COSTS") != nullptr || getenv("SB200_NO_FORK") != nullptr;
   const bool fork = P.is_visual && tc.use_tc && tc.n_tiles > 0 && !full_costs;
   if (fork) {
-    if ((rc = ens(f_decided, T)) || (rc = ens(f_excl, (size_t)scene_cap * track_cap + 16)) || (rc = ens(f_prewin, T * 4))) return rc;
+    if ((rc = ENS(f_decided, T)) || (rc = ENS(f_excl, (size_t)scene_cap * track_cap + 16)) || (rc = ENS(f_prewin, T * 4))) return rc;
     f.decided = f_decided.as<unsigned char>();
     f.excl = f_excl.as<unsigned char>();
     f.pre_winner = f_prewin.as<int>();
   }
   const bool derive_own = P.is_visual && P.use_own_area && f.in_own == nullptr && total > 0;
-  if (derive_own && ((rc = ens(f_own, T * 4)) || (rc = ens(f_ownovf, 16 + T * sizeof(int2))))) return rc;
+  if (derive_own && ((rc = ENS(f_own, T * 4)) || (rc = ENS(f_ownovf, 16 + T * sizeof(int2))))) return rc;
 
   // ======================================================================== nothing below can fail for capacity reasons:
   // the request is committed (epochs, ring slot, bounds of the frames in flight)
@@ -1154,6 +1186,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   if (sin) { CU(cudaEventRecord(sin->ev_read, stream)); sin->read_pending = true; }
   const double ms_launch = since(t_begin);
   if (wait) rc = drain();
+  host_ms_total += since(t_begin);
+  host_calls += 1;
   if (trace && prefetched && sin && wait) {
     float cms = 0.0f;
     if (cudaEventElapsedTime(&cms, sin->ev0, sin->ev) == cudaSuccess)
@@ -1163,6 +1197,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   return rc;
 }
 
+#undef ENS
 // =============================================================================================== C ABI
 extern "C" {
 
@@ -1311,6 +1346,12 @@ int sb200_work_counters(sb200_tracker* t, uint64_t* out3 /* [4] */, double* ms7 
 }
 
 uint64_t sb200_launch_count(void) { return sb::launch_count(); }
+
+int sb200_host_counters(sb200_tracker* t, double* out3 /* [3] */) {
+  if (!t || !out3) return fail(SB200_ERR_INVALID, "bad arguments");
+  out3[0] = (double)t->host_calls; out3[1] = t->host_ms_total; out3[2] = t->host_ms_blocked;
+  return 0;
+}
 
 int sb200_prefetch_inputs(sb200_tracker* t, int32_t total, const float* boxes, const float* features,
                           const uint8_t* has_feature, const float* quality, const int64_t* custom_ids,

@@ -369,9 +369,9 @@ __device__ __forceinline__ float refine_block_sum(const float* av, const float* 
   return reduce_add8_tc(t);
 }
 
-template <bool COSINE, bool TAIL>
-__global__ void __launch_bounds__(RF_WARPS * 32) vis_refine_kernel(Params p, TrackStore ts, Frame f, int* nan_flag) {
-  __shared__ float s_bs[RF_WARPS][32][RF_PITCH];
+template <bool COSINE, bool TAIL, int RP>
+__global__ void __launch_bounds__(RF_WARPS * 32, RP == 32 ? 6 : 8) vis_refine_kernel(Params p, TrackStore ts, Frame f, int* nan_flag) {
+  __shared__ float s_bs[RF_WARPS][RP][RF_PITCH];
   const int scene = blockIdx.y;
   if (f.vis_mode[scene] != 0) return;  // survivor list overflowed: this scene is computed densely
   const SceneDesc sc = f.scenes[scene];
@@ -381,13 +381,13 @@ __global__ void __launch_bounds__(RF_WARPS * 32) vis_refine_kernel(Params p, Tra
   const int D = p.feature_dim;
   float (*bs)[RF_PITCH] = s_bs[w];
   float vmax = nanf("");
-  // warps claim 32 survivors at a time from the scene's counter: however many survive, the scene's warps finish together
+  // warps claim RP survivors at a time from the scene's counter: however many survive, the scene's warps finish together
   for (;;) {
     int i0 = 0;
-    if (lane == 0) i0 = atomicAdd(f.refine_next + scene, 32);
+    if (lane == 0) i0 = atomicAdd(f.refine_next + scene, RP);
     i0 = __shfl_sync(0xffffffffu, i0, 0);
     if (i0 >= n_pairs) break;
-    const int npair = min(32, n_pairs - i0);
+    const int npair = min(RP, n_pairs - i0);
     VisPair mine;
     mine.g = 0; mine.row = 0; mine.scene = 0; mine.outcol = 0;
     if (lane < npair) mine = f.vis_pairs[sc.vis_lbase + i0 + lane];
@@ -757,13 +757,20 @@ int launch_vis_refine(const Params& p, const TrackStore& ts, const Frame& f, int
     note_launch();
     return 0;
   }
+  // 16 survivors per claim: half the parked block sums of 32, eight CTAs per SM instead of six (0.182 vs 0.200 ms at cfg5);
+  // SB200_REFINE_PAIRS=32 selects the wider claim
+  static const bool rp16 = !(getenv("SB200_REFINE_PAIRS") != nullptr && atoi(getenv("SB200_REFINE_PAIRS")) == 32);
+#define SB_RF(C, T)                                                                        \
+  do {                                                                                     \
+    if (rp16) vis_refine_kernel<C, T, 16><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f, nan_flag); \
+    else vis_refine_kernel<C, T, 32><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f, nan_flag);      \
+  } while (0)
   if (p.visual_kind == 1) {
-    if (tail) vis_refine_kernel<true, true><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f, nan_flag);
-    else vis_refine_kernel<true, false><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f, nan_flag);
+    if (tail) SB_RF(true, true); else SB_RF(true, false);
   } else {
-    if (tail) vis_refine_kernel<false, true><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f, nan_flag);
-    else vis_refine_kernel<false, false><<<grid, RF_WARPS * 32, 0, st>>>(p, ts, f, nan_flag);
+    if (tail) SB_RF(false, true); else SB_RF(false, false);
   }
+#undef SB_RF
   note_launch();
   return 0;
 }

@@ -102,6 +102,12 @@ class Tracker:
                 "stage_ms": dict(zip(("prep", "positional_cost", "visual_cost", "voting", "apply"), map(float, ms[:5]))),
                 "vis_screen_ms": float(ms[5]), "vis_refine_ms": float(ms[6]), "tc_frames": int(ms[7])}
 
+    def host_counters(self):
+        """sb200_host_counters: calls of the predict entry points, wall ms inside them, ms of that blocked on the device."""
+        o = np.zeros(3, np.float64)
+        check(self._L.sb200_host_counters(self._h, ptr(o)))
+        return {"calls": int(o[0]), "ms_total": float(o[1]), "ms_blocked": float(o[2])}
+
     def prefetch_inputs(self, boxes, features=None, has_feature=None, quality=None, custom_ids=None, own_area=None):
         """sb200_prefetch_inputs: start the H2D copy of a future request.  The arrays must be the very objects later
         passed to predict_batch (same memory) and C-contiguous with the right dtype (no conversion copies)."""
