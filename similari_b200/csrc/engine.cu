@@ -235,7 +235,7 @@ struct sb200_tracker {
   } stg[2];
   int stg_last = 1;   // staging set used by the most recent predict
   DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_apprank, f_appmeta, f_frameout, f_decided, f_excl, f_prewin, f_own, f_ownovf, f_dyn, f_ws, f_tmeta, f_rowinfo, f_slabc, f_slabm, f_slabmask,
+      f_status, f_featdst, f_apprank, f_appmeta, f_posgq, f_frameout, f_decided, f_excl, f_prewin, f_own, f_ownovf, f_dyn, f_ws, f_tmeta, f_rowinfo, f_slabc, f_slabm, f_slabmask,
       f_dscene, f_maxc, f_maxcval, f_drowb, f_dcolb, f_slabk, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
@@ -253,7 +253,7 @@ struct sb200_tracker {
                    &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl, &f_prewin, &f_own, &f_ownovf, &f_dyn, &b_idc, &f_ws, &f_tmeta, &f_rowinfo, &f_slabc, &f_slabm, &f_slabmask, &f_dscene, &f_maxc, &f_maxcval, &f_drowb, &f_dcolb, &f_slabk,
                    &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
                    &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
-                   &f_featdst, &f_apprank, &f_appmeta, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
+                   &f_featdst, &f_apprank, &f_appmeta, &f_posgq, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
     for (DBuf* b : all) b->release();
     if (stream) cudaStreamSynchronize(stream);
     h_small.release();
@@ -313,7 +313,8 @@ struct sb200_tracker {
     if ((rc = regrow(b_pred, &ts.pred, 6, ns, nt))) return rc;
     if ((rc = regrow(b_obs, &ts.obs, 6, ns, nt))) return rc;
     if ((rc = regrow(b_radius, &ts.radius, 1, ns, nt))) return rc;
-    if ((rc = regrow(b_kst, &ts.kst, sb::kStateFloats, ns, nt))) return rc;
+    if ((rc = regrow(b_kst, &ts.kst, sb::kStateStride, ns, nt))) return rc;
+    ts.kst_stride = sb::kStateStride;
     if (P.positional_kind == SB200_POS_IOU)
       if ((rc = regrow(b_vert, &ts.vert, 8, ns, nt))) return rc;
     if (hist_len > 1) {
@@ -383,7 +384,7 @@ struct sb200_tracker {
 
   int ensure_wasted(int64_t need) {
     if (need <= wb.cap) return 0;
-    int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(1024, (int64_t)wb.cap * 2));
+    int64_t ncap = std::max<int64_t>(need, std::max<int64_t>(1024, (int64_t)wb.cap * 3));
     // wasted records are drained by sb200_wasted; growing preserves the pending ones
     DBuf nid, nsc, nep, nle, npr, nob, nhp, nho;
     int rc;
@@ -739,7 +740,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       // a full ring: kDepth frames in flight plus this one, each bounded by the live tracks plus every detection queued before it
       const long long dets = std::max<long long>(total, (long long)std::max(opts.max_scenes_hint, n_scenes) * opts.max_dets_per_scene_hint);
       const long long ring_need = (long long)(kDepth + 1) * (live_ub + (long long)kDepth * dets);
-      if ((rc = ensure_wasted(wasted_count + std::max<long long>(ring_need, 2 * pipe_need) + 1))) return rc;
+      // and the records already waiting for collection doubled: a caller that collects rarely pays for few regrows
+      if ((rc = ensure_wasted(2 * wasted_count + std::max<long long>(ring_need, 2 * pipe_need) + 1))) return rc;
     }
     if (!b_idc.p) {
       if ((rc = b_idc.ensure(8))) return rc;
@@ -990,6 +992,15 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   f.refine_next = f.pos_cnt + 4 * n_scenes;
   f.status = f.pos_cnt + 5 * n_scenes;
   f.dense_cnt = f.pos_cnt + 6 * n_scenes;
+  // SB200_POS_GQ=1 (experiment): gated positional pairs of the frame in one queue, evaluated by a kernel of their own
+  if (getenv("SB200_POS_GQ") != nullptr) {
+    size_t gq_cap = (size_t)std::min<long long>(std::max<long long>(1, std::max<long long>(total, hint_dets) * 24), 1ll << 26);
+    if (const char* e = getenv("SB200_POS_GQ_CAP")) gq_cap = (size_t)std::max(1, atoi(e));   // tests: force the overflow path
+    if ((rc = ENS(f_posgq, 8 * gq_cap))) return rc;
+    f.pos_gq = f_posgq.as<int2>();
+    f.pos_gq_cnt = f.pos_cnt + 6 * n_scenes + 1;
+    f.pos_gq_cap = (int)gq_cap;
+  }
   f.vis_pairs = f_pairs.as<sb::VisPair>();
   f.vis_val = f_visval.as<float>();
   // outputs
@@ -1168,7 +1179,8 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     CU(cudaMemcpyAsync(ho + dyn_offset(n_scenes), f_dyn.p, sizeof(sb::FrameDyn), cudaMemcpyDeviceToHost, stream));
     CU(cudaMemcpyAsync(ho + dyn_offset(n_scenes) + sizeof(sb::FrameDyn), f.dense_cnt, 4, cudaMemcpyDeviceToHost, stream));
   }
-  if (trace && tc.dense && tc.n_tiles > 0) {
+  static const bool trace_dense = trace && atoi(getenv("SB200_TRACE")) >= 2;   // synchronises: level 2 only
+  if (trace_dense && tc.dense && tc.n_tiles > 0) {
     int hc[8] = {0};
     int vc = 0;
     CU(cudaMemcpyAsync(hc, tc.dbg_counts, sizeof(hc), cudaMemcpyDeviceToHost, stream));
@@ -1557,7 +1569,7 @@ static int64_t dump_scene(sb200_tracker* t, uint64_t scene_id, int64_t cap, bool
   CU(cudaMemcpyAsync(hle.data(), t->ts.length + base, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(hpr.data(), t->ts.pred + base * 6, 24 * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(hob.data(), t->ts.obs + base * 6, 24 * (size_t)n, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(hst.data(), t->ts.kst + base * 30, 120 * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpy2DAsync(hst.data(), 120, t->ts.kst + base * sb::kStateStride, 4 * (size_t)sb::kStateStride, 120, (size_t)n, cudaMemcpyDeviceToHost, st));
   if (t->P.is_visual) CU(cudaMemcpyAsync(hfc.data(), t->ts.feat_cnt + base, (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   int64_t k = 0;

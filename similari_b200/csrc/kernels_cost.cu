@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(TN * TY) pos_cost_kernel(Params p, TrackStore 
   float mean5[5], l5[5];
   double tv[8];
   if (POS == 0) {
-    const float* st = ts.kst + ti * kStateFloats;
+    const float* st = ts.kst + ti * ts.kst_stride;
     const float hh = st[4];
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -235,6 +235,7 @@ __global__ void pos_fill_none_kernel(Frame f, long long total4, long long total)
 }
 
 constexpr int PS_QCAP = 4096;
+constexpr int PS_UND = 96;     // lazy scan: up to this many open candidates take the unsorted path
 
 // exact metric of one gated (candidate, track) pair; valid results go to the dense matrix and the sparse list
 template <int POS>
@@ -246,7 +247,7 @@ __device__ __forceinline__ void pos_eval_pair(const Params& p, const TrackStore&
   const size_t ti = tbase + n;
   float v = nanf("");
   if (POS == 0) {
-    const float* st = ts.kst + ti * kStateFloats;
+    const float* st = ts.kst + ti * ts.kst_stride;
     float mean5[5], l5[5];
     const float hh = st[4];
 #pragma unroll
@@ -285,15 +286,54 @@ __device__ __forceinline__ void pos_eval_pair(const Params& p, const TrackStore&
   }
 }
 
+// Hands the CTA's gated pairs to the frame's global queue (one reservation per CTA, coalesced copy); without a global queue,
+// or when it is full, the CTA evaluates them itself, one pair per thread.  All threads of the CTA call this.
+template <int POS>
+__device__ __forceinline__ void pos_flush_queue(const Params& p, const TrackStore& ts, const Frame& f, const SceneDesc& sc,
+                                                int sidx, size_t tbase, const int2* queue, int qn, bool use_gq, float* out,
+                                                bool wdense, bool wlist, int* s_base) {
+  const int tid = threadIdx.x;
+  int fit = 0;
+  if (use_gq) {
+    // one reservation per CTA; what does not fit any more (the counter only ever grows: no holes) stays with the CTA
+    if (tid == 0) *s_base = qn > 0 ? atomicAdd(f.pos_gq_cnt, qn) : 0;
+    __syncthreads();
+    const int b = *s_base;
+    fit = b >= 0 ? max(0, min(qn, f.pos_gq_cap - b)) : 0;
+    for (int e = tid; e < fit; e += blockDim.x) f.pos_gq[b + e] = make_int2(sidx, (queue[e].x << 16) | queue[e].y);
+  }
+  for (int e = fit + tid; e < qn; e += blockDim.x) {
+    const int2 q = queue[e];
+    pos_eval_pair<POS>(p, ts, f, sc, sidx, tbase, q.x, q.y, out, wdense, wlist);
+  }
+  __syncthreads();
+}
+
+// the pairs of the frame's global queue, one per thread
+template <int POS>
+__global__ void __launch_bounds__(256) pos_eval_kernel(Params p, TrackStore ts, Frame f, int wdense_i, int wlist_i) {
+  const int cnt = min(*f.pos_gq_cnt, f.pos_gq_cap);
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += gridDim.x * blockDim.x) {
+    const int2 q = f.pos_gq[e];
+    const SceneDesc& sc = f.scenes[q.x];
+    pos_eval_pair<POS>(p, ts, f, sc, q.x, (size_t)sc.slot * ts.track_cap, q.y >> 16, q.y & 0xffff, f.pos + sc.pos_off, wdense_i != 0,
+                       wlist_i != 0);
+  }
+}
+
 // lazy_pass < 0: plain scan.  0: lazy (visual trackers) -- in scenes whose visual lists are complete only candidates the
 // visual pass left undecided and tracks it did not claim take part; 1: full scan of the scenes that ended in dense mode
 // although their visual lists were complete (their first scan was a lazy one).
 template <int POS>
-__global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, TrackStore ts, Frame f, int lazy_pass) {
+__global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, TrackStore ts, Frame f, int lazy_pass, int use_gq_i) {
   extern __shared__ __align__(16) unsigned char ps_smem[];
   __shared__ float s_rmax[PS_THREADS / 32];
   __shared__ int s_bad;
   __shared__ int s_qn;
+  __shared__ int s_nund;
+  __shared__ int s_gbase;
+  __shared__ int s_und[PS_UND];
+  const bool use_gq = use_gq_i != 0 && f.pos_gq != nullptr;
   const int sidx = blockIdx.x;
   const SceneDesc sc = f.scenes[sidx];
   const int N = sc.n, M = sc.m;
@@ -319,6 +359,48 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const size_t tbase = (size_t)sc.slot * ts.track_cap;
   if (tid == 0) s_bad = 0;
+  float* out = f.pos + sc.pos_off;
+  if (lazy) {
+    // The visual pass usually leaves a handful of candidates open (new objects, ambiguous votes).  For those the sort
+    // costs more than it saves: every (open candidate, track) pair goes through the same cheap gates directly -- the
+    // x-window of the sorted path only ever removes pairs these gates reject -- and the survivors are evaluated as below.
+    if (tid == 0) { s_nund = 0; s_qn = 0; }
+    __syncthreads();
+    for (int m = m_begin + tid; m < m_end; m += PS_THREADS)
+      if (!f.decided[sc.det_base + m]) {
+        const int k = atomicAdd(&s_nund, 1);
+        if (k < PS_UND) s_und[k] = m;
+      }
+    __syncthreads();
+    const int nund = s_nund;
+    if (nund == 0) return;
+    if (nund <= PS_UND) {
+      for (int n = tid; n < N; n += PS_THREADS) {
+        const float2 xy = *reinterpret_cast<const float2*>(ts.pred + (tbase + n) * 6);
+        kx[n] = xy.x; sy[n] = xy.y; sr[n] = ts.radius[tbase + n]; sep[n] = ts.epoch[tbase + n];
+        kidx[n] = excl[n];
+      }
+      __syncthreads();
+      int2* queue = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(sep + N) + 7) & ~(uintptr_t)7);
+      for (int c = wid; c < nund; c += PS_THREADS / 32) {   // a warp per open candidate, lanes over the tracks
+        const int m = s_und[c];
+        const int g = sc.det_base + m;
+        const float cx = f.c_box[(size_t)g * 6], cy = f.c_box[(size_t)g * 6 + 1], cr = f.c_radius[g];
+        for (int n = lane; n < N; n += 32) {
+          if (kidx[n]) continue;   // claimed by the visual pass
+          const float tx = kx[n], ty = sy[n], tr = sr[n];
+          if (!compat_ok(p, sc.epoch, sep[n], cx, cy, cr, tx, ty, tr) || too_far(cx, cy, cr, tx, ty, tr)) continue;
+          const int slot = atomicAdd(&s_qn, 1);
+          if (slot < PS_QCAP) queue[slot] = make_int2(m, n);
+          else pos_eval_pair<POS>(p, ts, f, sc, sidx, tbase, m, n, out, wdense, wlist);
+        }
+      }
+      __syncthreads();
+      pos_flush_queue<POS>(p, ts, f, sc, sidx, tbase, queue, min(s_qn, PS_QCAP), use_gq, out, wdense, wlist, &s_gbase);
+      return;
+    }
+    __syncthreads();
+  }
   float rmax = 0.0f;
   for (int n = tid; n < Np; n += PS_THREADS) {
     if (n < N) {
@@ -361,7 +443,6 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
     sep[i] = ts.epoch[tbase + n];
   }
   __syncthreads();
-  float* out = f.pos + sc.pos_off;
   if (lazy_pass == 1 && !f.pos_dense_all) {   // this CTA's candidate rows of the dense matrix: None everywhere first
     const float qnan = nanf("");
     for (long long i = (long long)m_begin * N + tid; i < (long long)m_end * N; i += PS_THREADS) out[i] = qnan;
@@ -395,18 +476,13 @@ __global__ void __launch_bounds__(PS_THREADS, 2) pos_scan_kernel(Params p, Track
         const float tx = kx[i], ty = sy[i], tr = sr[i];
         if (!compat_ok(p, sc.epoch, sep[i], cx, cy, cr, tx, ty, tr) || too_far(cx, cy, cr, tx, ty, tr)) continue;
         const int slot = atomicAdd(&s_qn, 1);
-        if (slot < PS_QCAP) queue[slot] = make_int2(m, i);
+        if (slot < PS_QCAP) queue[slot] = make_int2(m, kidx[i]);
         else pos_eval_pair<POS>(p, ts, f, sc, sidx, tbase, m, kidx[i], out, wdense, wlist);   // queue full: evaluate in place
       }
     }
     __syncthreads();
-    // ---- phase 2: the survivors, one per thread (no divergence on the gate)
-    const int qn = min(s_qn, PS_QCAP);
-    for (int e = tid; e < qn; e += PS_THREADS) {
-      const int2 q = queue[e];
-      pos_eval_pair<POS>(p, ts, f, sc, sidx, tbase, q.x, kidx[q.y], out, wdense, wlist);
-    }
-    __syncthreads();
+    // ---- phase 2: the survivors go to the frame's queue (or, without one, are evaluated here, one per thread)
+    pos_flush_queue<POS>(p, ts, f, sc, sidx, tbase, queue, min(s_qn, PS_QCAP), use_gq, out, wdense, wlist, &s_gbase);
   }
 }
 
@@ -440,14 +516,23 @@ static void pos_scan_impl(const Params& p, const TrackStore& ts, const Frame& f,
   // two CTAs fit an SM: with fewer scenes than that, several CTAs per scene (each at least 64 candidates)
   int nsplit = std::max(1, std::min(std::min(16, (max_m + 63) / 64), (2 * 148) / std::max(1, n_scenes)));
   dim3 grid(n_scenes, nsplit);
+  // optional: the gated pairs of passes -1 / 0 go to one queue of the frame and pos_eval_kernel evaluates them
+  // (SB200_POS_GQ=1; measured slower on B200 -- cfg4 positional stage 0.142 vs 0.063 ms, cfg2 0.078 vs 0.070 -- the pairs of
+  // a scene evaluate faster next to the shared-memory copy of its tracks than spread over the device: kept for experiments)
+  static const bool gq_on = getenv("SB200_POS_GQ") != nullptr && getenv("SB200_POS_GQ")[0] == '1';
+  const int use_gq = (gq_on && f.pos_gq != nullptr && lazy_pass != 1) ? 1 : 0;
+  const int wdense = (f.pos_dense_all || lazy_pass == 1) ? 1 : 0, wlist = lazy_pass != 1 ? 1 : 0;
   if (p.positional_kind == 0) {
     cudaFuncSetAttribute(pos_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pos_scan_kernel<0><<<grid, PS_THREADS, smem, st>>>(p, ts, f, lazy_pass);
+    pos_scan_kernel<0><<<grid, PS_THREADS, smem, st>>>(p, ts, f, lazy_pass, use_gq);
+    note_launch();
+    if (use_gq) { pos_eval_kernel<0><<<148 * 8, 256, 0, st>>>(p, ts, f, wdense, wlist); note_launch(); }
   } else {
     cudaFuncSetAttribute(pos_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    pos_scan_kernel<1><<<grid, PS_THREADS, smem, st>>>(p, ts, f, lazy_pass);
+    pos_scan_kernel<1><<<grid, PS_THREADS, smem, st>>>(p, ts, f, lazy_pass, use_gq);
+    note_launch();
+    if (use_gq) { pos_eval_kernel<1><<<148 * 8, 256, 0, st>>>(p, ts, f, wdense, wlist); note_launch(); }
   }
-  note_launch();
 }
 
 void launch_pos_scan(const Params& p, const TrackStore& ts, const Frame& f, int n_scenes, int max_m, int max_n,

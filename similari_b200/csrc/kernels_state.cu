@@ -20,6 +20,11 @@ constexpr int AT = 512;
 __device__ __forceinline__ void write_box(float* dst, const Box& b) {
   dst[0] = b.xc; dst[1] = b.yc; dst[2] = b.angle; dst[3] = b.aspect; dst[4] = b.height; dst[5] = b.conf;
 }
+// the store's own box rows (24-byte rows of a 256-byte aligned allocation): three 8-byte stores
+__device__ __forceinline__ void write_box_row(float* dst, const Box& b) {
+  float2* d2 = reinterpret_cast<float2*>(dst);
+  d2[0] = make_float2(b.xc, b.yc); d2[1] = make_float2(b.angle, b.aspect); d2[2] = make_float2(b.height, b.conf);
+}
 
 // Phase 1 of apply (one CTA per scene): rank of every new-track candidate among the scene's new candidates (candidate
 // order), the scene of every detection, and the scene's counters.  The per-detection work is phase 2, one thread each.
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(256) apply_kernel(Params p, TrackStore ts, Fra
       ts.length[idx] = 1;
       ts.vt[idx] = -1;
       o_id = tid64; o_len = 1; o_vt = -1;
-      write_box(ts.obs + idx * 6, raw);
+      write_box_row(ts.obs + idx * 6, raw);
       if (p.is_visual) {
         ts.obs_n[idx] = 1;
         ts.obs_phys[idx * K] = 0;
@@ -148,7 +153,17 @@ __global__ void __launch_bounds__(256) apply_kernel(Params p, TrackStore ts, Fra
       idx = (size_t)sc.slot * ts.track_cap + win;
       // every load of the merge first (one round trip to memory), then the arithmetic, then the stores
 #pragma unroll
-      for (int i = 0; i < kStateFloats; ++i) st2[i] = ts.kst[idx * kStateFloats + i];
+      if (ts.kst_stride == kStateStride) {   // 128-byte rows: eight 16-byte loads
+        const float4* r4 = reinterpret_cast<const float4*>(ts.kst + idx * kStateStride);
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = r4[i];
+#pragma unroll
+        for (int i = 0; i < kStateFloats; ++i) st2[i] = reinterpret_cast<const float*>(v)[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < kStateFloats; ++i) st2[i] = ts.kst[idx * ts.kst_stride + i];
+      }
       const unsigned int len0 = ts.length[idx];
       o_id = ts.id[idx];
       int on = 0;
@@ -171,7 +186,7 @@ __global__ void __launch_bounds__(256) apply_kernel(Params p, TrackStore ts, Fra
       pred = state_box(st, cb.conf);
       o_len = len0 + 1;
       ts.length[idx] = o_len;
-      write_box(ts.obs + idx * 6, cb);
+      write_box_row(ts.obs + idx * 6, cb);
       if (p.is_visual) {
         o_vt = (signed char)f.c_vt[g];
         ts.vt[idx] = o_vt;
@@ -223,19 +238,34 @@ __global__ void __launch_bounds__(256) apply_kernel(Params p, TrackStore ts, Fra
     }
     ts.epoch[idx] = sc.epoch;
     ts.custom[idx] = custom;
+    if (ts.kst_stride == kStateStride) {
+      float4 v[8];
 #pragma unroll
-    for (int i = 0; i < kStateFloats; ++i) ts.kst[idx * kStateFloats + i] = st[i];
-    write_box(ts.pred + idx * 6, pred);
+      for (int i = 0; i < 32; ++i) reinterpret_cast<float*>(v)[i] = i < kStateFloats ? st[i] : 0.0f;
+      float4* r4 = reinterpret_cast<float4*>(ts.kst + idx * kStateStride);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r4[i] = v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < kStateFloats; ++i) ts.kst[idx * ts.kst_stride + i] = st[i];
+    }
+    write_box_row(ts.pred + idx * 6, pred);
     ts.radius[idx] = box_radius(pred.aspect, pred.height);
-    if (p.positional_kind == 1) box_vertices(pred.xc, pred.yc, pred.angle, pred.aspect, pred.height, ts.vert + idx * 8);
+    if (p.positional_kind == 1) {
+      double vx[8];
+      box_vertices(pred.xc, pred.yc, pred.angle, pred.aspect, pred.height, vx);
+      double2* v2 = reinterpret_cast<double2*>(ts.vert + idx * 8);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v2[i] = make_double2(vx[2 * i], vx[2 * i + 1]);
+    }
     if (f.feat_dst) f.feat_dst[g] = fdst;
     if (ts.hist_len > 1) {   // update_history: observation number o_len - 1 goes to ring slot (o_len - 1) % hist_len
       const size_t hslot = (idx * ts.hist_len + (size_t)((o_len - 1u) % (unsigned int)ts.hist_len)) * 6;
-      write_box(ts.hist_pred + hslot, pred);
+      write_box_row(ts.hist_pred + hslot, pred);
       if (isnew) {
         const float* rb2 = f.in_boxes + (size_t)g * 6;
-        write_box(ts.hist_obs + hslot, Box{rb2[0], rb2[1], rb2[2], rb2[3], rb2[4], rb2[5]});
-      } else write_box(ts.hist_obs + hslot, cb);
+        write_box_row(ts.hist_obs + hslot, Box{rb2[0], rb2[1], rb2[2], rb2[3], rb2[4], rb2[5]});
+      } else write_box_row(ts.hist_obs + hslot, cb);
     }
     // SortTrack (src/trackers/sort.rs:286-311)
     if (f.o_ids) f.o_ids[g] = o_id;
@@ -478,7 +508,7 @@ __global__ void __launch_bounds__(WT) waste_kernel(Params p, TrackStore ts, cons
   }
   compact_rows(ts.pred, base, 6, s_dst, first, n);
   compact_rows(ts.obs, base, 6, s_dst, first, n);
-  compact_rows(ts.kst, base, kStateFloats, s_dst, first, n);
+  compact_rows(ts.kst, base, ts.kst_stride, s_dst, first, n);
   if (p.positional_kind == 1) compact_rows(ts.vert, base, 8, s_dst, first, n);
   if (ts.hist_len > 1) {
     compact_rows(ts.hist_pred, base, ts.hist_len * 6, s_dst, first, n);

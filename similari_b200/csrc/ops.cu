@@ -110,6 +110,7 @@ int sb200_sort_cost_matrix(int32_t positional_kind, float iou_threshold, float m
   ts.radius = sc.alloc<float>(n);
   ts.epoch = sc.alloc<unsigned int>(n);
   ts.vert = sc.alloc<double>((size_t)n * 8);
+  ts.kst_stride = 30;
   ts.kst = track_states30 ? sc.upload(track_states30, (size_t)n * 30) : sc.alloc<float>((size_t)n * 30, true);
   sb::Frame f;
   memset(&f, 0, sizeof(f));

@@ -20,6 +20,7 @@ namespace sb {
 
 constexpr int kMaxConstraints = 8;
 constexpr int kMaxObs = 8;  // visual_max_observations supported on device (reference default 5)
+constexpr int kStateStride = 32;   // floats per Kalman state row in the tracker's store (kStateFloats padded to 128 bytes)
 constexpr int kMaxHist = 64;  // box history kept per track on the device (history_length above it, or 0 = unlimited, is capped)
 
 struct Params {  // immutable per tracker, passed by value to kernels
@@ -95,7 +96,8 @@ struct TrackStore {
   float* pred;           // [idx][6] last predicted (posterior) box == observation attr box
   float* obs;            // [idx][6] last observed box
   float* radius;         // [idx]
-  float* kst;            // [idx][30]
+  float* kst;            // [idx][kst_stride]: 30 state floats per track (8 mean + 8x8 covariance upper part ... see sb_math.cuh)
+  int kst_stride;        // floats per row: 32 in the tracker's store (128-byte rows, 16-byte vector access), 30 for caller rows
   double* vert;          // [idx][8] vertex cache (IoU mode)
   // box history (SortAttributes::update_history, src/trackers/sort.rs:157-171): the last hist_len observed / predicted boxes
   // of every track as a ring, observation number j (0-based) in slot j % hist_len; null unless history_length > 1
@@ -181,6 +183,9 @@ struct Frame {  // per-request transient device buffers (a request may be proces
   unsigned char* excl;     // [slot * track_cap + n] track was claimed by the visual pass
   int* pre_winner;         // [total] the pre-pass's decision: track index the candidate won, -1 = decided as a new track
   int* dense_cnt;          // [1] scenes of the request in dense mode (null: unknown); lets the dense kernels leave at once
+  int2* pos_gq;            // gated (candidate, track) pairs of the whole frame: x = scene, y = m << 16 | n (null: evaluate in the scan kernel)
+  int* pos_gq_cnt;         // [1] entries of pos_gq (zeroed with the frame counters)
+  int pos_gq_cap;
   int* refine_next;        // [n_scenes] next unclaimed survivor of the scene (the refinement's warps claim 32 at a time)
   const int* dense_bad;    // [n_scenes] dense tensor-core path only: != 0 sends the scene to the exact SIMT kernels
   // outputs (device), any may be null
