@@ -519,7 +519,8 @@ static void pos_scan_impl(const Params& p, const TrackStore& ts, const Frame& f,
   // optional: the gated pairs of passes -1 / 0 go to one queue of the frame and pos_eval_kernel evaluates them
   // (SB200_POS_GQ=1; measured slower on B200 -- cfg4 positional stage 0.142 vs 0.063 ms, cfg2 0.078 vs 0.070 -- the pairs of
   // a scene evaluate faster next to the shared-memory copy of its tracks than spread over the device: kept for experiments)
-  static const bool gq_on = getenv("SB200_POS_GQ") != nullptr && getenv("SB200_POS_GQ")[0] == '1';
+  const char* gq_env = getenv("SB200_POS_GQ");   // read per launch: the parity test switches it on inside a running process
+  const bool gq_on = gq_env != nullptr && gq_env[0] == '1';
   const int use_gq = (gq_on && f.pos_gq != nullptr && lazy_pass != 1) ? 1 : 0;
   const int wdense = (f.pos_dense_all || lazy_pass == 1) ? 1 : 0, wlist = lazy_pass != 1 ? 1 : 0;
   if (p.positional_kind == 0) {
