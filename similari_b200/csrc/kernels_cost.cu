@@ -53,43 +53,55 @@ __device__ __forceinline__ float reduce_add8(const float* t) {
 // One warp per detection: squared norm in the reference's order (per 8-lane block reduce_add, blocks accumulated
 // sequentially) and, when the tensor-core screen will run, the BF16 operand copy of the row -- the feature row is
 // read from HBM once for both.
-__global__ void cand_norm_kernel(Params p, Frame f, __nv_bfloat16* bf16_out) {
+__global__ void cand_norm_kernel(Params p, Frame f, __nv_bfloat16* __restrict__ bf16_out) {
   int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (w >= f.total) return;
   w += f.det0;
   const int nblk = p.d8 / 8;
-  const float* row = f.in_feat + (size_t)w * p.feature_dim;
+  const float* __restrict__ row = f.in_feat + (size_t)w * p.feature_dim;
   const bool vec = (p.feature_dim % 4 == 0) && (reinterpret_cast<uintptr_t>(f.in_feat) & 15) == 0;
   float acc = 0.0f;
-  for (int base = 0; base < nblk; base += 32) {
-    int blk = base + lane;
-    float bs = 0.0f;
-    if (blk < nblk) {
-      float x[8];
-      if (vec && blk * 8 + 8 <= p.feature_dim) {
-        const float4 a = *reinterpret_cast<const float4*>(row + blk * 8);
-        const float4 b = *reinterpret_cast<const float4*>(row + blk * 8 + 4);
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-      } else {
+  // two rounds of 32 blocks per step: the loads of both are issued before anything waits for them (2 KB in flight per warp)
+  for (int base = 0; base < nblk; base += 64) {
+    float x[2][8];
+    bool have[2];
 #pragma unroll
-        for (int l = 0; l < 8; ++l) { int d = blk * 8 + l; x[l] = d < p.feature_dim ? row[d] : 0.0f; }
-      }
-      float t[8];
+    for (int h = 0; h < 2; ++h) {
+      const int blk = base + h * 32 + lane;
+      have[h] = blk < nblk;
+      if (have[h]) {
+        if (vec && blk * 8 + 8 <= p.feature_dim) {
+          const float4 a = __ldcs(reinterpret_cast<const float4*>(row + blk * 8));
+          const float4 b = __ldcs(reinterpret_cast<const float4*>(row + blk * 8 + 4));
+          x[h][0] = a.x; x[h][1] = a.y; x[h][2] = a.z; x[h][3] = a.w; x[h][4] = b.x; x[h][5] = b.y; x[h][6] = b.z; x[h][7] = b.w;
+        } else {
 #pragma unroll
-      for (int l = 0; l < 8; ++l) t[l] = x[l] * x[l];
-      bs = reduce_add8(t);
-      if (bf16_out) {
-        __nv_bfloat162 h[4];
-#pragma unroll
-        for (int l = 0; l < 4; ++l) h[l] = __floats2bfloat162_rn(x[2 * l], x[2 * l + 1]);
-        *reinterpret_cast<uint4*>(bf16_out + (size_t)w * p.d8 + blk * 8) = *reinterpret_cast<uint4*>(h);
+          for (int l = 0; l < 8; ++l) { int d = blk * 8 + l; x[h][l] = d < p.feature_dim ? row[d] : 0.0f; }
+        }
       }
     }
-    int cnt = min(32, nblk - base);
-    for (int j = 0; j < cnt; ++j) {
-      float v = __shfl_sync(0xffffffffu, bs, j);
-      acc = acc + v;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float bs = 0.0f;
+      if (have[h]) {
+        const int blk = base + h * 32 + lane;
+        float t[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) t[l] = x[h][l] * x[h][l];
+        bs = reduce_add8(t);
+        if (bf16_out) {
+          __nv_bfloat162 hh[4];
+#pragma unroll
+          for (int l = 0; l < 4; ++l) hh[l] = __floats2bfloat162_rn(x[h][2 * l], x[h][2 * l + 1]);
+          *reinterpret_cast<uint4*>(bf16_out + (size_t)w * p.d8 + blk * 8) = *reinterpret_cast<uint4*>(hh);
+        }
+      }
+      const int cnt = min(32, nblk - (base + h * 32));   // <= 0 for a round past the end
+      for (int j = 0; j < cnt; ++j) {
+        float v = __shfl_sync(0xffffffffu, bs, j);
+        acc = acc + v;
+      }
     }
   }
   if (lane == 0) f.c_norm2[w] = acc;

@@ -490,7 +490,11 @@ __global__ void __launch_bounds__(WT) waste_kernel(Params p, TrackStore ts, cons
         if (p.is_visual) {
           v_on = ts.obs_n[t]; v_fc = ts.feat_cnt[t];
           if (arena) v_fb = ts.fblk[t];
-          for (int k = 0; k < K; ++k) { v_ph[k] = ts.obs_phys[t * K + k]; v_hf[k] = ts.obs_hasf[t * K + k]; v_q[k] = ts.obs_q[t * K + k]; }
+          for (int k = 0; k < K; ++k) {   // slots at and beyond obs_n were never written
+            const bool have = k < (int)v_on;
+            v_ph[k] = have ? ts.obs_phys[t * K + k] : (unsigned char)0; v_hf[k] = have ? ts.obs_hasf[t * K + k] : (unsigned char)0;
+            v_q[k] = have ? ts.obs_q[t * K + k] : 0.0f;
+          }
         }
       } else d = -1;
     }
