@@ -279,11 +279,14 @@ struct sb200_tracker {
 
   // (re)allocates the track store for scene_cap x track_cap rows, preserving the live rows
   template <typename T>
-  int regrow(DBuf& b, T** field, int width, int new_scenes, int new_tracks) {
+  int regrow(DBuf& b, T** field, int width, int new_scenes, int new_tracks, bool zero = false) {
     size_t row = (size_t)width * sizeof(T);
     DBuf nb;
     int rc = nb.ensure(std::max<size_t>(1, (size_t)new_scenes * new_tracks * row));
     if (rc) return rc;
+    // rows that are moved whole although only partly written (the history rings of short tracks) start out defined
+    if (zero && cudaMemsetAsync(nb.p, 0, std::max<size_t>(1, (size_t)new_scenes * new_tracks * row), stream) != cudaSuccess)
+      return fail(SB200_ERR_CUDA, "store regrow memset failed");
     if (b.p && scene_cap > 0 && track_cap > 0) {
       cudaError_t e = cudaMemcpy2DAsync(nb.p, (size_t)new_tracks * row, b.p, (size_t)track_cap * row,
                                         (size_t)std::min(track_cap, new_tracks) * row, (size_t)scene_cap,
@@ -318,8 +321,8 @@ struct sb200_tracker {
     if (P.positional_kind == SB200_POS_IOU)
       if ((rc = regrow(b_vert, &ts.vert, 8, ns, nt))) return rc;
     if (hist_len > 1) {
-      if ((rc = regrow(b_hpred, &ts.hist_pred, 6 * hist_len, ns, nt))) return rc;
-      if ((rc = regrow(b_hobs, &ts.hist_obs, 6 * hist_len, ns, nt))) return rc;
+      if ((rc = regrow(b_hpred, &ts.hist_pred, 6 * hist_len, ns, nt, true))) return rc;
+      if ((rc = regrow(b_hobs, &ts.hist_obs, 6 * hist_len, ns, nt, true))) return rc;
       ts.hist_len = hist_len;
     }
     if (P.is_visual) {

@@ -462,7 +462,9 @@ __global__ void __launch_bounds__(WT) waste_kernel(Params p, TrackStore ts, cons
       for (int c = 0; c < 6; ++c) { wb.pred[(size_t)o * 6 + c] = ts.pred[(base + j) * 6 + c]; wb.obs[(size_t)o * 6 + c] = ts.obs[(base + j) * 6 + c]; }
       if (ts.hist_len > 1) {
         const int hw = ts.hist_len * 6;
-        for (int c = 0; c < hw; ++c) {
+        // observation j lives in ring slot j % hist_len: a track shorter than the ring has written slots [0, length) only
+        const int hv = (int)min((unsigned int)ts.hist_len, ts.length[base + j]) * 6;
+        for (int c = 0; c < hv; ++c) {
           wb.hist_pred[(size_t)o * hw + c] = ts.hist_pred[(base + j) * hw + c];
           wb.hist_obs[(size_t)o * hw + c] = ts.hist_obs[(base + j) * hw + c];
         }
