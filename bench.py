@@ -479,9 +479,15 @@ def main():
     D = cfg.feature_dim
     visual = D > 0
 
+    # capacity hint: with frames in flight the store is sized for upper bounds (every queued detection may become a track).
+    # A threshold that cuts nothing (--visual-threshold max / 10.0) also creates ~1.6 x the tracks of the headline metric;
+    # with 4 x it sat at the edge of a store regrow (8 GB of feature arena reallocated inside the timed region when the
+    # ring happened to be full), so those runs get 8 x.
+    tracks_hint = (8 if args.visual_threshold is not None else 4) * cfg.n_objects
+
     def new_tracker():
         t = eng.Tracker(tracker_options_for(name, default_options, device=local, max_scenes_hint=cfg.n_scenes,
-                                            max_tracks_per_scene_hint=4 * cfg.n_objects,
+                                            max_tracks_per_scene_hint=tracks_hint,
                                             max_dets_per_scene_hint=cfg.n_objects, **over))
         t.set_stream(torch.cuda.current_stream().cuda_stream)
         return t
