@@ -552,36 +552,38 @@ def main():
     t_dev = new_tracker()
     dboxes = [torch.from_numpy(np.ascontiguousarray(f["boxes"])).to(dev) for f in frames[: W + K]]
     dfeats = [torch.from_numpy(f["features"]).to(dev) if visual else None for f in frames[: W + K]]
-    d_ids = torch.zeros(max_total, dtype=torch.int64, device=dev)
-    d_ep = torch.zeros(max_total, dtype=torch.int32, device=dev)
-    d_len = torch.zeros(max_total, dtype=torch.int32, device=dev)
-    d_vt = torch.zeros(max_total, dtype=torch.uint8, device=dev)
+    # two sets of output columns: frame i writes set i & 1, so the gather of frame i can read its ids while frame i + 1 runs
+    d_ids = [torch.zeros(max_total, dtype=torch.int64, device=dev) for _ in range(2)]
+    d_ep = [torch.zeros(max_total, dtype=torch.int32, device=dev) for _ in range(2)]
+    d_len = [torch.zeros(max_total, dtype=torch.int32, device=dev) for _ in range(2)]
+    d_vt = [torch.zeros(max_total, dtype=torch.uint8, device=dev) for _ in range(2)]
     main_stream = torch.cuda.current_stream()
+    # the caller's stream does not wait for every frame (sb200_set_stream_join 0): successive frames overlap where they can;
+    # whoever consumes device-resident outputs joins explicitly (sb200_stream_join)
+    t_dev.set_stream(main_stream.cuda_stream, join_per_call=False)
     gather = None
     if world > 1:
-        # NCCL gather of the assigned track ids (the one exchange of the path), one step behind on a side stream: step i
-        # snapshots its ids (1 MB device copy) and the side stream gathers them while step i+1 computes
+        # NCCL gather of the assigned track ids (the one exchange of the path) on a side stream: that stream joins frame i
+        # (sb200_stream_join) and gathers its ids while frame i + 1 computes; frame i + 2, which rewrites the same output
+        # set, is ordered after that gather through the caller's stream
         gather = {"stream": torch.cuda.Stream(device=dev),
-                  "snap": [torch.zeros(max_total, dtype=torch.int64, device=dev) for _ in range(2)],
                   "buf": [torch.zeros(max_total * world, dtype=torch.int64, device=dev) for _ in range(2)],
-                  "ready": [torch.cuda.Event() for _ in range(2)], "done": [None, None]}
+                  "done": [None, None]}
     torch.cuda.synchronize()
 
     def step_dev(i):
         f = frames[i]
+        b = i & 1
+        if gather is not None and gather["done"][b] is not None:
+            main_stream.wait_event(gather["done"][b])   # the gather that read this output set two steps ago
         t_dev.predict_batch_device(f["scene_ids"], f["det_offsets"], dboxes[i].data_ptr(),
-                                   dfeats[i].data_ptr() if visual else 0, d_ids=d_ids.data_ptr(),
-                                   d_epochs=d_ep.data_ptr(), d_lengths=d_len.data_ptr(),
-                                   d_voting_types=d_vt.data_ptr())
+                                   dfeats[i].data_ptr() if visual else 0, d_ids=d_ids[b].data_ptr(),
+                                   d_epochs=d_ep[b].data_ptr(), d_lengths=d_len[b].data_ptr(),
+                                   d_voting_types=d_vt[b].data_ptr())
         if gather is not None:
-            b = i & 1
-            if gather["done"][b] is not None:
-                main_stream.wait_event(gather["done"][b])   # the gather that read this snapshot two steps ago
-            gather["snap"][b].copy_(d_ids, non_blocking=True)
-            gather["ready"][b].record(main_stream)
+            t_dev.stream_join(gather["stream"].cuda_stream)
             with torch.cuda.stream(gather["stream"]):
-                gather["stream"].wait_event(gather["ready"][b])
-                dist.all_gather_into_tensor(gather["buf"][b], gather["snap"][b])
+                dist.all_gather_into_tensor(gather["buf"][b], d_ids[b])
                 ev = torch.cuda.Event()
                 ev.record(gather["stream"])
                 gather["done"][b] = ev
@@ -602,6 +604,7 @@ def main():
         step_dev(i)
     th1 = time.perf_counter()
     h1 = t_dev.host_counters()
+    t_dev.stream_join(main_stream.cuda_stream)   # the timed span ends when the last frame has ended
     if gather is not None:
         for e in gather["done"]:
             if e is not None:
@@ -616,7 +619,7 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = eng.launch_count() - l0
     c1 = t_dev.work_counters()
-    ids_dev_last = d_ids[: len(frames[W + K - 1]["boxes"])].cpu().numpy().astype(np.uint64)
+    ids_dev_last = d_ids[(W + K - 1) & 1][: len(frames[W + K - 1]["boxes"])].cpu().numpy().astype(np.uint64)
     assert np.array_equal(ids_dev_last, ids_e2e_last), "device-pointer and host-pointer paths disagree"
     if gather is not None:   # every rank holds every shard's ids of the last step
         gl = gather["buf"][(W + K - 1) & 1].view(world, max_total)[rank][: len(ids_dev_last)].cpu().numpy().astype(np.uint64)

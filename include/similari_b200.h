@@ -115,9 +115,19 @@ int sb200_device_count(void);
 /* ---- tracker lifecycle (Sort::new ... ) ---- */
 int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out);
 void sb200_tracker_destroy(sb200_tracker* t);
-/* Makes the tracker launch on `cuda_stream` (a cudaStream_t) instead of its own stream, so that a caller can
- * bracket the work with its own CUDA events. */
+/* Orders the tracker's work with `cuda_stream` (a cudaStream_t; NULL is the legacy default stream): every predict call first waits
+ * for what that stream holds when the call is made (so device-resident inputs may be produced on it just before the call)
+ * and the stream waits for the call's frame (so its outputs can be consumed on it, and the caller can bracket the work
+ * with its own CUDA events).  The kernels themselves run on the tracker's own streams. */
 int sb200_tracker_set_stream(sb200_tracker* t, void* cuda_stream);
+/* per_call != 0 (the default): the caller's stream waits for the frame of every predict call.  0: it does not -- successive
+ * frames then overlap where they can (the next frame's candidate preparation runs under the current frame's cost kernels);
+ * a stream that consumes device-resident outputs waits for them explicitly with sb200_stream_join (or the host calls
+ * sb200_sync).  Counterpart of taking the results off PredictionBatchResult's channel when they are needed
+ * (src/trackers/batch.rs:24-38) instead of blocking in predict. */
+int sb200_set_stream_join(sb200_tracker* t, int32_t per_call);
+/* Makes `cuda_stream` wait (on the device) for every frame enqueued so far. */
+int sb200_stream_join(sb200_tracker* t, void* cuda_stream);
 
 /* VisualSortObservation::feature is an Option (src/trackers/visual_sort.rs:42-55): a tracker may see frames without any
  * feature before it learns the feature length.  Until a request has carried feature rows the dimension given at creation

@@ -83,7 +83,7 @@ EXPORTS = [
     "sb200_kalman_predict", "sb200_kalman_update", "sb200_nms", "sb200_own_area_shares", "sb200_host_alloc", "sb200_host_free",
     "sb200_predict_batch_async", "sb200_sync", "sb200_frames_in_flight", "sb200_work_counters", "sb200_launch_count",
     "sb200_set_feature_dim", "sb200_comm_unique_id", "sb200_comm_create", "sb200_comm_destroy", "sb200_shard_scatter",
-    "sb200_shard_gather", "sb200_wasted_history", "sb200_host_counters",
+    "sb200_shard_gather", "sb200_wasted_history", "sb200_host_counters", "sb200_set_stream_join", "sb200_stream_join",
 ]
 
 
@@ -105,6 +105,8 @@ def lib():
         "sb200_tracker_create": (C.c_int, [C.POINTER(Options), C.POINTER(vp)]),
         "sb200_tracker_destroy": (None, [vp]),
         "sb200_tracker_set_stream": (C.c_int, [vp, vp]),
+        "sb200_set_stream_join": (C.c_int, [vp, i32]),
+        "sb200_stream_join": (C.c_int, [vp, vp]),
         "sb200_predict_batch": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PredictOut)]),
         "sb200_prefetch_inputs": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
         "sb200_predict_batch_async": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(PredictOut)]),

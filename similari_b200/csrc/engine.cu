@@ -160,8 +160,24 @@ struct sb200_tracker {
   sb200_options opts{};
   sb::Params P{};
   int device = 0;
+  // `stream` is the tracker's own work stream.  A caller's stream (sb200_tracker_set_stream) is joined by events: the work
+  // of a call is ordered after what the caller's stream held when the call was made, and that stream waits for the call's
+  // frame -- the stream-order contract, without the library's kernels sitting in the caller's stream (so the library is free
+  // to start the next frame's candidate preparation under the current frame, see prep_stream).
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t user_stream = nullptr;   // valid when has_user_stream (0 is the legacy default stream)
+  bool has_user_stream = false;
+  bool join_per_call = true;   // the caller's stream waits for every call's frame (else: sb200_stream_join)
+  cudaEvent_t ev_join_req = nullptr;
+  cudaEvent_t ev_user_in = nullptr, ev_user_out = nullptr;
+  // candidate preparation (prep + norms / BF16 rows: needs the request only) one frame ahead, on its own stream, into one
+  // of two sets of candidate-side buffers
+  cudaStream_t prep_stream = nullptr;
+  cudaEvent_t ev_prep_done = nullptr, ev_set_free[2]{}, ev_inputs = nullptr;
+  bool set_busy[2]{};
+  bool prep_off = false;
+  unsigned long long frame_seq = 0;
   float kernel_ms[2]{};    // screen, refine(+mode) of the last absorbed frame
   bool tc_timed = false;
   cudaStream_t copy_stream = nullptr;
@@ -234,9 +250,10 @@ struct sb200_tracker {
     bool read_pending = false;
   } stg[2];
   int stg_last = 1;   // staging set used by the most recent predict
-  DBuf f_cbox, f_cradius, f_cconf, f_cvert, f_cflags, f_cnorm2, f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
-      f_status, f_featdst, f_apprank, f_appmeta, f_posgq, f_frameout, f_decided, f_excl, f_prewin, f_own, f_ownovf, f_dyn, f_ws, f_tmeta, f_rowinfo, f_slabc, f_slabm, f_slabmask,
-      f_dscene, f_maxc, f_maxcval, f_drowb, f_dcolb, f_slabk, f_cbf16, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
+  DBuf f_cbox2[2], f_cradius2[2], f_cconf2[2], f_cvert2[2], f_cflags2[2], f_cnorm22[2], f_cbf162[2], f_decided2[2];   // candidate side, two sets
+  DBuf f_winner, f_cvt, f_pos, f_vis, f_scenes, f_newcount,
+      f_status, f_featdst, f_apprank, f_appmeta, f_posgq, f_frameout, f_excl, f_prewin, f_own, f_ownovf, f_dyn, f_ws, f_tmeta, f_rowinfo, f_slabc, f_slabm, f_slabmask,
+      f_dscene, f_maxc, f_maxcval, f_drowb, f_dcolb, f_slabk, f_scene_max, f_tiles, f_pairs, f_colmeta, f_colgeo, f_colb, f_colvalid, f_rowmeta, f_poslist, f_counters, f_visval;
   int num_sms = 148;
   DBuf o_ids, o_epochs, o_lengths, o_vt, o_pred, o_obs;
   HBuf h_small;
@@ -249,12 +266,15 @@ struct sb200_tracker {
   ~sb200_tracker() {
     cudaSetDevice(device);
     DBuf* all[] = {&b_id, &b_epoch, &b_length, &b_custom, &b_vt, &b_pred, &b_obs, &b_radius, &b_kst, &b_vert, &b_hpred, &b_hobs, &w_hpred, &w_hobs, &b_feat,
-                   &b_feat_bf16, &f_cbf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_colb, &f_colvalid, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
-                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_decided, &f_excl, &f_prewin, &f_own, &f_ownovf, &f_dyn, &b_idc, &f_ws, &f_tmeta, &f_rowinfo, &f_slabc, &f_slabm, &f_slabmask, &f_dscene, &f_maxc, &f_maxcval, &f_drowb, &f_dcolb, &f_slabk,
-                   &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_cbox, &f_cradius, &f_cconf,
-                   &f_cvert, &f_cflags, &f_cnorm2, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
+                   &b_feat_bf16, &f_scene_max, &f_tiles, &f_pairs, &f_colmeta, &f_colgeo, &f_colb, &f_colvalid, &f_rowmeta, &f_poslist, &f_counters, &f_visval, &b_fnorm2, &b_obs_phys, &b_obs_hasf, &b_obs_q, &b_obs_n, &b_feat_cnt, &b_ntracks, &b_cur_epoch,
+                   &b_fblk, &b_blk_owner, &b_blk_free, &b_nfree, &b_atop, &f_frameout, &f_excl, &f_prewin, &f_own, &f_ownovf, &f_dyn, &b_idc, &f_ws, &f_tmeta, &f_rowinfo, &f_slabc, &f_slabm, &f_slabmask, &f_dscene, &f_maxc, &f_maxcval, &f_drowb, &f_dcolb, &f_slabk,
+                   &b_scene_ids, &w_count, &w_id, &w_scene, &w_epoch, &w_length, &w_pred, &w_obs, &f_winner, &f_cvt, &f_pos, &f_vis, &f_scenes, &f_newcount, &f_status,
                    &f_featdst, &f_apprank, &f_appmeta, &f_posgq, &o_ids, &o_epochs, &o_lengths, &o_vt, &o_pred, &o_obs};
     for (DBuf* b : all) b->release();
+    for (int k = 0; k < 2; ++k) {
+      f_cbox2[k].release(); f_cradius2[k].release(); f_cconf2[k].release(); f_cvert2[k].release(); f_cflags2[k].release();
+      f_cnorm22[k].release(); f_cbf162[k].release(); f_decided2[k].release();
+    }
     if (stream) cudaStreamSynchronize(stream);
     h_small.release();
     for (auto& g : stg) {
@@ -272,6 +292,8 @@ struct sb200_tracker {
     }
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (pos_stream) cudaStreamDestroy(pos_stream);
+    if (prep_stream) cudaStreamDestroy(prep_stream);
+    for (cudaEvent_t e : {ev_user_in, ev_user_out, ev_prep_done, ev_set_free[0], ev_set_free[1], ev_inputs, ev_join_req}) if (e) cudaEventDestroy(e);
     for (auto& e : ev_fork) if (e) cudaEventDestroy(e);
     if (ev_join) cudaEventDestroy(ev_join);
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -808,6 +830,10 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     pos_total = std::max(pos_total, hint_pos);
     if (P.is_visual) vis_total = std::max(vis_total, hint_pos * K);
   }
+  // candidate-side buffers: the set of this frame (the other one may still be read by the frame in front of it)
+  const int cset = (int)(frame_seq & 1);
+  DBuf &f_cbox = f_cbox2[cset], &f_cradius = f_cradius2[cset], &f_cconf = f_cconf2[cset], &f_cvert = f_cvert2[cset],
+       &f_cflags = f_cflags2[cset], &f_cnorm2 = f_cnorm22[cset], &f_cbf16 = f_cbf162[cset], &f_decided = f_decided2[cset];
   if ((rc = ENS(f_cbox, T * 24)) || (rc = ENS(f_cradius, T * 4)) || (rc = ENS(f_cconf, T * 4)) ||
       (rc = ENS(f_winner, T * 4)) || (rc = ENS(f_cvt, T)) || (rc = ENS(f_scenes, sizeof(sb::SceneDesc) * n_scenes)) ||
       (rc = ENS(f_newcount, 4 * (size_t)n_scenes)) || (rc = ENS(f_dyn, sizeof(sb::FrameDyn))) ||
@@ -1040,6 +1066,7 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   // the request is committed (epochs, ring slot, bounds of the frames in flight)
   for (int s = 0; s < n_scenes; ++s) epoch[last_req_slots[s]] += 1;
   if (features != nullptr && total > 0) seen_features = true;
+  frame_seq += 1;
   q.active = true;
   q.n_scenes = n_scenes;
   q.total = total;
@@ -1066,6 +1093,11 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
   } rollback{this, &q, true};
 
   const double ms_setup = since(t_begin);
+  if (has_user_stream) {   // everything the caller's stream holds now comes first
+    if (!ev_user_in) { CU(cudaEventCreateWithFlags(&ev_user_in, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&ev_user_out, cudaEventDisableTiming)); }
+    CU(cudaEventRecord(ev_user_in, user_stream));
+    CU(cudaStreamWaitEvent(stream, ev_user_in, 0));
+  }
   if (!device_io && !prefetched && total > 0) {
     const size_t n = (size_t)total;
     CU(cudaMemcpyAsync(sin->boxes.p, boxes, n * 24, cudaMemcpyHostToDevice, stream));
@@ -1116,7 +1148,34 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
                         reinterpret_cast<int2*>(f_ownovf.as<char>() + 16), stream);
     f.in_own = f_own.as<float>();
   }
-  sb::launch_prep(Pf, f, n_scenes, max_m, stream);
+  // Candidate preparation needs the request only (boxes, features): it runs on its own stream as soon as the inputs are there
+  // and the frame that read this set of candidate buffers (two frames back) has ended -- in the steady state under the
+  // tensor-core kernel of the frame in front.  (With derived own-area shares it needs the frame tables: main stream.)
+  if (!prep_stream && !prep_off) {
+    static const bool off = [] { const char* e = getenv("SB200_PREP_AHEAD"); return e && e[0] == '0'; }();
+    prep_off = off;
+    if (!prep_off) {
+      int lo = 0, hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU(cudaStreamCreateWithPriority(&prep_stream, cudaStreamNonBlocking, lo));
+      CU(cudaEventCreateWithFlags(&ev_prep_done, cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&ev_inputs, cudaEventDisableTiming));
+    }
+  }
+  const bool prep_ahead = prep_stream != nullptr && !derive_own && total > 0;
+  if (prep_ahead) {
+    if (has_user_stream) CU(cudaStreamWaitEvent(prep_stream, ev_user_in, 0));
+    if (!device_io) {   // staged inputs: the prefetch copy, or the copies issued above on the work stream
+      if (prefetched) CU(cudaStreamWaitEvent(prep_stream, sin->ev, 0));
+      else { CU(cudaEventRecord(ev_inputs, stream)); CU(cudaStreamWaitEvent(prep_stream, ev_inputs, 0)); }
+    }
+    if (set_busy[cset]) CU(cudaStreamWaitEvent(prep_stream, ev_set_free[cset], 0));
+    sb::launch_prep(Pf, f, n_scenes, max_m, prep_stream);
+    CU(cudaEventRecord(ev_prep_done, prep_stream));
+    CU(cudaStreamWaitEvent(stream, ev_prep_done, 0));
+  } else {
+    sb::launch_prep(Pf, f, n_scenes, max_m, stream);
+  }
   if (side_setup) CU(cudaStreamWaitEvent(stream, ev_join, 0));
   CU(cudaEventRecord(q.ev[1], stream));
   sb::TcArgs tcc = tc;
@@ -1197,6 +1256,13 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
             hc[0], hc[1], hc[2], hc[3], tot, mx);
   }
   CU(cudaEventRecord(q.done, stream));
+  if (!ev_set_free[cset]) CU(cudaEventCreateWithFlags(&ev_set_free[cset], cudaEventDisableTiming));
+  CU(cudaEventRecord(ev_set_free[cset], stream));   // this frame's candidate buffers may be rewritten after this point
+  set_busy[cset] = true;
+  if (has_user_stream && join_per_call) {   // the caller's stream continues after the frame
+    CU(cudaEventRecord(ev_user_out, stream));
+    CU(cudaStreamWaitEvent(user_stream, ev_user_out, 0));
+  }
   rollback.armed = false;
   if (sin) { CU(cudaEventRecord(sin->ev_read, stream)); sin->read_pending = true; }
   const double ms_launch = since(t_begin);
@@ -1263,7 +1329,10 @@ int sb200_tracker_create(const sb200_options* opts, sb200_tracker** out) {
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, opts->device) == cudaSuccess && sms > 0) t->num_sms = sms;
   }
-  cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  // numerically lower = more urgent: side stream (prio_hi) > work stream > candidate preparation (prio_lo)
+  cudaError_t e = cudaStreamCreateWithPriority(&t->stream, cudaStreamNonBlocking, prio_hi < prio_lo ? prio_hi + 1 : prio_lo);
   if (e != cudaSuccess) { delete t; return fail(SB200_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
   for (auto& g : t->stg) {
     e = cudaEventCreate(&g.ev);
@@ -1289,9 +1358,24 @@ int sb200_tracker_set_stream(sb200_tracker* t, void* cuda_stream) {
   int rc = t->drain();
   if (rc) return rc;
   CU(cudaStreamSynchronize(t->stream));
-  if (t->own_stream && t->stream) cudaStreamDestroy(t->stream);
-  t->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
-  t->own_stream = false;
+  // the tracker keeps its own work stream; the caller's stream is joined by events at every call (see `user_stream`)
+  t->user_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  t->has_user_stream = true;
+  return 0;
+}
+
+int sb200_set_stream_join(sb200_tracker* t, int32_t per_call) {
+  if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
+  t->join_per_call = per_call != 0;
+  return 0;
+}
+
+int sb200_stream_join(sb200_tracker* t, void* cuda_stream) {
+  if (!t) return fail(SB200_ERR_INVALID, "tracker is NULL");
+  CU(cudaSetDevice(t->device));
+  if (!t->ev_join_req) CU(cudaEventCreateWithFlags(&t->ev_join_req, cudaEventDisableTiming));
+  CU(cudaEventRecord(t->ev_join_req, t->stream));
+  CU(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(cuda_stream), t->ev_join_req, 0));
   return 0;
 }
 
@@ -1322,7 +1406,7 @@ int sb200_set_feature_dim(sb200_tracker* t, int32_t feature_dim) {
   t->P.feature_dim = feature_dim;
   t->P.d8 = (feature_dim + 7) / 8 * 8;
   t->opts.feature_dim = feature_dim;
-  t->b_feat.release(); t->b_feat_bf16.release(); t->f_cbf16.release();
+  t->b_feat.release(); t->b_feat_bf16.release(); t->f_cbf162[0].release(); t->f_cbf162[1].release();
   t->ts.feat = nullptr; t->ts.feat_bf16 = nullptr;
   const size_t rows = (size_t)t->scene_cap * t->track_cap * t->P.max_obs;
   if (rows > 0) {

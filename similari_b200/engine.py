@@ -40,8 +40,15 @@ class Tracker:
         except Exception:
             pass
 
-    def set_stream(self, cuda_stream: int):
+    def set_stream(self, cuda_stream: int, join_per_call: bool = True):
+        """Orders every call after what `cuda_stream` holds at that moment; with join_per_call the stream also waits for
+        each call's frame (else use stream_join / sync before consuming device-resident outputs)."""
         check(self._L.sb200_tracker_set_stream(self._h, C.c_void_p(cuda_stream)))
+        check(self._L.sb200_set_stream_join(self._h, 1 if join_per_call else 0))
+
+    def stream_join(self, cuda_stream: int):
+        """sb200_stream_join: `cuda_stream` waits on the device for every frame enqueued so far."""
+        check(self._L.sb200_stream_join(self._h, C.c_void_p(cuda_stream)))
 
     def predict_batch(self, scene_ids, det_offsets, boxes, features=None, has_feature=None, quality=None,
                       custom_ids=None, own_area=None, want=("ids", "epochs", "lengths", "voting_types", "predicted",
