@@ -122,8 +122,8 @@ void sb200_tracker_destroy(sb200_tracker* t);
 int sb200_tracker_set_stream(sb200_tracker* t, void* cuda_stream);
 /* per_call != 0 (the default): the caller's stream waits for the frame of every predict call.  0: it does not -- successive
  * frames then overlap where they can (the next frame's candidate preparation runs under the current frame's cost kernels);
- * a stream that consumes device-resident outputs waits for them explicitly with sb200_stream_join (or the host calls
- * sb200_sync).  Counterpart of taking the results off PredictionBatchResult's channel when they are needed
+ * a stream that consumes device-resident outputs -- or overwrites device-resident inputs of a frame that may still be
+ * running -- waits explicitly with sb200_stream_join (or the host calls sb200_sync).  Counterpart of taking the results off PredictionBatchResult's channel when they are needed
  * (src/trackers/batch.rs:24-38) instead of blocking in predict. */
 int sb200_set_stream_join(sb200_tracker* t, int32_t per_call);
 /* Makes `cuda_stream` wait (on the device) for every frame enqueued so far. */

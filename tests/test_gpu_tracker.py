@@ -604,3 +604,49 @@ def test_gated_pair_queue_overflow_is_evaluated_in_place(eng, oracle, kind, pos,
         kw.update(visual_kind=0, visual_threshold=0.7, feature_dim=64, visual_max_observations=3, visual_min_votes=2,
                   visual_minimal_track_length=1, min_confidence=0.1)
     run_frames(eng, oracle, cfg, 6, kw)
+
+
+@pytest.mark.parametrize("join_per_call", [True, False])
+def test_caller_stream_is_joined_by_events(eng, oracle, join_per_call):
+    """sb200_tracker_set_stream: the tracker runs on its own streams and is ordered with the caller's by events.  Inputs are
+    produced on the caller's stream right before each call (a device copy from a staging tensor into the buffer the call
+    reads -- the call must wait for it), outputs are consumed on that stream right after it (a device copy out of a buffer
+    the NEXT call overwrites): with join_per_call the stream waits for every frame by itself, without it
+    sb200_stream_join makes it wait.  Either way the snapshots must be the oracle's, frame by frame."""
+    import torch
+
+    from similari_b200.workload import Workload
+
+    cfg = small("cfg5", n_scenes=5, n_objects=50, oriented=False, canvas=(800.0, 600.0), feature_dim=64, drop_frac=0.1,
+                fresh_frac=0.1)
+    kw = dict(kind=3, positional_kind=1, iou_threshold=0.3, max_idle_epochs=2, visual_kind=0, visual_threshold=0.7,
+              feature_dim=64, visual_max_observations=3, visual_min_votes=2, visual_minimal_track_length=1, min_confidence=0.1)
+    g, o = both(eng, oracle, **kw)
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(device=dev)
+    g.set_stream(side.cuda_stream, join_per_call=join_per_call)
+    wl = Workload(cfg)
+    frames = [wl.next_frame() for _ in range(8)]
+    ref = [o.predict_batch(f["scene_ids"], f["det_offsets"], f["boxes"], features=f["features"]) for f in frames]
+    cap = max(len(f["boxes"]) for f in frames)
+    # staging tensors per frame (filled up front), ONE input buffer and ONE output buffer reused by every call
+    st_b = [torch.from_numpy(np.ascontiguousarray(f["boxes"])).to(dev) for f in frames]
+    st_f = [torch.from_numpy(np.ascontiguousarray(f["features"])).to(dev) for f in frames]
+    in_b = torch.zeros(cap, 6, dtype=torch.float32, device=dev)
+    in_f = torch.zeros(cap, 64, dtype=torch.float32, device=dev)
+    d_ids = torch.zeros(cap, dtype=torch.int64, device=dev)
+    snaps = []
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for f, sb_, sf_ in zip(frames, st_b, st_f):
+            n = len(f["boxes"])
+            in_b[:n].copy_(sb_, non_blocking=True)      # on the caller's stream, right before the call
+            in_f[:n].copy_(sf_, non_blocking=True)
+            g.predict_batch_device(f["scene_ids"], f["det_offsets"], in_b.data_ptr(), in_f.data_ptr(), d_ids=d_ids.data_ptr())
+            if not join_per_call:
+                g.stream_join(side.cuda_stream)
+            snaps.append(d_ids[:n].clone())             # on the caller's stream, right after the call
+    side.synchronize()
+    g.sync()
+    for fr, (sn, ro) in enumerate(zip(snaps, ref)):
+        assert np.array_equal(sn.cpu().numpy().astype(np.uint64), ro["ids"].astype(np.uint64)), fr
