@@ -766,7 +766,11 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       const long long dets = std::max<long long>(total, (long long)std::max(opts.max_scenes_hint, n_scenes) * opts.max_dets_per_scene_hint);
       const long long ring_need = (long long)(kDepth + 1) * (live_ub + (long long)kDepth * dets);
       // and the records already waiting for collection doubled: a caller that collects rarely pays for few regrows
-      if ((rc = ensure_wasted(2 * wasted_count + std::max<long long>(ring_need, 2 * pipe_need) + 1))) return rc;
+      // and several times that while it is cheap (<= ~2 GB of records): a regrow drains the ring and reallocates
+      const long long rec_bytes = 72 + (hist_len > 1 ? 48ll * hist_len : 0);
+      const long long base_need = std::max<long long>(ring_need, 2 * pipe_need);
+      const long long mult = std::max<long long>(1, std::min<long long>(8, (2ll << 30) / std::max<long long>(1, base_need * rec_bytes)));
+      if ((rc = ensure_wasted(2 * wasted_count + mult * base_need + 1))) return rc;
     }
     if (!b_idc.p) {
       if ((rc = b_idc.ensure(8))) return rc;
