@@ -175,6 +175,8 @@ struct sb200_tracker {
   // of two sets of candidate-side buffers
   cudaStream_t prep_stream = nullptr;
   cudaEvent_t ev_prep_done = nullptr, ev_set_free[2]{}, ev_inputs = nullptr;
+  cudaEvent_t ev_cost_done = nullptr;   // the cost kernels of the newest frame have been issued up to here (work stream)
+  bool cost_done_valid = false;
   bool set_busy[2]{};
   bool prep_off = false;
   unsigned long long frame_seq = 0;
@@ -293,7 +295,7 @@ struct sb200_tracker {
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (pos_stream) cudaStreamDestroy(pos_stream);
     if (prep_stream) cudaStreamDestroy(prep_stream);
-    for (cudaEvent_t e : {ev_user_in, ev_user_out, ev_prep_done, ev_set_free[0], ev_set_free[1], ev_inputs, ev_join_req}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ev_user_in, ev_user_out, ev_prep_done, ev_set_free[0], ev_set_free[1], ev_inputs, ev_join_req, ev_cost_done}) if (e) cudaEventDestroy(e);
     for (auto& e : ev_fork) if (e) cudaEventDestroy(e);
     if (ev_join) cudaEventDestroy(ev_join);
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -1176,6 +1178,12 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       else { CU(cudaEventRecord(ev_inputs, stream)); CU(cudaStreamWaitEvent(prep_stream, ev_inputs, 0)); }
     }
     if (set_busy[cset]) CU(cudaStreamWaitEvent(prep_stream, ev_set_free[cset], 0));
+    // SB200_PREP_AFTER=cost holds the preparation back until the frame in front has left its cost kernels, i.e. puts its HBM
+    // traffic under that frame's voting / apply instead of under its tensor-core kernel.  Measured at cfg5: the screen runs
+    // alone (0.243 ms, 0.717 of the BF16 peak, against 0.251 / 0.693) but apply + feature store lose 40 us to the
+    // contention and the step goes from 0.878 to 0.897 ms -- so the default is "as early as possible".
+    static const bool after_cost = [] { const char* e = getenv("SB200_PREP_AFTER"); return e && !strcmp(e, "cost"); }();
+    if (after_cost && cost_done_valid) CU(cudaStreamWaitEvent(prep_stream, ev_cost_done, 0));
     sb::launch_prep(Pf, f, n_scenes, max_m, prep_stream);
     CU(cudaEventRecord(ev_prep_done, prep_stream));
     CU(cudaStreamWaitEvent(stream, ev_prep_done, 0));
@@ -1210,6 +1218,11 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
     q.pos_forked = true;
   }
   CU(cudaEventRecord(q.ev[3], stream));
+  if (prep_stream) {
+    if (!ev_cost_done) CU(cudaEventCreateWithFlags(&ev_cost_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev_cost_done, stream));
+    cost_done_valid = true;
+  }
   int vr = sb::launch_voting(Pf, ts, f, n_scenes, max_m, max_n, stream);
   if (vr != 0) return fail(SB200_ERR_CUDA, "voting launch failed: %s", cudaGetErrorString((cudaError_t)vr));
   CU(cudaEventRecord(q.ev[4], stream));
