@@ -1178,11 +1178,12 @@ int sb200_tracker::predict(int32_t n_scenes, const uint64_t* scene_ids, const in
       else { CU(cudaEventRecord(ev_inputs, stream)); CU(cudaStreamWaitEvent(prep_stream, ev_inputs, 0)); }
     }
     if (set_busy[cset]) CU(cudaStreamWaitEvent(prep_stream, ev_set_free[cset], 0));
-    // SB200_PREP_AFTER=cost holds the preparation back until the frame in front has left its cost kernels, i.e. puts its HBM
-    // traffic under that frame's voting / apply instead of under its tensor-core kernel.  Measured at cfg5: the screen runs
-    // alone (0.243 ms, 0.717 of the BF16 peak, against 0.251 / 0.693) but apply + feature store lose 40 us to the
-    // contention and the step goes from 0.878 to 0.897 ms -- so the default is "as early as possible".
-    static const bool after_cost = [] { const char* e = getenv("SB200_PREP_AFTER"); return e && !strcmp(e, "cost"); }();
+    // ... and not before the frame in front has left its cost kernels: the preparation is HBM traffic; under that frame's
+    // tensor-core screen it costs the screen 3-6 % (0.248-0.26 ms instead of 0.243), under its voting / apply / feature store it
+    // costs those ~40 us.  Measured at cfg5: 0.897 ms/step with the screen at 0.717 of the BF16 peak here, against 0.875-0.88
+    // ms/step with the screen at 0.67-0.70 for SB200_PREP_AFTER=none (as early as possible).  The default keeps the
+    // tensor-core kernel undisturbed and the step time reproducible; a deployment that only counts frames sets "none".
+    static const bool after_cost = [] { const char* e = getenv("SB200_PREP_AFTER"); return !(e && !strcmp(e, "none")); }();
     if (after_cost && cost_done_valid) CU(cudaStreamWaitEvent(prep_stream, ev_cost_done, 0));
     sb::launch_prep(Pf, f, n_scenes, max_m, prep_stream);
     CU(cudaEventRecord(ev_prep_done, prep_stream));
